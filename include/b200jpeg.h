@@ -1,0 +1,149 @@
+/* b200jpeg.h - C ABI of the B200-native JPEG decode back end (libb200jpeg.so).
+ *
+ * Drop-in boundary for the MCU-decode hot path of jeun-990806/pim-jpeg-decoder.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference tree).  Plain C: pointers and sizes only,
+ * no C++ or torch types.  All functions return BJ_OK (0) or a negative bj_status; nothing throws, nothing exits,
+ * and there is NO CPU fallback: without a CUDA device every compute entry fails with BJ_ERR_CUDA.
+ *
+ * Threading: a bj_ctx is single-owner (one consumer thread per context, like the reference's `offloading`
+ * thread, src/decoder_host.cpp:213-350).  One context drives one GPU; one process per GPU.
+ * Ownership: the caller owns every host pointer it passes; the library owns device and pinned staging memory.
+ */
+#ifndef B200JPEG_H
+#define B200JPEG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    BJ_OK = 0,
+    BJ_ERR_ARG = -1,          /* bad argument */
+    BJ_ERR_CUDA = -2,         /* CUDA runtime/driver error (no device, launch failure ...) - see bj_last_error */
+    BJ_ERR_NOMEM = -3,
+    BJ_ERR_INVALID_JPEG = -4, /* the reference's read_JPEG would set header->valid = false */
+    BJ_ERR_UNSUPPORTED = -5,  /* valid for the reference's parser but not decodable by its baseline path (SOF2) */
+    BJ_ERR_CORRUPT_SCAN = -6  /* entropy-coded data inconsistent (the reference's decode_Huffman_data returns false) */
+} bj_status;
+
+typedef struct bj_ctx bj_ctx;
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Context.  Replaces: `auto pim = DpuSet::allocate(DPU_ALLOCATE_ALL)` + `pim.load(DPU_BINARY)`
+ * (src/decoder_host.cpp:32,268).  `device` is the CUDA ordinal (LOCAL_RANK in a one-process-per-GPU job). */
+int bj_create(bj_ctx **ctx, int device);
+void bj_destroy(bj_ctx *ctx);
+const char *bj_status_string(int status);
+const char *bj_last_error(const bj_ctx *ctx);   /* text of the last CUDA error seen by this context */
+int bj_device_sm_count(const bj_ctx *ctx);
+
+/* Pinned host memory for caller buffers (fast PCIe path).  Replaces nothing (UPMEM copies from pageable
+ * std::vector, src/decoder_host.cpp:25-30); optional. */
+void *bj_host_alloc(size_t bytes);
+void bj_host_free(void *p);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * COMPAT ENTRY = the DPU program.  Replaces the sequence
+ *     pim.copy("metadata_buffer", batch.metadata); pim.copy("mcus", batch.mcus);   src/decoder_host.cpp:276-277
+ *     pim.exec();                                                                    src/decoder_host.cpp:292
+ *     pim.copy(batch.mcus, "mcus");                                                  src/decoder_host.cpp:308
+ * i.e. src/decoder_dpu.c:82-390 run on `nchunk` DPUs.
+ *   metadata : [nchunk][276] u32, record layout of src/decoder_host.cpp:156-178 / src/decoder_dpu.c:112-132
+ *   mcus     : [nchunk][64*M*3] i16 in/out, layout [block][component][position][64] (src/decoder_dpu.c:134-156);
+ *              M = metadata[19] of the first non-idle chunk (MAX_MCU_PER_DPU, Makefile:2)
+ * In: Huffman-decoded, de-zigzagged coefficients.  Out: R,G,B as i16 in the same tiles.  Bit-exact, in place.
+ * The _device variant takes device pointers and a cudaStream_t (as void*) and does not synchronise. */
+int bj_exec_mcus(bj_ctx *ctx, const uint32_t *metadata, int16_t *mcus, int nchunk);
+int bj_exec_mcus_device(bj_ctx *ctx, const uint32_t *d_metadata, int16_t *d_mcus, int nchunk, int M, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Image descriptor: POD mirror of the reference's `Header` (src/headers/jpeg.h:146-179) for a baseline file.
+ * Filled by bj_parse_header (a restatement of read_JPEG's marker walk on in-memory bytes,
+ * src/jpeg_scanner.cpp:6-403) or by the caller from a `Header*` it already has. */
+typedef struct {
+    uint32_t width, height;
+    uint32_t mcu_w, mcu_h;            /* Header::mcu_width/height: ceil(w/8), ceil(h/8) */
+    uint32_t mcu_w_real, mcu_h_real;  /* Header::mcu_width_real/height_real */
+    uint32_t restart_interval;        /* in MCUs, 0 = none */
+    uint8_t ncomp;                    /* 1..3 */
+    uint8_t hs, vs;                   /* Header::h/v_sampling_factor (luma) */
+    uint8_t frame_type;               /* 0xC0 baseline / 0xC2 progressive */
+    uint8_t comp_h[3], comp_v[3];     /* ColorComponent::h/v_sampling_factor */
+    uint8_t qt_id[3], dc_id[3], ac_id[3];
+    uint8_t qt_set[4], dc_set[4], ac_set[4];
+    uint8_t scan_ncomp;               /* Header::components_in_scan */
+    uint16_t qt_zz[4][64];            /* quantisation tables in FILE (zig-zag) order; the reference's quirky
+                                         de-zigzag (src/headers/common.h:9-18) is applied inside the kernels */
+    uint8_t dc_offsets[4][17], dc_symbols[4][162];   /* HuffmanTable::offsets/symbols, src/headers/jpeg.h:129-134 */
+    uint8_t ac_offsets[4][17], ac_symbols[4][162];
+    uint64_t scan_off;                /* offset of the first entropy-coded byte in the file */
+    uint64_t scan_len;                /* raw scan bytes (stuffed, with RSTn) up to, not including, the EOI marker */
+} bj_image_desc;
+
+/* Replaces: read_JPEG (src/jpeg_scanner.cpp:345-436) minus the byte-at-a-time scan copy.
+ * BJ_ERR_INVALID_JPEG exactly where the reference sets valid=false; BJ_ERR_UNSUPPORTED for SOF2 or a scan that
+ * does not interleave all frame components (the reference cannot decode those either). */
+int bj_parse_header(const uint8_t *file, size_t len, bj_image_desc *desc);
+
+/* Output layouts of the full path. */
+typedef enum {
+    BJ_OUT_RGB8 = 0,   /* top-down packed R,G,B bytes, width*height*3 */
+    BJ_OUT_BMP = 1     /* the exact file bytes write_BMP produces (src/bmp_writer.cpp:19-67): 26-byte header,
+                          bottom-up B,G,R rows, width%4 zero bytes after every row */
+} bj_out_format;
+size_t bj_output_size(const bj_image_desc *desc, int format);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * FULL PATH, one call.  Replaces, per image, decode_Huffman_data (src/jpeg_scanner.cpp:707-756) + the DPU
+ * program + write_BMP's pixel gathering:  compressed file bytes in host memory -> decoded pixels in host memory.
+ *   files[i], lens[i] : the complete JPEG file i
+ *   outs[i]           : caller buffer of bj_output_size() bytes (discover with bj_parse_header), may be pinned
+ *   status[i]         : per-image bj_status (optional).  An invalid image is skipped like the reference does
+ *                       (src/decoder_host.cpp:120-123) and does not fail the batch.
+ * Internally: sub-batches double-buffered over pinned staging on CUDA streams; blocks until outs are written. */
+int bj_decode_batch(bj_ctx *ctx, const uint8_t *const *files, const size_t *lens, int n, int format,
+                    uint8_t *const *outs, int *status);
+
+/* FULL PATH, staged (device-resident batch) - what bj_decode_batch is made of, and what bench.py times with the
+ * inputs already in HBM. */
+typedef struct bj_batch bj_batch;
+int bj_batch_create(bj_ctx *ctx, const uint8_t *const *files, const size_t *lens, int n, int format, bj_batch **out);
+int bj_batch_upload(bj_batch *b, void *stream);                 /* H2D: file bytes + descriptors          */
+int bj_batch_decode(bj_batch *b, void *stream);                 /* all kernels; input and output stay in HBM */
+int bj_batch_download(bj_batch *b, uint8_t *const *outs, void *stream);   /* D2H into caller buffers, then sync */
+int bj_batch_status(const bj_batch *b, int *status /*[n]*/);
+void bj_batch_destroy(bj_batch *b);
+
+/* Introspection for tests and the benchmark. */
+typedef struct {
+    uint64_t pixels;            /* decoded pixels (valid images) */
+    uint64_t scan_bytes;        /* raw entropy-coded bytes */
+    uint64_t data_units;        /* 8x8 units = 128 B of coefficients each */
+    uint64_t out_bytes;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t subsequences;      /* Huffman decode threads */
+    uint32_t sync_rounds;       /* fix-up rounds the last bj_batch_decode needed */
+    uint32_t launches;          /* kernels launched by the last bj_batch_decode */
+    float ms_entropy, ms_idct;  /* CUDA-event time of the two stages of the last bj_batch_decode */
+} bj_batch_info;
+int bj_batch_get_info(const bj_batch *b, bj_batch_info *info);
+int bj_batch_device_output(const bj_batch *b, int i, void **dptr, size_t *bytes);
+int bj_batch_device_coefficients(const bj_batch *b, int i, void **dptr, size_t *bytes);  /* zig-zag i16 units */
+
+/* Stage-level entry for known-answer tests: dequant + IDCT + upsample + colour only, on caller-supplied
+ * coefficients (zig-zag order, DC un-differenced, MCU-interleaved unit order = what the entropy stage emits).
+ * Replaces: the DPU program on the fast layout. */
+int bj_stage_idct_color(bj_ctx *ctx, const bj_image_desc *desc, const int16_t *coef_zz, int format, uint8_t *out);
+
+/* Tunables (0 = default): Huffman subsequence size in bits (multiple of 32). */
+int bj_set_option(bj_ctx *ctx, const char *name, long value);
+
+/* Version / build info. */
+const char *bj_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200JPEG_H */

@@ -1,0 +1,169 @@
+// libb200jpeg.so - C ABI (include/b200jpeg.h) and host orchestration of the sm_100a kernels.
+// No CPU decode path exists in this library: every compute entry needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/b200jpeg.h"
+#include "bj_dev.h"
+#include "bj_host.h"
+#include "kernels_idct.cuh"
+#include "parse.h"
+#include "batch.h"
+
+using namespace bj;
+
+// ------------------------------------------------------------------------------------------------ context
+
+extern "C" const char *bj_status_string(int s) {
+    switch (s) {
+        case BJ_OK: return "ok";
+        case BJ_ERR_ARG: return "bad argument";
+        case BJ_ERR_CUDA: return "CUDA error";
+        case BJ_ERR_NOMEM: return "out of memory";
+        case BJ_ERR_INVALID_JPEG: return "invalid JPEG (the reference's read_JPEG rejects it)";
+        case BJ_ERR_UNSUPPORTED: return "unsupported JPEG (not a single-scan baseline file)";
+        case BJ_ERR_CORRUPT_SCAN: return "corrupt entropy-coded data";
+    }
+    return "unknown status";
+}
+
+extern "C" const char *bj_build_info(void) { return "b200jpeg sm_100a (CUDA " BJ_STR(CUDART_VERSION) "), built " __DATE__; }
+
+extern "C" int bj_create(bj_ctx **out, int device) {
+    if (!out) return BJ_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fprintf(stderr, "b200jpeg: no CUDA device (%s) - this library has no CPU fallback\n", cudaGetErrorString(e));
+        return BJ_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) return BJ_ERR_ARG;
+    bj_ctx *c = new (std::nothrow) bj_ctx();
+    if (!c) return BJ_ERR_NOMEM;
+    c->device = device;
+    if (c->check(cudaSetDevice(device)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (c->check(cudaGetDeviceProperties(&prop, device)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    if (c->check(cudaFuncSetAttribute(k_idct_color, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemIdctColor)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
+    if (batch_kernels_init(c) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
+    for (int i = 0; i < 2; i++)
+        if (c->check(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
+    *out = c;
+    return BJ_OK;
+}
+
+extern "C" void bj_destroy(bj_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &p : c->pool) p.release();
+    for (int i = 0; i < 2; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    delete c;
+}
+
+extern "C" const char *bj_last_error(const bj_ctx *c) { return c ? c->last_error.c_str() : "null context"; }
+extern "C" int bj_device_sm_count(const bj_ctx *c) { return c ? c->sm_count : 0; }
+
+extern "C" void *bj_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void bj_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
+    if (!c || !name) return BJ_ERR_ARG;
+    if (!strcmp(name, "subseq_bits")) { if (value < 128 || value % 32) return BJ_ERR_ARG; c->subseq_bits = (int)value; return BJ_OK; }
+    if (!strcmp(name, "sub_batch_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_bytes = (size_t)value; return BJ_OK; }
+    return BJ_ERR_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------ compat entry
+
+extern "C" int bj_exec_mcus_device(bj_ctx *c, const uint32_t *d_md, int16_t *d_mcus, int nchunk, int M, void *stream) {
+    if (!c || !d_md || !d_mcus || nchunk < 0 || M < 4) return BJ_ERR_ARG;
+    if (nchunk == 0) return BJ_OK;
+    const int blk_per_chunk = M / 4;
+    const long long nblk = (long long)nchunk * blk_per_chunk;
+    const int grid = (int)((nblk + 15) / 16);
+    k_exec_mcus<<<grid, kTileThreads, 0, (cudaStream_t)stream>>>(d_md, d_mcus, nchunk, blk_per_chunk, 64 * M * 3);
+    return c->check(cudaGetLastError());
+}
+
+extern "C" int bj_exec_mcus(bj_ctx *c, const uint32_t *metadata, int16_t *mcus, int nchunk) {
+    if (!c || !metadata || !mcus || nchunk < 0) return BJ_ERR_ARG;
+    if (nchunk == 0) return BJ_OK;
+    int M = 0;                                   // MAX_MCU_PER_DPU as the host compiled it (metadata[19], decoder_host.cpp:172)
+    for (int i = 0; i < nchunk && M == 0; i++) M = (int)metadata[(size_t)i * 276 + 19];
+    if (M == 0) return BJ_OK;                    // only idle DPUs: the program touches nothing
+    if (M < 4) return BJ_ERR_ARG;
+    if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
+    const size_t md_bytes = (size_t)nchunk * 276 * 4, mc_bytes = (size_t)nchunk * 64 * M * 3 * 2;
+    DevBuf &dmd = c->pool[POOL_COMPAT_MD], &dmc = c->pool[POOL_COMPAT_MCUS];
+    if (dmd.reserve(md_bytes) != BJ_OK || dmc.reserve(mc_bytes) != BJ_OK) return BJ_ERR_NOMEM;
+    cudaStream_t s = c->streams[0];
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    // the three pim.copy calls + pim.exec of src/decoder_host.cpp:276-308
+    int rc = c->check(cudaMemcpyAsync(dmd.p, metadata, md_bytes, cudaMemcpyHostToDevice, s));
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dmc.p, mcus, mc_bytes, cudaMemcpyHostToDevice, s));
+    cudaEventRecord(e0, s);
+    if (rc == BJ_OK) rc = bj_exec_mcus_device(c, (const uint32_t *)dmd.p, (int16_t *)dmc.p, nchunk, M, s);
+    cudaEventRecord(e1, s);
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(mcus, dmc.p, mc_bytes, cudaMemcpyDeviceToHost, s));
+    if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
+    if (rc == BJ_OK) cudaEventElapsedTime(&c->last_exec_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ descriptors
+
+extern "C" int bj_parse_header(const uint8_t *file, size_t len, bj_image_desc *desc) {
+    if (!file || !desc) return BJ_ERR_ARG;
+    return parse_header(file, len, desc);
+}
+
+extern "C" size_t bj_output_size(const bj_image_desc *d, int format) {
+    if (!d) return 0;
+    const size_t w = d->width, h = d->height;
+    if (format == BJ_OUT_RGB8) return w * h * 3;
+    if (format == BJ_OUT_BMP) return 26 + h * (w * 3 + w % 4);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stage entry
+
+extern "C" int bj_stage_idct_color(bj_ctx *c, const bj_image_desc *desc, const int16_t *coef_zz, int format, uint8_t *out) {
+    if (!c || !desc || !coef_zz || !out) return BJ_ERR_ARG;
+    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+    if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
+    ImgDev im;
+    std::vector<TileDev> tiles;
+    Geometry g = geometry_of(*desc);
+    fill_imgdev(*desc, g, format, /*du_base=*/0, /*out_base=*/0, &im);
+    append_tiles(g, 0, &tiles);
+    const size_t coef_bytes = (size_t)g.ndu * 128, out_bytes = bj_output_size(desc, format);
+    DevBuf &dco = c->pool[POOL_COEF], &dout = c->pool[POOL_OUT], &dim = c->pool[POOL_IMGS], &dti = c->pool[POOL_TILES];
+    if (dco.reserve(coef_bytes) || dout.reserve(out_bytes + 64) || dim.reserve(sizeof(im)) || dti.reserve(tiles.size() * sizeof(TileDev))) return BJ_ERR_NOMEM;
+    cudaStream_t s = c->streams[0];
+    int rc = c->check(cudaMemcpyAsync(dco.p, coef_zz, coef_bytes, cudaMemcpyHostToDevice, s));
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dim.p, &im, sizeof(im), cudaMemcpyHostToDevice, s));
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dti.p, tiles.data(), tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
+    if (rc == BJ_OK) {
+        k_idct_color<<<(unsigned)tiles.size(), kTileThreads, kSmemIdctColor, s>>>((const int16_t *)dco.p, (const ImgDev *)dim.p, (const TileDev *)dti.p, (uint8_t *)dout.p);
+        rc = c->check(cudaGetLastError());
+    }
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(out, dout.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
+    return rc;
+}

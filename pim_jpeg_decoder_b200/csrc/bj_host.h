@@ -1,0 +1,114 @@
+// Host-side plumbing of the library: context, grow-only device buffers, per-image geometry.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/b200jpeg.h"
+#include "bj_dev.h"
+
+#define BJ_STR2(x) #x
+#define BJ_STR(x) BJ_STR2(x)
+
+namespace bj {
+
+// Grow-only device allocation: batches reuse HBM instead of paying cudaMalloc per call.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return BJ_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return BJ_ERR_NOMEM; }
+        cap = want;
+        return BJ_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum { POOL_COMPAT_MD = 0, POOL_COMPAT_MCUS, POOL_COEF, POOL_OUT, POOL_IMGS, POOL_TILES, POOL_COUNT };
+
+}  // namespace bj
+
+struct bj_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int subseq_bits = 0;                 // 0 = default
+    size_t sub_batch_bytes = 0;          // 0 = default
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    bj::DevBuf pool[bj::POOL_COUNT];
+    std::string last_error;
+    float last_exec_ms = 0.f;
+    int check(cudaError_t e) {
+        if (e == cudaSuccess) return BJ_OK;
+        last_error = cudaGetErrorString(e);
+        cudaGetLastError();
+        return BJ_ERR_CUDA;
+    }
+};
+
+namespace bj {
+
+struct Geometry {
+    uint32_t nmx, nmy, nmcu, bpm, ndu;   // MCUs per row/column, total, data units per MCU, total data units
+    uint32_t tile_mcus;                  // MCUs per K2/K3 tile
+};
+
+inline Geometry geometry_of(const bj_image_desc &d) {
+    Geometry g;
+    g.nmx = (d.mcu_w + d.hs - 1) / d.hs;
+    g.nmy = (d.mcu_h + d.vs - 1) / d.vs;
+    g.nmcu = g.nmx * g.nmy;
+    g.bpm = 0;
+    for (int j = 0; j < d.ncomp; j++) g.bpm += (uint32_t)d.comp_h[j] * d.comp_v[j];
+    g.ndu = g.nmcu * g.bpm;
+    g.tile_mcus = kTileThreads / g.bpm;
+    return g;
+}
+
+// out_base: byte offset of this image's output inside the batch output buffer.
+inline void fill_imgdev(const bj_image_desc &d, const Geometry &g, int format, uint32_t du_base, uint64_t out_base, ImgDev *im) {
+    memset(im, 0, sizeof(*im));
+    im->width = d.width; im->height = d.height;
+    im->nmx = g.nmx; im->nmy = g.nmy;
+    im->du_base = du_base;
+    im->hs = d.hs; im->vs = d.vs; im->ncomp = d.ncomp; im->bpm = (uint8_t)g.bpm;
+    im->row_bytes = d.width * 3;
+    im->valid = 1;
+    if (format == BJ_OUT_BMP) {
+        im->row_pad = d.width % 4;
+        im->out_pitch = d.width * 3 + im->row_pad;
+        im->out_row0 = out_base + 26 + (uint64_t)(d.height - 1) * im->out_pitch;
+        im->row_dir = -1;
+        im->bgr = 1;
+    } else {
+        im->row_pad = 0;
+        im->out_pitch = d.width * 3;
+        im->out_row0 = out_base;
+        im->row_dir = 1;
+        im->bgr = 0;
+    }
+    // The reference forwards quantisation tables to the DPUs only up to the first unset table id
+    // (src/decoder_host.cpp:173-178): a table behind a gap reads as zeros.
+    bool reachable[4];
+    bool ok = true;
+    for (int t = 0; t < 4; t++) { ok = ok && d.qt_set[t]; reachable[t] = ok; }
+    for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 64; k++)
+            im->q16[j][k] = (j < d.ncomp && reachable[d.qt_id[j] & 3]) ? ((uint32_t)d.qt_zz[d.qt_id[j] & 3][k] << 16) : 0u;
+}
+
+inline void append_tiles(const Geometry &g, uint32_t img, std::vector<TileDev> *tiles) {
+    for (uint32_t my = 0; my < g.nmy; my++)
+        for (uint32_t mx = 0; mx < g.nmx; mx += g.tile_mcus) {
+            TileDev t;
+            t.img = img; t.my = (uint16_t)my; t.mx0 = (uint16_t)mx;
+            t.nm = (uint16_t)std::min<uint32_t>(g.tile_mcus, g.nmx - mx);
+            t.pad_ = 0;
+            tiles->push_back(t);
+        }
+}
+
+}  // namespace bj

@@ -1,0 +1,300 @@
+// K2+K3: dequantise + 8x8 IDCT + chroma upsample + YCbCr->RGB + store, fused.  sm_100a.
+//
+//   k_idct_color : fast layout.  Zig-zag i16 coefficient units in, packed 8-bit pixels out (RGB8 or BMP bytes).
+//   k_exec_mcus  : the reference's own `mcus` tile layout in and out, in place = src/decoder_dpu.c as a kernel
+//                  (the pim.exec() stand-in of src/decoder_host.cpp:292).
+//
+// Both: one thread owns one 8x8 unit for dequant + IDCT (all 64 values in registers, no shuffles), units are
+// staged through shared memory with 128-bit accesses and an XOR-8 chunk swizzle (bank-conflict free for both the
+// unit-major IDCT phase and the row-major colour phase), colour conversion is a second warp-cooperative phase
+// whose lanes walk along pixel rows, and pixels leave through 128-bit global stores.
+#pragma once
+#include "bj_dev.h"
+#include "idct_color.cuh"
+
+namespace bj {
+
+constexpr int kSmemDu = kTileThreads * 128;              // 24576 B: coefficient units, then samples, in place
+constexpr int kSmemQ = 1024;                             // 3 * kQPitch words, padded
+constexpr int kRgbFront = 16;                            // slack so the misaligned copy-out may read 15 B early
+constexpr int kRgbMax = 1536 * 8 * 3;                    // widest tile: gray, 192 MCUs x 8 px x 8 rows x 3 B
+constexpr int kSmemIdctColor = kSmemDu + kSmemQ + kRgbFront + kRgbMax + 64;
+
+__device__ __forceinline__ uint4 pack_row(const int (&X)[64], int r) {
+    uint4 v;
+    v.x = __byte_perm(X[r * 8 + 0], X[r * 8 + 1], 0x5410);
+    v.y = __byte_perm(X[r * 8 + 2], X[r * 8 + 3], 0x5410);
+    v.z = __byte_perm(X[r * 8 + 4], X[r * 8 + 5], 0x5410);
+    v.w = __byte_perm(X[r * 8 + 6], X[r * 8 + 7], 0x5410);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ fast layout
+__global__ void __launch_bounds__(kTileThreads, 3)
+k_idct_color(const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs, const TileDev *__restrict__ tiles,
+             uint8_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint4 *s_du = reinterpret_cast<uint4 *>(smem);
+    uint32_t *s_q = reinterpret_cast<uint32_t *>(smem + kSmemDu);
+    uint8_t *s_rgb = smem + kSmemDu + kSmemQ + kRgbFront;
+
+    const int tid = threadIdx.x;
+    const TileDev t = tiles[blockIdx.x];
+    const ImgDev *__restrict__ im = imgs + t.img;
+    const int hs = im->hs, vs = im->vs, ncomp = im->ncomp, bpm = im->bpm;
+    const int nm = t.nm, ndu = nm * bpm;
+
+    // ---- stage 0: dequant tables + this tile's coefficient units (contiguous in HBM) -> smem, coalesced 16 B
+    for (int i = tid; i < 3 * kQPitch; i += kTileThreads) s_q[i] = (&im->q16[0][0])[i];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(coef) +
+                           ((size_t)im->du_base + (size_t)(t.my * im->nmx + t.mx0) * bpm) * 8;
+        for (int q = tid; q < ndu * 8; q += kTileThreads) {
+            const uint4 v = __ldcs(src + q);
+            const int du = q >> 3, c = q & 7;
+            s_du[du * 8 + (c ^ (du & 7))] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 1: one thread = one unit: de-zigzag (with the reference's 48/52 quirk), dequantise, IDCT
+    if (tid < ndu) {
+        const int du = tid, sw = du & 7;
+        const int k = du % bpm, ny = hs * vs;
+        const int comp = k < ny ? 0 : k - ny + 1;
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(s_q + comp * kQPitch);
+        int X[64];
+        unsigned raw48 = 0, raw52 = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint4 v = s_du[du * 8 + (c ^ sw)];
+            const uint4 qa = q4[2 * c], qb = q4[2 * c + 1];
+            // (w * (q<<16)) mod 2^32 only sees the low 16 bits of w: no unpack needed for the low halves
+            X[zz2nat(8 * c + 0)] = (int)(v.x * qa.x);
+            X[zz2nat(8 * c + 1)] = (int)((v.x >> 16) * qa.y);
+            X[zz2nat(8 * c + 2)] = (int)(v.y * qa.z);
+            X[zz2nat(8 * c + 3)] = (int)((v.y >> 16) * qa.w);
+            X[zz2nat(8 * c + 4)] = (int)(v.z * qb.x);
+            X[zz2nat(8 * c + 5)] = (int)((v.z >> 16) * qb.y);
+            X[zz2nat(8 * c + 6)] = (int)(v.w * qb.z);
+            X[zz2nat(8 * c + 7)] = (int)((v.w >> 16) * qb.w);
+            if (c == 6) { raw48 = v.x & 0xFFFFu; raw52 = v.z & 0xFFFFu; }
+        }
+        {   // src/headers/common.h:16: index 48 and 52 both land on natural 38 (52 wins when present), 58 stays 0;
+            // the quantiser at natural 38 is the one read at index 52 (src/jpeg_scanner.cpp:306,311).
+            const unsigned q52 = s_q[comp * kQPitch + 52];
+            X[38] = (int)((raw52 != 0 ? raw52 : raw48) * q52);
+            X[58] = 0;
+        }
+        idct8x8(X);
+#pragma unroll
+        for (int r = 0; r < 8; r++) s_du[du * 8 + (r ^ sw)] = pack_row(X, r);
+    }
+    __syncthreads();
+
+    // ---- stage 2: colour.  One item = 8 horizontally adjacent pixels (one row of one luma unit); consecutive
+    // lanes take consecutive segments of the same pixel row.  Result: 24 bytes into the staging tile.
+    const int nseg = nm * hs;             // 8-pixel segments per tile row
+    const int rows = vs * 8;
+    const int pitch = nseg * 24;
+    {
+        const unsigned inv = nseg > 1 ? (0xFFFFFFFFu / (unsigned)nseg + 1u) : 0u;
+        const int items = rows * nseg;
+        const bool bgr = im->bgr != 0;
+        for (int it = tid; it < items; it += kTileThreads) {
+            const int py = nseg > 1 ? (int)__umulhi((unsigned)it, inv) : it;
+            const int s = it - py * nseg;
+            const int m = hs == 2 ? (s >> 1) : s, bx = hs == 2 ? (s & 1) : 0;
+            const int by = py >> 3, r = py & 7;
+            const int ydu = m * bpm + by * hs + bx;
+            const uint4 yv = s_du[ydu * 8 + (r ^ (ydu & 7))];
+            int y[8] = {sext_lo(yv.x), sext_hi(yv.x), sext_lo(yv.y), sext_hi(yv.y),
+                        sext_lo(yv.z), sext_hi(yv.z), sext_lo(yv.w), sext_hi(yv.w)};
+            ChromaTerms ct[8];
+            if (ncomp >= 2) {
+                const int cdu = m * bpm + hs * vs;
+                const int rc = vs == 2 ? (by * 4 + (r >> 1)) : r;
+                const uint4 cbv = s_du[cdu * 8 + (rc ^ (cdu & 7))];
+                uint4 crv = make_uint4(0, 0, 0, 0);
+                if (ncomp >= 3) crv = s_du[(cdu + 1) * 8 + (rc ^ ((cdu + 1) & 7))];
+                if (hs == 2) {
+                    const unsigned cb0 = bx ? cbv.z : cbv.x, cb1 = bx ? cbv.w : cbv.y;
+                    const unsigned cr0 = bx ? crv.z : crv.x, cr1 = bx ? crv.w : crv.y;
+                    ct[0] = ct[1] = chroma_terms(sext_lo(cb0), sext_lo(cr0));
+                    ct[2] = ct[3] = chroma_terms(sext_hi(cb0), sext_hi(cr0));
+                    ct[4] = ct[5] = chroma_terms(sext_lo(cb1), sext_lo(cr1));
+                    ct[6] = ct[7] = chroma_terms(sext_hi(cb1), sext_hi(cr1));
+                } else {
+                    ct[0] = chroma_terms(sext_lo(cbv.x), sext_lo(crv.x)); ct[1] = chroma_terms(sext_hi(cbv.x), sext_hi(crv.x));
+                    ct[2] = chroma_terms(sext_lo(cbv.y), sext_lo(crv.y)); ct[3] = chroma_terms(sext_hi(cbv.y), sext_hi(crv.y));
+                    ct[4] = chroma_terms(sext_lo(cbv.z), sext_lo(crv.z)); ct[5] = chroma_terms(sext_hi(cbv.z), sext_hi(crv.z));
+                    ct[6] = chroma_terms(sext_lo(cbv.w), sext_lo(crv.w)); ct[7] = chroma_terms(sext_hi(cbv.w), sext_hi(crv.w));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) { ct[i].r = 128; ct[i].g = 128; ct[i].b = 128; }
+            }
+            int c0[8], c1[8], c2[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int R = y[i] + ct[i].r, G = y[i] + ct[i].g, B = y[i] + ct[i].b;
+                c0[i] = bgr ? B : R; c1[i] = G; c2[i] = bgr ? R : B;
+            }
+            uint2 *dst = reinterpret_cast<uint2 *>(s_rgb + py * pitch + s * 24);
+            dst[0] = make_uint2(pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]));
+            dst[1] = make_uint2(pack_sat4(c2[2], c0[3], c1[3], c2[3]), pack_sat4(c0[4], c1[4], c2[4], c0[5]));
+            dst[2] = make_uint2(pack_sat4(c1[5], c2[5], c0[6], c1[6]), pack_sat4(c2[6], c0[7], c1[7], c2[7]));
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 3: copy-out.  Each pixel row of the tile is a contiguous byte run in HBM with arbitrary
+    // alignment; it is written as 16-byte-aligned 128-bit stores whose payload is funnel-shifted out of the
+    // staging tile; only the first/last chunk of a run (and BMP pad bytes) go bytewise.
+    {
+        const int x0 = t.mx0 * hs * 8, y0 = t.my * vs * 8;
+        const int wpx = min(nseg * 8, (int)im->width - x0);
+        const int rows_valid = min(rows, (int)im->height - y0);
+        const int payload = wpx * 3;
+        const int len = payload + ((x0 + nseg * 8 >= (int)im->width) ? (int)im->row_pad : 0);
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < rows_valid; r += kTileThreads / 32) {
+            const long long off = (long long)im->out_row0 + (long long)im->row_dir * (long long)(y0 + r) * (long long)im->out_pitch + (long long)x0 * 3;
+            uint8_t *g = out + off;
+            const int mis = (int)((uintptr_t)g & 15);
+            uint8_t *a0 = g - mis;
+            const int nchunks = (mis + len + 15) >> 4;
+            const uint8_t *sp = s_rgb + r * pitch;
+            for (int i = lane; i < nchunks; i += 32) {
+                const int so = i * 16 - mis;                       // staging byte offset of this chunk, >= -15
+                const uint8_t *p = sp + so;
+                const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+                const unsigned sh = (a & 3u) * 8u;
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(p - (a & 3u));
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+                uint4 v;
+                v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+                v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+                if (so >= 0 && so + 16 <= payload) {
+                    __stcs(reinterpret_cast<uint4 *>(a0 + i * 16), v);
+                } else {
+                    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int b = 0; b < 16; b++) {
+                        const int idx = so + b;
+                        if (idx >= 0 && idx < len) a0[i * 16 + b] = idx < payload ? (uint8_t)(vv[b >> 2] >> ((b & 3) * 8)) : (uint8_t)0;
+                    }
+                }
+            }
+        }
+        // BMP file header (src/bmp_writer.cpp:26-41), written by the tile that owns the image's first MCU:
+        // 'B','M', size(4), 0(4), 0x1A(4), 12(4), width(2), height(2), 1(2), 24(2)
+        if (im->bgr && t.my == 0 && t.mx0 == 0 && tid < 26) {
+            const unsigned W = im->width, H = im->height;
+            const unsigned size = 26u + H * W * 3u + im->row_pad * H;
+            unsigned v = 0;
+            if (tid == 0) v = 'B';
+            else if (tid == 1) v = 'M';
+            else if (tid < 6) v = size >> ((tid - 2) * 8);
+            else if (tid == 10) v = 0x1A;
+            else if (tid == 14) v = 12;
+            else if (tid == 18) v = W;
+            else if (tid == 19) v = W >> 8;
+            else if (tid == 20) v = H;
+            else if (tid == 21) v = H >> 8;
+            else if (tid == 22) v = 1;
+            else if (tid == 24) v = 24;
+            const long long hdr = (long long)im->out_row0 - (long long)(H - 1) * (long long)im->out_pitch - 26;
+            out[hdr + tid] = (uint8_t)v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ compat layout
+// 16 blocks (= 16 x 3 components x 4 positions = 192 units) of the reference's `mcus` buffer per CTA.
+// Unit (blk, comp, pos) sits at blk*768 + comp*256 + pos*64 shorts (src/decoder_dpu.c:134-156).
+__global__ void __launch_bounds__(kTileThreads)
+k_exec_mcus(const uint32_t *__restrict__ md_all, int16_t *__restrict__ mcus, int nchunk, int blk_per_chunk, int chunk_len) {
+    __shared__ uint4 s_t[kTileThreads * 8];
+    const int tid = threadIdx.x;
+    const int lb = tid / 12, tt = tid - lb * 12, comp = tt >> 2, pos = tt & 3;
+    const int blk = blockIdx.x * 16 + lb;
+    const int chunk = blk / blk_per_chunk, bi = blk - chunk * blk_per_chunk;
+    const bool in_range = chunk < nchunk;
+    const uint32_t *md = md_all + (size_t)(in_range ? chunk : 0) * 276;
+    // an idle DPU (all-zero record) processes metadata[19]/4 = 0 blocks (src/decoder_dpu.c:130): leave untouched
+    const bool active = in_range && bi < (int)(md[19] / 4);
+    int16_t *base = mcus + (size_t)(in_range ? chunk : 0) * chunk_len + (size_t)bi * 768;
+
+    if (active) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(base + comp * 256 + pos * 64);
+        const unsigned ncomp = md[4];
+        const bool deq = (unsigned)comp < ncomp;                         // src/decoder_dpu.c:167: only real components
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(md + 20 + 64 * (deq ? (md[7 + comp] & 3u) : 0u));
+        int X[64];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint4 v = src[c];
+            uint4 qa = make_uint4(1, 1, 1, 1), qb = qa;
+            if (deq) { qa = __ldg(q4 + 2 * c); qb = __ldg(q4 + 2 * c + 1); }
+            X[8 * c + 0] = (int)(v.x * (qa.x << 16)); X[8 * c + 1] = (int)((v.x >> 16) * (qa.y << 16));
+            X[8 * c + 2] = (int)(v.y * (qa.z << 16)); X[8 * c + 3] = (int)((v.y >> 16) * (qa.w << 16));
+            X[8 * c + 4] = (int)(v.z * (qb.x << 16)); X[8 * c + 5] = (int)((v.z >> 16) * (qb.y << 16));
+            X[8 * c + 6] = (int)(v.w * (qb.z << 16)); X[8 * c + 7] = (int)((v.w >> 16) * (qb.w << 16));
+        }
+        idct8x8(X);
+#pragma unroll
+        for (int r = 0; r < 8; r++) s_t[tid * 8 + (r ^ (tid & 7))] = pack_row(X, r);
+    }
+    __syncthreads();
+
+    // colour: item = (block, position, row); all 3 output components of that row
+    for (int it = tid; it < 16 * 4 * 8; it += kTileThreads) {
+        const int ib = it >> 5, p = (it >> 3) & 3, r = it & 7;
+        const int b2 = blockIdx.x * 16 + ib;
+        const int ch2 = b2 / blk_per_chunk, bi2 = b2 - ch2 * blk_per_chunk;
+        if (ch2 >= nchunk) continue;
+        const uint32_t *m2 = md_all + (size_t)ch2 * 276;
+        if (bi2 >= (int)(m2[19] / 4)) continue;
+        const unsigned vs = m2[5], hs = m2[6];
+        int16_t *ob = mcus + (size_t)ch2 * chunk_len + (size_t)bi2 * 768 + p * 64 + r * 8;
+        const int u0 = ib * 12;                                            // unit index of (ib, comp 0, pos 0)
+        auto row_of = [&](int unit, int row) { return s_t[unit * 8 + (row ^ (unit & 7))]; };
+        const uint4 yv = row_of(u0 + p, r);
+        if (!((vs == 1 || vs == 2) && (hs == 1 || hs == 2))) {
+            // no branch of convert_colorspace matches (src/decoder_dpu.c:332-355): IDCT output stays
+            *reinterpret_cast<uint4 *>(ob) = yv;
+            *reinterpret_cast<uint4 *>(ob + 256) = row_of(u0 + 4 + p, r);
+            *reinterpret_cast<uint4 *>(ob + 512) = row_of(u0 + 8 + p, r);
+            continue;
+        }
+        // which chroma position / quadrant feeds luma position p (src/decoder_dpu.c:332-355)
+        int cpos, vq, hq;
+        if (vs == 1 && hs == 1) { cpos = p; vq = 0; hq = 0; }
+        else if (vs == 2 && hs == 1) { cpos = p & 1; vq = p >> 1; hq = 0; }
+        else if (vs == 1 && hs == 2) { cpos = p & 2; vq = 0; hq = p & 1; }
+        else { cpos = 0; vq = p >> 1; hq = p & 1; }
+        const int rc = (vs == 2 ? (r >> 1) : r) + 4 * vq;                  // src/decoder_dpu.c:370
+        const uint4 cbv = row_of(u0 + 4 + cpos, rc), crv = row_of(u0 + 8 + cpos, rc);
+        const unsigned cbw[4] = {cbv.x, cbv.y, cbv.z, cbv.w}, crw[4] = {crv.x, crv.y, crv.z, crv.w};
+        const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
+        int R[8], G[8], B[8];
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            const int cx = (hs == 2 ? (x >> 1) : x) + 4 * hq;
+            unsigned cbs = 0, crs = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) if ((cx >> 1) == j) { cbs = cbw[j]; crs = crw[j]; }
+            const int cb = (cx & 1) ? sext_hi(cbs) : sext_lo(cbs);
+            const int cr = (cx & 1) ? sext_hi(crs) : sext_lo(crs);
+            const int yy = (x & 1) ? sext_hi(yw[x >> 1]) : sext_lo(yw[x >> 1]);
+            const ChromaTerms t = chroma_terms(cb, cr);
+            R[x] = clamp255(yy + t.r); G[x] = clamp255(yy + t.g); B[x] = clamp255(yy + t.b);
+        }
+        *reinterpret_cast<uint4 *>(ob) = make_uint4(R[0] | (R[1] << 16), R[2] | (R[3] << 16), R[4] | (R[5] << 16), R[6] | (R[7] << 16));
+        *reinterpret_cast<uint4 *>(ob + 256) = make_uint4(G[0] | (G[1] << 16), G[2] | (G[3] << 16), G[4] | (G[5] << 16), G[6] | (G[7] << 16));
+        *reinterpret_cast<uint4 *>(ob + 512) = make_uint4(B[0] | (B[1] << 16), B[2] | (B[3] << 16), B[4] | (B[5] << 16), B[6] | (B[7] << 16));
+    }
+}
+
+}  // namespace bj
