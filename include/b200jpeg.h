@@ -111,8 +111,12 @@ int bj_decode_batch(bj_ctx *ctx, const uint8_t *const *files, const size_t *lens
 typedef struct bj_batch bj_batch;
 int bj_batch_create(bj_ctx *ctx, const uint8_t *const *files, const size_t *lens, int n, int format, bj_batch **out);
 int bj_batch_upload(bj_batch *b, void *stream);                 /* H2D: file bytes + descriptors          */
-int bj_batch_decode(bj_batch *b, void *stream);                 /* all kernels; input and output stay in HBM */
+int bj_batch_decode(bj_batch *b, void *stream);                 /* enqueue all kernels; input and output stay in HBM */
+int bj_batch_sync(bj_batch *b);                                 /* wait; settles the (rare) extra Huffman fix-up rounds */
 int bj_batch_download(bj_batch *b, uint8_t *const *outs, void *stream);   /* D2H into caller buffers, then sync */
+/* Where image i sits in the batch's device output buffer.  A caller that lays its host buffers out the same way
+ * (outs[i] = base + offset_i) gets one large copy instead of one per image.  Returns the image's parse status. */
+int bj_batch_output_offset(const bj_batch *b, int i, size_t *offset, size_t *bytes);
 int bj_batch_status(const bj_batch *b, int *status /*[n]*/);
 void bj_batch_destroy(bj_batch *b);
 
@@ -137,8 +141,20 @@ int bj_batch_device_coefficients(const bj_batch *b, int i, void **dptr, size_t *
  * Replaces: the DPU program on the fast layout. */
 int bj_stage_idct_color(bj_ctx *ctx, const bj_image_desc *desc, const int16_t *coef_zz, int format, uint8_t *out);
 
-/* Tunables (0 = default): Huffman subsequence size in bits (multiple of 32). */
+/* Stage-level entry for known-answer tests: un-stuffing + Huffman decode only (kernels K0/K1).  Output = what
+ * decode_Huffman_data (src/jpeg_scanner.cpp:707-756) produces, but in zig-zag order and MCU-interleaved unit order
+ * (ndu * 64 shorts).  *status = BJ_OK or BJ_ERR_CORRUPT_SCAN. */
+int bj_stage_entropy(bj_ctx *ctx, const uint8_t *file, size_t len, int16_t *coef_zz, size_t capacity_bytes, int *status);
+
+/* Tunables (0 = default):
+ *   "subseq_bits"      Huffman sub-sequence size in bits (multiple of 32, >= 128)
+ *   "sync_rounds"      launches of the fix-up kernel before convergence is first checked
+ *   "sub_batch_bytes"  compressed bytes per sub-batch of bj_decode_batch */
 int bj_set_option(bj_ctx *ctx, const char *name, long value);
+/* Counters of the last call: "exec_ms" (kernel time of bj_exec_mcus - the reference's "DPU execution" profile line,
+ * src/decoder_host.cpp:291-294), "decode_batch_sub_batches", "decode_batch_launches", "decode_batch_h2d_bytes",
+ * "decode_batch_d2h_bytes". */
+int bj_get_stat(const bj_ctx *ctx, const char *name, double *value);
 
 /* Version / build info. */
 const char *bj_build_info(void);

@@ -66,6 +66,7 @@ extern "C" void bj_destroy(bj_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &p : c->pool) p.release();
+    for (auto &b : c->slots) if (b) { b->release(); delete b; b = nullptr; }
     for (int i = 0; i < 2; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     delete c;
 }
@@ -84,6 +85,17 @@ extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
     if (!c || !name) return BJ_ERR_ARG;
     if (!strcmp(name, "subseq_bits")) { if (value < 128 || value % 32) return BJ_ERR_ARG; c->subseq_bits = (int)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_bytes = (size_t)value; return BJ_OK; }
+    if (!strcmp(name, "sync_rounds")) { if (value < 0 || value > kMaxRounds) return BJ_ERR_ARG; c->sync_rounds = (int)value; return BJ_OK; }
+    return BJ_ERR_ARG;
+}
+
+extern "C" int bj_get_stat(const bj_ctx *c, const char *name, double *value) {
+    if (!c || !name || !value) return BJ_ERR_ARG;
+    if (!strcmp(name, "exec_ms")) { *value = c->last_exec_ms; return BJ_OK; }                 // kernel time of the last bj_exec_mcus
+    if (!strcmp(name, "decode_batch_sub_batches")) { *value = c->stats[0]; return BJ_OK; }    // of the last bj_decode_batch
+    if (!strcmp(name, "decode_batch_launches")) { *value = c->stats[1]; return BJ_OK; }
+    if (!strcmp(name, "decode_batch_h2d_bytes")) { *value = c->stats[2]; return BJ_OK; }
+    if (!strcmp(name, "decode_batch_d2h_bytes")) { *value = c->stats[3]; return BJ_OK; }
     return BJ_ERR_ARG;
 }
 
@@ -165,5 +177,147 @@ extern "C" int bj_stage_idct_color(bj_ctx *c, const bj_image_desc *desc, const i
     }
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(out, dout.p, out_bytes, cudaMemcpyDeviceToHost, s));
     if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ full path, staged
+
+extern "C" int bj_batch_create(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, bj_batch **out) {
+    if (!c || !out || n < 0 || (n > 0 && (!files || !lens))) return BJ_ERR_ARG;
+    *out = nullptr;
+    bj_batch *b = new (std::nothrow) bj_batch();
+    if (!b) return BJ_ERR_NOMEM;
+    const int rc = batch_assign(b, c, files, lens, n, format);
+    if (rc != BJ_OK) { b->release(); delete b; return rc; }
+    *out = b;
+    return BJ_OK;
+}
+
+extern "C" void bj_batch_destroy(bj_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    if (b->last_stream) cudaStreamSynchronize(b->last_stream);
+    b->release();
+    delete b;
+}
+
+static cudaStream_t stream_or_default(bj_batch *b, void *stream) { return stream ? (cudaStream_t)stream : b->ctx->streams[0]; }
+
+extern "C" int bj_batch_upload(bj_batch *b, void *stream) { return b ? batch_upload(b, stream_or_default(b, stream)) : BJ_ERR_ARG; }
+extern "C" int bj_batch_decode(bj_batch *b, void *stream) { return b ? batch_decode(b, stream_or_default(b, stream)) : BJ_ERR_ARG; }
+extern "C" int bj_batch_sync(bj_batch *b) { return b ? batch_sync(b) : BJ_ERR_ARG; }
+extern "C" int bj_batch_download(bj_batch *b, uint8_t *const *outs, void *stream) {
+    if (!b || (b->n > 0 && !outs)) return BJ_ERR_ARG;
+    return batch_download(b, outs, stream_or_default(b, stream));
+}
+
+extern "C" int bj_batch_status(const bj_batch *b, int *status) {
+    if (!b || !status) return BJ_ERR_ARG;
+    for (int i = 0; i < b->n; i++) status[i] = batch_image_status(b, i);
+    return BJ_OK;
+}
+
+extern "C" int bj_batch_get_info(const bj_batch *b, bj_batch_info *info) {
+    if (!b || !info) return BJ_ERR_ARG;
+    memset(info, 0, sizeof(*info));
+    info->pixels = b->pixels; info->scan_bytes = b->scan_bytes; info->data_units = b->coef_units; info->out_bytes = b->out_bytes;
+    info->h2d_bytes = b->files_bytes + b->meta_bytes; info->d2h_bytes = b->d2h_bytes;
+    uint32_t nsub = 0;
+    if (b->synced) for (int i = 0; i < b->n; i++) nsub += const_cast<bj_batch *>(b)->h_state()[i].nsub;
+    info->subsequences = nsub; info->sync_rounds = b->sync_rounds; info->launches = b->launches;
+    info->ms_entropy = b->ms_entropy; info->ms_idct = b->ms_idct;
+    return BJ_OK;
+}
+
+extern "C" int bj_batch_output_offset(const bj_batch *b, int i, size_t *offset, size_t *bytes) {
+    if (!b || i < 0 || i >= b->n) return BJ_ERR_ARG;
+    if (offset) *offset = b->out_off[i];
+    if (bytes) *bytes = b->out_size[i];
+    return b->parse_status[i];
+}
+
+extern "C" int bj_batch_device_output(const bj_batch *b, int i, void **dptr, size_t *bytes) {
+    if (!b || i < 0 || i >= b->n || b->parse_status[i] != BJ_OK) return BJ_ERR_ARG;
+    if (dptr) *dptr = (uint8_t *)b->d_out.p + b->out_off[i];
+    if (bytes) *bytes = b->out_size[i];
+    return BJ_OK;
+}
+
+extern "C" int bj_batch_device_coefficients(const bj_batch *b, int i, void **dptr, size_t *bytes) {
+    if (!b || i < 0 || i >= b->n || b->parse_status[i] != BJ_OK) return BJ_ERR_ARG;
+    if (dptr) *dptr = (int16_t *)b->d_coef.p + (size_t)b->du_base[i] * 64;
+    if (bytes) *bytes = (size_t)b->ndu[i] * 128;
+    return BJ_OK;
+}
+
+// Stage-level entry for known-answer tests: K0 + K1 only; coefficients (zig-zag, DC un-differenced) back to the host.
+extern "C" int bj_stage_entropy(bj_ctx *c, const uint8_t *file, size_t len, int16_t *coef_zz, size_t capacity_bytes, int *status) {
+    if (!c || !file || !coef_zz) return BJ_ERR_ARG;
+    bj_batch *b = nullptr;
+    const uint8_t *files[1] = {file};
+    const size_t lens[1] = {len};
+    int rc = bj_batch_create(c, files, lens, 1, BJ_OUT_RGB8, &b);
+    if (rc != BJ_OK) return rc;
+    if (b->parse_status[0] != BJ_OK) { rc = b->parse_status[0]; bj_batch_destroy(b); return rc; }
+    if ((size_t)b->ndu[0] * 128 > capacity_bytes) { bj_batch_destroy(b); return BJ_ERR_ARG; }
+    cudaStream_t s = c->streams[0];
+    rc = batch_upload(b, s);
+    if (rc == BJ_OK) rc = batch_decode(b, s);
+    if (rc == BJ_OK) rc = batch_sync(b);
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(coef_zz, b->d_coef.p, (size_t)b->ndu[0] * 128, cudaMemcpyDeviceToHost, s));
+    if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
+    if (rc == BJ_OK && status) *status = batch_image_status(b, 0);
+    bj_batch_destroy(b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ full path, one call
+// Sub-batches alternate between two batch objects and two streams: while sub-batch k decodes and copies out, the
+// host parses and packs sub-batch k+1 and its H2D copy runs on the other stream.
+extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format,
+                               uint8_t *const *outs, int *status) {
+    if (!c || n < 0 || (n > 0 && (!files || !lens || !outs))) return BJ_ERR_ARG;
+    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+    if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
+    const size_t budget = c->sub_batch_bytes ? c->sub_batch_bytes : ((size_t)48 << 20);    // compressed bytes per sub-batch
+    for (auto &b : c->slots) if (!b) { b = new (std::nothrow) bj_batch(); if (!b) return BJ_ERR_NOMEM; }
+    int first[2] = {0, 0}, count[2] = {0, 0};
+    bool busy[2] = {false, false};
+    double nsub = 0, launches = 0, h2d = 0, d2h = 0;
+    int rc = BJ_OK;
+    auto finish = [&](int slot) -> int {
+        bj_batch *b = c->slots[slot];
+        int r = batch_sync(b);
+        if (r == BJ_OK && b->h_flags()[b->rounds - 1] != 0)          // extra rounds ran: the early copy-out is stale
+            r = batch_download(b, outs + first[slot], c->streams[slot]);
+        if (r == BJ_OK && status) for (int i = 0; i < count[slot]; i++) status[first[slot] + i] = batch_image_status(b, i);
+        launches += b->launches; h2d += (double)(b->files_bytes + b->meta_bytes); d2h += (double)b->d2h_bytes;
+        busy[slot] = false;
+        return r;
+    };
+    int i0 = 0, k = 0;
+    while (rc == BJ_OK && i0 < n) {
+        int i1 = i0;
+        size_t bytes = 0;
+        while (i1 < n && (i1 == i0 || bytes + lens[i1] <= budget)) bytes += lens[i1++];
+        const int slot = k & 1;
+        if (busy[slot]) rc = finish(slot);
+        if (rc != BJ_OK) break;
+        bj_batch *b = c->slots[slot];
+        cudaStream_t s = c->streams[slot];
+        rc = batch_assign(b, c, files + i0, lens + i0, i1 - i0, format);
+        if (rc == BJ_OK) rc = batch_upload(b, s);
+        if (rc == BJ_OK) rc = batch_decode(b, s);
+        if (rc == BJ_OK) {                                            // enqueue the copy-out behind the kernels, no host wait
+            b->synced = true;                                         // (checked for real in finish())
+            rc = batch_download_async(b, outs + i0, s);
+            b->synced = false;
+        }
+        first[slot] = i0; count[slot] = i1 - i0; busy[slot] = true;
+        nsub += 1;
+        i0 = i1; k++;
+    }
+    for (int slot = 0; slot < 2; slot++) if (busy[slot]) { const int r = finish(slot); if (rc == BJ_OK) rc = r; }
+    c->stats[0] = nsub; c->stats[1] = launches; c->stats[2] = h2d; c->stats[3] = d2h;
     return rc;
 }

@@ -1,4 +1,358 @@
-// placeholder until the entropy stage lands
+// Host orchestration of the full path: a batch of JPEG files -> kernels K0..K3 -> pixels.
+// Replaces, per image, the producer half of the reference's pipeline (read_JPEG's scan copy + decode_Huffman_data,
+// src/decoder_host.cpp:119-181) and its consumer half (pim.copy / pim.exec / pim.copy, :268-312) with one
+// asynchronous sequence of kernel launches on a CUDA stream.  Nothing here decodes on the CPU: the host parses
+// headers (parse.h), builds the per-image descriptors and lookup tables, and packs bytes for one H2D copy.
 #pragma once
+#include <map>
+#include <string>
+#include <vector>
+
 #include "bj_host.h"
-namespace bj { inline int batch_kernels_init(bj_ctx *) { return BJ_OK; } }
+#include "kernels_huff.cuh"
+#include "kernels_idct.cuh"
+#include "parse.h"
+
+namespace bj {
+
+struct PinBuf {                       // grow-only pinned host allocation
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return BJ_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 4096;
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; return BJ_ERR_NOMEM; }
+        cap = want;
+        return BJ_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kSmemHuffWriteMax = kSmemHuffStage + 6 * kLutCap * 2;
+constexpr int kSmemHuffSyncMax = 6 * kLutCap * 2;
+
+inline int batch_kernels_init(bj_ctx *c) {
+    if (c->check(cudaFuncSetAttribute(k_huff_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffWriteMax)) != BJ_OK) return BJ_ERR_CUDA;
+    if (c->check(cudaFuncSetAttribute(k_huff_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
+    return BJ_OK;
+}
+
+}  // namespace bj
+
+struct bj_batch {
+    bj_ctx *ctx = nullptr;
+    int n = 0, format = 0;
+    uint32_t sub_bytes = 128;
+    int rounds = 3;
+
+    std::vector<bj_image_desc> desc;
+    std::vector<int> parse_status;
+    std::vector<size_t> out_off, out_size;
+    std::vector<uint64_t> file_off;
+    std::vector<uint32_t> du_base, ndu;
+
+    // host staging (pinned): file bytes; descriptor blob; results
+    bj::PinBuf h_files, h_meta, h_res;
+    size_t files_bytes = 0, meta_bytes = 0;
+    // offsets inside the descriptor blob
+    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_utile = 0, o_lut = 0;
+    uint32_t n_idct_tiles = 0, n_blk = 0, n_utile = 0, n_lut = 0, n_seg_entries = 0, n_sub_slots = 0, max_slots = 1;
+    size_t clean_words = 0, coef_units = 0, out_bytes = 0;
+    uint64_t pixels = 0, scan_bytes = 0;
+
+    // device
+    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_tilecnt, d_blkagg, d_state, d_flags, d_coef, d_out;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t last_stream = nullptr;
+    bool uploaded = false, decoded = false, synced = false;
+    uint32_t launches = 0, sync_rounds = 0;
+    float ms_entropy = 0.f, ms_idct = 0.f;
+    uint64_t d2h_bytes = 0;
+
+    bj::HuffImgState *h_state() { return reinterpret_cast<bj::HuffImgState *>(h_res.p); }
+    uint32_t *h_flags() { return reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(h_res.p) + bj::align_up((size_t)n * sizeof(bj::HuffImgState), 64)); }
+    template <class T> T *dmeta(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(d_meta.p) + off); }
+    template <class T> T *hmeta(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(h_meta.p) + off); }
+
+    void release() {
+        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_tilecnt, &d_blkagg, &d_state, &d_flags, &d_coef, &d_out}) b->release();
+        h_files.release(); h_meta.release(); h_res.release();
+        for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    }
+};
+
+namespace bj {
+
+constexpr int kMaxRounds = 64;
+
+// (Re)fill a batch object from a list of files: parse, lay out, pack.  Host work only (plus buffer growth).
+inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format) {
+    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+    b->ctx = c; b->n = n; b->format = format;
+    b->sub_bytes = c->subseq_bits ? (uint32_t)c->subseq_bits / 8 : 128u;
+    b->uploaded = b->decoded = b->synced = false;
+    b->desc.resize(n); b->parse_status.assign(n, BJ_OK);
+    b->out_off.assign(n, 0); b->out_size.assign(n, 0); b->file_off.assign(n, 0);
+    b->du_base.assign(n, 0); b->ndu.assign(n, 0);
+    if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
+    for (auto &e : b->ev) if (!e && c->check(cudaEventCreate(&e)) != BJ_OK) return BJ_ERR_CUDA;
+
+    // ---- parse + layout
+    std::vector<HuffImg> himg(n);
+    std::vector<ImgDev> idev(n);
+    std::vector<TileDev> tiles;
+    std::vector<uint32_t> blk_img, utile_img;
+    std::vector<uint16_t> luts;
+    std::map<std::string, int> lut_index;
+    size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
+    uint32_t seg_entries = 0, nblk = 0;
+    b->pixels = 0; b->scan_bytes = 0; b->max_slots = 1;
+    for (int i = 0; i < n; i++) {
+        bj_image_desc &d = b->desc[i];
+        HuffImg &hi = himg[i];
+        memset(&hi, 0, sizeof(hi));
+        memset(&idev[i], 0, sizeof(ImgDev));
+        int rc = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &d) : BJ_ERR_INVALID_JPEG;
+        Geometry g;
+        if (rc == BJ_OK) {
+            g = geometry_of(d);
+            // tables -> pool (deduplicated across the batch)
+            int slots[6], nslot = 0;
+            for (int j = 0; j < 3 && rc == BJ_OK; j++) {
+                const int jj = j < d.ncomp ? j : 0;
+                for (int ac = 0; ac < 2 && rc == BJ_OK; ac++) {
+                    const uint8_t *off = ac ? d.ac_offsets[d.ac_id[jj]] : d.dc_offsets[d.dc_id[jj]];
+                    const uint8_t *sym = ac ? d.ac_symbols[d.ac_id[jj]] : d.dc_symbols[d.dc_id[jj]];
+                    std::string key((const char *)off, 17);
+                    key.append((const char *)sym, off[16] > 162 ? 162 : off[16]);
+                    auto it = lut_index.find(key);
+                    int idx;
+                    if (it == lut_index.end()) {
+                        idx = (int)(luts.size() / kLutCap);
+                        luts.resize(luts.size() + kLutCap);
+                        if (build_lut(off, sym, &luts[(size_t)idx * kLutCap]) < 0) rc = BJ_ERR_UNSUPPORTED;
+                        lut_index[key] = idx;
+                    } else idx = it->second;
+                    int s = 0;
+                    while (s < nslot && slots[s] != idx) s++;
+                    if (s == nslot) slots[nslot++] = idx;
+                    (ac ? hi.ac_slot : hi.dc_slot)[j] = (uint8_t)s;
+                }
+            }
+            hi.nslot = (uint8_t)nslot;
+            for (int s = 0; s < nslot; s++) hi.slot_lut[s] = (uint16_t)slots[s];
+            if ((uint32_t)nslot > b->max_slots) b->max_slots = (uint32_t)nslot;
+            if (luts.size() / kLutCap > 65535) rc = BJ_ERR_UNSUPPORTED;
+        }
+        b->parse_status[i] = rc;
+        b->file_off[i] = fbytes;
+        hi.seg_base = seg_entries;
+        hi.blk_base = nblk;
+        hi.sub_base = nblk * kHuffThreads;
+        hi.tile_base = (uint32_t)utile_img.size();
+        hi.clean_word0 = (uint32_t)clean_words;
+        hi.du_base = (uint32_t)coef_units;
+        if (rc != BJ_OK) { seg_entries += 2; continue; }
+        fbytes += align_up(lens[i] + 16, 16);
+        hi.valid = 1;
+        hi.raw_off = b->file_off[i] + d.scan_off;
+        hi.raw_len = (uint32_t)d.scan_len;
+        const uint64_t a0 = hi.raw_off & ~(uint64_t)15;
+        hi.ntile = (uint32_t)((hi.raw_off - a0 + hi.raw_len + kUnstuffTile - 1) / kUnstuffTile);
+        for (uint32_t t = 0; t < hi.ntile; t++) utile_img.push_back((uint32_t)i);
+        hi.nmcu = g.nmcu; hi.ri = d.restart_interval;
+        hi.nseg = hi.ri ? (g.nmcu + hi.ri - 1) / hi.ri : 1u;
+        hi.bpm = (uint8_t)g.bpm; hi.ny = (uint8_t)(d.hs * d.vs); hi.ncomp = d.ncomp;
+        hi.ndu = g.ndu;
+        const uint32_t sub_cap = (uint32_t)((hi.raw_len + b->sub_bytes - 1) / b->sub_bytes) + hi.nseg;
+        hi.nblk = (sub_cap + kHuffThreads - 1) / kHuffThreads;
+        for (uint32_t k = 0; k < hi.nblk; k++) blk_img.push_back((uint32_t)i);
+        nblk += hi.nblk;
+        seg_entries += hi.nseg + 1;
+        clean_words += hi.raw_len / 4 + 4;
+        b->du_base[i] = (uint32_t)coef_units; b->ndu[i] = g.ndu;
+        coef_units += g.ndu;
+        b->out_size[i] = bj_output_size(&d, format);
+        b->out_off[i] = out_bytes;
+        fill_imgdev(d, g, format, hi.du_base, out_bytes, &idev[i]);
+        out_bytes += align_up(b->out_size[i], 16);
+        append_tiles(g, (uint32_t)i, &tiles);
+        b->pixels += (uint64_t)d.width * d.height;
+        b->scan_bytes += d.scan_len;
+        if (coef_units > 0xFFFFFFF0ull || clean_words > 0xFFFFFFF0ull) return BJ_ERR_ARG;   // split the batch
+    }
+    b->files_bytes = fbytes + 64; b->clean_words = clean_words + 16; b->coef_units = coef_units; b->out_bytes = out_bytes;
+    b->n_idct_tiles = (uint32_t)tiles.size(); b->n_blk = nblk; b->n_utile = (uint32_t)utile_img.size();
+    b->n_lut = (uint32_t)(luts.size() / kLutCap); b->n_seg_entries = seg_entries; b->n_sub_slots = nblk * kHuffThreads;
+
+    // ---- descriptor blob
+    size_t o = 0;
+    b->o_himg = o;  o = align_up(o + (size_t)n * sizeof(HuffImg), 256);
+    b->o_idev = o;  o = align_up(o + (size_t)n * sizeof(ImgDev), 256);
+    b->o_tiles = o; o = align_up(o + tiles.size() * sizeof(TileDev), 256);
+    b->o_blk = o;   o = align_up(o + blk_img.size() * 4, 256);
+    b->o_utile = o; o = align_up(o + utile_img.size() * 4, 256);
+    b->o_lut = o;   o = align_up(o + luts.size() * 2, 256);
+    b->meta_bytes = o;
+    if (b->h_meta.reserve(o) || b->h_files.reserve(b->files_bytes) ||
+        b->h_res.reserve(align_up((size_t)n * sizeof(HuffImgState), 64) + kMaxRounds * 4 + 64)) return BJ_ERR_NOMEM;
+    if (n) { memcpy(b->hmeta<HuffImg>(b->o_himg), himg.data(), (size_t)n * sizeof(HuffImg)); memcpy(b->hmeta<ImgDev>(b->o_idev), idev.data(), (size_t)n * sizeof(ImgDev)); }
+    if (!tiles.empty()) memcpy(b->hmeta<TileDev>(b->o_tiles), tiles.data(), tiles.size() * sizeof(TileDev));
+    if (!blk_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_blk), blk_img.data(), blk_img.size() * 4);
+    if (!utile_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_utile), utile_img.data(), utile_img.size() * 4);
+    if (!luts.empty()) memcpy(b->hmeta<uint16_t>(b->o_lut), luts.data(), luts.size() * 2);
+    // ---- pack the file bytes
+    uint8_t *hf = reinterpret_cast<uint8_t *>(b->h_files.p);
+    for (int i = 0; i < n; i++) {
+        if (b->parse_status[i] != BJ_OK) continue;
+        memcpy(hf + b->file_off[i], files[i], lens[i]);
+        memset(hf + b->file_off[i] + lens[i], 0, align_up(lens[i] + 16, 16) - lens[i]);
+    }
+    // ---- device buffers
+    if (b->d_files.reserve(b->files_bytes) || b->d_meta.reserve(b->meta_bytes) || b->d_clean.reserve(b->clean_words * 4) ||
+        b->d_seg.reserve((size_t)(seg_entries + 2) * 4 * 2) || b->d_subseg.reserve((size_t)b->n_sub_slots * 4 + 16) ||
+        b->d_stin.reserve((size_t)b->n_sub_slots * 8 + 16) || b->d_stout.reserve((size_t)b->n_sub_slots * 8 + 16) ||
+        b->d_tot.reserve((size_t)b->n_sub_slots * 16 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 16 + 16) ||
+        b->d_tilecnt.reserve((size_t)b->n_utile * 8 + 16) || b->d_blkagg.reserve((size_t)nblk * sizeof(BlkAgg) + 16) ||
+        b->d_state.reserve((size_t)n * sizeof(HuffImgState) + 16) || b->d_flags.reserve(kMaxRounds * 4) ||
+        b->d_coef.reserve(coef_units * 128 + 16) || b->d_out.reserve(out_bytes + 64)) return BJ_ERR_NOMEM;
+    return BJ_OK;
+}
+
+inline int batch_upload(bj_batch *b, cudaStream_t s) {
+    bj_ctx *c = b->ctx;
+    if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
+    b->last_stream = s;
+    if (b->n == 0) { b->uploaded = true; return BJ_OK; }
+    int rc = c->check(cudaMemcpyAsync(b->d_files.p, b->h_files.p, b->files_bytes, cudaMemcpyHostToDevice, s));
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(b->d_meta.p, b->h_meta.p, b->meta_bytes, cudaMemcpyHostToDevice, s));
+    b->uploaded = rc == BJ_OK;
+    return rc;
+}
+
+// Launch sync rounds [r0, r1) and everything after them.
+inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
+    bj_ctx *c = b->ctx;
+    const HuffImg *himg = b->dmeta<HuffImg>(b->o_himg);
+    const ImgDev *idev = b->dmeta<ImgDev>(b->o_idev);
+    const TileDev *tiles = b->dmeta<TileDev>(b->o_tiles);
+    const uint32_t *blk_img = b->dmeta<uint32_t>(b->o_blk);
+    const uint32_t *utile_img = b->dmeta<uint32_t>(b->o_utile);
+    const uint16_t *luts = b->dmeta<uint16_t>(b->o_lut);
+    HuffImgState *st = (HuffImgState *)b->d_state.p;
+    uint32_t *seg_off = (uint32_t *)b->d_seg.p, *seg_sub0 = seg_off + b->n_seg_entries + 2;
+    uint32_t *sub_seg = (uint32_t *)b->d_subseg.p, *flags = (uint32_t *)b->d_flags.p;
+    uint32_t *clean = (uint32_t *)b->d_clean.p;
+    uint2 *st_in = (uint2 *)b->d_stin.p, *st_out = (uint2 *)b->d_stout.p, *tile_cnt = (uint2 *)b->d_tilecnt.p;
+    uint4 *tot = (uint4 *)b->d_tot.p, *pre = (uint4 *)b->d_pre.p;
+    BlkAgg *agg = (BlkAgg *)b->d_blkagg.p;
+    const int n = b->n;
+    const size_t lut_smem = (size_t)b->max_slots * kLutCap * 2;
+    if (r0 == 0) {
+        cudaEventRecord(b->ev[0], s);
+        cudaMemsetAsync(flags, 0, kMaxRounds * 4, s);
+        if (b->n_utile) k_unstuff_count<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_cnt);
+        k_unstuff_scan<<<(n + 3) / 4, 128, 0, s>>>(himg, n, tile_cnt, st, seg_off);
+        if (b->n_utile) k_unstuff_write<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_cnt, st, clean, seg_off);
+        k_subseq_table<<<n, 256, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg, b->sub_bytes);
+        b->launches = 2 + (b->n_utile ? 2 : 0);
+        b->sync_rounds = 0;
+    }
+    if (b->n_blk) {
+        for (int r = r0; r < r1; r++) {
+            k_huff_sync<<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts, st_in, st_out, tot, pre, agg, flags, r, b->sub_bytes);
+            b->launches++; b->sync_rounds++;
+        }
+        k_huff_write<<<b->n_blk, kHuffThreads, kSmemHuffStage + lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts, st_in, pre, agg, (int16_t *)b->d_coef.p, b->sub_bytes);
+        b->launches++;
+    }
+    {
+        const int gx = n >= 592 ? 1 : (592 + n - 1) / n;
+        k_zero_tail<<<dim3(n, gx > 64 ? 64 : gx), 256, 0, s>>>(himg, st, (int16_t *)b->d_coef.p);
+        b->launches++;
+    }
+    cudaEventRecord(b->ev[1], s);
+    if (b->n_idct_tiles) {
+        k_idct_color<<<b->n_idct_tiles, kTileThreads, kSmemIdctColor, s>>>((const int16_t *)b->d_coef.p, idev, tiles, (uint8_t *)b->d_out.p);
+        b->launches++;
+    }
+    cudaEventRecord(b->ev[2], s);
+    cudaMemcpyAsync(b->h_state(), st, (size_t)n * sizeof(HuffImgState), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(b->h_flags(), flags, kMaxRounds * 4, cudaMemcpyDeviceToHost, s);
+    return c->check(cudaGetLastError());
+}
+
+inline int batch_decode(bj_batch *b, cudaStream_t s) {
+    bj_ctx *c = b->ctx;
+    if (!b->uploaded) return BJ_ERR_ARG;
+    if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
+    b->last_stream = s;
+    b->decoded = true; b->synced = false;
+    if (b->n == 0) return BJ_OK;
+    b->rounds = c->sync_rounds > 0 ? c->sync_rounds : 3;
+    return batch_launch(b, s, 0, b->rounds);
+}
+
+// Wait for the decode; if the last fix-up round still changed something (a sub-sequence that needed more than a
+// whole CTA to synchronise - pathological), run more rounds and redo what depends on them.
+inline int batch_sync(bj_batch *b) {
+    bj_ctx *c = b->ctx;
+    if (!b->decoded) return BJ_ERR_ARG;
+    if (b->n == 0) { b->synced = true; return BJ_OK; }
+    cudaStream_t s = b->last_stream;
+    int rc = c->check(cudaStreamSynchronize(s));
+    int r = b->rounds;
+    while (rc == BJ_OK && b->n_blk && b->h_flags()[r - 1] != 0) {
+        if (r + 2 > kMaxRounds) { c->last_error = "entropy stage did not converge"; return BJ_ERR_CUDA; }
+        rc = batch_launch(b, s, r, r + 2);
+        if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
+        r += 2;
+    }
+    if (rc == BJ_OK) {
+        cudaEventElapsedTime(&b->ms_entropy, b->ev[0], b->ev[1]);
+        cudaEventElapsedTime(&b->ms_idct, b->ev[1], b->ev[2]);
+        b->synced = true;
+    }
+    return rc;
+}
+
+// Enqueue the device->host copies of every decoded image (no host wait).
+inline int batch_download_async(bj_batch *b, uint8_t *const *outs, cudaStream_t s) {
+    bj_ctx *c = b->ctx;
+    int rc = BJ_OK;
+    b->d2h_bytes = 0;
+    // coalesce images whose host buffers are laid out like the device buffer (see bj_batch_output_offset)
+    int i = 0;
+    while (rc == BJ_OK && i < b->n) {
+        if (b->parse_status[i] != BJ_OK || !outs[i]) { i++; continue; }
+        int k = i;
+        size_t end = b->out_off[i] + b->out_size[i];
+        while (k + 1 < b->n && b->parse_status[k + 1] == BJ_OK && outs[k + 1] &&
+               outs[k + 1] == outs[i] + (b->out_off[k + 1] - b->out_off[i])) { k++; end = b->out_off[k] + b->out_size[k]; }
+        rc = c->check(cudaMemcpyAsync(outs[i], (const uint8_t *)b->d_out.p + b->out_off[i], end - b->out_off[i], cudaMemcpyDeviceToHost, s));
+        b->d2h_bytes += end - b->out_off[i];
+        i = k + 1;
+    }
+    return rc;
+}
+
+inline int batch_download(bj_batch *b, uint8_t *const *outs, cudaStream_t s) {
+    if (!b->decoded) return BJ_ERR_ARG;
+    int rc = BJ_OK;
+    if (!b->synced) rc = batch_sync(b);           // the (rare) extra fix-up rounds must be settled before copying out
+    if (rc == BJ_OK) rc = batch_download_async(b, outs, s);
+    if (rc == BJ_OK) rc = b->ctx->check(cudaStreamSynchronize(s));
+    return rc;
+}
+
+inline int batch_image_status(const bj_batch *b, int i) {
+    if (b->parse_status[i] != BJ_OK) return b->parse_status[i];
+    if (b->synced && const_cast<bj_batch *>(b)->h_state()[i].status) return BJ_ERR_CORRUPT_SCAN;
+    return BJ_OK;
+}
+
+}  // namespace bj

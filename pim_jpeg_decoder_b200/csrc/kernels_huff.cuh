@@ -1,0 +1,500 @@
+// K0/K1: entropy stage on sm_100a.  Replaces the host-side, single-threaded, bit-serial Huffman decode of the
+// reference (src/jpeg_scanner.cpp:405-520, 707-756) with data-parallel kernels:
+//
+//   k_unstuff_count / k_unstuff_scan / k_unstuff_write   (K0)  raw scan bytes -> un-stuffed big-endian words,
+//                                                          restart-segment byte offsets
+//   k_subseq_table                                        (K0d) per image: split every segment into sub-sequences
+//   k_huff_sync                                           (K1b) speculative decode of every sub-sequence + fix-up
+//                                                          to the fixed point inside a CTA, block-level prefix sums
+//                                                          (unit counts and DC sums - K1c is folded in here)
+//   k_huff_write                                          (K1a) final decode from the synchronised entry states,
+//                                                          whole 128-byte units stored with 128-bit stores
+//   k_zero_tail                                                 units the reference never reached read as zero
+//
+// All arithmetic/semantics live in huff_core.h (shared with the CPU emulation used by the tests).
+#pragma once
+#include "bj_dev.h"
+#include "huff_core.h"
+
+namespace bj {
+
+constexpr int kHuffThreads = 256;          // sub-sequences per CTA
+constexpr int kUnstuffThreads = 256;
+constexpr int kUnstuffTile = kUnstuffThreads * 16;   // raw bytes per CTA of K0
+
+// Per image, written by the host.
+struct HuffImg {
+    uint64_t raw_off;        // offset of the first scan byte in the batch's file buffer
+    uint32_t raw_len;        // raw scan bytes (stuffed, with RSTn)
+    uint32_t clean_word0;    // first word of this image's un-stuffed stream
+    uint32_t tile_base, ntile;
+    uint32_t seg_base;       // index into seg_off / seg_sub0 (nseg + 1 entries each)
+    uint32_t nseg;           // segments expected from the header: ceil(nmcu / RI), 1 without DRI
+    uint32_t sub_base;       // first sub-sequence slot (multiple of kHuffThreads)
+    uint32_t blk_base, nblk; // CTAs of k_huff_sync / k_huff_write
+    uint32_t du_base, ndu;
+    uint32_t nmcu, ri;       // ri = restart interval in MCUs (0: none)
+    uint8_t bpm, ny, ncomp, nslot;
+    uint16_t slot_lut[6];    // table pool index of each staged slot
+    uint8_t dc_slot[3], ac_slot[3];
+    uint8_t valid, pad_[3];
+};
+
+// Per image, written by the kernels.
+struct HuffImgState {
+    uint32_t clean_len;      // un-stuffed bytes
+    uint32_t nrst;           // RSTn markers found
+    uint32_t nseg;           // segments actually decoded: min(nrst + 1, expected)
+    uint32_t nsub;           // sub-sequences
+    uint32_t first_zero;     // first unit (image-local) the reference never reached; >= ndu if none
+    uint32_t status;         // 0 ok, 1 corrupt entropy-coded data
+    uint32_t pad_[2];
+};
+
+struct BlkAgg {              // totals of one CTA since its last segment head (or since its start)
+    uint32_t n, dc01, dc2, has_head;
+};
+
+// ------------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += t; }
+    return v;
+}
+
+// exclusive scan of two counters over the CTA; returns totals through tot_a/tot_b
+template <int NT>
+__device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_t &ea, uint32_t &eb, uint32_t &tot_a,
+                                                 uint32_t &tot_b, uint32_t *s_tmp /* 2 * NT/32 + 2 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ia = warp_incl_scan(a), ib = warp_incl_scan(b);
+    if (lane == 31) { s_tmp[warp] = ia; s_tmp[NT / 32 + warp] = ib; }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wa = lane < NT / 32 ? s_tmp[lane] : 0u, wb = lane < NT / 32 ? s_tmp[NT / 32 + lane] : 0u;
+        const uint32_t sa = warp_incl_scan(wa), sb = warp_incl_scan(wb);
+        if (lane < NT / 32) { s_tmp[lane] = sa - wa; s_tmp[NT / 32 + lane] = sb - wb; }
+        if (lane == 31) { s_tmp[2 * (NT / 32)] = sa; s_tmp[2 * (NT / 32) + 1] = sb; }
+    }
+    __syncthreads();
+    ea = ia - a + s_tmp[warp];
+    eb = ib - b + s_tmp[NT / 32 + warp];
+    tot_a = s_tmp[2 * (NT / 32)];
+    tot_b = s_tmp[2 * (NT / 32) + 1];
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ K0: un-stuff
+// One thread classifies 16 raw bytes (aligned 16-byte chunk of the file buffer).  keep: bit i = byte i survives;
+// rst: bit i = byte i is the code byte of an RSTn marker.
+__device__ __forceinline__ void classify16(const uint8_t *__restrict__ files, const HuffImg &im, uint32_t tile, uint32_t &keep,
+                                           uint32_t &rst, uint4 &bytes) {
+    const uint64_t a0 = (im.raw_off & ~(uint64_t)15) + (uint64_t)tile * kUnstuffTile + (uint64_t)threadIdx.x * 16;
+    const int64_t r0 = (int64_t)a0 - (int64_t)im.raw_off;                  // scan-relative index of byte 0 (may be < 0)
+    keep = 0; rst = 0;
+    bytes = make_uint4(0, 0, 0, 0);
+    if (r0 >= (int64_t)im.raw_len || r0 + 16 <= 0) return;
+    bytes = __ldg(reinterpret_cast<const uint4 *>(files + a0));
+    unsigned prev = (r0 > 0) ? (unsigned)__ldg(files + a0 - 1) : 0u;
+    const unsigned after = (r0 + 16 < (int64_t)im.raw_len) ? (unsigned)__ldg(files + a0 + 16) : 0xFFu;
+    const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const unsigned b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+        unsigned next = i < 15 ? ((w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFFu) : after;
+        const int64_t r = r0 + i;
+        if (r + 1 >= (int64_t)im.raw_len) next = 0xFFu;                    // what follows the scan is the EOI's FF
+        const bool in = r >= 0 && r < (int64_t)im.raw_len;
+        const unsigned pv = r == 0 ? 0u : prev;
+        if (in && scan_keep(pv, b, next)) keep |= 1u << i;
+        if (in && scan_is_rst(pv, b)) rst |= 1u << i;
+        prev = b;
+    }
+}
+
+__global__ void __launch_bounds__(kUnstuffThreads)
+k_unstuff_count(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img,
+                uint2 *__restrict__ tile_cnt) {
+    __shared__ uint32_t s_tmp[2 * (kUnstuffThreads / 32) + 2];
+    const HuffImg &im = imgs[tile_img[blockIdx.x]];
+    uint32_t keep, rst;
+    uint4 bytes;
+    classify16(files, im, blockIdx.x - im.tile_base, keep, rst, bytes);
+    uint32_t ea, eb, ta, tb;
+    block_excl_scan2<kUnstuffThreads>(__popc(keep), __popc(rst), ea, eb, ta, tb, s_tmp);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = make_uint2(ta, tb);
+}
+
+// one warp per image: exclusive scan of its tiles' counts (in place), totals into the image state
+__global__ void __launch_bounds__(128)
+k_unstuff_scan(const HuffImg *__restrict__ imgs, int nimg, uint2 *__restrict__ tile_cnt, HuffImgState *__restrict__ st,
+               uint32_t *__restrict__ seg_off) {
+    const int img = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (img >= nimg) return;
+    const HuffImg &im = imgs[img];
+    uint32_t ca = 0, cb = 0;
+    for (uint32_t t0 = 0; t0 < im.ntile; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        uint2 v = t < im.ntile ? tile_cnt[im.tile_base + t] : make_uint2(0, 0);
+        const uint32_t ia = warp_incl_scan(v.x), ib = warp_incl_scan(v.y);
+        if (t < im.ntile) tile_cnt[im.tile_base + t] = make_uint2(ca + ia - v.x, cb + ib - v.y);
+        ca += __shfl_sync(0xFFFFFFFFu, ia, 31);
+        cb += __shfl_sync(0xFFFFFFFFu, ib, 31);
+    }
+    if (lane == 0) {
+        HuffImgState s;
+        s.clean_len = ca; s.nrst = cb;
+        s.nseg = min(cb + 1u, im.nseg);
+        s.nsub = 0;
+        // segments whose marker is missing are never decoded: everything from their first unit on reads as zero
+        s.first_zero = (s.nseg < im.nseg) ? s.nseg * im.ri * im.bpm : 0xFFFFFFFFu;
+        s.status = (im.ri != 0 && cb + 1u != im.nseg) ? 1u : 0u;
+        s.pad_[0] = s.pad_[1] = 0;
+        if (!im.valid) { s.nseg = 0; s.clean_len = 0; }
+        st[img] = s;
+        seg_off[im.seg_base] = 0;
+        seg_off[im.seg_base + s.nseg] = ca;
+    }
+}
+
+__global__ void __launch_bounds__(kUnstuffThreads)
+k_unstuff_write(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img,
+                const uint2 *__restrict__ tile_ex, const HuffImgState *__restrict__ st, uint32_t *__restrict__ clean,
+                uint32_t *__restrict__ seg_off) {
+    __shared__ uint32_t s_tmp[2 * (kUnstuffThreads / 32) + 2];
+    const uint32_t img = tile_img[blockIdx.x];
+    const HuffImg &im = imgs[img];
+    uint32_t keep, rst;
+    uint4 bytes;
+    classify16(files, im, blockIdx.x - im.tile_base, keep, rst, bytes);
+    uint32_t ea, eb, ta, tb;
+    block_excl_scan2<kUnstuffThreads>(__popc(keep), __popc(rst), ea, eb, ta, tb, s_tmp);
+    if ((keep | rst) == 0) return;
+    const uint2 base = tile_ex[blockIdx.x];
+    uint32_t o = base.x + ea, sidx = base.y + eb + 1;
+    const uint32_t nseg = st[img].nseg;
+    uint8_t *cb = reinterpret_cast<uint8_t *>(clean + im.clean_word0);
+    const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (keep & (1u << i)) { cb[o ^ 3u] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8)); o++; }
+        if (rst & (1u << i)) { if (sidx < nseg) seg_off[im.seg_base + sidx] = o; sidx++; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K0d: sub-sequences
+// One CTA per image.  Segment s of the image covers un-stuffed bytes [seg_off[s], seg_off[s+1]) and is cut into
+// max(1, ceil(len / sub_bytes)) sub-sequences; seg_sub0[s] = index of its first one, sub_seg[j] = owner segment.
+__global__ void __launch_bounds__(256)
+k_subseq_table(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ st, const uint32_t *__restrict__ seg_off,
+               uint32_t *__restrict__ seg_sub0, uint32_t *__restrict__ sub_seg, uint32_t sub_bytes) {
+    __shared__ uint32_t s_tmp[2 * 8 + 2];
+    __shared__ uint32_t s_first[257];
+    const HuffImg &im = imgs[blockIdx.x];
+    const uint32_t nseg = st[blockIdx.x].nseg;
+    uint32_t carry = 0;
+    for (uint32_t s0 = 0; s0 < nseg; s0 += 256) {
+        const uint32_t s = s0 + threadIdx.x;
+        uint32_t cnt = 0;
+        if (s < nseg) {
+            const uint32_t len = seg_off[im.seg_base + s + 1] - seg_off[im.seg_base + s];
+            cnt = max(1u, (len + sub_bytes - 1) / sub_bytes);
+        }
+        uint32_t ex, e2, tot, t2;
+        block_excl_scan2<256>(cnt, 0u, ex, e2, tot, t2, s_tmp);
+        s_first[threadIdx.x] = carry + ex;
+        if (threadIdx.x == 0) s_first[256] = carry + tot;
+        if (s < nseg) seg_sub0[im.seg_base + s] = carry + ex;
+        __syncthreads();
+        if (nseg > 1) {
+            // fill sub_seg for this chunk's sub-sequences: binary search among the chunk's segment starts
+            const uint32_t nchunk = min(256u, nseg - s0);
+            for (uint32_t j = s_first[0] + threadIdx.x; j < s_first[256]; j += 256) {
+                uint32_t lo = 0, hi = nchunk;                             // last k with s_first[k] <= j
+                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= j) lo = mid; else hi = mid; }
+                sub_seg[im.sub_base + j] = s0 + lo;
+            }
+        }
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { st[blockIdx.x].nsub = carry; seg_sub0[im.seg_base + nseg] = carry; }
+}
+
+// ------------------------------------------------------------------------------------------------ K1 common
+struct SubInfo {
+    uint32_t seg, k;
+    uint32_t start_bit, end_bit, data_end_bit;
+    bool head, last;
+};
+
+__device__ __forceinline__ SubInfo sub_info(const HuffImg &im, const HuffImgState &is, uint32_t j, const uint32_t *__restrict__ seg_off,
+                                            const uint32_t *__restrict__ seg_sub0, const uint32_t *__restrict__ sub_seg, uint32_t sub_bytes) {
+    SubInfo u;
+    u.seg = is.nseg > 1 ? sub_seg[im.sub_base + j] : 0u;
+    const uint32_t j0 = seg_sub0[im.seg_base + u.seg], j1 = seg_sub0[im.seg_base + u.seg + 1];
+    u.k = j - j0;
+    const uint32_t b0 = seg_off[im.seg_base + u.seg], b1 = seg_off[im.seg_base + u.seg + 1];
+    u.start_bit = (b0 + u.k * sub_bytes) * 8u;
+    u.end_bit = min(b0 + (u.k + 1u) * sub_bytes, b1) * 8u;
+    u.data_end_bit = b1 * 8u;
+    u.head = u.k == 0;
+    u.last = j + 1 == j1;
+    return u;
+}
+
+// stage the image's tables (nslot * kLutCap entries) into shared memory, 16 bytes per thread per step
+__device__ __forceinline__ void stage_luts(const HuffImg &im, const uint16_t *__restrict__ lut_pool, uint16_t *s_lut, HuffGeom &g) {
+    const int per = kLutCap * 2 / 16;                                     // uint4 per table
+    for (int i = threadIdx.x; i < im.nslot * per; i += blockDim.x) {
+        const int slot = i / per, q = i - slot * per;
+        reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(lut_pool + (size_t)im.slot_lut[slot] * kLutCap) + q);
+    }
+    g.bpm = im.bpm; g.ny = im.ny;
+#pragma unroll
+    for (int j = 0; j < 3; j++) g.tab[j] = (uint32_t)im.dc_slot[j] * kLutCap | ((uint32_t)im.ac_slot[j] * kLutCap) << 16;
+}
+
+__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (lo & 0xFFFFu) | (hi << 16); }
+
+// ------------------------------------------------------------------------------------------------ K1b: synchronise
+// round 0: every sub-sequence starts from the guess (own first bit, unit 0, DC expected) - exact for segment
+//          heads - and the CTA iterates  decode -> hand exit state to the successor  until nothing changes.
+//          Work is compacted: only sub-sequences whose entry state changed are decoded again, by the first
+//          threads of the CTA.
+// round r>0: the first sub-sequence of the CTA takes the exit state of the previous CTA's last one; if that
+//          differs from what it used, the CTA re-converges.  flags[r] counts CTAs that changed in round r; the
+//          host launches rounds until a round reports 0.
+__global__ void __launch_bounds__(kHuffThreads)
+k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
+            const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
+            const uint32_t *__restrict__ sub_seg, const uint16_t *__restrict__ lut_pool, uint2 *__restrict__ st_in,
+            uint2 *__restrict__ st_out, uint4 *__restrict__ sub_tot, uint4 *__restrict__ sub_pre, BlkAgg *__restrict__ blk_agg,
+            uint32_t *__restrict__ flags, int round, uint32_t sub_bytes) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem_raw);
+    __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
+    __shared__ uint4 s_tot[kHuffThreads];
+    __shared__ uint32_t s_end[kHuffThreads];
+    __shared__ uint16_t s_work[2][kHuffThreads];
+    __shared__ uint32_t s_nwork[2];
+    __shared__ uint32_t s_flag;
+    __shared__ uint32_t s_w[4][kHuffThreads / 32 + 1];
+    __shared__ uint32_t s_wf[kHuffThreads / 32 + 1];
+
+    const uint32_t img = blk_img[blockIdx.x];
+    const HuffImg &im = imgs[img];
+    const HuffImgState is = ist[img];
+    const int tid = threadIdx.x;
+    const uint32_t j = (blockIdx.x - im.blk_base) * kHuffThreads + tid;    // image-local sub-sequence
+    const uint32_t gj = im.sub_base + j;
+    const uint32_t first_j = (blockIdx.x - im.blk_base) * kHuffThreads;
+    if (first_j >= is.nsub) return;                                        // whole CTA beyond the image's sub-sequences
+    const bool active = j < is.nsub;
+
+    SubInfo u;
+    u.head = false; u.end_bit = 0; u.start_bit = 0;
+    if (active) u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg, sub_bytes);
+
+    if (tid == 0) { s_nwork[0] = 0; s_nwork[1] = 0; s_flag = 0; }
+    __syncthreads();
+    bool need = false;
+    if (round == 0) {
+        if (active) { s_in[tid] = make_uint2(u.start_bit, 0u); need = true; }
+    } else {
+        if (active) { s_in[tid] = st_in[gj]; s_out[tid] = st_out[gj]; s_tot[tid] = sub_tot[gj]; }
+        if (tid == 0 && !u.head && j > 0) {
+            const uint2 prev = st_out[gj - 1];
+            if (prev.x != s_in[0].x || prev.y != s_in[0].y) { s_in[0] = prev; need = true; s_flag = 1; }
+        }
+    }
+    s_end[tid] = u.end_bit;
+    if (need) s_work[0][atomicAdd(&s_nwork[0], 1u)] = (uint16_t)tid;
+    __syncthreads();
+    if (round > 0 && s_flag == 0) return;                                   // nothing changed at this CTA's entry
+
+    HuffGeom g;
+    stage_luts(im, lut_pool, s_lut, g);
+    const uint32_t *__restrict__ words = clean + im.clean_word0;
+
+    int cur = 0;
+    for (;;) {
+        __syncthreads();
+        const uint32_t nw = s_nwork[cur];
+        if (nw == 0) break;
+        for (uint32_t w = tid; w < nw; w += kHuffThreads) {
+            const uint32_t item = s_work[cur][w];
+            BitReader rd;
+            rd.w = words;
+            HuffState in;
+            in.p = s_in[item].x; in.cz = s_in[item].y;
+            SubTotals t;
+            const HuffState o = decode_span(rd, s_lut, g, in, s_end[item], &t);
+            s_out[item] = make_uint2(o.p, o.cz);
+            s_tot[item] = make_uint4(t.n, t.dc[0], t.dc[1], t.dc[2]);
+        }
+        if (tid == 0) s_nwork[cur ^ 1] = 0;
+        __syncthreads();
+        if (active && tid > 0 && !u.head) {
+            const uint2 prev = s_out[tid - 1], mine = s_in[tid];
+            if (prev.x != mine.x || prev.y != mine.y) {
+                s_in[tid] = prev;
+                s_work[cur ^ 1][atomicAdd(&s_nwork[cur ^ 1], 1u)] = (uint16_t)tid;
+            }
+        }
+        cur ^= 1;
+    }
+
+    // segmented exclusive scan over the CTA of (units started, DC sums), restarting at segment heads
+    uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0, f = 0;
+    if (active) { const uint4 t = s_tot[tid]; v0 = t.x; v1 = t.y; v2 = t.z; v3 = t.w; f = u.head ? 1u : 0u; }
+    const uint32_t own0 = v0, own1 = v1, own2 = v2, own3 = v3;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, v0, d), t1 = __shfl_up_sync(0xFFFFFFFFu, v1, d);
+        const uint32_t t2 = __shfl_up_sync(0xFFFFFFFFu, v2, d), t3 = __shfl_up_sync(0xFFFFFFFFu, v3, d);
+        const uint32_t tf = __shfl_up_sync(0xFFFFFFFFu, f, d);
+        if (lane >= d) { if (!f) { v0 += t0; v1 += t1; v2 += t2; v3 += t3; } f |= tf; }
+    }
+    if (lane == 31) { s_w[0][warp] = v0; s_w[1][warp] = v1; s_w[2][warp] = v2; s_w[3][warp] = v3; s_wf[warp] = f; }
+    __syncthreads();
+    if (tid == 0) {                                                        // 8 warp totals: serial segmented scan
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, cf = 0;
+        for (int w = 0; w < kHuffThreads / 32; w++) {
+            const uint32_t a0 = s_w[0][w], a1 = s_w[1][w], a2 = s_w[2][w], a3 = s_w[3][w], af = s_wf[w];
+            s_w[0][w] = c0; s_w[1][w] = c1; s_w[2][w] = c2; s_w[3][w] = c3; s_wf[w] = cf;      // carry INTO warp w
+            if (af) { c0 = a0; c1 = a1; c2 = a2; c3 = a3; cf = 1; } else { c0 += a0; c1 += a1; c2 += a2; c3 += a3; }
+        }
+        BlkAgg a;
+        a.n = c0; a.dc01 = pack16(c1, c2); a.dc2 = c3 & 0xFFFFu; a.has_head = cf;
+        blk_agg[blockIdx.x] = a;
+    }
+    __syncthreads();
+    if (active) {
+        uint32_t hf = f;
+        if (!f) { v0 += s_w[0][warp]; v1 += s_w[1][warp]; v2 += s_w[2][warp]; v3 += s_w[3][warp]; hf = s_wf[warp]; }
+        // exclusive: a head starts from zero; otherwise inclusive minus own
+        uint4 pre;
+        if (u.head) pre = make_uint4(0u, 0u, 0u, 1u);
+        else pre = make_uint4(v0 - own0, pack16(v1 - own1, v2 - own2), (v3 - own3) & 0xFFFFu, hf);
+        st_in[gj] = s_in[tid];
+        st_out[gj] = s_out[tid];
+        sub_tot[gj] = s_tot[tid];
+        sub_pre[gj] = pre;                                                 // .w: a head precedes inside this CTA
+    }
+    if (round > 0 && tid == 0) atomicAdd(&flags[round], 1u);
+}
+
+// ------------------------------------------------------------------------------------------------ K1a: write
+// Per-thread unit staging in shared memory, column layout: word w of thread t at [w * NT + t] - every access
+// of a warp falls into 32 different banks whatever the zig-zag index.
+struct SmemUnitSink {
+    uint32_t *col;           // &stage[tid]
+    int16_t *out;            // image's first unit
+    uint32_t ndu;
+    __device__ __forceinline__ void put(uint32_t zz, int16_t v) {
+        reinterpret_cast<int16_t *>(col + (zz >> 1) * kHuffThreads)[zz & 1u] = v;
+    }
+    __device__ __forceinline__ void flush(uint32_t du) {
+        uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)du * 64);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint4 v;
+            v.x = col[(4 * q + 0) * kHuffThreads]; v.y = col[(4 * q + 1) * kHuffThreads];
+            v.z = col[(4 * q + 2) * kHuffThreads]; v.w = col[(4 * q + 3) * kHuffThreads];
+            col[(4 * q + 0) * kHuffThreads] = 0; col[(4 * q + 1) * kHuffThreads] = 0;
+            col[(4 * q + 2) * kHuffThreads] = 0; col[(4 * q + 3) * kHuffThreads] = 0;
+            if (du < ndu) dst[q] = v;
+        }
+    }
+};
+
+constexpr int kSmemHuffStage = kHuffThreads * 128;
+
+__global__ void __launch_bounds__(kHuffThreads)
+k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
+             const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
+             const uint32_t *__restrict__ sub_seg, const uint16_t *__restrict__ lut_pool, const uint2 *__restrict__ st_in,
+             const uint4 *__restrict__ sub_pre, const BlkAgg *__restrict__ blk_agg, int16_t *__restrict__ coef, uint32_t sub_bytes) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw);
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem_raw + kSmemHuffStage);
+    __shared__ uint32_t s_red[4][kHuffThreads / 32];
+    __shared__ int s_h;
+
+    const uint32_t img = blk_img[blockIdx.x];
+    const HuffImg &im = imgs[img];
+    const HuffImgState is = ist[img];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lb = blockIdx.x - im.blk_base;
+    const uint32_t j = lb * kHuffThreads + tid;
+    if (lb * kHuffThreads >= is.nsub) return;
+    const bool active = j < is.nsub;
+
+    // carry into this CTA: totals of the previous CTAs of the image back to the last one that contains a head
+    if (tid == 0) s_h = 0;
+    __syncthreads();
+    {
+        int h = -1;
+        for (int b = (int)lb - 1 - tid; b >= 0; b -= kHuffThreads)
+            if (blk_agg[im.blk_base + b].has_head) { h = b; break; }
+        if (h >= 0) atomicMax(&s_h, h);
+    }
+    __syncthreads();
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int b = s_h + tid; b < (int)lb; b += kHuffThreads) {
+        const BlkAgg a = blk_agg[im.blk_base + b];
+        c0 += a.n; c1 += a.dc01 & 0xFFFFu; c2 += a.dc01 >> 16; c3 += a.dc2;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, d); c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, d);
+        c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, d); c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, d);
+    }
+    if (lane == 0) { s_red[0][warp] = c0; s_red[1][warp] = c1; s_red[2][warp] = c2; s_red[3][warp] = c3; }
+    for (int i = tid; i < 32 * kHuffThreads; i += kHuffThreads) s_stage[i] = 0;
+    HuffGeom g;
+    stage_luts(im, lut_pool, s_lut, g);
+    __syncthreads();
+    c0 = c1 = c2 = c3 = 0;
+#pragma unroll
+    for (int w = 0; w < kHuffThreads / 32; w++) { c0 += s_red[0][w]; c1 += s_red[1][w]; c2 += s_red[2][w]; c3 += s_red[3][w]; }
+
+    if (!active) return;
+    const SubInfo u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg, sub_bytes);
+    const uint4 pre = sub_pre[im.sub_base + j];
+    uint32_t n_ex = pre.x, p0 = pre.y & 0xFFFFu, p1 = pre.y >> 16, p2 = pre.z;
+    if (!pre.w) { n_ex += c0; p0 += c1; p1 += c2; p2 += c3; }
+    const uint32_t du0 = u.seg * im.ri * im.bpm;
+    const uint32_t du_end = (im.ri ? min(im.nmcu, (u.seg + 1u) * im.ri) : im.nmcu) * im.bpm;
+    const uint2 sin = st_in[im.sub_base + j];
+    HuffState in;
+    in.p = sin.x; in.cz = sin.y;
+    BitReader rd;
+    rd.w = clean + im.clean_word0;
+    SmemUnitSink sink;
+    sink.col = s_stage + tid;
+    sink.out = coef + (size_t)im.du_base * 64;
+    sink.ndu = im.ndu;
+    const uint32_t pred[3] = {p0, p1, p2};
+    const WriteResult r = write_span(rd, s_lut, g, in, u.end_bit, u.data_end_bit, du0 + n_ex, du_end, u.last, pred, sink);
+    if (r.first_zero != 0xFFFFFFFFu) {
+        atomicMin(&ist[img].first_zero, r.first_zero);
+        ist[img].status = 1u;
+    }
+}
+
+// Units from first_zero on were never reached by the reference's decoder: they read as zero.  grid = (nimg, slices).
+__global__ void __launch_bounds__(256)
+k_zero_tail(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, int16_t *__restrict__ coef) {
+    const HuffImg &im = imgs[blockIdx.x];
+    const uint32_t fz = im.valid ? ist[blockIdx.x].first_zero : 0u;
+    if (fz >= im.ndu) return;
+    uint4 *p = reinterpret_cast<uint4 *>(coef + ((size_t)im.du_base + fz) * 64);
+    const size_t n = (size_t)(im.ndu - fz) * 8;
+    for (size_t i = (size_t)blockIdx.y * 256 + threadIdx.x; i < n; i += (size_t)gridDim.y * 256) p[i] = make_uint4(0, 0, 0, 0);
+}
+
+}  // namespace bj

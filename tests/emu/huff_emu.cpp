@@ -1,0 +1,162 @@
+// TEST INFRASTRUCTURE - host-side emulation of the entropy-stage kernels' data flow.
+//
+// Compiles the product's device/host-shared core (pim_jpeg_decoder_b200/csrc/huff_core.h, parse.h) with g++ and
+// runs the same algorithm the CUDA kernels run - un-stuff + segment table, speculative sub-sequence decode,
+// fix-up rounds until a fixed point, per-segment prefix sums, owner-writes-whole-unit pass - sequentially on the
+// CPU, so the algorithm can be checked against the oracle without a GPU.  It is NOT linked into libb200jpeg.so
+// and is only loaded by tests/test_huff_emu.py.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../pim_jpeg_decoder_b200/csrc/huff_core.h"
+#include "../../pim_jpeg_decoder_b200/csrc/parse.h"
+
+using namespace bj;
+
+namespace {
+struct HostSink {
+    int16_t unit[64];
+    int16_t *out;
+    uint32_t ndu;
+    std::vector<uint8_t> *written;
+    HostSink() { memset(unit, 0, sizeof(unit)); }
+    void put(uint32_t zz, int16_t v) { unit[zz] = v; }
+    void flush(uint32_t du) {
+        if (du < ndu) { memcpy(out + (size_t)du * 64, unit, sizeof(unit)); (*written)[du]++; }
+        memset(unit, 0, sizeof(unit));
+    }
+};
+}  // namespace
+
+// Returns 0 ok, <0 parse status.  info[0] = fix-up rounds, info[1] = first_zero (UINT32_MAX none), info[2] = nsub,
+// info[3] = number of units written more or less than once (must be 0 for a clean stream)
+extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16_t *coef_zz, uint32_t *info) {
+    bj_image_desc d;
+    int rc = parse_header(file, len, &d);
+    if (rc != BJ_OK) return rc;
+    const uint32_t nmx = (d.mcu_w + d.hs - 1) / d.hs, nmy = (d.mcu_h + d.vs - 1) / d.vs, nmcu = nmx * nmy;
+    uint32_t bpm = 0;
+    for (int j = 0; j < d.ncomp; j++) bpm += d.comp_h[j] * d.comp_v[j];
+    const uint32_t ndu = nmcu * bpm;
+    const uint32_t ri = d.restart_interval;
+    const uint32_t nseg_expected = ri ? (nmcu + ri - 1) / ri : 1;
+
+    // K0: classify, compact (byte o stored at o ^ 3), segment starts
+    const uint8_t *raw = file + d.scan_off;
+    const size_t rl = d.scan_len;
+    std::vector<uint8_t> clean(((rl + 3) / 4 + 4) * 4, 0);
+    std::vector<uint32_t> seg_off(1, 0);
+    size_t o = 0;
+    for (size_t i = 0; i < rl; i++) {
+        const unsigned prev = i ? raw[i - 1] : 0u, b = raw[i], next = i + 1 < rl ? raw[i + 1] : 0xFFu;
+        if (scan_keep(prev, b, next)) { clean[o ^ 3] = (uint8_t)b; o++; }
+        else if (scan_is_rst(prev, b) && seg_off.size() < nseg_expected) seg_off.push_back((uint32_t)o);
+    }
+    const uint32_t clean_len = (uint32_t)o;
+    const uint32_t nseg = (uint32_t)seg_off.size();
+    seg_off.push_back(clean_len);
+    uint32_t first_zero = nseg < nseg_expected ? nseg * ri * bpm : 0xFFFFFFFFu;
+
+    // tables
+    std::vector<uint16_t> luts(6 * kLutCap);
+    HuffGeom g;
+    g.bpm = bpm; g.ny = (uint32_t)d.hs * d.vs;
+    for (int j = 0; j < 3; j++) {
+        const int jj = j < d.ncomp ? j : 0;
+        if (build_lut(d.dc_offsets[d.dc_id[jj]], d.dc_symbols[d.dc_id[jj]], &luts[(2 * j) * kLutCap]) < 0) return -100;
+        if (build_lut(d.ac_offsets[d.ac_id[jj]], d.ac_symbols[d.ac_id[jj]], &luts[(2 * j + 1) * kLutCap]) < 0) return -100;
+        g.tab[j] = (uint32_t)((2 * j) * kLutCap) | ((uint32_t)((2 * j + 1) * kLutCap) << 16);
+    }
+
+    // sub-sequence table
+    struct Sub { uint32_t seg, start_bit, end_bit; bool head, last; };
+    std::vector<Sub> subs;
+    for (uint32_t s = 0; s < nseg; s++) {
+        const uint32_t b0 = seg_off[s], b1 = seg_off[s + 1];
+        const uint32_t ns = std::max<uint32_t>(1, (b1 - b0 + sub_bytes - 1) / sub_bytes);
+        for (uint32_t k = 0; k < ns; k++) {
+            Sub u;
+            u.seg = s; u.head = k == 0; u.last = k + 1 == ns;
+            u.start_bit = (b0 + k * sub_bytes) * 8;
+            u.end_bit = std::min<uint32_t>(b0 + (k + 1) * sub_bytes, b1) * 8;
+            subs.push_back(u);
+        }
+    }
+    const size_t ns = subs.size();
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(clean.data());
+
+    // pass 1: Jacobi rounds to the fixed point  in[i+1] == out[i]
+    std::vector<HuffState> in(ns), out(ns);
+    std::vector<SubTotals> tot(ns);
+    std::vector<uint8_t> need(ns, 1);
+    for (size_t i = 0; i < ns; i++) { in[i].p = subs[i].start_bit; in[i].cz = 0; }
+    uint32_t rounds = 0;
+    for (;;) {
+        bool any = false;
+        for (size_t i = 0; i < ns; i++) {
+            if (!need[i]) continue;
+            BitReader rd; rd.w = words;
+            out[i] = decode_span(rd, luts.data(), g, in[i], subs[i].end_bit, &tot[i]);
+            need[i] = 0; any = true;
+        }
+        if (!any) break;
+        rounds++;
+        for (size_t i = ns; i-- > 1;) {
+            if (subs[i].head) continue;
+            if (!same_state(in[i], out[i - 1])) { in[i] = out[i - 1]; need[i] = 1; }
+        }
+    }
+
+    // prefix sums per segment, then the write pass
+    std::vector<uint8_t> written(ndu, 0);
+    uint32_t n_ex = 0, dc_ex[3] = {0, 0, 0};
+    for (size_t i = 0; i < ns; i++) {
+        const Sub &u = subs[i];
+        if (u.head) { n_ex = 0; dc_ex[0] = dc_ex[1] = dc_ex[2] = 0; }
+        const uint32_t du0 = u.seg * ri * bpm;
+        const uint32_t du_end = (ri ? std::min(nmcu, (u.seg + 1) * ri) : nmcu) * bpm;
+        HostSink sink;
+        sink.out = coef_zz; sink.ndu = ndu; sink.written = &written;
+        BitReader rd; rd.w = words;
+        const uint32_t pred[3] = {dc_ex[0], dc_ex[1], dc_ex[2]};
+        const WriteResult r = write_span(rd, luts.data(), g, in[i], u.end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex, du_end,
+                                         u.last, pred, sink);
+        first_zero = std::min(first_zero, r.first_zero);
+        n_ex += tot[i].n;
+        for (int k = 0; k < 3; k++) dc_ex[k] += tot[i].dc[k];
+    }
+    // zero tail (what the cleanup kernel does)
+    uint32_t odd = 0;
+    const uint32_t lim = std::min(first_zero, ndu);
+    for (uint32_t u = 0; u < lim; u++) odd += written[u] != 1;
+    if (first_zero < ndu) memset(coef_zz + (size_t)first_zero * 64, 0, (size_t)(ndu - first_zero) * 128);
+    info[0] = rounds; info[1] = first_zero; info[2] = (uint32_t)ns; info[3] = odd;
+    return 0;
+}
+
+extern "C" int emu_parse(const uint8_t *file, size_t len, bj_image_desc *d) { return parse_header(file, len, d); }
+
+// Direct access to the table builder: decode one symbol bit-serially the way the reference does and via the table.
+extern "C" int emu_lut_check(const uint8_t *offsets, const uint8_t *symbols) {
+    std::vector<uint16_t> lut(kLutCap);
+    if (build_lut(offsets, symbols, lut.data()) < 0) return -1;
+    uint32_t codes[162];
+    uint32_t code = 0;
+    for (int l = 0; l < 16; l++) { for (unsigned j = offsets[l]; j < offsets[l + 1]; j++) codes[j] = code++; code <<= 1; }
+    int bad = 0;
+    for (uint32_t w = 0; w < 65536; w++) {               // every 16-bit window
+        uint32_t want = 0;
+        uint32_t cw = 0;
+        for (int l = 0; l < 16 && !want; l++) {
+            cw = (cw << 1) | ((w >> (15 - l)) & 1);
+            for (unsigned j = offsets[l]; j < offsets[l + 1]; j++)
+                if (cw == codes[j]) { want = ((uint32_t)(l + 1) << 8) | symbols[j]; break; }
+        }
+        if (lut_lookup(lut.data(), w << 16) != want) bad++;
+    }
+    return bad;
+}

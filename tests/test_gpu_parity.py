@@ -1,0 +1,226 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every comparison is BIT-EXACT (tolerance 0): the
+reference's path is all-integer.  All calls go through the C ABI (libb200jpeg.so)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import jpeg_synth as js
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def dec():
+    import pim_jpeg_decoder_b200 as bj
+    d = bj.Decoder(0)
+    yield d
+    d.close()
+
+
+def _names(include_invalid=False):
+    import json
+    with open(os.path.join(HERE, "golden", "golden.json")) as f:
+        g = json.load(f)
+    return sorted(k for k, v in g.items() if include_invalid or not v.get("invalid"))
+
+
+def _load(golden, golden_dir, name):
+    return open(os.path.join(golden_dir, golden[name]["file"]), "rb").read()
+
+
+# ------------------------------------------------------------------ compat entry = the DPU program (K2+K3, ref layout)
+
+@pytest.mark.parametrize("name", _names())
+def test_exec_mcus_matches_reference_buffers(dec, name, golden, golden_dir):
+    """bj_exec_mcus on the reference's own metadata/mcus buffers == pim.exec(): memcmp of the whole buffer."""
+    r = ol.Restated(_load(golden, golden_dir, name), restart_mode=1)
+    got = dec.exec_mcus(r.metadata, r.mcus_pre)
+    assert np.array_equal(got, r.mcus_post)
+    assert sha(got) == golden[name]["mcus_post_sha256"]          # the hash the REAL reference produced
+
+
+@pytest.mark.parametrize("vs,hs,ncomp", [(1, 1, 3), (2, 1, 3), (1, 2, 3), (2, 2, 3), (1, 1, 1), (2, 2, 1), (0, 0, 0), (3, 1, 3)])
+@pytest.mark.parametrize("full_range", [False, True])
+def test_exec_mcus_random_buffers(dec, vs, hs, ncomp, full_range):
+    """Random coefficient buffers incl. values that wrap 16 and 32 bits; idle DPUs (all-zero metadata) untouched."""
+    from test_oracle import _random_exec_case
+    rng = np.random.default_rng(vs * 100 + hs * 10 + ncomp + (1000 if full_range else 0))
+    md, mcus = _random_exec_case(rng, vs, hs, max(ncomp, 1), 37, full_range)
+    if ncomp == 0:
+        md[:] = 0
+    md[5] = 0                                                   # one idle DPU in the middle of the batch
+    got = dec.exec_mcus(md, mcus)
+    assert np.array_equal(got, ol.restate_exec_mcus(md, mcus))
+
+
+# ------------------------------------------------------------------ stage tests on the fast layout
+
+@pytest.mark.parametrize("name", _names())
+def test_stage_idct_color_from_oracle_coefficients(dec, name, golden, golden_dir):
+    import pim_jpeg_decoder_b200 as bj
+    data = _load(golden, golden_dir, name)
+    r = ol.Restated(data, restart_mode=0)
+    st, d = bj.parse_header(data)
+    assert st == 0
+    bmp = dec.stage_idct_color(d, r.coef_zz, bj.BJ_OUT_BMP)
+    assert np.array_equal(bmp, r.bmp)
+    rgb = dec.stage_idct_color(d, r.coef_zz, bj.BJ_OUT_RGB8)
+    assert np.array_equal(rgb.reshape(r.rgb.shape), r.rgb)
+
+
+@pytest.mark.parametrize("name", _names())
+def test_stage_entropy_matches_oracle_coefficients(dec, name, golden, golden_dir):
+    data = _load(golden, golden_dir, name)
+    r = ol.Restated(data, restart_mode=0)
+    coef, status = dec.stage_entropy(data)
+    assert status == 0
+    assert np.array_equal(coef, r.coef_zz)
+
+
+@pytest.mark.parametrize("bits", [128, 256, 1024, 4096])
+def test_stage_entropy_subsequence_sizes(dec, bits, golden, golden_dir):
+    dec.set_option("subseq_bits", bits)
+    try:
+        for name in ("ilsvrc_444", "p420_320x240", "enc_444_100x60_ri1", "p420_q100_64x64", "gray_ri3_64x48"):
+            data = _load(golden, golden_dir, name)
+            coef, status = dec.stage_entropy(data)
+            assert status == 0
+            assert np.array_equal(coef, ol.Restated(data, 0).coef_zz), (name, bits)
+    finally:
+        dec.set_option("subseq_bits", 1024)
+
+
+# ------------------------------------------------------------------ full path against the reference's BMPs
+
+@pytest.mark.parametrize("name", _names())
+def test_full_path_bmp_matches_reference_hash(dec, name, golden, golden_dir):
+    """Compressed bytes -> BMP bytes; the SHA-256 must be the one the REAL reference produced (golden.json).
+    For subsampled files with restart markers the restart-parity rule applies: `expect` names the restart-free twin."""
+    import pim_jpeg_decoder_b200 as bj
+    data = _load(golden, golden_dir, name)
+    outs, status = dec.decode([data], bj.BJ_OUT_BMP)
+    assert status == [0]
+    assert sha(outs[0]) == golden[golden[name]["expect"]]["bmp_sha256"]
+
+
+def test_full_path_batch_mixed(dec, golden, golden_dir):
+    """All fixtures in ONE batch (mixed sizes, samplings, restart intervals, invalid files in between)."""
+    import pim_jpeg_decoder_b200 as bj
+    names = _names(include_invalid=True)
+    files = [_load(golden, golden_dir, n) for n in names]
+    for fmt in (bj.BJ_OUT_BMP, bj.BJ_OUT_RGB8):
+        outs, status = dec.decode(files, fmt)
+        for n, o, st, data in zip(names, outs, status, files):
+            if golden[n].get("invalid"):
+                assert st == bj.BJ_ERR_INVALID_JPEG and o is None
+                continue
+            assert st == 0, n
+            r = ol.Restated(data, 0)
+            if fmt == bj.BJ_OUT_BMP:
+                assert sha(o) == golden[golden[n]["expect"]]["bmp_sha256"], n
+            else:
+                assert np.array_equal(o.reshape(r.rgb.shape), r.rgb), n
+
+
+def test_full_path_sub_batching(dec, golden, golden_dir):
+    """Force many sub-batches through the double-buffered one-call path."""
+    import pim_jpeg_decoder_b200 as bj
+    names = [n for n in _names()] * 3
+    files = [_load(golden, golden_dir, n) for n in names]
+    dec.set_option("sub_batch_bytes", 1 << 16)
+    try:
+        outs, status = dec.decode(files, bj.BJ_OUT_BMP)
+        assert dec.stat("decode_batch_sub_batches") > 4
+    finally:
+        dec.set_option("sub_batch_bytes", 48 << 20)
+    for n, o, st in zip(names, outs, status):
+        assert st == 0 and sha(o) == golden[golden[n]["expect"]]["bmp_sha256"], n
+
+
+@pytest.mark.parametrize("w,h,sub,gray,ri", [(500, 375, 2, False, 0), (375, 500, 2, False, 0), (640, 480, 0, False, 0),
+                                             (640, 480, 1, False, 0), (224, 224, 2, True, 0), (1024, 768, 2, False, 0),
+                                             (512, 384, 0, False, 8), (400, 300, 2, True, 5)])
+def test_full_path_synthetic_vs_oracle(dec, w, h, sub, gray, ri):
+    """The generator of SURVEY.md 8d; the oracle (restatement pinned to the reference) decodes the same bytes."""
+    import pim_jpeg_decoder_b200 as bj
+    data = js.synth_jpeg(w, h, seed=w * 7 + h, subsampling=sub, gray=gray, restart_blocks=ri)
+    r = ol.Restated(data, 0)
+    outs, status = dec.decode([data], bj.BJ_OUT_BMP)
+    assert status == [0]
+    assert np.array_equal(outs[0], r.bmp)
+
+
+def test_config3_restart_parity_rule(dec):
+    """Config 3 shape (4:2:0 + restart interval 8), reduced size: GPU output == reference decode of the
+    restart-free twin; the reference's own decode of the DRI file differs (its restart test is
+    wrong for subsampled files)."""
+    import pim_jpeg_decoder_b200 as bj
+    rgb = js.synth_rgb(960, 544, 0)
+    with_ri = js.pil_jpeg(rgb, 90, 2, restart_blocks=8)
+    twin = js.pil_jpeg(rgb, 90, 2)
+    outs, status = dec.decode([with_ri, twin], bj.BJ_OUT_BMP)
+    assert status == [0, 0]
+    want = ol.Restated(twin, 0).bmp
+    assert np.array_equal(outs[0], want) and np.array_equal(outs[1], want)
+    assert not np.array_equal(ol.Restated(with_ri, 1).bmp, want)
+
+
+def test_truncated_scan_matches_reference_partial_image(dec):
+    """The reference ignores the Huffman failure and writes the partial image (src/decoder_host.cpp:181);
+    undecoded units stay zero -> grey.  Same pixels here, plus a per-image status."""
+    import pim_jpeg_decoder_b200 as bj
+    data = js.synth_jpeg(320, 240, seed=9, subsampling=2)
+    bad = data[: len(data) - 2 - 3000] + b"\xFF\xD9"
+    r = ol.Restated(bad, 0)
+    assert r.huff_rc != 0
+    outs, status = dec.decode([bad, data], bj.BJ_OUT_BMP)
+    assert status == [bj.BJ_ERR_CORRUPT_SCAN, 0]
+    assert np.array_equal(outs[0], r.bmp)
+    assert np.array_equal(outs[1], ol.Restated(data, 0).bmp)
+
+
+def test_large_image_properties(dec):
+    """Full-size config-4 shapes (3840x2160 4:4:4 and gray, no restart markers): checked through size-independent
+    properties - the image decodes identically alone, inside a batch, and at another sub-sequence size - plus an
+    oracle comparison on the 4:4:4 one (the C oracle takes ~1 s for it)."""
+    import pim_jpeg_decoder_b200 as bj
+    a = js.synth_jpeg(3840, 2160, seed=1, subsampling=0)
+    g = js.synth_jpeg(3840, 2160, seed=2, gray=True)
+    small = js.synth_jpeg(100, 80, seed=3)
+    o1, s1 = dec.decode([a], bj.BJ_OUT_RGB8)
+    o2, s2 = dec.decode([small, g, a, small], bj.BJ_OUT_RGB8)
+    assert s1 == [0] and s2 == [0, 0, 0, 0]
+    assert np.array_equal(o1[0], o2[2]) and np.array_equal(o2[0], o2[3])
+    dec.set_option("subseq_bits", 2048)
+    try:
+        o3, s3 = dec.decode([g, a], bj.BJ_OUT_RGB8)
+    finally:
+        dec.set_option("subseq_bits", 1024)
+    assert np.array_equal(o3[0], o2[1]) and np.array_equal(o3[1], o1[0])
+    r = ol.Restated(a, 0)
+    assert np.array_equal(o1[0].reshape(r.rgb.shape), r.rgb)
+
+
+def test_decode_files_cli_behaviour(dec, tmp_path, golden, golden_dir):
+    """`./bin/decoder a.jpg b.jpg` writes a.bmp / b.bmp beside the inputs (src/decoder_host.cpp:328-330)."""
+    import shutil
+    import pim_jpeg_decoder_b200 as bj
+    names = ["ilsvrc_444", "p420_50x37", "bad_not_jpeg"]
+    paths = []
+    for n in names:
+        p = str(tmp_path / golden[n]["file"])
+        shutil.copy(os.path.join(golden_dir, golden[n]["file"]), p)
+        paths.append(p)
+    res = bj.decode_files(paths, decoder=dec)
+    assert res[paths[2]] == bj.BJ_ERR_INVALID_JPEG and not os.path.exists(paths[2][:-4] + ".bmp")
+    for n, p in zip(names[:2], paths[:2]):
+        assert sha(np.fromfile(p[:-4] + ".bmp", dtype=np.uint8)) == golden[n]["bmp_sha256"]

@@ -1,0 +1,98 @@
+"""CPU tests of the entropy stage's ALGORITHM: the product's shared device/host core (huff_core.h, parse.h),
+driven by a sequential host emulation of the kernels' data flow (tests/emu/huff_emu.cpp), against the oracle.
+
+The GPU kernels themselves are covered by the ``-m gpu`` tests; this file checks what can be checked without one:
+the lookup-table builder, the byte classification, the speculative decode + fix-up fixed point, the prefix sums
+and the owner-writes-whole-unit rule, on every golden fixture and on synthetic images, at several sub-sequence
+sizes (small sizes force units and even single symbols to straddle sub-sequences).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import jpeg_synth as js
+import oracle_lib as ol
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu", "libhuffemu.so")
+
+
+def emu():
+    src = os.path.join(HERE, "emu", "huff_emu.cpp")
+    core = os.path.join(ol.ROOT, "pim_jpeg_decoder_b200", "csrc", "huff_core.h")
+    if not os.path.exists(EMU) or os.path.getmtime(EMU) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", EMU, src], check=True)
+    lib = C.CDLL(EMU)
+    lib.emu_entropy.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    lib.emu_lut_check.argtypes = [C.c_void_p, C.c_void_p]
+    return lib
+
+
+def run_emu(data, sub_bytes):
+    r = ol.Restated(data, restart_mode=0)
+    assert r.valid
+    buf = np.frombuffer(data, dtype=np.uint8)
+    got = np.full_like(r.coef_zz, 0x5A5A)          # poison: every unit must be written (or zero-filled)
+    info = np.zeros(4, dtype=np.uint32)
+    rc = emu().emu_entropy(ol._ptr(buf), len(data), sub_bytes, ol._ptr(got), ol._ptr(info))
+    assert rc == 0
+    return r, got, info
+
+
+def _golden_names():
+    import json
+    with open(os.path.join(HERE, "golden", "golden.json")) as f:
+        g = json.load(f)
+    return sorted(k for k, v in g.items() if not v.get("invalid"))
+
+
+@pytest.mark.parametrize("sub_bytes", [4, 32, 128, 1024])
+@pytest.mark.parametrize("name", _golden_names())
+def test_emulated_entropy_stage_matches_oracle(name, sub_bytes, golden, golden_dir):
+    data = open(os.path.join(golden_dir, golden[name]["file"]), "rb").read()
+    r, got, info = run_emu(data, sub_bytes)
+    assert r.huff_rc == 0
+    assert info[3] == 0, "a data unit was written twice or never"
+    assert info[1] == 0xFFFFFFFF
+    assert np.array_equal(got, r.coef_zz)
+
+
+@pytest.mark.parametrize("w,h,sub,gray,ri", [(500, 375, 2, False, 0), (500, 375, 0, False, 0), (640, 480, 1, False, 0),
+                                             (320, 200, 2, True, 0), (512, 512, 2, False, 8), (333, 111, 0, False, 5)])
+def test_emulated_entropy_stage_synthetic(w, h, sub, gray, ri):
+    data = js.synth_jpeg(w, h, seed=w + h, subsampling=sub, gray=gray, restart_blocks=ri)
+    r, got, info = run_emu(data, 128)
+    assert r.huff_rc == 0 and info[3] == 0
+    assert np.array_equal(got, r.coef_zz)
+    assert info[0] < 40            # fix-up rounds stay small: the stream self-synchronises
+
+
+def test_truncated_scan_zero_fills_like_the_reference():
+    """Cut the entropy-coded data short: the reference stops at the failing unit and leaves the rest zero."""
+    data = bytearray(js.synth_jpeg(160, 120, seed=3, subsampling=2))
+    cut = len(data) - 2 - 900
+    bad = bytes(data[:cut]) + b"\xFF\xD9"
+    r, got, info = run_emu(bad, 128)
+    assert r.huff_rc != 0
+    assert info[1] != 0xFFFFFFFF
+    assert np.array_equal(got, r.coef_zz)
+
+
+def test_lut_matches_bit_serial_search():
+    lib = emu()
+    dht, _ = js.std_tables()
+    for key, (counts, syms) in dht.items():
+        off = np.zeros(17, dtype=np.uint8)
+        off[1:] = np.cumsum(counts)
+        sy = np.zeros(162, dtype=np.uint8)
+        sy[:len(syms)] = syms
+        assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy)) == 0, key
+    # an optimised table set and a deliberately odd one (sparse lengths incl. 16-bit DC codes)
+    off = np.zeros(17, dtype=np.uint8)
+    counts = [0, 1, 0, 0, 2, 0, 0, 0, 3, 0, 0, 5, 0, 0, 7, 20]
+    off[1:] = np.cumsum(counts)
+    sy = np.arange(162, dtype=np.uint8)
+    assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy)) == 0
