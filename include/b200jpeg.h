@@ -115,7 +115,8 @@ int bj_batch_decode(bj_batch *b, void *stream);                 /* enqueue all k
 int bj_batch_sync(bj_batch *b);                                 /* wait; settles the (rare) extra Huffman fix-up rounds */
 int bj_batch_download(bj_batch *b, uint8_t *const *outs, void *stream);   /* D2H into caller buffers, then sync */
 /* Where image i sits in the batch's device output buffer.  A caller that lays its host buffers out the same way
- * (outs[i] = base + offset_i) gets one large copy instead of one per image.  Returns the image's parse status. */
+ * (outs[i] = base + offset_i) and sets option "packed_outputs" gets one large copy instead of one per image.
+ * Returns the image's parse status. */
 int bj_batch_output_offset(const bj_batch *b, int i, size_t *offset, size_t *bytes);
 int bj_batch_status(const bj_batch *b, int *status /*[n]*/);
 void bj_batch_destroy(bj_batch *b);
@@ -131,6 +132,8 @@ typedef struct {
     uint32_t sync_rounds;       /* fix-up rounds the last bj_batch_decode needed */
     uint32_t launches;          /* kernels launched by the last bj_batch_decode */
     float ms_entropy, ms_idct;  /* CUDA-event time of the two stages of the last bj_batch_decode */
+    float ms_unstuff, ms_sync, ms_write;   /* ms_entropy split: K0 (un-stuff + tables), K1 fix-up rounds, K1 write pass */
+    uint64_t clean_bytes;       /* entropy-coded bytes after un-stuffing / marker removal */
 } bj_batch_info;
 int bj_batch_get_info(const bj_batch *b, bj_batch_info *info);
 int bj_batch_device_output(const bj_batch *b, int i, void **dptr, size_t *bytes);
@@ -149,7 +152,10 @@ int bj_stage_entropy(bj_ctx *ctx, const uint8_t *file, size_t len, int16_t *coef
 /* Tunables (0 = default):
  *   "subseq_bits"      Huffman sub-sequence size in bits (multiple of 32, >= 128)
  *   "sync_rounds"      launches of the fix-up kernel before convergence is first checked
- *   "sub_batch_bytes"  compressed bytes per sub-batch of bj_decode_batch */
+ *   "sub_batch_bytes"  compressed bytes per sub-batch of bj_decode_batch
+ *   "packed_outputs"   1: output pointers that follow bj_batch_output_offset's layout (outs[i] = base + offset_i,
+ *                      for the one-call path: offsets restart at 0 in every sub-batch) belong to ONE allocation,
+ *                      so runs of images are copied out in one transfer, padding bytes included */
 int bj_set_option(bj_ctx *ctx, const char *name, long value);
 /* Counters of the last call: "exec_ms" (kernel time of bj_exec_mcus - the reference's "DPU execution" profile line,
  * src/decoder_host.cpp:291-294), "decode_batch_sub_batches", "decode_batch_launches", "decode_batch_h2d_bytes",

@@ -48,6 +48,8 @@ class BatchInfo(C.Structure):
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("subsequences", C.c_uint32), ("sync_rounds", C.c_uint32), ("launches", C.c_uint32),
         ("ms_entropy", C.c_float), ("ms_idct", C.c_float),
+        ("ms_unstuff", C.c_float), ("ms_sync", C.c_float), ("ms_write", C.c_float),
+        ("clean_bytes", C.c_uint64),
     ]
 
 

@@ -85,6 +85,7 @@ extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
     if (!c || !name) return BJ_ERR_ARG;
     if (!strcmp(name, "subseq_bits")) { if (value < 128 || value % 32) return BJ_ERR_ARG; c->subseq_bits = (int)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_bytes = (size_t)value; return BJ_OK; }
+    if (!strcmp(name, "packed_outputs")) { c->packed_outputs = value != 0; return BJ_OK; }
     if (!strcmp(name, "sync_rounds")) { if (value < 0 || value > kMaxRounds) return BJ_ERR_ARG; c->sync_rounds = (int)value; return BJ_OK; }
     return BJ_ERR_ARG;
 }
@@ -226,6 +227,9 @@ extern "C" int bj_batch_get_info(const bj_batch *b, bj_batch_info *info) {
     if (b->synced) for (int i = 0; i < b->n; i++) nsub += const_cast<bj_batch *>(b)->h_state()[i].nsub;
     info->subsequences = nsub; info->sync_rounds = b->sync_rounds; info->launches = b->launches;
     info->ms_entropy = b->ms_entropy; info->ms_idct = b->ms_idct;
+    info->ms_unstuff = b->ms_unstuff; info->ms_sync = b->ms_sync; info->ms_write = b->ms_write;
+    info->clean_bytes = 0;
+    if (b->synced) for (int i = 0; i < b->n; i++) info->clean_bytes += const_cast<bj_batch *>(b)->h_state()[i].clean_len;
     return BJ_OK;
 }
 

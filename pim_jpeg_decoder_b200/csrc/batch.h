@@ -66,11 +66,11 @@ struct bj_batch {
 
     // device
     bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_tilecnt, d_blkagg, d_state, d_flags, d_coef, d_out;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels
     cudaStream_t last_stream = nullptr;
     bool uploaded = false, decoded = false, synced = false;
     uint32_t launches = 0, sync_rounds = 0;
-    float ms_entropy = 0.f, ms_idct = 0.f;
+    float ms_entropy = 0.f, ms_idct = 0.f, ms_unstuff = 0.f, ms_sync = 0.f, ms_write = 0.f;
     uint64_t d2h_bytes = 0;
 
     bj::HuffImgState *h_state() { return reinterpret_cast<bj::HuffImgState *>(h_res.p); }
@@ -261,12 +261,14 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
         k_subseq_table<<<n, 256, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg, b->sub_bytes);
         b->launches = 2 + (b->n_utile ? 2 : 0);
         b->sync_rounds = 0;
+        cudaEventRecord(b->ev[1], s);
     }
     if (b->n_blk) {
         for (int r = r0; r < r1; r++) {
             k_huff_sync<<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts, st_in, st_out, tot, pre, agg, flags, r, b->sub_bytes);
             b->launches++; b->sync_rounds++;
         }
+        cudaEventRecord(b->ev[2], s);
         k_huff_write<<<b->n_blk, kHuffThreads, kSmemHuffStage + lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts, st_in, pre, agg, (int16_t *)b->d_coef.p, b->sub_bytes);
         b->launches++;
     }
@@ -275,12 +277,13 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
         k_zero_tail<<<dim3(n, gx > 64 ? 64 : gx), 256, 0, s>>>(himg, st, (int16_t *)b->d_coef.p);
         b->launches++;
     }
-    cudaEventRecord(b->ev[1], s);
+    if (!b->n_blk) cudaEventRecord(b->ev[2], s);
+    cudaEventRecord(b->ev[3], s);
     if (b->n_idct_tiles) {
         k_idct_color<<<b->n_idct_tiles, kTileThreads, kSmemIdctColor, s>>>((const int16_t *)b->d_coef.p, idev, tiles, (uint8_t *)b->d_out.p);
         b->launches++;
     }
-    cudaEventRecord(b->ev[2], s);
+    cudaEventRecord(b->ev[4], s);
     cudaMemcpyAsync(b->h_state(), st, (size_t)n * sizeof(HuffImgState), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(b->h_flags(), flags, kMaxRounds * 4, cudaMemcpyDeviceToHost, s);
     return c->check(cudaGetLastError());
@@ -313,8 +316,11 @@ inline int batch_sync(bj_batch *b) {
         r += 2;
     }
     if (rc == BJ_OK) {
-        cudaEventElapsedTime(&b->ms_entropy, b->ev[0], b->ev[1]);
-        cudaEventElapsedTime(&b->ms_idct, b->ev[1], b->ev[2]);
+        cudaEventElapsedTime(&b->ms_entropy, b->ev[0], b->ev[3]);
+        cudaEventElapsedTime(&b->ms_unstuff, b->ev[0], b->ev[1]);
+        cudaEventElapsedTime(&b->ms_sync, b->ev[1], b->ev[2]);        // (only the last group of rounds if extra ones ran)
+        cudaEventElapsedTime(&b->ms_write, b->ev[2], b->ev[3]);
+        cudaEventElapsedTime(&b->ms_idct, b->ev[3], b->ev[4]);
         b->synced = true;
     }
     return rc;
@@ -325,13 +331,16 @@ inline int batch_download_async(bj_batch *b, uint8_t *const *outs, cudaStream_t 
     bj_ctx *c = b->ctx;
     int rc = BJ_OK;
     b->d2h_bytes = 0;
-    // coalesce images whose host buffers are laid out like the device buffer (see bj_batch_output_offset)
+    // option "packed_outputs": the caller states that host buffers laid out like the device buffer (see
+    // bj_batch_output_offset) are one allocation, so runs of images go out as one copy (the <= 15 padding bytes
+    // between them are overwritten).  Never inferred from pointer values alone: two separate heap blocks can
+    // sit at exactly that distance, with allocator metadata in between.
     int i = 0;
     while (rc == BJ_OK && i < b->n) {
         if (b->parse_status[i] != BJ_OK || !outs[i]) { i++; continue; }
         int k = i;
         size_t end = b->out_off[i] + b->out_size[i];
-        while (k + 1 < b->n && b->parse_status[k + 1] == BJ_OK && outs[k + 1] &&
+        while (c->packed_outputs && k + 1 < b->n && b->parse_status[k + 1] == BJ_OK && outs[k + 1] &&
                outs[k + 1] == outs[i] + (b->out_off[k + 1] - b->out_off[i])) { k++; end = b->out_off[k] + b->out_size[k]; }
         rc = c->check(cudaMemcpyAsync(outs[i], (const uint8_t *)b->d_out.p + b->out_off[i], end - b->out_off[i], cudaMemcpyDeviceToHost, s));
         b->d2h_bytes += end - b->out_off[i];

@@ -37,6 +37,7 @@ struct bj_ctx {
     int sm_count = 0;
     int subseq_bits = 0;                 // 0 = default
     size_t sub_batch_bytes = 0;          // 0 = default
+    int packed_outputs = 0;              // see batch_download_async
     int sync_rounds = 0;                 // 0 = default (3 launches of the fix-up kernel before the first check)
     struct bj_batch *slots[2] = {nullptr, nullptr};   // sub-batches of bj_decode_batch (double buffering)
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
