@@ -74,24 +74,27 @@ class Batch:
             self.sizes.append(nb.value)
         self.total_out = max((o + s for o, s in zip(self.offsets, self.sizes)), default=0)
 
-    def upload(self):
-        L.check(L.lib().bj_batch_upload(self.h, None), "bj_batch_upload", self.dec.ctx)
+    def upload(self, stream=None):
+        """stream: a cudaStream_t as an integer (e.g. torch.cuda.Stream().cuda_stream); None = the context's own."""
+        L.check(L.lib().bj_batch_upload(self.h, stream), "bj_batch_upload", self.dec.ctx)
 
-    def decode(self):
-        L.check(L.lib().bj_batch_decode(self.h, None), "bj_batch_decode", self.dec.ctx)
+    def decode(self, stream=None):
+        L.check(L.lib().bj_batch_decode(self.h, stream), "bj_batch_decode", self.dec.ctx)
 
     def sync(self):
         L.check(L.lib().bj_batch_sync(self.h), "bj_batch_sync", self.dec.ctx)
 
-    def download(self, out=None):
-        """Copy every decoded image to the host.  `out`: uint8 array of total_out bytes (e.g. PinnedBuffer.array)
-        laid out like the device buffer; returns the list of per-image views."""
+    def download(self, out=None, only=None):
+        """Copy decoded images to the host.  `out`: uint8 array of total_out bytes (e.g. PinnedBuffer.array) laid
+        out like the device buffer; `only`: indices to copy (default all).  Returns per-image views (None = skipped)."""
         if out is None:
             out = np.zeros(self.total_out, dtype=np.uint8)
         base = out.ctypes.data
-        ptrs = (C.c_void_p * max(self.n, 1))(*[base + o if st == L.BJ_OK else None for o, st in zip(self.offsets, self.parse_status)])
+        want = set(range(self.n)) if only is None else set(only)
+        ok = [st == L.BJ_OK and i in want for i, st in enumerate(self.parse_status)]
+        ptrs = (C.c_void_p * max(self.n, 1))(*[base + o if k else None for o, k in zip(self.offsets, ok)])
         L.check(L.lib().bj_batch_download(self.h, ptrs, None), "bj_batch_download", self.dec.ctx)
-        return [out[o:o + s] if st == L.BJ_OK else None for o, s, st in zip(self.offsets, self.sizes, self.parse_status)]
+        return [out[o:o + s] if k else None for o, s, k in zip(self.offsets, self.sizes, ok)]
 
     def status(self):
         st = (C.c_int * max(self.n, 1))()

@@ -11,13 +11,27 @@ import io
 import numpy as np
 
 
+_FIELDS = {}
+
+
+def _field(w, h):
+    """The seed-independent smooth part of synth_rgb (cached per size: it dominates generation time)."""
+    f = _FIELDS.get((w, h))
+    if f is None:
+        y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+        r = 128 + 100 * np.sin(x / 37.0) * np.cos(y / 23.0)
+        g = 128 + 90 * np.sin((x + y) / 51.0)
+        b = 128 + 80 * np.cos(x / 17.0 - y / 29.0)
+        f = np.stack([r, g, b], axis=-1)
+        if len(_FIELDS) > 16:
+            _FIELDS.clear()
+        _FIELDS[(w, h)] = f
+    return f
+
+
 def synth_rgb(w, h, seed):
     rng = np.random.default_rng(seed)
-    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
-    r = 128 + 100 * np.sin(x / 37.0) * np.cos(y / 23.0)
-    g = 128 + 90 * np.sin((x + y) / 51.0)
-    b = 128 + 80 * np.cos(x / 17.0 - y / 29.0)
-    img = np.stack([r, g, b], axis=-1) + rng.normal(0.0, 12.0, size=(h, w, 3))
+    img = _field(w, h) + rng.normal(0.0, 12.0, size=(h, w, 3))
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
