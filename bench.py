@@ -89,6 +89,9 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.perf_counter()                # NVML start-up can stall the GPU for seconds: wait it out here,
+            while not self.rows and time.perf_counter() - t0 < 20:    # not inside a timed step
+                time.sleep(0.05)
         except OSError:
             self.proc = None
 

@@ -137,7 +137,8 @@ typedef struct {
 } bj_batch_info;
 int bj_batch_get_info(const bj_batch *b, bj_batch_info *info);
 int bj_batch_device_output(const bj_batch *b, int i, void **dptr, size_t *bytes);
-int bj_batch_device_coefficients(const bj_batch *b, int i, void **dptr, size_t *bytes);  /* zig-zag i16 units */
+/* zig-zag i16 units (slot 0 of every unit unused) + the plane of predicted DC values, one i16 per unit */
+int bj_batch_device_coefficients(const bj_batch *b, int i, void **dptr, size_t *bytes, void **dc_dptr);
 
 /* Stage-level entry for known-answer tests: dequant + IDCT + upsample + colour only, on caller-supplied
  * coefficients (zig-zag order, DC un-differenced, MCU-interleaved unit order = what the entropy stage emits).

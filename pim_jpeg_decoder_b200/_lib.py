@@ -77,7 +77,7 @@ SYMBOLS = {
     "bj_batch_get_info": (C.c_int, [C.c_void_p, C.POINTER(BatchInfo)]),
     "bj_batch_output_offset": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "bj_batch_device_output": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
-    "bj_batch_device_coefficients": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "bj_batch_device_coefficients": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]),
     "bj_stage_idct_color": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.c_void_p, C.c_int, C.c_void_p]),
     "bj_stage_entropy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "bj_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),

@@ -173,7 +173,7 @@ extern "C" int bj_stage_idct_color(bj_ctx *c, const bj_image_desc *desc, const i
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dim.p, &im, sizeof(im), cudaMemcpyHostToDevice, s));
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dti.p, tiles.data(), tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
     if (rc == BJ_OK) {
-        k_idct_color<<<(unsigned)tiles.size(), kTileThreads, kSmemIdctColor, s>>>((const int16_t *)dco.p, (const ImgDev *)dim.p, (const TileDev *)dti.p, (uint8_t *)dout.p);
+        k_idct_color<<<(unsigned)tiles.size(), kTileThreads, kSmemIdctColor, s>>>((const int16_t *)dco.p, nullptr, (const ImgDev *)dim.p, (const TileDev *)dti.p, (uint8_t *)dout.p);
         rc = c->check(cudaGetLastError());
     }
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(out, dout.p, out_bytes, cudaMemcpyDeviceToHost, s));
@@ -247,10 +247,11 @@ extern "C" int bj_batch_device_output(const bj_batch *b, int i, void **dptr, siz
     return BJ_OK;
 }
 
-extern "C" int bj_batch_device_coefficients(const bj_batch *b, int i, void **dptr, size_t *bytes) {
+extern "C" int bj_batch_device_coefficients(const bj_batch *b, int i, void **dptr, size_t *bytes, void **dc_dptr) {
     if (!b || i < 0 || i >= b->n || b->parse_status[i] != BJ_OK) return BJ_ERR_ARG;
     if (dptr) *dptr = (int16_t *)b->d_coef.p + (size_t)b->du_base[i] * 64;
     if (bytes) *bytes = (size_t)b->ndu[i] * 128;
+    if (dc_dptr) *dc_dptr = (int16_t *)b->d_dc.p + b->du_base[i];
     return BJ_OK;
 }
 
@@ -268,8 +269,11 @@ extern "C" int bj_stage_entropy(bj_ctx *c, const uint8_t *file, size_t len, int1
     rc = batch_upload(b, s);
     if (rc == BJ_OK) rc = batch_decode(b, s);
     if (rc == BJ_OK) rc = batch_sync(b);
+    std::vector<int16_t> dcs(b->ndu[0]);
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(coef_zz, b->d_coef.p, (size_t)b->ndu[0] * 128, cudaMemcpyDeviceToHost, s));
+    if (rc == BJ_OK && b->ndu[0]) rc = c->check(cudaMemcpyAsync(dcs.data(), b->d_dc.p, (size_t)b->ndu[0] * 2, cudaMemcpyDeviceToHost, s));
     if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
+    if (rc == BJ_OK) for (uint32_t u = 0; u < b->ndu[0]; u++) coef_zz[(size_t)u * 64] = dcs[u];   // the device keeps DC in its own plane
     if (rc == BJ_OK && status) *status = batch_image_status(b, 0);
     bj_batch_destroy(b);
     return rc;

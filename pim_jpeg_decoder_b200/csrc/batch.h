@@ -32,8 +32,9 @@ struct PinBuf {                       // grow-only pinned host allocation
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-constexpr int kSmemHuffWriteMax = kSmemHuffStage + 6 * kLutCap * 2;
-constexpr int kSmemHuffSyncMax = 6 * kLutCap * 2;
+constexpr int kSmemLutMax = 3 * (kLutCapDC + kLutCapAC) * 4;
+constexpr int kSmemHuffWriteMax = kSmemHuffStage + kSmemLutMax;
+constexpr int kSmemHuffSyncMax = kSmemLutMax;
 
 inline int batch_kernels_init(bj_ctx *c) {
     if (c->check(cudaFuncSetAttribute(k_huff_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffWriteMax)) != BJ_OK) return BJ_ERR_CUDA;
@@ -59,13 +60,13 @@ struct bj_batch {
     bj::PinBuf h_files, h_meta, h_res;
     size_t files_bytes = 0, meta_bytes = 0;
     // offsets inside the descriptor blob
-    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_utile = 0, o_lut = 0;
-    uint32_t n_idct_tiles = 0, n_blk = 0, n_utile = 0, n_lut = 0, n_seg_entries = 0, n_sub_slots = 0, max_slots = 1;
+    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_utile = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0;
+    uint32_t n_idct_tiles = 0, n_blk = 0, n_utile = 0, n_dcc = 0, n_seg_entries = 0, n_sub_slots = 0, lut_smem = 0;
     size_t clean_words = 0, coef_units = 0, out_bytes = 0;
     uint64_t pixels = 0, scan_bytes = 0;
 
     // device
-    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_tilecnt, d_blkagg, d_state, d_flags, d_coef, d_out;
+    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_tilecnt, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels
     cudaStream_t last_stream = nullptr;
     bool uploaded = false, decoded = false, synced = false;
@@ -79,7 +80,7 @@ struct bj_batch {
     template <class T> T *hmeta(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(h_meta.p) + off); }
 
     void release() {
-        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_tilecnt, &d_blkagg, &d_state, &d_flags, &d_coef, &d_out}) b->release();
+        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_tilecnt, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
         h_files.release(); h_meta.release(); h_res.release();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     }
@@ -105,12 +106,12 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     std::vector<HuffImg> himg(n);
     std::vector<ImgDev> idev(n);
     std::vector<TileDev> tiles;
-    std::vector<uint32_t> blk_img, utile_img;
-    std::vector<uint16_t> luts;
-    std::map<std::string, int> lut_index;
+    std::vector<uint32_t> blk_img, utile_img, dcc_img;
+    std::vector<uint32_t> luts_dc, luts_ac;
+    std::map<std::string, int> lut_index[2];
     size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
     uint32_t seg_entries = 0, nblk = 0;
-    b->pixels = 0; b->scan_bytes = 0; b->max_slots = 1;
+    b->pixels = 0; b->scan_bytes = 0; b->lut_smem = 0;
     for (int i = 0; i < n; i++) {
         bj_image_desc &d = b->desc[i];
         HuffImg &hi = himg[i];
@@ -120,33 +121,36 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         Geometry g;
         if (rc == BJ_OK) {
             g = geometry_of(d);
-            // tables -> pool (deduplicated across the batch)
-            int slots[6], nslot = 0;
-            for (int j = 0; j < 3 && rc == BJ_OK; j++) {
-                const int jj = j < d.ncomp ? j : 0;
-                for (int ac = 0; ac < 2 && rc == BJ_OK; ac++) {
+            // tables -> pools (deduplicated across the batch); per image the distinct ones become staged slots
+            for (int ac = 0; ac < 2 && rc == BJ_OK; ac++) {
+                std::vector<uint32_t> &pool = ac ? luts_ac : luts_dc;
+                const size_t cap = ac ? kLutCapAC : kLutCapDC;
+                int slots[3], nslot = 0;
+                for (int j = 0; j < 3 && rc == BJ_OK; j++) {
+                    const int jj = j < d.ncomp ? j : 0;
                     const uint8_t *off = ac ? d.ac_offsets[d.ac_id[jj]] : d.dc_offsets[d.dc_id[jj]];
                     const uint8_t *sym = ac ? d.ac_symbols[d.ac_id[jj]] : d.dc_symbols[d.dc_id[jj]];
                     std::string key((const char *)off, 17);
                     key.append((const char *)sym, off[16] > 162 ? 162 : off[16]);
-                    auto it = lut_index.find(key);
+                    auto it = lut_index[ac].find(key);
                     int idx;
-                    if (it == lut_index.end()) {
-                        idx = (int)(luts.size() / kLutCap);
-                        luts.resize(luts.size() + kLutCap);
-                        if (build_lut(off, sym, &luts[(size_t)idx * kLutCap]) < 0) rc = BJ_ERR_UNSUPPORTED;
-                        lut_index[key] = idx;
+                    if (it == lut_index[ac].end()) {
+                        idx = (int)(pool.size() / cap);
+                        pool.resize(pool.size() + cap);
+                        if (build_lut(off, sym, ac != 0, &pool[(size_t)idx * cap]) < 0) rc = BJ_ERR_UNSUPPORTED;
+                        lut_index[ac][key] = idx;
+                        if (idx > 65535) rc = BJ_ERR_UNSUPPORTED;
                     } else idx = it->second;
                     int s = 0;
                     while (s < nslot && slots[s] != idx) s++;
                     if (s == nslot) slots[nslot++] = idx;
                     (ac ? hi.ac_slot : hi.dc_slot)[j] = (uint8_t)s;
                 }
+                (ac ? hi.nac : hi.ndc) = (uint8_t)nslot;
+                for (int s = 0; s < nslot; s++) (ac ? hi.ac_lut : hi.dc_lut)[s] = (uint16_t)slots[s];
             }
-            hi.nslot = (uint8_t)nslot;
-            for (int s = 0; s < nslot; s++) hi.slot_lut[s] = (uint16_t)slots[s];
-            if ((uint32_t)nslot > b->max_slots) b->max_slots = (uint32_t)nslot;
-            if (luts.size() / kLutCap > 65535) rc = BJ_ERR_UNSUPPORTED;
+            const uint32_t smem = ((uint32_t)hi.ndc * kLutCapDC + (uint32_t)hi.nac * kLutCapAC) * 4;
+            if (smem > b->lut_smem) b->lut_smem = smem;
         }
         b->parse_status[i] = rc;
         b->file_off[i] = fbytes;
@@ -156,7 +160,8 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         hi.tile_base = (uint32_t)utile_img.size();
         hi.clean_word0 = (uint32_t)clean_words;
         hi.du_base = (uint32_t)coef_units;
-        if (rc != BJ_OK) { seg_entries += 2; continue; }
+        hi.dcc_base = (uint32_t)dcc_img.size();
+        if (rc != BJ_OK) { seg_entries += 2; hi.ndc = hi.nac = 0; continue; }
         fbytes += align_up(lens[i] + 16, 16);
         hi.valid = 1;
         hi.raw_off = b->file_off[i] + d.scan_off;
@@ -172,6 +177,8 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         hi.nblk = (sub_cap + kHuffThreads - 1) / kHuffThreads;
         for (uint32_t k = 0; k < hi.nblk; k++) blk_img.push_back((uint32_t)i);
         nblk += hi.nblk;
+        hi.ndcc = (g.nmcu + kDcThreads - 1) / kDcThreads;
+        for (uint32_t k = 0; k < hi.ndcc; k++) dcc_img.push_back((uint32_t)i);
         seg_entries += hi.nseg + 1;
         clean_words += hi.raw_len / 4 + 4;
         b->du_base[i] = (uint32_t)coef_units; b->ndu[i] = g.ndu;
@@ -179,6 +186,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         b->out_size[i] = bj_output_size(&d, format);
         b->out_off[i] = out_bytes;
         fill_imgdev(d, g, format, hi.du_base, out_bytes, &idev[i]);
+        idev[i].dc_sep = 1;
         out_bytes += align_up(b->out_size[i], 16);
         append_tiles(g, (uint32_t)i, &tiles);
         b->pixels += (uint64_t)d.width * d.height;
@@ -187,7 +195,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     }
     b->files_bytes = fbytes + 64; b->clean_words = clean_words + 16; b->coef_units = coef_units; b->out_bytes = out_bytes;
     b->n_idct_tiles = (uint32_t)tiles.size(); b->n_blk = nblk; b->n_utile = (uint32_t)utile_img.size();
-    b->n_lut = (uint32_t)(luts.size() / kLutCap); b->n_seg_entries = seg_entries; b->n_sub_slots = nblk * kHuffThreads;
+    b->n_dcc = (uint32_t)dcc_img.size(); b->n_seg_entries = seg_entries; b->n_sub_slots = nblk * kHuffThreads;
 
     // ---- descriptor blob
     size_t o = 0;
@@ -196,7 +204,9 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     b->o_tiles = o; o = align_up(o + tiles.size() * sizeof(TileDev), 256);
     b->o_blk = o;   o = align_up(o + blk_img.size() * 4, 256);
     b->o_utile = o; o = align_up(o + utile_img.size() * 4, 256);
-    b->o_lut = o;   o = align_up(o + luts.size() * 2, 256);
+    b->o_dcc = o;   o = align_up(o + dcc_img.size() * 4, 256);
+    b->o_lutdc = o; o = align_up(o + luts_dc.size() * 4, 256);
+    b->o_lutac = o; o = align_up(o + luts_ac.size() * 4, 256);
     b->meta_bytes = o;
     if (b->h_meta.reserve(o) || b->h_files.reserve(b->files_bytes) ||
         b->h_res.reserve(align_up((size_t)n * sizeof(HuffImgState), 64) + kMaxRounds * 4 + 64)) return BJ_ERR_NOMEM;
@@ -204,7 +214,9 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     if (!tiles.empty()) memcpy(b->hmeta<TileDev>(b->o_tiles), tiles.data(), tiles.size() * sizeof(TileDev));
     if (!blk_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_blk), blk_img.data(), blk_img.size() * 4);
     if (!utile_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_utile), utile_img.data(), utile_img.size() * 4);
-    if (!luts.empty()) memcpy(b->hmeta<uint16_t>(b->o_lut), luts.data(), luts.size() * 2);
+    if (!dcc_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_dcc), dcc_img.data(), dcc_img.size() * 4);
+    if (!luts_dc.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutdc), luts_dc.data(), luts_dc.size() * 4);
+    if (!luts_ac.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutac), luts_ac.data(), luts_ac.size() * 4);
     // ---- pack the file bytes
     uint8_t *hf = reinterpret_cast<uint8_t *>(b->h_files.p);
     for (int i = 0; i < n; i++) {
@@ -216,7 +228,8 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     if (b->d_files.reserve(b->files_bytes) || b->d_meta.reserve(b->meta_bytes) || b->d_clean.reserve(b->clean_words * 4) ||
         b->d_seg.reserve((size_t)(seg_entries + 2) * 4 * 2) || b->d_subseg.reserve((size_t)b->n_sub_slots * 4 + 16) ||
         b->d_stin.reserve((size_t)b->n_sub_slots * 8 + 16) || b->d_stout.reserve((size_t)b->n_sub_slots * 8 + 16) ||
-        b->d_tot.reserve((size_t)b->n_sub_slots * 16 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 16 + 16) ||
+        b->d_tot.reserve((size_t)b->n_sub_slots * 4 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 8 + 16) ||
+        b->d_dc.reserve(coef_units * 2 + 64) || b->d_dcagg.reserve((size_t)b->n_dcc * sizeof(DcAgg) + 16) ||
         b->d_tilecnt.reserve((size_t)b->n_utile * 8 + 16) || b->d_blkagg.reserve((size_t)nblk * sizeof(BlkAgg) + 16) ||
         b->d_state.reserve((size_t)n * sizeof(HuffImgState) + 16) || b->d_flags.reserve(kMaxRounds * 4) ||
         b->d_coef.reserve(coef_units * 128 + 16) || b->d_out.reserve(out_bytes + 64)) return BJ_ERR_NOMEM;
@@ -242,16 +255,20 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     const TileDev *tiles = b->dmeta<TileDev>(b->o_tiles);
     const uint32_t *blk_img = b->dmeta<uint32_t>(b->o_blk);
     const uint32_t *utile_img = b->dmeta<uint32_t>(b->o_utile);
-    const uint16_t *luts = b->dmeta<uint16_t>(b->o_lut);
+    const uint32_t *dcc_img = b->dmeta<uint32_t>(b->o_dcc);
+    const uint32_t *luts_dc = b->dmeta<uint32_t>(b->o_lutdc), *luts_ac = b->dmeta<uint32_t>(b->o_lutac);
+    int16_t *dcp = (int16_t *)b->d_dc.p;
+    DcAgg *dcagg = (DcAgg *)b->d_dcagg.p;
     HuffImgState *st = (HuffImgState *)b->d_state.p;
     uint32_t *seg_off = (uint32_t *)b->d_seg.p, *seg_sub0 = seg_off + b->n_seg_entries + 2;
     uint32_t *sub_seg = (uint32_t *)b->d_subseg.p, *flags = (uint32_t *)b->d_flags.p;
     uint32_t *clean = (uint32_t *)b->d_clean.p;
     uint2 *st_in = (uint2 *)b->d_stin.p, *st_out = (uint2 *)b->d_stout.p, *tile_cnt = (uint2 *)b->d_tilecnt.p;
-    uint4 *tot = (uint4 *)b->d_tot.p, *pre = (uint4 *)b->d_pre.p;
+    uint32_t *tot = (uint32_t *)b->d_tot.p;
+    uint2 *pre = (uint2 *)b->d_pre.p;
     BlkAgg *agg = (BlkAgg *)b->d_blkagg.p;
     const int n = b->n;
-    const size_t lut_smem = (size_t)b->max_slots * kLutCap * 2;
+    const size_t lut_smem = b->lut_smem;
     if (r0 == 0) {
         cudaEventRecord(b->ev[0], s);
         cudaMemsetAsync(flags, 0, kMaxRounds * 4, s);
@@ -265,11 +282,11 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     }
     if (b->n_blk) {
         for (int r = r0; r < r1; r++) {
-            k_huff_sync<<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts, st_in, st_out, tot, pre, agg, flags, r, b->sub_bytes);
+            k_huff_sync<<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_ac, st_in, st_out, tot, pre, agg, flags, r, b->sub_bytes);
             b->launches++; b->sync_rounds++;
         }
         cudaEventRecord(b->ev[2], s);
-        k_huff_write<<<b->n_blk, kHuffThreads, kSmemHuffStage + lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts, st_in, pre, agg, (int16_t *)b->d_coef.p, b->sub_bytes);
+        k_huff_write<<<b->n_blk, kHuffThreads, kSmemHuffStage + lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_ac, st_in, pre, agg, (int16_t *)b->d_coef.p, dcp, b->sub_bytes);
         b->launches++;
     }
     {
@@ -277,10 +294,15 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
         k_zero_tail<<<dim3(n, gx > 64 ? 64 : gx), 256, 0, s>>>(himg, st, (int16_t *)b->d_coef.p);
         b->launches++;
     }
+    if (b->n_dcc) {
+        k_dc_predict<0><<<b->n_dcc, kDcThreads, 0, s>>>(himg, st, dcc_img, dcp, dcagg);
+        k_dc_predict<1><<<b->n_dcc, kDcThreads, 0, s>>>(himg, st, dcc_img, dcp, dcagg);
+        b->launches += 2;
+    }
     if (!b->n_blk) cudaEventRecord(b->ev[2], s);
     cudaEventRecord(b->ev[3], s);
     if (b->n_idct_tiles) {
-        k_idct_color<<<b->n_idct_tiles, kTileThreads, kSmemIdctColor, s>>>((const int16_t *)b->d_coef.p, idev, tiles, (uint8_t *)b->d_out.p);
+        k_idct_color<<<b->n_idct_tiles, kTileThreads, kSmemIdctColor, s>>>((const int16_t *)b->d_coef.p, dcp, idev, tiles, (uint8_t *)b->d_out.p);
         b->launches++;
     }
     cudaEventRecord(b->ev[4], s);

@@ -22,7 +22,8 @@ struct ImgDev {
     uint8_t  hs, vs, ncomp, bpm;  // luma sampling, components, data units per MCU
     uint8_t  bgr;                 // 1: B,G,R byte order (BMP)
     uint8_t  valid;
-    uint8_t  pad_[2];
+    uint8_t  dc_sep;              // 1: slot 0 of every unit is unused, the DC value comes from the DC plane at du_base + unit
+    uint8_t  pad_[1];
     uint32_t q16[3][kQPitch];     // per component: (quantiser << 16) in ZIG-ZAG order (file order)
 };
 

@@ -21,21 +21,41 @@
 namespace bj {
 
 // ------------------------------------------------------------------------------------------------ lookup tables
-// One table per Huffman table: kRootBits-bit root + second-level tables for longer codes, 16-bit entries.
-//   leaf  : bit15 = 0, bits 12..8 = code length (1..16), bits 7..0 = symbol;  0 = no code with this prefix
-//   link  : bit15 = 1, bits 14..12 = k (second-level index width, 1..16-kRootBits), bits 11..0 = offset of the
-//           second-level table (2^k leaves) from the start of this table
-constexpr int kRootBits = 10;
-constexpr int kLutCap = 2048;              // entries per table (4 KB)
-constexpr uint32_t kLutLink = 0x8000u;
+// One table per Huffman table: kRootBits-bit root + second-level tables for longer codes.  Entries are 32 bits
+// and carry everything a decode step needs, precomputed per table class (DC / AC), so the inner loop is a load,
+// two adds and a compare:
+//   bits  5..0   stream bits the step consumes: code length + magnitude bits (>= 1, also for "no such code")
+//   bits 12..6   zig-zag advance: 1 for a DC symbol, run + 1 for an AC symbol, 64 for end-of-block
+//   bits 16..13  magnitude size (0 for a step the reference would refuse)
+//   bits 21..17  code length
+//   bit  22      bad: the reference stops here - no code, DC category > 11, AC size > 10
+//                (src/jpeg_scanner.cpp:470-478, :490-511)
+//   bit  23      AC end-of-block
+//   bit  31      link (root only): bits 19..16 = k, bits 15..0 = offset of a 2^k-entry second-level table
+constexpr int kRootBitsDC = 9, kRootBitsAC = 11;      // > 11-bit AC codes are ~0.2 % of symbols at q = 90
+constexpr int kLutCapDC = 1024, kLutCapAC = 2560;     // entries per table (4 KB / 10 KB)
+constexpr uint32_t kLutLink = 0x80000000u;
+constexpr uint32_t kLutBad = 1u << 22;
+constexpr uint32_t kLutEob = 1u << 23;
+BJ_HD constexpr int lut_root_bits(bool ac) { return ac ? kRootBitsAC : kRootBitsDC; }
+BJ_HD constexpr int lut_cap(bool ac) { return ac ? kLutCapAC : kLutCapDC; }
+
+inline uint32_t lut_leaf(int len, unsigned sym, bool ac) {
+    const unsigned run = ac ? sym >> 4 : 0, size = ac ? (sym & 15u) : sym;
+    const bool eob = ac && sym == 0;
+    const bool bad = ac ? size > 10 : sym > 11;
+    const unsigned sz = bad ? 0u : size;
+    return (uint32_t)(len + sz) | ((eob ? 64u : run + 1u) << 6) | (sz << 13) | ((uint32_t)len << 17) | (bad ? kLutBad : 0u) | (eob ? kLutEob : 0u);
+}
+constexpr uint32_t kLutNoCode = 1u | (1u << 6) | kLutBad;      // no code with this prefix: skip one bit
 
 // Host: build one table.  Returns the number of entries used, or -1 if the second-level tables do not fit.
 // Over-subscribed (invalid) tables keep the reference's behaviour: the shortest matching code wins and codes
-// that do not fit their length never match.
-inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], uint16_t *lut) {
-    const int R = kRootBits;
-    memset(lut, 0, sizeof(uint16_t) * kLutCap);
-    uint8_t maxlen[1 << kRootBits];
+// that do not fit their length never match (get_next_symbol compares the l-bit prefix with the stored code).
+inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], bool ac, uint32_t *lut) {
+    const int R = lut_root_bits(ac), kLutCap = lut_cap(ac);
+    for (int i = 0; i < kLutCap; i++) lut[i] = 0;
+    uint8_t maxlen[1 << kRootBitsAC];
     memset(maxlen, 0, sizeof(maxlen));
     uint32_t code = 0;
     for (int l = 1; l <= 16; l++) {                       // codes that fit the root
@@ -44,7 +64,7 @@ inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], uint
             if (l > R || (cv >> l)) continue;
             const uint32_t first = cv << (R - l), cnt = 1u << (R - l);
             for (uint32_t i = 0; i < cnt; i++)
-                if (lut[first + i] == 0) lut[first + i] = (uint16_t)((l << 8) | symbols[j]);
+                if (lut[first + i] == 0) lut[first + i] = lut_leaf(l, symbols[j], ac);
         }
         code <<= 1;
     }
@@ -56,7 +76,7 @@ inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], uint
             const uint32_t pre = cv >> (l - R);
             if (lut[pre] != 0 && !(lut[pre] & kLutLink)) continue;      // a shorter code owns this prefix
             if (l > maxlen[pre]) maxlen[pre] = (uint8_t)l;
-            lut[pre] = (uint16_t)kLutLink;
+            lut[pre] = kLutLink;
         }
         code <<= 1;
     }
@@ -65,7 +85,7 @@ inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], uint
         if (!maxlen[pre]) continue;
         const int k = maxlen[pre] - R;
         if (next + (1 << k) > kLutCap) return -1;
-        lut[pre] = (uint16_t)(kLutLink | (k << 12) | next);
+        lut[pre] = kLutLink | ((uint32_t)k << 16) | (uint32_t)next;
         next += 1 << k;
     }
     code = 0;
@@ -75,24 +95,23 @@ inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], uint
             if (l <= R || (cv >> l)) continue;
             const uint32_t pre = cv >> (l - R);
             if (!(lut[pre] & kLutLink)) continue;
-            const int k = (lut[pre] >> 12) & 7, rem = l - R;
-            const uint32_t base = lut[pre] & 0xFFFu;
+            const int k = (lut[pre] >> 16) & 15, rem = l - R;
+            const uint32_t base = lut[pre] & 0xFFFFu;
             const uint32_t first = (cv & ((1u << rem) - 1)) << (k - rem), cnt = 1u << (k - rem);
             for (uint32_t i = 0; i < cnt; i++)
-                if (lut[base + first + i] == 0) lut[base + first + i] = (uint16_t)((l << 8) | symbols[j]);
+                if (lut[base + first + i] == 0) lut[base + first + i] = lut_leaf(l, symbols[j], ac);
         }
         code <<= 1;
     }
+    for (int i = 0; i < kLutCap; i++) if (lut[i] == 0) lut[i] = kLutNoCode;
     return next;
 }
 
-// win = the next 32 bits of the stream, MSB first.  Returns (length << 8) | symbol, 0 if no code matches.
-BJ_HD uint32_t lut_lookup(const uint16_t *lut, uint32_t win) {
-    uint32_t e = lut[win >> (32 - kRootBits)];
-    if (e & kLutLink) {
-        const uint32_t k = (e >> 12) & 7u;
-        e = lut[(e & 0xFFFu) + ((win << kRootBits) >> (32 - k))];
-    }
+// win = the next 32 bits of the stream, MSB first.
+BJ_HD uint32_t lut_lookup(const uint32_t *lut, uint32_t win, bool ac) {
+    const uint32_t R = ac ? kRootBitsAC : kRootBitsDC;
+    uint32_t e = lut[win >> (32u - R)];
+    if (e & kLutLink) e = lut[(e & 0xFFFFu) + ((win << R) >> (32u - ((e >> 16) & 15u)))];
     return e;
 }
 
@@ -115,20 +134,19 @@ BJ_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, uint32_t s) {      // top 32 b
 }
 
 struct BitReader {
-    const uint32_t *w;      // image's un-stuffed stream, word 0 = bits 0..31
-    uint32_t wi, cur, nxt;
-    BJ_HD uint32_t ld(uint32_t i) const {
+    const uint32_t *q;      // -> word wi of the image's un-stuffed stream (word 0 = bits 0..31)
+    uint32_t wi, cur, nxt, nx2;   // words wi, wi+1, wi+2: the load for a word is issued one word ahead of its use
+    BJ_HD static uint32_t ld(const uint32_t *a) {
 #ifdef __CUDA_ARCH__
-        return __ldg(w + i);
+        return __ldg(a);
 #else
-        return w[i];
+        return *a;
 #endif
     }
-    BJ_HD void seek(uint32_t p) { wi = p >> 5; cur = ld(wi); nxt = ld(wi + 1); }
-    // p never moves by more than 31 bits between calls
+    BJ_HD void seek(const uint32_t *words, uint32_t p) { wi = p >> 5; q = words + wi; cur = ld(q); nxt = ld(q + 1); nx2 = ld(q + 2); }
+    // p never moves by more than 31 bits between calls, so the word index grows by at most one
     BJ_HD uint32_t window(uint32_t p) {
-        const uint32_t i = p >> 5;
-        if (i != wi) { cur = nxt; nxt = ld(i + 1); wi = i; }
+        if ((p >> 5) != wi) { cur = nxt; nxt = nx2; q++; wi++; nx2 = ld(q + 2); }
         return funnel_l(cur, nxt, p & 31u);
     }
 };
@@ -146,87 +164,49 @@ BJ_HD bool same_state(const HuffState &a, const HuffState &b) { return a.p == b.
 struct HuffGeom {
     uint32_t bpm;           // data units per MCU
     uint32_t ny;            // luma units per MCU (hs * vs); unit c belongs to component c < ny ? 0 : c - ny + 1
-    uint32_t tab[3];        // per component: dc table offset | ac table offset << 16  (units of kLutCap entries... see below)
+    uint32_t tab[3];        // per component: DC table entry offset | AC table entry offset << 16 (from the staged base)
 };
 BJ_HD uint32_t comp_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? 0u : c - g.ny + 1u; }
 BJ_HD uint32_t tabs_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.tab[0] : (c == g.ny ? g.tab[1] : g.tab[2]); }
 
-// What one step consumed/produced.
-struct Sym {
-    uint32_t bits;          // stream bits consumed (>= 1)
-    int32_t value;          // extended coefficient / DC difference (0 when size == 0)
-    uint32_t run, size;
-    bool eob;               // AC end-of-block
-    bool bad;               // the reference would stop here: no code, DC category > 11, AC size > 10
-};
-
-// Decode one symbol (+ its magnitude bits) from the window.  dc: a DC symbol is expected.
-BJ_HD Sym decode_symbol(const uint16_t *lut, uint32_t win, bool dc) {
-    Sym s;
-    const uint32_t e = lut_lookup(lut, win);
-    const uint32_t len = e >> 8, sym = e & 0xFFu;
-    s.run = dc ? 0u : sym >> 4;
-    s.size = dc ? sym : (sym & 15u);
-    s.eob = !dc && sym == 0u && e != 0u;
-    s.bad = e == 0u || (dc ? sym > 11u : (s.size > 10u));
-    if (s.bad) s.size = 0;
-    const uint32_t t = win << len;                        // len <= 16
-    const uint32_t raw = s.size ? (t >> (32u - s.size)) : 0u;
-    // magnitude extension, src/jpeg_scanner.cpp:480-482 / :513-516: first bit 0 => negative
-    s.value = (int32_t)raw - ((s.size && !(t >> 31)) ? (int32_t)((1u << s.size) - 1u) : 0);
-    s.bits = (len ? len : 1u) + s.size;
-    return s;
-}
-
-// Advance (c, z) over one symbol.  Returns true when the unit ended.  `overflow` = the reference's
-// "i + run >= 64" error (src/jpeg_scanner.cpp:497-500); the speculative passes treat it as a unit end.
-BJ_HD bool advance_state(const HuffGeom &g, uint32_t &c, uint32_t &z, const Sym &s, bool *overflow) {
-    *overflow = false;
-    uint32_t zn;
-    if (z == 0) zn = 1;
-    else if (s.eob) zn = 64;
-    else {
-        *overflow = z + s.run >= 64u;
-        zn = z + s.run + 1u;
-    }
-    if (zn >= 64u) { z = 0; c = (c + 1u == g.bpm) ? 0u : c + 1u; return true; }
-    z = zn;
-    return false;
+// Magnitude extension of the `size` bits that follow a `len`-bit code in the window
+// (src/jpeg_scanner.cpp:480-482 / :513-516: first bit 0 => negative).  size 0 gives 0.
+BJ_HD int32_t extend_value(uint32_t win, uint32_t len, uint32_t size) {
+    const uint32_t t = win << len;                                        // len <= 16
+    const uint32_t raw = funnel_l(0u, t, size);                           // top `size` bits of t
+    return (int32_t)raw + (((int32_t)t >= 0) ? 1 - (int32_t)(1u << size) : 0);
 }
 
 // ------------------------------------------------------------------------------------------------ pass 1: synchronise
-// Totals of one sub-sequence for the prefix sums: data units whose DC symbol starts inside it and, per component,
-// the sum of those DC differences (mod 2^16 arithmetic is enough: the reference truncates the predictor to a
-// short after every unit, src/jpeg_scanner.cpp:485-486, which is a ring homomorphism).
-struct SubTotals {
-    uint32_t n;
-    uint32_t dc[3];
-};
-
-// Decode from `st` until the position reaches end_bit (first symbol boundary at or after it).  Errors do not
-// stop a speculative decode (a wrong guess must not poison its successors): a bad symbol advances at least one
-// bit and the unit simply continues.  With the true entry state the result is the true exit state up to the
-// first real error, which the write pass detects and reports.
-BJ_HD HuffState decode_span(BitReader &rd, const uint16_t *luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
-                            SubTotals *tot) {
+// Decode from `st` until the position reaches end_bit (first symbol boundary at or after it).  Only the decoder
+// state is tracked - no values - plus the number of data units whose DC symbol starts inside the span (for the
+// prefix sum that tells every sub-sequence which unit it starts in).  Errors do not stop a speculative decode
+// (a wrong guess must not poison its successors): a refused symbol consumes its code bits (at least one) and the
+// unit simply continues; an over-long run ends the unit.  With the true entry state the result is the true exit
+// state up to the first real error, which the write pass detects and reports.
+BJ_HD HuffState decode_span(const uint32_t *words, const uint32_t *luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
+                            uint32_t *units_started) {
     uint32_t p = st.p, c = st.cz >> 8, z = st.cz & 0xFFu;
-    uint32_t n = 0, d0 = 0, d1 = 0, d2 = 0;
+    uint32_t ends = 0;
+    const uint32_t entered_mid = z != 0 ? 1u : 0u;
     uint32_t tabs = tabs_of(g, c);
-    if (p < end_bit) rd.seek(p);
+    BitReader rd;
+    if (p < end_bit) rd.seek(words, p);
     while (p < end_bit) {
-        const bool dc = z == 0;
-        const Sym s = decode_symbol(luts + (dc ? (tabs & 0xFFFFu) : (tabs >> 16)), rd.window(p), dc);
-        if (dc) {
-            n++;
-            const uint32_t k = comp_of(g, c);
-            const uint32_t v = s.bad ? 0u : (uint32_t)s.value;
-            if (k == 0) d0 += v; else if (k == 1) d1 += v; else d2 += v;
+        const uint32_t win = rd.window(p);
+        const bool ac = z != 0;
+        const uint32_t e = lut_lookup(luts + (ac ? (tabs >> 16) : (tabs & 0xFFFFu)), win, ac);
+        p += e & 63u;
+        z += (e >> 6) & 127u;
+        if (z >= 64u) {
+            z = 0;
+            ends++;
+            c = (c + 1u == g.bpm) ? 0u : c + 1u;
+            tabs = tabs_of(g, c);
         }
-        p += s.bits;
-        bool ovf;
-        if (advance_state(g, c, z, s, &ovf)) tabs = tabs_of(g, c);
     }
-    tot->n = n; tot->dc[0] = d0; tot->dc[1] = d1; tot->dc[2] = d2;
+    // started = ended + (one still open at the exit) - (the one that was already open at the entry)
+    *units_started = ends + (z != 0 ? 1u : 0u) - entered_mid;
     HuffState o;
     o.p = p; o.cz = (c << 8) | z;
     return o;
@@ -236,60 +216,68 @@ BJ_HD HuffState decode_span(BitReader &rd, const uint16_t *luts, const HuffGeom 
 // Ownership rule: a data unit belongs to the sub-sequence in which its DC symbol starts; the owner decodes the
 // whole unit (running past its own end if necessary) and stores all 64 coefficients at once, so every unit is
 // written exactly once, by one thread, with no zero-fill pass.  A sub-sequence entered mid-unit first skips to
-// the end of that unit without storing anything.
+// the end of that unit without storing anything.  DC DIFFERENCES go to a separate compact plane (2 bytes per
+// unit); the prediction sums over it are a separate, tiny scan (K1c) and slot 0 of every unit stays zero.
 //
-// Sink concept:  void put(uint32_t zz, int16_t v);  void flush(uint32_t du);   (flush also clears the unit)
+// Sink concept:  void put(uint32_t zz, int16_t v);  void dc(uint32_t du, int16_t diff);  void flush(uint32_t du);
+// (flush also clears the staged unit)
 struct WriteResult {
     uint32_t first_zero;    // first unit index that must read as zero because the reference stopped; UINT32_MAX if none
 };
 
 template <class Sink>
-BJ_HD WriteResult write_span(BitReader &rd, const uint16_t *luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
-                             uint32_t data_end_bit, uint32_t du, uint32_t du_end, bool last_of_segment,
-                             const uint32_t pred_in[3], Sink &sink) {
+BJ_HD WriteResult write_span(const uint32_t *words, const uint32_t *luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
+                             uint32_t data_end_bit, uint32_t du, uint32_t du_end, bool last_of_segment, Sink &sink) {
     WriteResult res;
     res.first_zero = 0xFFFFFFFFu;
     uint32_t p = st.p, c = st.cz >> 8, z = st.cz & 0xFFu;
-    uint32_t pred0 = pred_in[0], pred1 = pred_in[1], pred2 = pred_in[2];
     uint32_t tabs = tabs_of(g, c);
     bool owned = false;
-    rd.seek(p);
+    BitReader rd;
+    rd.seek(words, p);
     for (;;) {
-        const bool dc = z == 0;
-        if (dc) {
-            if (p >= end_bit || du >= du_end) break;
-            owned = true;
-        } else if (!owned && p >= end_bit) break;
-        const Sym s = decode_symbol(luts + (dc ? (tabs & 0xFFFFu) : (tabs >> 16)), rd.window(p), dc);
-        p += s.bits;
-        const uint32_t z0 = z, k = comp_of(g, c);             // a DC symbol never ends a unit, so c is this unit's
-        bool ovf;
-        const bool ended = advance_state(g, c, z, s, &ovf);
+        const bool ac = z != 0;
+        if ((!ac || !owned) && p >= end_bit) break;         // a new unit would start (or a foreign one continue) past my end
+        if (!ac && du >= du_end) break;                     // the segment's last unit is done: the rest is padding
+        owned = owned || !ac;
+        const uint32_t win = rd.window(p);
+        const uint32_t e = lut_lookup(luts + (ac ? (tabs >> 16) : (tabs & 0xFFFFu)), win, ac);
+        p += e & 63u;
+        const uint32_t zn = z + ((e >> 6) & 127u);
         if (owned) {
-            // the reference's failure points, src/jpeg_scanner.cpp:470-478 (DC) and :490-511 (AC); running out of
-            // bits inside a symbol fails too (BitReader::read_bit returns -1)
-            if (s.bad || ovf || p > data_end_bit) {
+            // the reference's failure points: refused symbol, run past the end of the unit ("i + run >= 64",
+            // src/jpeg_scanner.cpp:497-500), or bits running out inside a symbol (BitReader::read_bit returns -1)
+            if ((e & kLutBad) || (!(e & kLutEob) && zn > 64u) || p > data_end_bit) {
                 // a failed DC leaves the unit untouched (zero); a failed AC keeps what was stored before it
-                if (dc) res.first_zero = du;
+                if (!ac) res.first_zero = du;
                 else { sink.flush(du); res.first_zero = du + 1; }
                 return res;
             }
-            if (dc) {
-                uint32_t pr;
-                if (k == 0) { pred0 += (uint32_t)s.value; pr = pred0; }
-                else if (k == 1) { pred1 += (uint32_t)s.value; pr = pred1; }
-                else { pred2 += (uint32_t)s.value; pr = pred2; }
-                sink.put(0, (int16_t)(uint16_t)pr);
-            } else if (!s.eob) {
-                sink.put(z0 + s.run, (int16_t)s.value);       // size 0 (ZRL and friends) stores a literal 0
-            }
-            if (ended) { sink.flush(du); du++; owned = false; }
+            const int32_t v = extend_value(win, (e >> 17) & 31u, (e >> 13) & 15u);
+            if (!ac) sink.dc(du, (int16_t)v);               // |diff| < 2^11
+            else if (v != 0) sink.put(zn - 1u, (int16_t)v); // size 0 (ZRL and friends) would store a literal 0: already there
         }
-        if (ended) tabs = tabs_of(g, c);
+        if (zn >= 64u) {
+            if (owned) { sink.flush(du); du++; owned = false; }
+            z = 0;
+            c = (c + 1u == g.bpm) ? 0u : c + 1u;
+            tabs = tabs_of(g, c);
+        } else z = zn;
     }
     // the last sub-sequence of a segment must have produced the segment's last unit
     if (last_of_segment && du < du_end) res.first_zero = du;
     return res;
+}
+
+// ------------------------------------------------------------------------------------------------ K1c: DC prediction
+// Per MCU: turn the DC differences of its units (decode order: luma units, then Cb, then Cr) into predicted
+// values given the three running predictors, which are updated (src/jpeg_scanner.cpp:485-486; everything mod 2^16).
+BJ_HD void dc_predict_mcu(const HuffGeom &g, int16_t *dcs, uint32_t pred[3]) {
+    for (uint32_t c = 0; c < g.bpm; c++) {
+        const uint32_t k = comp_of(g, c);
+        pred[k] += (uint32_t)(uint16_t)dcs[c];
+        dcs[c] = (int16_t)(uint16_t)pred[k];
+    }
 }
 
 }  // namespace bj

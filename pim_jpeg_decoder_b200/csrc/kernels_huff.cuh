@@ -34,10 +34,12 @@ struct HuffImg {
     uint32_t blk_base, nblk; // CTAs of k_huff_sync / k_huff_write
     uint32_t du_base, ndu;
     uint32_t nmcu, ri;       // ri = restart interval in MCUs (0: none)
-    uint8_t bpm, ny, ncomp, nslot;
-    uint16_t slot_lut[6];    // table pool index of each staged slot
-    uint8_t dc_slot[3], ac_slot[3];
-    uint8_t valid, pad_[3];
+    uint32_t dcc_base, ndcc; // CTAs of the DC prediction kernels (kDcThreads MCUs each)
+    uint8_t bpm, ny, ncomp, valid;
+    uint8_t ndc, nac;        // distinct DC / AC tables of this image = staged slots
+    uint16_t dc_lut[3], ac_lut[3];   // pool index of each staged DC / AC slot
+    uint8_t dc_slot[3], ac_slot[3];  // per component: staged slot
+    uint8_t pad_[2];
 };
 
 // Per image, written by the kernels.
@@ -51,9 +53,13 @@ struct HuffImgState {
     uint32_t pad_[2];
 };
 
-struct BlkAgg {              // totals of one CTA since its last segment head (or since its start)
-    uint32_t n, dc01, dc2, has_head;
+struct BlkAgg {              // units started in one CTA since its last segment head (or since its start)
+    uint32_t n, has_head;
 };
+struct DcAgg {               // DC difference sums of one chunk of MCUs since its last restart (or since its start)
+    uint32_t s0, s1, s2, has_head;
+};
+constexpr int kDcThreads = 256;
 
 // ------------------------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
@@ -244,16 +250,24 @@ __device__ __forceinline__ SubInfo sub_info(const HuffImg &im, const HuffImgStat
     return u;
 }
 
-// stage the image's tables (nslot * kLutCap entries) into shared memory, 16 bytes per thread per step
-__device__ __forceinline__ void stage_luts(const HuffImg &im, const uint16_t *__restrict__ lut_pool, uint16_t *s_lut, HuffGeom &g) {
-    const int per = kLutCap * 2 / 16;                                     // uint4 per table
-    for (int i = threadIdx.x; i < im.nslot * per; i += blockDim.x) {
-        const int slot = i / per, q = i - slot * per;
-        reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(lut_pool + (size_t)im.slot_lut[slot] * kLutCap) + q);
+// stage the image's tables into shared memory (DC slots first, then AC slots), 16 bytes per thread per step
+__device__ __forceinline__ void stage_luts(const HuffImg &im, const uint32_t *__restrict__ lut_dc_pool,
+                                           const uint32_t *__restrict__ lut_ac_pool, uint32_t *s_lut, HuffGeom &g) {
+    constexpr int per_dc = kLutCapDC / 4, per_ac = kLutCapAC / 4;          // uint4 per table
+    uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+    for (int i = threadIdx.x; i < im.ndc * per_dc; i += blockDim.x) {
+        const int slot = i / per_dc, q = i - slot * per_dc;
+        dst[i] = __ldg(reinterpret_cast<const uint4 *>(lut_dc_pool + (size_t)im.dc_lut[slot] * kLutCapDC) + q);
+    }
+    uint4 *dst_ac = dst + im.ndc * per_dc;
+    for (int i = threadIdx.x; i < im.nac * per_ac; i += blockDim.x) {
+        const int slot = i / per_ac, q = i - slot * per_ac;
+        dst_ac[i] = __ldg(reinterpret_cast<const uint4 *>(lut_ac_pool + (size_t)im.ac_lut[slot] * kLutCapAC) + q);
     }
     g.bpm = im.bpm; g.ny = im.ny;
 #pragma unroll
-    for (int j = 0; j < 3; j++) g.tab[j] = (uint32_t)im.dc_slot[j] * kLutCap | ((uint32_t)im.ac_slot[j] * kLutCap) << 16;
+    for (int j = 0; j < 3; j++)
+        g.tab[j] = (uint32_t)im.dc_slot[j] * kLutCapDC | ((uint32_t)im.ndc * kLutCapDC + (uint32_t)im.ac_slot[j] * kLutCapAC) << 16;
 }
 
 __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (lo & 0xFFFFu) | (hi << 16); }
@@ -269,18 +283,18 @@ __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (l
 __global__ void __launch_bounds__(kHuffThreads)
 k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
             const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
-            const uint32_t *__restrict__ sub_seg, const uint16_t *__restrict__ lut_pool, uint2 *__restrict__ st_in,
-            uint2 *__restrict__ st_out, uint4 *__restrict__ sub_tot, uint4 *__restrict__ sub_pre, BlkAgg *__restrict__ blk_agg,
-            uint32_t *__restrict__ flags, int round, uint32_t sub_bytes) {
+            const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
+            uint2 *__restrict__ st_in, uint2 *__restrict__ st_out, uint32_t *__restrict__ sub_tot, uint2 *__restrict__ sub_pre,
+            BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round, uint32_t sub_bytes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem_raw);
+    uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
-    __shared__ uint4 s_tot[kHuffThreads];
+    __shared__ uint32_t s_tot[kHuffThreads];
     __shared__ uint32_t s_end[kHuffThreads];
     __shared__ uint16_t s_work[2][kHuffThreads];
     __shared__ uint32_t s_nwork[2];
     __shared__ uint32_t s_flag;
-    __shared__ uint32_t s_w[4][kHuffThreads / 32 + 1];
+    __shared__ uint32_t s_w[kHuffThreads / 32 + 1];
     __shared__ uint32_t s_wf[kHuffThreads / 32 + 1];
 
     const uint32_t img = blk_img[blockIdx.x];
@@ -315,7 +329,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     if (round > 0 && s_flag == 0) return;                                   // nothing changed at this CTA's entry
 
     HuffGeom g;
-    stage_luts(im, lut_pool, s_lut, g);
+    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g);
     const uint32_t *__restrict__ words = clean + im.clean_word0;
 
     int cur = 0;
@@ -325,14 +339,12 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
         if (nw == 0) break;
         for (uint32_t w = tid; w < nw; w += kHuffThreads) {
             const uint32_t item = s_work[cur][w];
-            BitReader rd;
-            rd.w = words;
             HuffState in;
             in.p = s_in[item].x; in.cz = s_in[item].y;
-            SubTotals t;
-            const HuffState o = decode_span(rd, s_lut, g, in, s_end[item], &t);
+            uint32_t started;
+            const HuffState o = decode_span(words, s_lut, g, in, s_end[item], &started);
             s_out[item] = make_uint2(o.p, o.cz);
-            s_tot[item] = make_uint4(t.n, t.dc[0], t.dc[1], t.dc[2]);
+            s_tot[item] = started;
         }
         if (tid == 0) s_nwork[cur ^ 1] = 0;
         __syncthreads();
@@ -346,67 +358,65 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
         cur ^= 1;
     }
 
-    // segmented exclusive scan over the CTA of (units started, DC sums), restarting at segment heads
-    uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0, f = 0;
-    if (active) { const uint4 t = s_tot[tid]; v0 = t.x; v1 = t.y; v2 = t.z; v3 = t.w; f = u.head ? 1u : 0u; }
-    const uint32_t own0 = v0, own1 = v1, own2 = v2, own3 = v3;
+    // segmented exclusive scan over the CTA of the units started, restarting at segment heads
+    uint32_t v0 = 0, f = 0;
+    if (active) { v0 = s_tot[tid]; f = u.head ? 1u : 0u; }
+    const uint32_t own0 = v0;
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, v0, d), t1 = __shfl_up_sync(0xFFFFFFFFu, v1, d);
-        const uint32_t t2 = __shfl_up_sync(0xFFFFFFFFu, v2, d), t3 = __shfl_up_sync(0xFFFFFFFFu, v3, d);
+        const uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, v0, d);
         const uint32_t tf = __shfl_up_sync(0xFFFFFFFFu, f, d);
-        if (lane >= d) { if (!f) { v0 += t0; v1 += t1; v2 += t2; v3 += t3; } f |= tf; }
+        if (lane >= d) { if (!f) v0 += t0; f |= tf; }
     }
-    if (lane == 31) { s_w[0][warp] = v0; s_w[1][warp] = v1; s_w[2][warp] = v2; s_w[3][warp] = v3; s_wf[warp] = f; }
+    if (lane == 31) { s_w[warp] = v0; s_wf[warp] = f; }
     __syncthreads();
     if (tid == 0) {                                                        // 8 warp totals: serial segmented scan
-        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, cf = 0;
+        uint32_t c0 = 0, cf = 0;
         for (int w = 0; w < kHuffThreads / 32; w++) {
-            const uint32_t a0 = s_w[0][w], a1 = s_w[1][w], a2 = s_w[2][w], a3 = s_w[3][w], af = s_wf[w];
-            s_w[0][w] = c0; s_w[1][w] = c1; s_w[2][w] = c2; s_w[3][w] = c3; s_wf[w] = cf;      // carry INTO warp w
-            if (af) { c0 = a0; c1 = a1; c2 = a2; c3 = a3; cf = 1; } else { c0 += a0; c1 += a1; c2 += a2; c3 += a3; }
+            const uint32_t a0 = s_w[w], af = s_wf[w];
+            s_w[w] = c0; s_wf[w] = cf;                                     // carry INTO warp w
+            if (af) { c0 = a0; cf = 1; } else c0 += a0;
         }
         BlkAgg a;
-        a.n = c0; a.dc01 = pack16(c1, c2); a.dc2 = c3 & 0xFFFFu; a.has_head = cf;
+        a.n = c0; a.has_head = cf;
         blk_agg[blockIdx.x] = a;
     }
     __syncthreads();
     if (active) {
         uint32_t hf = f;
-        if (!f) { v0 += s_w[0][warp]; v1 += s_w[1][warp]; v2 += s_w[2][warp]; v3 += s_w[3][warp]; hf = s_wf[warp]; }
+        if (!f) { v0 += s_w[warp]; hf = s_wf[warp]; }
         // exclusive: a head starts from zero; otherwise inclusive minus own
-        uint4 pre;
-        if (u.head) pre = make_uint4(0u, 0u, 0u, 1u);
-        else pre = make_uint4(v0 - own0, pack16(v1 - own1, v2 - own2), (v3 - own3) & 0xFFFFu, hf);
         st_in[gj] = s_in[tid];
         st_out[gj] = s_out[tid];
         sub_tot[gj] = s_tot[tid];
-        sub_pre[gj] = pre;                                                 // .w: a head precedes inside this CTA
+        sub_pre[gj] = u.head ? make_uint2(0u, 1u) : make_uint2(v0 - own0, hf);   // .y: a head precedes inside this CTA
     }
     if (round > 0 && tid == 0) atomicAdd(&flags[round], 1u);
 }
 
 // ------------------------------------------------------------------------------------------------ K1a: write
-// Per-thread unit staging in shared memory, column layout: word w of thread t at [w * NT + t] - every access
-// of a warp falls into 32 different banks whatever the zig-zag index.
+// Per-thread unit staging in shared memory: thread t owns the 128 bytes at t * 128, its 16-byte chunk q stored
+// at chunk position q ^ (t & 7), so a finished unit leaves with eight 128-bit shared loads + eight 128-bit global
+// stores, and the 2-byte puts of a warp spread over the banks.
 struct SmemUnitSink {
-    uint32_t *col;           // &stage[tid]
+    uint8_t *row;            // stage + tid * 128
+    uint32_t sw;             // tid & 7
     int16_t *out;            // image's first unit
+    int16_t *dcp;            // image's first entry in the DC plane
     uint32_t ndu;
+    __device__ __forceinline__ void dc(uint32_t du, int16_t diff) { if (du < ndu) dcp[du] = diff; }
     __device__ __forceinline__ void put(uint32_t zz, int16_t v) {
-        reinterpret_cast<int16_t *>(col + (zz >> 1) * kHuffThreads)[zz & 1u] = v;
+        *reinterpret_cast<int16_t *>(row + ((((zz >> 3) ^ sw) << 4) | ((zz & 7u) << 1))) = v;
     }
     __device__ __forceinline__ void flush(uint32_t du) {
         uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)du * 64);
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            uint4 v;
-            v.x = col[(4 * q + 0) * kHuffThreads]; v.y = col[(4 * q + 1) * kHuffThreads];
-            v.z = col[(4 * q + 2) * kHuffThreads]; v.w = col[(4 * q + 3) * kHuffThreads];
-            col[(4 * q + 0) * kHuffThreads] = 0; col[(4 * q + 1) * kHuffThreads] = 0;
-            col[(4 * q + 2) * kHuffThreads] = 0; col[(4 * q + 3) * kHuffThreads] = 0;
-            if (du < ndu) dst[q] = v;
+        for (uint32_t q = 0; q < 8; q++) {
+            uint4 *src = reinterpret_cast<uint4 *>(row + ((q ^ sw) << 4));
+            const uint4 v = *src;
+            *src = make_uint4(0, 0, 0, 0);
+            if (du < ndu) __stcs(dst + q, v);
         }
     }
 };
@@ -416,12 +426,13 @@ constexpr int kSmemHuffStage = kHuffThreads * 128;
 __global__ void __launch_bounds__(kHuffThreads)
 k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
              const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
-             const uint32_t *__restrict__ sub_seg, const uint16_t *__restrict__ lut_pool, const uint2 *__restrict__ st_in,
-             const uint4 *__restrict__ sub_pre, const BlkAgg *__restrict__ blk_agg, int16_t *__restrict__ coef, uint32_t sub_bytes) {
+             const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
+             const uint2 *__restrict__ st_in, const uint2 *__restrict__ sub_pre, const BlkAgg *__restrict__ blk_agg,
+             int16_t *__restrict__ coef, int16_t *__restrict__ dc_plane, uint32_t sub_bytes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw);
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem_raw + kSmemHuffStage);
-    __shared__ uint32_t s_red[4][kHuffThreads / 32];
+    uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw + kSmemHuffStage);
+    __shared__ uint32_t s_red[kHuffThreads / 32];
     __shared__ int s_h;
 
     const uint32_t img = blk_img[blockIdx.x];
@@ -443,43 +454,35 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
         if (h >= 0) atomicMax(&s_h, h);
     }
     __syncthreads();
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    for (int b = s_h + tid; b < (int)lb; b += kHuffThreads) {
-        const BlkAgg a = blk_agg[im.blk_base + b];
-        c0 += a.n; c1 += a.dc01 & 0xFFFFu; c2 += a.dc01 >> 16; c3 += a.dc2;
-    }
+    uint32_t c0 = 0;
+    for (int b = s_h + tid; b < (int)lb; b += kHuffThreads) c0 += blk_agg[im.blk_base + b].n;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, d); c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, d);
-        c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, d); c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, d);
-    }
-    if (lane == 0) { s_red[0][warp] = c0; s_red[1][warp] = c1; s_red[2][warp] = c2; s_red[3][warp] = c3; }
+    for (int d = 16; d > 0; d >>= 1) c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, d);
+    if (lane == 0) s_red[warp] = c0;
     for (int i = tid; i < 32 * kHuffThreads; i += kHuffThreads) s_stage[i] = 0;
     HuffGeom g;
-    stage_luts(im, lut_pool, s_lut, g);
+    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g);
     __syncthreads();
-    c0 = c1 = c2 = c3 = 0;
+    c0 = 0;
 #pragma unroll
-    for (int w = 0; w < kHuffThreads / 32; w++) { c0 += s_red[0][w]; c1 += s_red[1][w]; c2 += s_red[2][w]; c3 += s_red[3][w]; }
+    for (int w = 0; w < kHuffThreads / 32; w++) c0 += s_red[w];
 
     if (!active) return;
     const SubInfo u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg, sub_bytes);
-    const uint4 pre = sub_pre[im.sub_base + j];
-    uint32_t n_ex = pre.x, p0 = pre.y & 0xFFFFu, p1 = pre.y >> 16, p2 = pre.z;
-    if (!pre.w) { n_ex += c0; p0 += c1; p1 += c2; p2 += c3; }
+    const uint2 pre = sub_pre[im.sub_base + j];
+    const uint32_t n_ex = pre.x + (pre.y ? 0u : c0);
     const uint32_t du0 = u.seg * im.ri * im.bpm;
     const uint32_t du_end = (im.ri ? min(im.nmcu, (u.seg + 1u) * im.ri) : im.nmcu) * im.bpm;
     const uint2 sin = st_in[im.sub_base + j];
     HuffState in;
     in.p = sin.x; in.cz = sin.y;
-    BitReader rd;
-    rd.w = clean + im.clean_word0;
     SmemUnitSink sink;
-    sink.col = s_stage + tid;
+    sink.row = reinterpret_cast<uint8_t *>(s_stage) + tid * 128;
+    sink.sw = tid & 7;
     sink.out = coef + (size_t)im.du_base * 64;
+    sink.dcp = dc_plane + im.du_base;
     sink.ndu = im.ndu;
-    const uint32_t pred[3] = {p0, p1, p2};
-    const WriteResult r = write_span(rd, s_lut, g, in, u.end_bit, u.data_end_bit, du0 + n_ex, du_end, u.last, pred, sink);
+    const WriteResult r = write_span(clean + im.clean_word0, s_lut, g, in, u.end_bit, u.data_end_bit, du0 + n_ex, du_end, u.last, sink);
     if (r.first_zero != 0xFFFFFFFFu) {
         atomicMin(&ist[img].first_zero, r.first_zero);
         ist[img].status = 1u;
@@ -495,6 +498,108 @@ k_zero_tail(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     uint4 *p = reinterpret_cast<uint4 *>(coef + ((size_t)im.du_base + fz) * 64);
     const size_t n = (size_t)(im.ndu - fz) * 8;
     for (size_t i = (size_t)blockIdx.y * 256 + threadIdx.x; i < n; i += (size_t)gridDim.y * 256) p[i] = make_uint4(0, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------ K1c: DC prediction
+// The write pass leaves DC DIFFERENCES in a compact plane (one short per unit, decode order).  Two tiny kernels
+// turn them into predicted values in place: one thread per MCU sums its differences per component, a segmented
+// scan (restarting at every restart interval) runs over the CTA, PHASE 0 publishes the chunk's totals, PHASE 1
+// adds the totals of the preceding chunks back to the last restart and rewrites the plane.  Units the reference
+// never reached (>= first_zero) read as zero.
+template <int PHASE>
+__global__ void __launch_bounds__(kDcThreads)
+k_dc_predict(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, const uint32_t *__restrict__ dcc_img,
+             int16_t *__restrict__ dc_plane, DcAgg *__restrict__ dc_agg) {
+    __shared__ uint32_t s_w[3][kDcThreads / 32 + 1];
+    __shared__ uint32_t s_wf[kDcThreads / 32 + 1];
+    __shared__ uint32_t s_red[3][kDcThreads / 32];
+    __shared__ int s_h;
+    const uint32_t img = dcc_img[blockIdx.x];
+    const HuffImg &im = imgs[img];
+    const uint32_t fz = ist[img].first_zero;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lc = blockIdx.x - im.dcc_base;
+    const uint32_t m = lc * kDcThreads + tid;
+    const bool active = m < im.nmcu;
+    HuffGeom g;
+    g.bpm = im.bpm; g.ny = im.ny; g.tab[0] = g.tab[1] = g.tab[2] = 0;
+    int16_t *p = dc_plane + im.du_base + (size_t)m * im.bpm;
+    int16_t d[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t v0 = 0, v1 = 0, v2 = 0, f = 0;
+    if (active) {
+#pragma unroll
+        for (uint32_t c = 0; c < 6; c++) {
+            if (c < g.bpm) {
+                d[c] = (m * g.bpm + c < fz) ? p[c] : (int16_t)0;
+                const uint32_t k = comp_of(g, c), x = (uint32_t)(uint16_t)d[c];
+                if (k == 0) v0 += x; else if (k == 1) v1 += x; else v2 += x;
+            }
+        }
+        f = (m == 0 || (im.ri != 0 && m % im.ri == 0)) ? 1u : 0u;
+    }
+    const uint32_t own0 = v0, own1 = v1, own2 = v2, head = f;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, v0, dd), t1 = __shfl_up_sync(0xFFFFFFFFu, v1, dd);
+        const uint32_t t2 = __shfl_up_sync(0xFFFFFFFFu, v2, dd), tf = __shfl_up_sync(0xFFFFFFFFu, f, dd);
+        if (lane >= dd) { if (!f) { v0 += t0; v1 += t1; v2 += t2; } f |= tf; }
+    }
+    if (lane == 31) { s_w[0][warp] = v0; s_w[1][warp] = v1; s_w[2][warp] = v2; s_wf[warp] = f; }
+    if (tid == 0) s_h = 0;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t c0 = 0, c1 = 0, c2 = 0, cf = 0;
+        for (int w = 0; w < kDcThreads / 32; w++) {
+            const uint32_t a0 = s_w[0][w], a1 = s_w[1][w], a2 = s_w[2][w], af = s_wf[w];
+            s_w[0][w] = c0; s_w[1][w] = c1; s_w[2][w] = c2; s_wf[w] = cf;
+            if (af) { c0 = a0; c1 = a1; c2 = a2; cf = 1; } else { c0 += a0; c1 += a1; c2 += a2; }
+        }
+        if (PHASE == 0) {
+            DcAgg a;
+            a.s0 = c0; a.s1 = c1; a.s2 = c2; a.has_head = cf;
+            dc_agg[blockIdx.x] = a;
+        }
+    }
+    if (PHASE == 0) return;
+    // carry from the preceding chunks of this image, back to the last one that contains a restart
+    {
+        int h = -1;
+        for (int b = (int)lc - 1 - tid; b >= 0; b -= kDcThreads)
+            if (dc_agg[im.dcc_base + b].has_head) { h = b; break; }
+        if (h >= 0) atomicMax(&s_h, h);
+    }
+    __syncthreads();
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+    for (int b = s_h + tid; b < (int)lc; b += kDcThreads) {
+        const DcAgg a = dc_agg[im.dcc_base + b];
+        c0 += a.s0; c1 += a.s1; c2 += a.s2;
+    }
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) {
+        c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, dd); c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, dd); c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, dd);
+    }
+    if (lane == 0) { s_red[0][warp] = c0; s_red[1][warp] = c1; s_red[2][warp] = c2; }
+    __syncthreads();
+    if (!active) return;
+    uint32_t hf = f;
+    if (!f) { v0 += s_w[0][warp]; v1 += s_w[1][warp]; v2 += s_w[2][warp]; hf = s_wf[warp]; }
+    uint32_t pred[3] = {0, 0, 0};
+    if (!head) {
+        pred[0] = v0 - own0; pred[1] = v1 - own1; pred[2] = v2 - own2;      // exclusive within the CTA
+        if (!hf) {
+#pragma unroll
+            for (int w = 0; w < kDcThreads / 32; w++) { pred[0] += s_red[0][w]; pred[1] += s_red[1][w]; pred[2] += s_red[2][w]; }
+        }
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < 6; c++) {
+        if (c < g.bpm) {
+            const uint32_t k = comp_of(g, c);
+            const uint32_t pr = (k == 0 ? pred[0] : (k == 1 ? pred[1] : pred[2])) + (uint32_t)(uint16_t)d[c];
+            if (k == 0) pred[0] = pr; else if (k == 1) pred[1] = pr; else pred[2] = pr;
+            p[c] = (m * g.bpm + c < fz) ? (int16_t)(uint16_t)pr : (int16_t)0;
+        }
+    }
 }
 
 }  // namespace bj

@@ -31,8 +31,8 @@ __device__ __forceinline__ uint4 pack_row(const int (&X)[64], int r) {
 
 // ------------------------------------------------------------------------------------------------ fast layout
 __global__ void __launch_bounds__(kTileThreads, 3)
-k_idct_color(const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs, const TileDev *__restrict__ tiles,
-             uint8_t *__restrict__ out) {
+k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_plane, const ImgDev *__restrict__ imgs,
+             const TileDev *__restrict__ tiles, uint8_t *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint4 *s_du = reinterpret_cast<uint4 *>(smem);
     uint32_t *s_q = reinterpret_cast<uint32_t *>(smem + kSmemDu);
@@ -65,9 +65,13 @@ k_idct_color(const int16_t *__restrict__ coef, const ImgDev *__restrict__ imgs, 
         const uint4 *q4 = reinterpret_cast<const uint4 *>(s_q + comp * kQPitch);
         int X[64];
         unsigned raw48 = 0, raw52 = 0;
+        // the entropy stage keeps predicted DC values in a separate plane (one short per unit)
+        unsigned dcv = 0;
+        if (im->dc_sep) dcv = (unsigned short)__ldg(dc_plane + (size_t)im->du_base + (size_t)(t.my * im->nmx + t.mx0) * bpm + du);
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const uint4 v = s_du[du * 8 + (c ^ sw)];
+            uint4 v = s_du[du * 8 + (c ^ sw)];
+            if (c == 0 && im->dc_sep) v.x = (v.x & 0xFFFF0000u) | dcv;
             const uint4 qa = q4[2 * c], qb = q4[2 * c + 1];
             // (w * (q<<16)) mod 2^32 only sees the low 16 bits of w: no unpack needed for the low halves
             X[zz2nat(8 * c + 0)] = (int)(v.x * qa.x);

@@ -21,10 +21,12 @@ namespace {
 struct HostSink {
     int16_t unit[64];
     int16_t *out;
+    int16_t *dcp;
     uint32_t ndu;
     std::vector<uint8_t> *written;
     HostSink() { memset(unit, 0, sizeof(unit)); }
     void put(uint32_t zz, int16_t v) { unit[zz] = v; }
+    void dc(uint32_t du, int16_t diff) { if (du < ndu) dcp[du] = diff; }
     void flush(uint32_t du) {
         if (du < ndu) { memcpy(out + (size_t)du * 64, unit, sizeof(unit)); (*written)[du]++; }
         memset(unit, 0, sizeof(unit));
@@ -62,14 +64,15 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
     uint32_t first_zero = nseg < nseg_expected ? nseg * ri * bpm : 0xFFFFFFFFu;
 
     // tables
-    std::vector<uint16_t> luts(6 * kLutCap);
+    std::vector<uint32_t> luts(3 * (kLutCapDC + kLutCapAC));
     HuffGeom g;
     g.bpm = bpm; g.ny = (uint32_t)d.hs * d.vs;
     for (int j = 0; j < 3; j++) {
         const int jj = j < d.ncomp ? j : 0;
-        if (build_lut(d.dc_offsets[d.dc_id[jj]], d.dc_symbols[d.dc_id[jj]], &luts[(2 * j) * kLutCap]) < 0) return -100;
-        if (build_lut(d.ac_offsets[d.ac_id[jj]], d.ac_symbols[d.ac_id[jj]], &luts[(2 * j + 1) * kLutCap]) < 0) return -100;
-        g.tab[j] = (uint32_t)((2 * j) * kLutCap) | ((uint32_t)((2 * j + 1) * kLutCap) << 16);
+        const uint32_t odc = j * kLutCapDC, oac = 3 * kLutCapDC + j * kLutCapAC;
+        if (build_lut(d.dc_offsets[d.dc_id[jj]], d.dc_symbols[d.dc_id[jj]], false, &luts[odc]) < 0) return -100;
+        if (build_lut(d.ac_offsets[d.ac_id[jj]], d.ac_symbols[d.ac_id[jj]], true, &luts[oac]) < 0) return -100;
+        g.tab[j] = odc | (oac << 16);
     }
 
     // sub-sequence table
@@ -91,7 +94,7 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
 
     // pass 1: Jacobi rounds to the fixed point  in[i+1] == out[i]
     std::vector<HuffState> in(ns), out(ns);
-    std::vector<SubTotals> tot(ns);
+    std::vector<uint32_t> tot(ns);
     std::vector<uint8_t> need(ns, 1);
     for (size_t i = 0; i < ns; i++) { in[i].p = subs[i].start_bit; in[i].cz = 0; }
     uint32_t rounds = 0;
@@ -99,8 +102,7 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
         bool any = false;
         for (size_t i = 0; i < ns; i++) {
             if (!need[i]) continue;
-            BitReader rd; rd.w = words;
-            out[i] = decode_span(rd, luts.data(), g, in[i], subs[i].end_bit, &tot[i]);
+            out[i] = decode_span(words, luts.data(), g, in[i], subs[i].end_bit, &tot[i]);
             need[i] = 0; any = true;
         }
         if (!any) break;
@@ -111,23 +113,31 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
         }
     }
 
-    // prefix sums per segment, then the write pass
+    // prefix sum of the units started per segment, then the write pass (DC differences into their own plane)
     std::vector<uint8_t> written(ndu, 0);
-    uint32_t n_ex = 0, dc_ex[3] = {0, 0, 0};
+    std::vector<int16_t> dcp(ndu, 0x5A5A);
+    uint32_t n_ex = 0;
     for (size_t i = 0; i < ns; i++) {
         const Sub &u = subs[i];
-        if (u.head) { n_ex = 0; dc_ex[0] = dc_ex[1] = dc_ex[2] = 0; }
+        if (u.head) n_ex = 0;
         const uint32_t du0 = u.seg * ri * bpm;
         const uint32_t du_end = (ri ? std::min(nmcu, (u.seg + 1) * ri) : nmcu) * bpm;
         HostSink sink;
-        sink.out = coef_zz; sink.ndu = ndu; sink.written = &written;
-        BitReader rd; rd.w = words;
-        const uint32_t pred[3] = {dc_ex[0], dc_ex[1], dc_ex[2]};
-        const WriteResult r = write_span(rd, luts.data(), g, in[i], u.end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex, du_end,
-                                         u.last, pred, sink);
+        sink.out = coef_zz; sink.dcp = dcp.data(); sink.ndu = ndu; sink.written = &written;
+        const WriteResult r = write_span(words, luts.data(), g, in[i], u.end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex, du_end,
+                                         u.last, sink);
         first_zero = std::min(first_zero, r.first_zero);
-        n_ex += tot[i].n;
-        for (int k = 0; k < 3; k++) dc_ex[k] += tot[i].dc[k];
+        n_ex += tot[i];
+    }
+    // K1c: DC prediction over the plane, restarting at every restart interval; then merged into slot 0 for the comparison
+    {
+        uint32_t pred[3] = {0, 0, 0};
+        for (uint32_t m = 0; m < nmcu; m++) {
+            if (ri && m % ri == 0) pred[0] = pred[1] = pred[2] = 0;
+            for (uint32_t c = 0; c < bpm; c++) if (m * bpm + c >= first_zero) dcp[m * bpm + c] = 0;
+            dc_predict_mcu(g, &dcp[(size_t)m * bpm], pred);
+        }
+        for (uint32_t u = 0; u < ndu; u++) coef_zz[(size_t)u * 64] = u < first_zero ? dcp[u] : (int16_t)0;
     }
     // zero tail (what the cleanup kernel does)
     uint32_t odd = 0;
@@ -140,23 +150,25 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
 
 extern "C" int emu_parse(const uint8_t *file, size_t len, bj_image_desc *d) { return parse_header(file, len, d); }
 
-// Direct access to the table builder: decode one symbol bit-serially the way the reference does and via the table.
-extern "C" int emu_lut_check(const uint8_t *offsets, const uint8_t *symbols) {
-    std::vector<uint16_t> lut(kLutCap);
-    if (build_lut(offsets, symbols, lut.data()) < 0) return -1;
+// Direct access to the table builder: every 16-bit window is decoded bit-serially the way the reference does
+// (generate_codes + get_next_symbol) and via the table; the entry's fields must describe that symbol.
+extern "C" int emu_lut_check(const uint8_t *offsets, const uint8_t *symbols, int ac) {
+    std::vector<uint32_t> lut(lut_cap(ac != 0));
+    if (build_lut(offsets, symbols, ac != 0, lut.data()) < 0) return -1;
     uint32_t codes[162];
     uint32_t code = 0;
     for (int l = 0; l < 16; l++) { for (unsigned j = offsets[l]; j < offsets[l + 1]; j++) codes[j] = code++; code <<= 1; }
     int bad = 0;
     for (uint32_t w = 0; w < 65536; w++) {               // every 16-bit window
-        uint32_t want = 0;
+        uint32_t want = kLutNoCode;
         uint32_t cw = 0;
-        for (int l = 0; l < 16 && !want; l++) {
+        bool found = false;
+        for (int l = 0; l < 16 && !found; l++) {
             cw = (cw << 1) | ((w >> (15 - l)) & 1);
             for (unsigned j = offsets[l]; j < offsets[l + 1]; j++)
-                if (cw == codes[j]) { want = ((uint32_t)(l + 1) << 8) | symbols[j]; break; }
+                if (cw == codes[j]) { want = lut_leaf(l + 1, symbols[j], ac != 0); found = true; break; }
         }
-        if (lut_lookup(lut.data(), w << 16) != want) bad++;
+        if (lut_lookup(lut.data(), w << 16, ac != 0) != want) bad++;
     }
     return bad;
 }

@@ -27,7 +27,7 @@ def emu():
         subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", EMU, src], check=True)
     lib = C.CDLL(EMU)
     lib.emu_entropy.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
-    lib.emu_lut_check.argtypes = [C.c_void_p, C.c_void_p]
+    lib.emu_lut_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     return lib
 
 
@@ -89,10 +89,11 @@ def test_lut_matches_bit_serial_search():
         off[1:] = np.cumsum(counts)
         sy = np.zeros(162, dtype=np.uint8)
         sy[:len(syms)] = syms
-        assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy)) == 0, key
+        assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy), key[0]) == 0, key
     # an optimised table set and a deliberately odd one (sparse lengths incl. 16-bit DC codes)
     off = np.zeros(17, dtype=np.uint8)
     counts = [0, 1, 0, 0, 2, 0, 0, 0, 3, 0, 0, 5, 0, 0, 7, 20]
     off[1:] = np.cumsum(counts)
     sy = np.arange(162, dtype=np.uint8)
-    assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy)) == 0
+    assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy), 0) == 0
+    assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy), 1) == 0
