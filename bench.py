@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--subseq-bits", type=int, default=0)
     ap.add_argument("--sync-rounds", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--sub-batch-mb", type=int, default=0, help="compressed MB per sub-batch of the one-call path (0 = library default)")
+    ap.add_argument("--host-threads", type=int, default=0, help="host worker threads of the one-call path (0 = library default)")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--gen-workers", type=int, default=min(32, os.cpu_count() or 1))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -317,11 +319,13 @@ def main():
     if not args.no_e2e:
         in_total = sum(len(b) for b in blobs)
         pin_in = bj.PinnedBuffer(in_total)
-        views, o = [], 0
+        in_off, o = [], 0
         for b in blobs:
             pin_in.array[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
-            views.append(pin_in.array[o:o + len(b)])
+            in_off.append(o)
             o += len(b)
+        in_off = np.array(in_off, dtype=np.uint64)
+        in_len = np.array([len(b) for b in blobs], dtype=np.uint64)
         sizes = []
         for b in blobs[:1] if len(set(specs)) == 1 else blobs:
             st, d = bj.parse_header(b)
@@ -333,15 +337,21 @@ def main():
             offs.append(o)
             o += (s + 15) // 16 * 16
         pin_out = bj.PinnedBuffer(o)
-        outs = [pin_out.array[a:a + s] for a, s in zip(offs, sizes)]
+        out_off = np.array(offs, dtype=np.uint64)
         dec.set_option("packed_outputs", 1)
+        if args.sub_batch_mb:
+            dec.set_option("sub_batch_bytes", args.sub_batch_mb << 20)
+        if args.host_threads:
+            dec.set_option("host_threads", args.host_threads)
         k2 = args.e2e_steps or max(2, min(args.steps, 5))
         for _ in range(max(1, min(args.warmup, 2))):
-            dec.decode(views, bj.BJ_OUT_BMP, outs)
+            dec.decode_packed(pin_in.array, in_off, in_len, pin_out.array, out_off, bj.BJ_OUT_BMP)
         barrier()
+        host_ms = wait_ms = 0.0
         t0 = time.perf_counter()
         for _ in range(k2):
-            _, st = dec.decode(views, bj.BJ_OUT_BMP, outs)
+            st = dec.decode_packed(pin_in.array, in_off, in_len, pin_out.array, out_off, bj.BJ_OUT_BMP)
+            host_ms += dec.stat("decode_batch_host_ms"); wait_ms += dec.stat("decode_batch_wait_ms")
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         windows.append((t0, t1))
@@ -351,11 +361,13 @@ def main():
         e2e_s = float(te.item())
         if rank == 0:
             import hashlib
-            assert hashlib.sha256(outs[0].tobytes()).hexdigest() == first_hash, "e2e and device-resident paths disagree"
+            assert not st.any(), "e2e: images failed to decode"
+            assert hashlib.sha256(pin_out.array[:sizes[0]].tobytes()).hexdigest() == first_hash, "e2e and device-resident paths disagree"
         e2e = {"value": px * world * k2 / e2e_s / 1e6, "unit": UNIT, "images_per_s": batch_n * world * k2 / e2e_s,
                "ms_per_step": 1e3 * e2e_s / k2, "steps": k2,
                "h2d_bytes_per_step": int(dec.stat("decode_batch_h2d_bytes")), "d2h_bytes_per_step": int(dec.stat("decode_batch_d2h_bytes")),
-               "sub_batches_per_step": int(dec.stat("decode_batch_sub_batches")),
+               "sub_batches_per_step": int(dec.stat("decode_batch_sub_batches")), "host_threads": int(dec.stat("host_threads")),
+               "host_prepare_ms_per_step": host_ms / k2, "host_wait_gpu_ms_per_step": wait_ms / k2,
                "timer": "host wall clock around the blocking bj_decode_batch call (pinned host buffers in and out), max over ranks"}
         pin_in.free()
         pin_out.free()

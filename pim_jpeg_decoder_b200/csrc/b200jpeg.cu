@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <time.h>
 #include <string>
 #include <vector>
 
@@ -55,8 +56,12 @@ extern "C" int bj_create(bj_ctx **out, int device) {
     c->sm_count = prop.multiProcessorCount;
     if (c->check(cudaFuncSetAttribute(k_idct_color, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemIdctColor)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
     if (batch_kernels_init(c) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < kSlots; i++)
         if (c->check(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
+    {
+        const unsigned hw = std::thread::hardware_concurrency();
+        c->host_pool.resize(std::max(1, std::min(8, (int)hw / 2)));
+    }
     *out = c;
     return BJ_OK;
 }
@@ -67,7 +72,7 @@ extern "C" void bj_destroy(bj_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &p : c->pool) p.release();
     for (auto &b : c->slots) if (b) { b->release(); delete b; b = nullptr; }
-    for (int i = 0; i < 2; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    for (int i = 0; i < kSlots; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     delete c;
 }
 
@@ -86,6 +91,7 @@ extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
     if (!strcmp(name, "subseq_bits")) { if (value < 128 || value % 32) return BJ_ERR_ARG; c->subseq_bits = (int)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_bytes = (size_t)value; return BJ_OK; }
     if (!strcmp(name, "packed_outputs")) { c->packed_outputs = value != 0; return BJ_OK; }
+    if (!strcmp(name, "host_threads")) { if (value < 1 || value > 256) return BJ_ERR_ARG; c->host_pool.resize((int)value); return BJ_OK; }
     if (!strcmp(name, "sync_rounds")) { if (value < 0 || value > kMaxRounds) return BJ_ERR_ARG; c->sync_rounds = (int)value; return BJ_OK; }
     return BJ_ERR_ARG;
 }
@@ -97,6 +103,9 @@ extern "C" int bj_get_stat(const bj_ctx *c, const char *name, double *value) {
     if (!strcmp(name, "decode_batch_launches")) { *value = c->stats[1]; return BJ_OK; }
     if (!strcmp(name, "decode_batch_h2d_bytes")) { *value = c->stats[2]; return BJ_OK; }
     if (!strcmp(name, "decode_batch_d2h_bytes")) { *value = c->stats[3]; return BJ_OK; }
+    if (!strcmp(name, "decode_batch_host_ms")) { *value = c->stats[4]; return BJ_OK; }        // parse + layout + pack, summed
+    if (!strcmp(name, "decode_batch_wait_ms")) { *value = c->stats[5]; return BJ_OK; }        // host blocked on the GPU, summed
+    if (!strcmp(name, "host_threads")) { *value = c->host_pool.threads(); return BJ_OK; }
     return BJ_ERR_ARG;
 }
 
@@ -280,24 +289,33 @@ extern "C" int bj_stage_entropy(bj_ctx *c, const uint8_t *file, size_t len, int1
 }
 
 // ------------------------------------------------------------------------------------------------ full path, one call
-// Sub-batches alternate between two batch objects and two streams: while sub-batch k decodes and copies out, the
-// host parses and packs sub-batch k+1 and its H2D copy runs on the other stream.
+// Sub-batches rotate over kSlots batch objects, each with its own stream: while sub-batch k copies out (PCIe D2H is
+// the bound of this call: 3 bytes per pixel), sub-batch k+1 decodes and the host parses and packs sub-batch k+2
+// on the worker pool.
+static double wall_ms() {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+
 extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format,
                                uint8_t *const *outs, int *status) {
     if (!c || n < 0 || (n > 0 && (!files || !lens || !outs))) return BJ_ERR_ARG;
     if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
     if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
-    const size_t budget = c->sub_batch_bytes ? c->sub_batch_bytes : ((size_t)48 << 20);    // compressed bytes per sub-batch
+    const size_t budget = c->sub_batch_bytes ? c->sub_batch_bytes : ((size_t)24 << 20);    // compressed bytes per sub-batch
     for (auto &b : c->slots) if (!b) { b = new (std::nothrow) bj_batch(); if (!b) return BJ_ERR_NOMEM; }
-    int first[2] = {0, 0}, count[2] = {0, 0};
-    bool busy[2] = {false, false};
-    double nsub = 0, launches = 0, h2d = 0, d2h = 0;
+    int first[kSlots] = {}, count[kSlots] = {};
+    bool busy[kSlots] = {};
+    double nsub = 0, launches = 0, h2d = 0, d2h = 0, host_ms = 0, wait_ms = 0;
     int rc = BJ_OK;
     auto finish = [&](int slot) -> int {
         bj_batch *b = c->slots[slot];
+        const double t0 = wall_ms();
         int r = batch_sync(b);
-        if (r == BJ_OK && b->h_flags()[b->rounds - 1] != 0)          // extra rounds ran: the early copy-out is stale
+        if (r == BJ_OK && b->n_blk && b->h_flags()[b->rounds - 1] != 0)   // extra rounds ran: the early copy-out is stale
             r = batch_download(b, outs + first[slot], c->streams[slot]);
+        wait_ms += wall_ms() - t0;
         if (r == BJ_OK && status) for (int i = 0; i < count[slot]; i++) status[first[slot] + i] = batch_image_status(b, i);
         launches += b->launches; h2d += (double)(b->files_bytes + b->meta_bytes); d2h += (double)b->d2h_bytes;
         busy[slot] = false;
@@ -308,12 +326,14 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
         int i1 = i0;
         size_t bytes = 0;
         while (i1 < n && (i1 == i0 || bytes + lens[i1] <= budget)) bytes += lens[i1++];
-        const int slot = k & 1;
+        const int slot = k % kSlots;
         if (busy[slot]) rc = finish(slot);
         if (rc != BJ_OK) break;
         bj_batch *b = c->slots[slot];
         cudaStream_t s = c->streams[slot];
+        const double t0 = wall_ms();
         rc = batch_assign(b, c, files + i0, lens + i0, i1 - i0, format);
+        host_ms += wall_ms() - t0;
         if (rc == BJ_OK) rc = batch_upload(b, s);
         if (rc == BJ_OK) rc = batch_decode(b, s);
         if (rc == BJ_OK) {                                            // enqueue the copy-out behind the kernels, no host wait
@@ -325,7 +345,8 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
         nsub += 1;
         i0 = i1; k++;
     }
-    for (int slot = 0; slot < 2; slot++) if (busy[slot]) { const int r = finish(slot); if (rc == BJ_OK) rc = r; }
-    c->stats[0] = nsub; c->stats[1] = launches; c->stats[2] = h2d; c->stats[3] = d2h;
+    // drain in submission order
+    for (int j = 0; j < kSlots; j++) { const int slot = (k + j) % kSlots; if (busy[slot]) { const int r = finish(slot); if (rc == BJ_OK) rc = r; } }
+    c->stats[0] = nsub; c->stats[1] = launches; c->stats[2] = h2d; c->stats[3] = d2h; c->stats[4] = host_ms; c->stats[5] = wait_ms;
     return rc;
 }

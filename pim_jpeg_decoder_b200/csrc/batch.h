@@ -102,7 +102,13 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
     for (auto &e : b->ev) if (!e && c->check(cudaEventCreate(&e)) != BJ_OK) return BJ_ERR_CUDA;
 
-    // ---- parse + layout
+    // ---- parse (per image, independent: worker pool)
+    c->host_pool.parallel_for(n, 32, [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++)
+            b->parse_status[i] = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &b->desc[i]) : BJ_ERR_INVALID_JPEG;
+    });
+
+    // ---- layout (serial: prefix sums over the batch)
     std::vector<HuffImg> himg(n);
     std::vector<ImgDev> idev(n);
     std::vector<TileDev> tiles;
@@ -111,16 +117,32 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     std::map<std::string, int> lut_index[2];
     size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
     uint32_t seg_entries = 0, nblk = 0;
+    int prev = -1;                                  // last valid image: its table slots are reused when the tables match
     b->pixels = 0; b->scan_bytes = 0; b->lut_smem = 0;
+    auto same_tables = [](const bj_image_desc &a, const bj_image_desc &q) {
+        if (a.ncomp != q.ncomp || memcmp(a.dc_id, q.dc_id, 3) || memcmp(a.ac_id, q.ac_id, 3)) return false;
+        for (int j = 0; j < a.ncomp; j++) {
+            const int di = a.dc_id[j], ai = a.ac_id[j];
+            if (memcmp(a.dc_offsets[di], q.dc_offsets[di], 17) || memcmp(a.dc_symbols[di], q.dc_symbols[di], a.dc_offsets[di][16] > 162 ? 162 : a.dc_offsets[di][16]) ||
+                memcmp(a.ac_offsets[ai], q.ac_offsets[ai], 17) || memcmp(a.ac_symbols[ai], q.ac_symbols[ai], a.ac_offsets[ai][16] > 162 ? 162 : a.ac_offsets[ai][16])) return false;
+        }
+        return true;
+    };
     for (int i = 0; i < n; i++) {
         bj_image_desc &d = b->desc[i];
         HuffImg &hi = himg[i];
         memset(&hi, 0, sizeof(hi));
         memset(&idev[i], 0, sizeof(ImgDev));
-        int rc = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &d) : BJ_ERR_INVALID_JPEG;
+        int rc = b->parse_status[i];
         Geometry g;
         if (rc == BJ_OK) {
             g = geometry_of(d);
+            if (prev >= 0 && same_tables(d, b->desc[prev])) {
+                const HuffImg &hp = himg[prev];
+                hi.ndc = hp.ndc; hi.nac = hp.nac;
+                memcpy(hi.dc_lut, hp.dc_lut, sizeof(hi.dc_lut)); memcpy(hi.ac_lut, hp.ac_lut, sizeof(hi.ac_lut));
+                memcpy(hi.dc_slot, hp.dc_slot, sizeof(hi.dc_slot)); memcpy(hi.ac_slot, hp.ac_slot, sizeof(hi.ac_slot));
+            } else
             // tables -> pools (deduplicated across the batch); per image the distinct ones become staged slots
             for (int ac = 0; ac < 2 && rc == BJ_OK; ac++) {
                 std::vector<uint32_t> &pool = ac ? luts_ac : luts_dc;
@@ -149,6 +171,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
                 (ac ? hi.nac : hi.ndc) = (uint8_t)nslot;
                 for (int s = 0; s < nslot; s++) (ac ? hi.ac_lut : hi.dc_lut)[s] = (uint16_t)slots[s];
             }
+            if (rc == BJ_OK) prev = i;
             const uint32_t smem = ((uint32_t)hi.ndc * kLutCapDC + (uint32_t)hi.nac * kLutCapAC) * 4;
             if (smem > b->lut_smem) b->lut_smem = smem;
         }
@@ -217,13 +240,15 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     if (!dcc_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_dcc), dcc_img.data(), dcc_img.size() * 4);
     if (!luts_dc.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutdc), luts_dc.data(), luts_dc.size() * 4);
     if (!luts_ac.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutac), luts_ac.data(), luts_ac.size() * 4);
-    // ---- pack the file bytes
+    // ---- pack the file bytes (per image, independent: worker pool)
     uint8_t *hf = reinterpret_cast<uint8_t *>(b->h_files.p);
-    for (int i = 0; i < n; i++) {
-        if (b->parse_status[i] != BJ_OK) continue;
-        memcpy(hf + b->file_off[i], files[i], lens[i]);
-        memset(hf + b->file_off[i] + lens[i], 0, align_up(lens[i] + 16, 16) - lens[i]);
-    }
+    c->host_pool.parallel_for(n, 16, [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++) {
+            if (b->parse_status[i] != BJ_OK) continue;
+            memcpy(hf + b->file_off[i], files[i], lens[i]);
+            memset(hf + b->file_off[i] + lens[i], 0, align_up(lens[i] + 16, 16) - lens[i]);
+        }
+    });
     // ---- device buffers
     if (b->d_files.reserve(b->files_bytes) || b->d_meta.reserve(b->meta_bytes) || b->d_clean.reserve(b->clean_words * 4) ||
         b->d_seg.reserve((size_t)(seg_entries + 2) * 4 * 2) || b->d_subseg.reserve((size_t)b->n_sub_slots * 4 + 16) ||

@@ -2,7 +2,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/b200jpeg.h"
 #include "bj_dev.h"
@@ -28,6 +35,75 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Host worker pool: the per-image host work of a batch (header parse, packing file bytes into pinned staging) is
+// independent per image, like everything else on this path; the calling thread takes part.  Replaces the
+// reference's single producer thread (src/decoder_host.cpp:101-211).
+class HostPool {
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int, int)> *job_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, chunk_ = 1, epoch_ = 0, active_ = 0;
+    bool stop_ = false;
+
+    void drain() {
+        for (;;) {
+            const int b = next_.fetch_add(chunk_);
+            if (b >= n_) break;
+            (*job_)(b, b + chunk_ < n_ ? b + chunk_ : n_);
+        }
+    }
+    void run() {
+        int seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return stop_ || epoch_ != seen; });
+                if (stop_) return;
+                seen = epoch_;
+            }
+            drain();
+            {
+                std::lock_guard<std::mutex> l(m_);
+                if (--active_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
+
+public:
+    int threads() const { return (int)workers_.size() + 1; }
+    void resize(int nthreads) {                       // total threads including the caller
+        shutdown();
+        stop_ = false;
+        for (int i = 1; i < nthreads; i++) workers_.emplace_back([this] { run(); });
+    }
+    void shutdown() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+        workers_.clear();
+    }
+    ~HostPool() { shutdown(); }
+    // fn(begin, end) over [0, n) in chunks; returns when all of it is done
+    void parallel_for(int n, int chunk, const std::function<void(int, int)> &fn) {
+        if (n <= 0) return;
+        if (workers_.empty() || n <= chunk) { fn(0, n); return; }
+        {
+            std::lock_guard<std::mutex> l(m_);
+            job_ = &fn; n_ = n; chunk_ = chunk > 0 ? chunk : 1; next_.store(0);
+            active_ = (int)workers_.size();
+            epoch_++;
+        }
+        cv_.notify_all();
+        drain();
+        std::unique_lock<std::mutex> l(m_);
+        done_cv_.wait(l, [&] { return active_ == 0; });
+    }
+};
+
+constexpr int kSlots = 3;             // sub-batches in flight inside bj_decode_batch
+
 enum { POOL_COMPAT_MD = 0, POOL_COMPAT_MCUS, POOL_COEF, POOL_OUT, POOL_IMGS, POOL_TILES, POOL_COUNT };
 
 }  // namespace bj
@@ -39,9 +115,11 @@ struct bj_ctx {
     size_t sub_batch_bytes = 0;          // 0 = default
     int packed_outputs = 0;              // see batch_download_async
     int sync_rounds = 0;                 // 0 = default (3 launches of the fix-up kernel before the first check)
-    struct bj_batch *slots[2] = {nullptr, nullptr};   // sub-batches of bj_decode_batch (double buffering)
+    struct bj_batch *slots[bj::kSlots] = {};          // sub-batches of bj_decode_batch in flight (one stream each)
+    bj::HostPool host_pool;
+    int host_threads = 0;                // 0 = default: min(8, hardware threads / 2)
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaStream_t streams[bj::kSlots] = {};
     bj::DevBuf pool[bj::POOL_COUNT];
     std::string last_error;
     float last_exec_ms = 0.f;

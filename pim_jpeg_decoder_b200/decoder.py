@@ -51,7 +51,7 @@ def _file_arrays(files):
     """list of bytes / uint8 arrays -> (keepalive arrays, char** , size_t*)"""
     arrs = [f if isinstance(f, np.ndarray) else np.frombuffer(f, dtype=np.uint8) for f in files]
     n = len(arrs)
-    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+    ptrs = (C.c_void_p * max(n, 1))(*[a.__array_interface__["data"][0] for a in arrs])
     lens = (C.c_size_t * max(n, 1))(*[a.size for a in arrs])
     return arrs, ptrs, lens
 
@@ -193,11 +193,26 @@ class Decoder:
             for f in files:
                 st, d = parse_header(f)
                 outs.append(np.zeros(L.lib().bj_output_size(C.byref(d), fmt), dtype=np.uint8) if st == L.BJ_OK else None)
-        optrs = (C.c_void_p * max(n, 1))(*[o.ctypes.data if o is not None else None for o in outs])
+        optrs = (C.c_void_p * max(n, 1))(*[o.__array_interface__["data"][0] if o is not None else None for o in outs])
         status = (C.c_int * max(n, 1))()
         L.check(L.lib().bj_decode_batch(self.ctx, ptrs, lens, n, fmt, optrs, status), "bj_decode_batch", self.ctx)
         st = list(status)[:n]
         return [o if s in (L.BJ_OK, L.BJ_ERR_CORRUPT_SCAN) else None for o, s in zip(outs, st)], st
+
+
+    def decode_packed(self, src, src_off, src_len, dst, dst_off, fmt=L.BJ_OUT_RGB8):
+        """bj_decode_batch for a batch-pipeline caller: the n files sit in ONE host buffer `src` (uint8 array, ideally
+        a PinnedBuffer) at byte offsets `src_off` with lengths `src_len`; image i is written to `dst[dst_off[i]:]`
+        (bj_output_size bytes).  The pointer tables are built with vector arithmetic, so the host-side cost per
+        call does not grow with a Python loop over images.  Returns the per-image status as an int32 array."""
+        n = len(src_off)
+        ip = (np.asarray(src_off, dtype=np.uint64) + np.uint64(src.__array_interface__["data"][0]))
+        il = np.ascontiguousarray(src_len, dtype=np.uint64)
+        op = (np.asarray(dst_off, dtype=np.uint64) + np.uint64(dst.__array_interface__["data"][0]))
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        L.check(L.lib().bj_decode_batch(self.ctx, ip.ctypes.data_as(C.c_void_p), il.ctypes.data_as(C.c_void_p), n, fmt,
+                                        op.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p)), "bj_decode_batch", self.ctx)
+        return status[:n]
 
 
 def shard_by_size(sizes, world_size):

@@ -141,9 +141,48 @@ def test_full_path_sub_batching(dec, golden, golden_dir):
         outs, status = dec.decode(files, bj.BJ_OUT_BMP)
         assert dec.stat("decode_batch_sub_batches") > 4
     finally:
-        dec.set_option("sub_batch_bytes", 48 << 20)
+        dec.set_option("sub_batch_bytes", 24 << 20)
     for n, o, st in zip(names, outs, status):
         assert st == 0 and sha(o) == golden[golden[n]["expect"]]["bmp_sha256"], n
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_decode_packed_host_threads(dec, threads, golden, golden_dir):
+    """The batch-pipeline form of the one-call path (all files in one pinned buffer, outputs in another), with the
+    host parse/pack work on 1 and on 5 worker threads, over 3 slots of small sub-batches."""
+    import pim_jpeg_decoder_b200 as bj
+    names = _names(include_invalid=True) * 4
+    files = [_load(golden, golden_dir, n) for n in names]
+    src = bj.PinnedBuffer(sum(len(f) for f in files))
+    src_off, o = [], 0
+    for f in files:
+        src.array[o:o + len(f)] = np.frombuffer(f, dtype=np.uint8)
+        src_off.append(o)
+        o += len(f)
+    sizes = []
+    for f in files:
+        st, d = bj.parse_header(f)
+        sizes.append(bj.lib().bj_output_size(d, bj.BJ_OUT_BMP) if st == 0 else 0)
+    dst_off = np.concatenate([[0], np.cumsum([(s + 15) // 16 * 16 for s in sizes])])[:-1]
+    dst = bj.PinnedBuffer(int(dst_off[-1]) + sizes[-1] + 16)
+    dst.array[:] = 0x5A
+    dec.set_option("host_threads", threads)
+    dec.set_option("sub_batch_bytes", 1 << 16)
+    dec.set_option("packed_outputs", 1)
+    try:
+        status = dec.decode_packed(src.array, src_off, [len(f) for f in files], dst.array, dst_off, bj.BJ_OUT_BMP)
+        assert dec.stat("host_threads") == threads and dec.stat("decode_batch_sub_batches") > 6
+    finally:
+        dec.set_option("sub_batch_bytes", 24 << 20)
+        dec.set_option("packed_outputs", 0)
+        dec.set_option("host_threads", 4)
+    for n, st, off, size in zip(names, status, dst_off, sizes):
+        if golden[n].get("invalid"):
+            assert st == bj.BJ_ERR_INVALID_JPEG
+        else:
+            assert st == 0 and sha(dst.array[int(off):int(off) + size]) == golden[golden[n]["expect"]]["bmp_sha256"], n
+    src.free()
+    dst.free()
 
 
 @pytest.mark.parametrize("w,h,sub,gray,ri", [(500, 375, 2, False, 0), (375, 500, 2, False, 0), (640, 480, 0, False, 0),
