@@ -60,7 +60,7 @@ extern "C" int bj_create(bj_ctx **out, int device) {
         if (c->check(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
     {
         const unsigned hw = std::thread::hardware_concurrency();
-        c->host_pool.resize(std::max(1, std::min(8, (int)hw / 2)));
+        c->host_pool.resize(std::max(1, std::min(4, (int)hw / 2)));   // measured on the 16-core B200 box: 4 is the knee, more only contends with the copy engines
     }
     *out = c;
     return BJ_OK;

@@ -117,7 +117,7 @@ struct bj_ctx {
     int sync_rounds = 0;                 // 0 = default (3 launches of the fix-up kernel before the first check)
     struct bj_batch *slots[bj::kSlots] = {};          // sub-batches of bj_decode_batch in flight (one stream each)
     bj::HostPool host_pool;
-    int host_threads = 0;                // 0 = default: min(8, hardware threads / 2)
+    int host_threads = 0;                // 0 = default: min(4, hardware threads / 2)
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaStream_t streams[bj::kSlots] = {};
     bj::DevBuf pool[bj::POOL_COUNT];
