@@ -115,6 +115,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     std::vector<uint32_t> blk_img, utile_img, dcc_img;
     std::vector<uint32_t> luts_dc, luts_ac;
     std::map<std::string, int> lut_index[2];
+    std::vector<uint16_t> lut_n4[2];                // per pooled table: used size in 16-byte chunks
     size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
     uint32_t seg_entries = 0, nblk = 0;
     int prev = -1;                                  // last valid image: its table slots are reused when the tables match
@@ -142,6 +143,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
                 hi.ndc = hp.ndc; hi.nac = hp.nac;
                 memcpy(hi.dc_lut, hp.dc_lut, sizeof(hi.dc_lut)); memcpy(hi.ac_lut, hp.ac_lut, sizeof(hi.ac_lut));
                 memcpy(hi.dc_slot, hp.dc_slot, sizeof(hi.dc_slot)); memcpy(hi.ac_slot, hp.ac_slot, sizeof(hi.ac_slot));
+                memcpy(hi.dc_n4, hp.dc_n4, sizeof(hi.dc_n4)); memcpy(hi.ac_n4, hp.ac_n4, sizeof(hi.ac_n4));
             } else
             // tables -> pools (deduplicated across the batch); per image the distinct ones become staged slots
             for (int ac = 0; ac < 2 && rc == BJ_OK; ac++) {
@@ -159,7 +161,9 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
                     if (it == lut_index[ac].end()) {
                         idx = (int)(pool.size() / cap);
                         pool.resize(pool.size() + cap);
-                        if (build_lut(off, sym, ac != 0, &pool[(size_t)idx * cap]) < 0) rc = BJ_ERR_UNSUPPORTED;
+                        const int used = build_lut(off, sym, ac != 0, &pool[(size_t)idx * cap]);
+                        if (used < 0) rc = BJ_ERR_UNSUPPORTED;
+                        lut_n4[ac].push_back((uint16_t)((std::max(used, 0) + 3) / 4));
                         lut_index[ac][key] = idx;
                         if (idx > 65535) rc = BJ_ERR_UNSUPPORTED;
                     } else idx = it->second;
@@ -169,10 +173,15 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
                     (ac ? hi.ac_slot : hi.dc_slot)[j] = (uint8_t)s;
                 }
                 (ac ? hi.nac : hi.ndc) = (uint8_t)nslot;
-                for (int s = 0; s < nslot; s++) (ac ? hi.ac_lut : hi.dc_lut)[s] = (uint16_t)slots[s];
+                for (int s = 0; s < nslot; s++) {
+                    (ac ? hi.ac_lut : hi.dc_lut)[s] = (uint16_t)slots[s];
+                    (ac ? hi.ac_n4 : hi.dc_n4)[s] = lut_n4[ac][slots[s]];
+                }
             }
             if (rc == BJ_OK) prev = i;
-            const uint32_t smem = ((uint32_t)hi.ndc * kLutCapDC + (uint32_t)hi.nac * kLutCapAC) * 4;
+            uint32_t smem = 0;
+            for (int s = 0; s < hi.ndc; s++) smem += hi.dc_n4[s] * 16u;
+            for (int s = 0; s < hi.nac; s++) smem += hi.ac_n4[s] * 16u;
             if (smem > b->lut_smem) b->lut_smem = smem;
         }
         b->parse_status[i] = rc;

@@ -21,41 +21,46 @@
 namespace bj {
 
 // ------------------------------------------------------------------------------------------------ lookup tables
-// One table per Huffman table: kRootBits-bit root + second-level tables for longer codes.  Entries are 32 bits
-// and carry everything a decode step needs, precomputed per table class (DC / AC), so the inner loop is a load,
-// two adds and a compare:
-//   bits  5..0   stream bits the step consumes: code length + magnitude bits (>= 1, also for "no such code")
-//   bits 12..6   zig-zag advance: 1 for a DC symbol, run + 1 for an AC symbol, 64 for end-of-block
-//   bits 16..13  magnitude size (0 for a step the reference would refuse)
-//   bits 21..17  code length
-//   bit  22      bad: the reference stops here - no code, DC category > 11, AC size > 10
+// One table per Huffman table: a kRootBits-bit root + second-level tables for longer codes.  Entries are 32 bits
+// and carry everything a decode step needs, precomputed per table class (DC / AC).  The two low bytes ARE the
+// increment of the packed decoder state S = (bit position << 8) | zig-zag index, so a step is: window, load, add.
+//   bits  7..0   zig-zag advance: 1 for a DC symbol, run + 1 for an AC symbol, 64 for end-of-block
+//   bits 15..8   stream bits the step consumes: code length + magnitude bits (1..27, also for "no such code")
+//   bits 20..16  code length            } each at the bottom of a byte with the bits up to the next multiple of 5
+//   bits 27..24  magnitude size         } clear, so `e >> 16` / `e >> 24` feed wrap-mode (mod 32) shifts unmasked;
+//                                         size is 0 for a step the reference would refuse
+//   bit  29      bad: the reference stops here - no code, DC category > 11, AC size > 10
 //                (src/jpeg_scanner.cpp:470-478, :490-511)
-//   bit  23      AC end-of-block
-//   bit  31      link (root only): bits 19..16 = k, bits 15..0 = offset of a 2^k-entry second-level table
-constexpr int kRootBitsDC = 9, kRootBitsAC = 11;      // > 11-bit AC codes are ~0.2 % of symbols at q = 90
-constexpr int kLutCapDC = 1024, kLutCapAC = 2560;     // entries per table (4 KB / 10 KB)
+//   bit  30      AC end-of-block
+//   bit  31      link (root only): bits 19..16 = k, bits 15..0 = BYTE offset (from the table's first entry) of a
+//                2^k-entry second-level table indexed by the k bits that follow the root bits
+constexpr int kRootBits = 10;                         // > 10-bit codes are ~0.4 % of symbols at q = 90
+// entries per table in the pools (root + second level).  For a canonical code the second level needs about one
+// entry per long code plus < 64 per code length (long codes are numerically contiguous), far below these caps.
+constexpr int kLutCapDC = 1536, kLutCapAC = 1792;
 constexpr uint32_t kLutLink = 0x80000000u;
-constexpr uint32_t kLutBad = 1u << 22;
-constexpr uint32_t kLutEob = 1u << 23;
-BJ_HD constexpr int lut_root_bits(bool ac) { return ac ? kRootBitsAC : kRootBitsDC; }
+constexpr uint32_t kLutBad = 1u << 29;
+constexpr uint32_t kLutEob = 1u << 30;
 BJ_HD constexpr int lut_cap(bool ac) { return ac ? kLutCapAC : kLutCapDC; }
+BJ_HD uint32_t lut_len(uint32_t e) { return (e >> 16) & 31u; }
+BJ_HD uint32_t lut_size(uint32_t e) { return (e >> 24) & 15u; }
 
 inline uint32_t lut_leaf(int len, unsigned sym, bool ac) {
     const unsigned run = ac ? sym >> 4 : 0, size = ac ? (sym & 15u) : sym;
     const bool eob = ac && sym == 0;
     const bool bad = ac ? size > 10 : sym > 11;
     const unsigned sz = bad ? 0u : size;
-    return (uint32_t)(len + sz) | ((eob ? 64u : run + 1u) << 6) | (sz << 13) | ((uint32_t)len << 17) | (bad ? kLutBad : 0u) | (eob ? kLutEob : 0u);
+    return (eob ? 64u : run + 1u) | ((uint32_t)(len + sz) << 8) | ((uint32_t)len << 16) | (sz << 24) | (bad ? kLutBad : 0u) | (eob ? kLutEob : 0u);
 }
-constexpr uint32_t kLutNoCode = 1u | (1u << 6) | kLutBad;      // no code with this prefix: skip one bit
+constexpr uint32_t kLutNoCode = 1u | (1u << 8) | kLutBad;      // no code with this prefix: skip one bit
 
 // Host: build one table.  Returns the number of entries used, or -1 if the second-level tables do not fit.
 // Over-subscribed (invalid) tables keep the reference's behaviour: the shortest matching code wins and codes
 // that do not fit their length never match (get_next_symbol compares the l-bit prefix with the stored code).
 inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], bool ac, uint32_t *lut) {
-    const int R = lut_root_bits(ac), kLutCap = lut_cap(ac);
+    const int R = kRootBits, kLutCap = lut_cap(ac);
     for (int i = 0; i < kLutCap; i++) lut[i] = 0;
-    uint8_t maxlen[1 << kRootBitsAC];
+    uint8_t maxlen[1 << kRootBits];
     memset(maxlen, 0, sizeof(maxlen));
     uint32_t code = 0;
     for (int l = 1; l <= 16; l++) {                       // codes that fit the root
@@ -85,7 +90,7 @@ inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], bool
         if (!maxlen[pre]) continue;
         const int k = maxlen[pre] - R;
         if (next + (1 << k) > kLutCap) return -1;
-        lut[pre] = kLutLink | ((uint32_t)k << 16) | (uint32_t)next;
+        lut[pre] = kLutLink | ((uint32_t)k << 16) | ((uint32_t)next * 4u);
         next += 1 << k;
     }
     code = 0;
@@ -96,22 +101,39 @@ inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], bool
             const uint32_t pre = cv >> (l - R);
             if (!(lut[pre] & kLutLink)) continue;
             const int k = (lut[pre] >> 16) & 15, rem = l - R;
-            const uint32_t base = lut[pre] & 0xFFFFu;
+            const uint32_t base = (lut[pre] & 0xFFFFu) / 4u;
             const uint32_t first = (cv & ((1u << rem) - 1)) << (k - rem), cnt = 1u << (k - rem);
             for (uint32_t i = 0; i < cnt; i++)
                 if (lut[base + first + i] == 0) lut[base + first + i] = lut_leaf(l, symbols[j], ac);
         }
         code <<= 1;
     }
-    for (int i = 0; i < kLutCap; i++) if (lut[i] == 0) lut[i] = kLutNoCode;
+    for (int i = 0; i < next; i++) if (lut[i] == 0) lut[i] = kLutNoCode;
     return next;
 }
 
-// win = the next 32 bits of the stream, MSB first.
-BJ_HD uint32_t lut_lookup(const uint32_t *lut, uint32_t win, bool ac) {
-    const uint32_t R = ac ? kRootBitsAC : kRootBitsDC;
-    uint32_t e = lut[win >> (32u - R)];
-    if (e & kLutLink) e = lut[(e & 0xFFFFu) + ((win << R) >> (32u - ((e >> 16) & 15u)))];
+// Where the staged tables live.  On the device: a 32-bit shared-memory address (loads are ld.shared with no
+// generic-address arithmetic in the decode loop); on the host: a pointer.  Table positions are BYTE offsets.
+struct LutMem {
+#ifdef __CUDA_ARCH__
+    uint32_t base;
+    __device__ __forceinline__ void attach(const uint32_t *smem) { base = (uint32_t)__cvta_generic_to_shared(smem); }
+    __device__ __forceinline__ uint32_t ld(uint32_t byte_off) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
+        return v;
+    }
+#else
+    const uint32_t *base;
+    void attach(const uint32_t *tables) { base = tables; }
+    uint32_t ld(uint32_t byte_off) const { return base[byte_off >> 2]; }
+#endif
+};
+
+// win = the next 32 bits of the stream, MSB first; tab = byte offset of the table.
+BJ_HD uint32_t lut_lookup(const LutMem &m, uint32_t tab, uint32_t win) {
+    uint32_t e = m.ld(tab + ((win >> (32 - kRootBits)) << 2));
+    if (__builtin_expect((int32_t)e < 0, 0)) e = m.ld(tab + (e & 0xFFFFu) + (((win << kRootBits) >> (32u - ((e >> 16) & 15u))) << 2));
     return e;
 }
 
@@ -125,17 +147,24 @@ BJ_HD bool scan_is_rst(unsigned prev, unsigned b) { return prev == 0xFFu && b >=
 // ------------------------------------------------------------------------------------------------ bit reader
 // The un-stuffed stream is stored as 32-bit words whose most significant byte is the earliest byte (the
 // un-stuff kernel writes byte o to address o ^ 3), so a window is two aligned words and one funnel shift.
-BJ_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, uint32_t s) {      // top 32 bits of (hi:lo) << s, s in 0..31
+BJ_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, uint32_t s) {      // top 32 bits of (hi:lo) << (s mod 32)
 #ifdef __CUDA_ARCH__
     return __funnelshift_l(lo, hi, s);
 #else
+    s &= 31u;
     return s ? (hi << s) | (lo >> (32 - s)) : hi;
 #endif
 }
 
-struct BitReader {
-    const uint32_t *q;      // -> word wi of the image's un-stuffed stream (word 0 = bits 0..31)
-    uint32_t wi, cur, nxt, nx2;   // words wi, wi+1, wi+2: the load for a word is issued one word ahead of its use
+// Decoder positions inside one span are kept as  S = (bit offset from `origin` << 8) | zig-zag index, `origin`
+// being the 32-bit-aligned stream position at or before the span's first bit.  A step adds the low 16 bits of a
+// table entry.  The zig-zag index never exceeds 127 (63 + 64), so bit 6 set means "unit complete" and the byte
+// never carries into the position.  A symbol consumes at most 27 bits, so the word index grows by at most one.
+constexpr uint32_t kWordS = 32u << 8;
+struct BitStream {
+    const uint32_t *w;            // -> word holding the current position
+    uint32_t cur, nxt, nx2;       // that word and the two after it (the load runs one word ahead of its use)
+    uint32_t word_end;            // S value of the first bit after `cur`
     BJ_HD static uint32_t ld(const uint32_t *a) {
 #ifdef __CUDA_ARCH__
         return __ldg(a);
@@ -143,11 +172,15 @@ struct BitReader {
         return *a;
 #endif
     }
-    BJ_HD void seek(const uint32_t *words, uint32_t p) { wi = p >> 5; q = words + wi; cur = ld(q); nxt = ld(q + 1); nx2 = ld(q + 2); }
-    // p never moves by more than 31 bits between calls, so the word index grows by at most one
-    BJ_HD uint32_t window(uint32_t p) {
-        if ((p >> 5) != wi) { cur = nxt; nxt = nx2; q++; wi++; nx2 = ld(q + 2); }
-        return funnel_l(cur, nxt, p & 31u);
+    BJ_HD void open(const uint32_t *words, uint32_t p) {
+        w = words + (p >> 5);
+        cur = ld(w); nxt = ld(w + 1); nx2 = ld(w + 2);
+        word_end = kWordS;
+    }
+    BJ_HD void advance() { cur = nxt; nxt = nx2; w++; nx2 = ld(w + 2); word_end += kWordS; }
+    BJ_HD uint32_t window(uint32_t S) {
+        if (S >= word_end) advance();
+        return funnel_l(cur, nxt, S >> 8);
     }
 };
 
@@ -160,11 +193,11 @@ struct HuffState {
 };
 BJ_HD bool same_state(const HuffState &a, const HuffState &b) { return a.p == b.p && a.cz == b.cz; }
 
-// Per image: geometry of an MCU and where each component's tables sit (entry offsets into the staged tables).
+// Per image: geometry of an MCU and where each component's tables sit.
 struct HuffGeom {
     uint32_t bpm;           // data units per MCU
     uint32_t ny;            // luma units per MCU (hs * vs); unit c belongs to component c < ny ? 0 : c - ny + 1
-    uint32_t tab[3];        // per component: DC table entry offset | AC table entry offset << 16 (from the staged base)
+    uint32_t tab[3];        // per component: DC table byte offset | AC table byte offset << 16 (from the staged base)
 };
 BJ_HD uint32_t comp_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? 0u : c - g.ny + 1u; }
 BJ_HD uint32_t tabs_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.tab[0] : (c == g.ny ? g.tab[1] : g.tab[2]); }
@@ -173,8 +206,15 @@ BJ_HD uint32_t tabs_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.tab[
 // (src/jpeg_scanner.cpp:480-482 / :513-516: first bit 0 => negative).  size 0 gives 0.
 BJ_HD int32_t extend_value(uint32_t win, uint32_t len, uint32_t size) {
     const uint32_t t = win << len;                                        // len <= 16
-    const uint32_t raw = funnel_l(0u, t, size);                           // top `size` bits of t
+    const uint32_t raw = funnel_l(0u, t, size);                           // top `size` bits of t (size <= 11)
     return (int32_t)raw + (((int32_t)t >= 0) ? 1 - (int32_t)(1u << size) : 0);
+}
+// The same from a table entry; all shifts are wrap-mode (mod 32), fed by plain shifts of the entry.
+BJ_HD int32_t extend_entry(uint32_t win, uint32_t e) {
+    const uint32_t t = funnel_l(win, 0u, e >> 16);                        // win << len
+    const uint32_t raw = funnel_l(0u, t, e >> 24);                        // top `size` bits of t
+    const uint32_t m = funnel_l(0xFFFFFFFFu, 0u, e >> 24) + 1u;           // 1 - 2^size
+    return (int32_t)(raw + (m & ~(uint32_t)((int32_t)t >> 31)));
 }
 
 // ------------------------------------------------------------------------------------------------ pass 1: synchronise
@@ -184,31 +224,43 @@ BJ_HD int32_t extend_value(uint32_t win, uint32_t len, uint32_t size) {
 // (a wrong guess must not poison its successors): a refused symbol consumes its code bits (at least one) and the
 // unit simply continues; an over-long run ends the unit.  With the true entry state the result is the true exit
 // state up to the first real error, which the write pass detects and reports.
-BJ_HD HuffState decode_span(const uint32_t *words, const uint32_t *luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
+// The inner loop runs to the end of the current stream word or of the span, whichever comes first, so a step is:
+// funnel shift, table load, add, unit-complete test, limit test.
+BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
                             uint32_t *units_started) {
-    uint32_t p = st.p, c = st.cz >> 8, z = st.cz & 0xFFu;
+    *units_started = 0;
+    if (st.p >= end_bit) return st;
+    const uint32_t origin = st.p & ~31u;
+    uint32_t c = st.cz >> 8;
+    uint32_t S = ((st.p - origin) << 8) | (st.cz & 0xFFu);
+    const uint32_t endS = (end_bit - origin) << 8;
+    const uint32_t entered_mid = (S & 0xFFu) ? 1u : 0u;
     uint32_t ends = 0;
-    const uint32_t entered_mid = z != 0 ? 1u : 0u;
     uint32_t tabs = tabs_of(g, c);
-    BitReader rd;
-    if (p < end_bit) rd.seek(words, p);
-    while (p < end_bit) {
-        const uint32_t win = rd.window(p);
-        const bool ac = z != 0;
-        const uint32_t e = lut_lookup(luts + (ac ? (tabs >> 16) : (tabs & 0xFFFFu)), win, ac);
-        p += e & 63u;
-        z += (e >> 6) & 127u;
-        if (z >= 64u) {
-            z = 0;
-            ends++;
-            c = (c + 1u == g.bpm) ? 0u : c + 1u;
-            tabs = tabs_of(g, c);
+    uint32_t tab = entered_mid ? (tabs >> 16) : (tabs & 0xFFFFu);
+    BitStream bs;
+    bs.open(words, st.p);
+    for (;;) {
+        const uint32_t limit = endS < bs.word_end ? endS : bs.word_end;
+        while (S < limit) {
+            const uint32_t e = lut_lookup(luts, tab, funnel_l(bs.cur, bs.nxt, S >> 8));
+            S += e & 0xFFFFu;
+            tab = tabs >> 16;
+            if (S & 0x40u) {                                              // zig-zag index >= 64: unit complete
+                S &= ~0xFFu;
+                ends++;
+                c = (c + 1u == g.bpm) ? 0u : c + 1u;
+                tabs = tabs_of(g, c);
+                tab = tabs & 0xFFFFu;
+            }
         }
+        if (S >= endS) break;
+        bs.advance();
     }
     // started = ended + (one still open at the exit) - (the one that was already open at the entry)
-    *units_started = ends + (z != 0 ? 1u : 0u) - entered_mid;
+    *units_started = ends + ((S & 0xFFu) ? 1u : 0u) - entered_mid;
     HuffState o;
-    o.p = p; o.cz = (c << 8) | z;
+    o.p = origin + (S >> 8); o.cz = (c << 8) | (S & 0xFFu);
     return o;
 }
 
@@ -226,43 +278,81 @@ struct WriteResult {
 };
 
 template <class Sink>
-BJ_HD WriteResult write_span(const uint32_t *words, const uint32_t *luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
+BJ_HD WriteResult write_span(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
                              uint32_t data_end_bit, uint32_t du, uint32_t du_end, bool last_of_segment, Sink &sink) {
     WriteResult res;
     res.first_zero = 0xFFFFFFFFu;
-    uint32_t p = st.p, c = st.cz >> 8, z = st.cz & 0xFFu;
+    const uint32_t origin = st.p & ~31u;
+    uint32_t c = st.cz >> 8;
+    uint32_t S = ((st.p - origin) << 8) | (st.cz & 0xFFu);
+    const uint32_t endS = end_bit > origin ? (end_bit - origin) << 8 : 0u;
+    // S > dataS  <=>  the position is past the end of the segment's data: bits ran out inside the symbol
+    // (BitReader::read_bit returns -1 in the reference)
+    // (saturated: a position inside a span stays far below 2^24 bits from its origin)
+    const uint32_t data_rel = data_end_bit >= origin ? data_end_bit - origin : 0u;
+    const uint32_t dataS = ((data_rel < 0xFFFFFFu ? data_rel : 0xFFFFFFu) << 8) | 0xFFu;
     uint32_t tabs = tabs_of(g, c);
-    bool owned = false;
-    BitReader rd;
-    rd.seek(words, p);
-    for (;;) {
-        const bool ac = z != 0;
-        if ((!ac || !owned) && p >= end_bit) break;         // a new unit would start (or a foreign one continue) past my end
-        if (!ac && du >= du_end) break;                     // the segment's last unit is done: the rest is padding
-        owned = owned || !ac;
-        const uint32_t win = rd.window(p);
-        const uint32_t e = lut_lookup(luts + (ac ? (tabs >> 16) : (tabs & 0xFFFFu)), win, ac);
-        p += e & 63u;
-        const uint32_t zn = z + ((e >> 6) & 127u);
-        if (owned) {
-            // the reference's failure points: refused symbol, run past the end of the unit ("i + run >= 64",
-            // src/jpeg_scanner.cpp:497-500), or bits running out inside a symbol (BitReader::read_bit returns -1)
-            if ((e & kLutBad) || (!(e & kLutEob) && zn > 64u) || p > data_end_bit) {
-                // a failed DC leaves the unit untouched (zero); a failed AC keeps what was stored before it
-                if (!ac) res.first_zero = du;
-                else { sink.flush(du); res.first_zero = du + 1; }
-                return res;
-            }
-            const int32_t v = extend_value(win, (e >> 17) & 31u, (e >> 13) & 15u);
-            if (!ac) sink.dc(du, (int16_t)v);               // |diff| < 2^11
-            else if (v != 0) sink.put(zn - 1u, (int16_t)v); // size 0 (ZRL and friends) would store a literal 0: already there
+    BitStream bs;
+    bs.open(words, st.p);
+    bool stop = false;
+    if (S & 0xFFu) {                                      // entered inside a unit that belongs to a predecessor: skip it
+        for (;;) {
+            if (S >= endS) { stop = true; break; }
+            const uint32_t e = lut_lookup(luts, tabs >> 16, bs.window(S));
+            S += e & 0xFFFFu;
+            if (S & 0x40u) break;
         }
-        if (zn >= 64u) {
-            if (owned) { sink.flush(du); du++; owned = false; }
-            z = 0;
+        if (!stop) {
+            S &= ~0xFFu;
             c = (c + 1u == g.bpm) ? 0u : c + 1u;
             tabs = tabs_of(g, c);
-        } else z = zn;
+        }
+    }
+    while (!stop) {
+        // a unit starts here: mine if it starts before my end and the segment still has units to give
+        if (S >= endS || du >= du_end) break;
+        {
+            const uint32_t win = bs.window(S);
+            const uint32_t e = lut_lookup(luts, tabs & 0xFFFFu, win);
+            const uint32_t Sn = S + (e & 0xFFFFu);
+            // a failed DC leaves the unit untouched (zero)
+            if ((e & kLutBad) || Sn > dataS) { res.first_zero = du; return res; }
+            sink.dc(du, (int16_t)extend_entry(win, e));                   // |diff| < 2^11
+            S = Sn;
+        }
+        const uint32_t tab = tabs >> 16;
+        // AC symbols.  The reference's failure points: refused symbol, bits running out inside a symbol, run past
+        // the end of the unit ("i + run >= 64", src/jpeg_scanner.cpp:497-500).  A failed AC keeps what was stored
+        // before it.  The zig-zag index is >= 1 here, so an index above 64 means end-of-block or an over-long run.
+        bool open = true, failed = false;
+        while (open) {
+            while (S < bs.word_end) {
+                const uint32_t win = funnel_l(bs.cur, bs.nxt, S >> 8);
+                const uint32_t e = lut_lookup(luts, tab, win);
+                const uint32_t Sn = S + (e & 0xFFFFu);
+                if (__builtin_expect((e & kLutBad) || Sn > dataS, 0)) { failed = true; open = false; break; }
+                if (Sn & 0x40u) {                                         // index >= 64: the unit ends one way or another
+                    const uint32_t zn = Sn & 0xFFu;
+                    if (zn == 64u) {
+                        const int32_t v = extend_entry(win, e);
+                        if (v != 0) sink.put(63u, (int16_t)v);
+                    } else if (!(e & kLutEob)) failed = true;
+                    S = Sn;
+                    open = false;
+                    break;
+                }
+                const int32_t v = extend_entry(win, e);
+                if (v != 0) sink.put((Sn & 0xFFu) - 1u, (int16_t)v);    // size 0 (ZRL and friends) would store a literal 0: already there
+                S = Sn;
+            }
+            if (open) bs.advance();
+        }
+        sink.flush(du);
+        if (failed) { res.first_zero = du + 1; return res; }
+        du++;
+        S &= ~0xFFu;
+        c = (c + 1u == g.bpm) ? 0u : c + 1u;
+        tabs = tabs_of(g, c);
     }
     // the last sub-sequence of a segment must have produced the segment's last unit
     if (last_of_segment && du < du_end) res.first_zero = du;

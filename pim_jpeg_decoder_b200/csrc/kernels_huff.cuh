@@ -40,6 +40,8 @@ struct HuffImg {
     uint16_t dc_lut[3], ac_lut[3];   // pool index of each staged DC / AC slot
     uint8_t dc_slot[3], ac_slot[3];  // per component: staged slot
     uint8_t pad_[2];
+    uint16_t dc_n4[3], ac_n4[3];     // used size of each staged table in 16-byte chunks (tables are staged packed)
+    uint32_t pad2_;
 };
 
 // Per image, written by the kernels.
@@ -250,24 +252,39 @@ __device__ __forceinline__ SubInfo sub_info(const HuffImg &im, const HuffImgStat
     return u;
 }
 
-// stage the image's tables into shared memory (DC slots first, then AC slots), 16 bytes per thread per step
+// stage the image's tables into shared memory, packed (DC slots first, then AC slots; only the used part of every
+// table), 16 bytes per thread per step.  Returns where they are through `g` (byte offsets) and `luts`.
 __device__ __forceinline__ void stage_luts(const HuffImg &im, const uint32_t *__restrict__ lut_dc_pool,
-                                           const uint32_t *__restrict__ lut_ac_pool, uint32_t *s_lut, HuffGeom &g) {
-    constexpr int per_dc = kLutCapDC / 4, per_ac = kLutCapAC / 4;          // uint4 per table
+                                           const uint32_t *__restrict__ lut_ac_pool, uint32_t *s_lut, HuffGeom &g, LutMem &luts) {
     uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-    for (int i = threadIdx.x; i < im.ndc * per_dc; i += blockDim.x) {
-        const int slot = i / per_dc, q = i - slot * per_dc;
-        dst[i] = __ldg(reinterpret_cast<const uint4 *>(lut_dc_pool + (size_t)im.dc_lut[slot] * kLutCapDC) + q);
+    uint32_t off = 0, dc_off[3] = {0, 0, 0}, ac_off[3] = {0, 0, 0};
+#pragma unroll
+    for (int slot = 0; slot < 3; slot++) {
+        if (slot < im.ndc) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(lut_dc_pool + (size_t)im.dc_lut[slot] * kLutCapDC);
+            const uint32_t n4 = im.dc_n4[slot];
+            for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[off + i] = __ldg(src + i);
+            dc_off[slot] = off * 16u;
+            off += n4;
+        }
     }
-    uint4 *dst_ac = dst + im.ndc * per_dc;
-    for (int i = threadIdx.x; i < im.nac * per_ac; i += blockDim.x) {
-        const int slot = i / per_ac, q = i - slot * per_ac;
-        dst_ac[i] = __ldg(reinterpret_cast<const uint4 *>(lut_ac_pool + (size_t)im.ac_lut[slot] * kLutCapAC) + q);
+#pragma unroll
+    for (int slot = 0; slot < 3; slot++) {
+        if (slot < im.nac) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(lut_ac_pool + (size_t)im.ac_lut[slot] * kLutCapAC);
+            const uint32_t n4 = im.ac_n4[slot];
+            for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[off + i] = __ldg(src + i);
+            ac_off[slot] = off * 16u;
+            off += n4;
+        }
     }
     g.bpm = im.bpm; g.ny = im.ny;
 #pragma unroll
-    for (int j = 0; j < 3; j++)
-        g.tab[j] = (uint32_t)im.dc_slot[j] * kLutCapDC | ((uint32_t)im.ndc * kLutCapDC + (uint32_t)im.ac_slot[j] * kLutCapAC) << 16;
+    for (int j = 0; j < 3; j++) {
+        const uint32_t ds = im.dc_slot[j], as = im.ac_slot[j];
+        g.tab[j] = (ds == 0 ? dc_off[0] : ds == 1 ? dc_off[1] : dc_off[2]) | (as == 0 ? ac_off[0] : as == 1 ? ac_off[1] : ac_off[2]) << 16;
+    }
+    luts.attach(s_lut);
 }
 
 __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (lo & 0xFFFFu) | (hi << 16); }
@@ -280,7 +297,7 @@ __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (l
 // round r>0: the first sub-sequence of the CTA takes the exit state of the previous CTA's last one; if that
 //          differs from what it used, the CTA re-converges.  flags[r] counts CTAs that changed in round r; the
 //          host launches rounds until a round reports 0.
-__global__ void __launch_bounds__(kHuffThreads)
+__global__ void __launch_bounds__(kHuffThreads, 6)
 k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
             const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
             const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
@@ -329,7 +346,8 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     if (round > 0 && s_flag == 0) return;                                   // nothing changed at this CTA's entry
 
     HuffGeom g;
-    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g);
+    LutMem luts;
+    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g, luts);
     const uint32_t *__restrict__ words = clean + im.clean_word0;
 
     int cur = 0;
@@ -342,7 +360,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
             HuffState in;
             in.p = s_in[item].x; in.cz = s_in[item].y;
             uint32_t started;
-            const HuffState o = decode_span(words, s_lut, g, in, s_end[item], &started);
+            const HuffState o = decode_span(words, luts, g, in, s_end[item], &started);
             s_out[item] = make_uint2(o.p, o.cz);
             s_tot[item] = started;
         }
@@ -400,22 +418,24 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
 // at chunk position q ^ (t & 7), so a finished unit leaves with eight 128-bit shared loads + eight 128-bit global
 // stores, and the 2-byte puts of a warp spread over the banks.
 struct SmemUnitSink {
-    uint8_t *row;            // stage + tid * 128
-    uint32_t sw;             // tid & 7
+    uint32_t row;            // shared-memory address of stage + tid * 128
+    uint32_t sw16;           // (tid & 7) << 4
     int16_t *out;            // image's first unit
     int16_t *dcp;            // image's first entry in the DC plane
     uint32_t ndu;
     __device__ __forceinline__ void dc(uint32_t du, int16_t diff) { if (du < ndu) dcp[du] = diff; }
+    // chunk (zz >> 3) ^ sw, element zz & 7  ==  byte (zz * 2) ^ (sw << 4)
     __device__ __forceinline__ void put(uint32_t zz, int16_t v) {
-        *reinterpret_cast<int16_t *>(row + ((((zz >> 3) ^ sw) << 4) | ((zz & 7u) << 1))) = v;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + ((zz << 1) ^ sw16)), "h"(v) : "memory");
     }
     __device__ __forceinline__ void flush(uint32_t du) {
         uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)du * 64);
 #pragma unroll
         for (uint32_t q = 0; q < 8; q++) {
-            uint4 *src = reinterpret_cast<uint4 *>(row + ((q ^ sw) << 4));
-            const uint4 v = *src;
-            *src = make_uint4(0, 0, 0, 0);
+            const uint32_t a = row + ((q << 4) ^ sw16);
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
             if (du < ndu) __stcs(dst + q, v);
         }
     }
@@ -461,7 +481,8 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     if (lane == 0) s_red[warp] = c0;
     for (int i = tid; i < 32 * kHuffThreads; i += kHuffThreads) s_stage[i] = 0;
     HuffGeom g;
-    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g);
+    LutMem luts;
+    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g, luts);
     __syncthreads();
     c0 = 0;
 #pragma unroll
@@ -477,12 +498,12 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     HuffState in;
     in.p = sin.x; in.cz = sin.y;
     SmemUnitSink sink;
-    sink.row = reinterpret_cast<uint8_t *>(s_stage) + tid * 128;
-    sink.sw = tid & 7;
+    sink.row = (uint32_t)__cvta_generic_to_shared(s_stage) + tid * 128;
+    sink.sw16 = (tid & 7) << 4;
     sink.out = coef + (size_t)im.du_base * 64;
     sink.dcp = dc_plane + im.du_base;
     sink.ndu = im.ndu;
-    const WriteResult r = write_span(clean + im.clean_word0, s_lut, g, in, u.end_bit, u.data_end_bit, du0 + n_ex, du_end, u.last, sink);
+    const WriteResult r = write_span(clean + im.clean_word0, luts, g, in, u.end_bit, u.data_end_bit, du0 + n_ex, du_end, u.last, sink);
     if (r.first_zero != 0xFFFFFFFFu) {
         atomicMin(&ist[img].first_zero, r.first_zero);
         ist[img].status = 1u;

@@ -72,8 +72,11 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
         const uint32_t odc = j * kLutCapDC, oac = 3 * kLutCapDC + j * kLutCapAC;
         if (build_lut(d.dc_offsets[d.dc_id[jj]], d.dc_symbols[d.dc_id[jj]], false, &luts[odc]) < 0) return -100;
         if (build_lut(d.ac_offsets[d.ac_id[jj]], d.ac_symbols[d.ac_id[jj]], true, &luts[oac]) < 0) return -100;
-        g.tab[j] = odc | (oac << 16);
+        g.tab[j] = (odc * 4) | ((oac * 4) << 16);
     }
+
+    LutMem lm;
+    lm.attach(luts.data());
 
     // sub-sequence table
     struct Sub { uint32_t seg, start_bit, end_bit; bool head, last; };
@@ -102,7 +105,7 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
         bool any = false;
         for (size_t i = 0; i < ns; i++) {
             if (!need[i]) continue;
-            out[i] = decode_span(words, luts.data(), g, in[i], subs[i].end_bit, &tot[i]);
+            out[i] = decode_span(words, lm, g, in[i], subs[i].end_bit, &tot[i]);
             need[i] = 0; any = true;
         }
         if (!any) break;
@@ -124,7 +127,7 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
         const uint32_t du_end = (ri ? std::min(nmcu, (u.seg + 1) * ri) : nmcu) * bpm;
         HostSink sink;
         sink.out = coef_zz; sink.dcp = dcp.data(); sink.ndu = ndu; sink.written = &written;
-        const WriteResult r = write_span(words, luts.data(), g, in[i], u.end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex, du_end,
+        const WriteResult r = write_span(words, lm, g, in[i], u.end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex, du_end,
                                          u.last, sink);
         first_zero = std::min(first_zero, r.first_zero);
         n_ex += tot[i];
@@ -168,7 +171,9 @@ extern "C" int emu_lut_check(const uint8_t *offsets, const uint8_t *symbols, int
             for (unsigned j = offsets[l]; j < offsets[l + 1]; j++)
                 if (cw == codes[j]) { want = lut_leaf(l + 1, symbols[j], ac != 0); found = true; break; }
         }
-        if (lut_lookup(lut.data(), w << 16, ac != 0) != want) bad++;
+        LutMem lm;
+        lm.attach(lut.data());
+        if (lut_lookup(lm, 0, w << 16) != want) bad++;
     }
     return bad;
 }

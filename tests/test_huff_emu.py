@@ -70,6 +70,17 @@ def test_emulated_entropy_stage_synthetic(w, h, sub, gray, ri):
     assert info[0] < 40            # fix-up rounds stay small: the stream self-synchronises
 
 
+def test_emulated_entropy_stage_long_restart_free_stream():
+    """A restart-free scan longer than 2^24 bits: positions inside a span are kept relative to the span's origin
+    in 24 bits, and the end of the DATA (the whole scan here) must saturate instead of wrapping."""
+    data = js.synth_jpeg(2048, 1600, seed=77, subsampling=0)
+    r = ol.Restated(data, 0)
+    assert (r.h.scan_len * 8) > (1 << 24)
+    _, got, info = run_emu(data, 512)
+    assert info[1] == 0xFFFFFFFF and info[3] == 0
+    assert np.array_equal(got, r.coef_zz)
+
+
 def test_truncated_scan_zero_fills_like_the_reference():
     """Cut the entropy-coded data short: the reference stops at the failing unit and leaves the rest zero."""
     data = bytearray(js.synth_jpeg(160, 120, seed=3, subsampling=2))
