@@ -34,6 +34,10 @@ struct HostSink {
 };
 }  // namespace
 
+// optional: per Jacobi round, how many sub-sequences were decoded (set by emu_set_round_hist; 64 entries)
+static uint32_t *g_round_hist = nullptr;
+extern "C" void emu_set_round_hist(uint32_t *hist) { g_round_hist = hist; }
+
 // Returns 0 ok, <0 parse status.  info[0] = fix-up rounds, info[1] = first_zero (UINT32_MAX none), info[2] = nsub,
 // info[3] = number of units written more or less than once (must be 0 for a clean stream)
 extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16_t *coef_zz, uint32_t *info) {
@@ -103,6 +107,7 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
     uint32_t rounds = 0;
     for (;;) {
         bool any = false;
+        if (g_round_hist && rounds < 64) { uint32_t cnt = 0; for (size_t i = 0; i < ns; i++) cnt += need[i]; g_round_hist[rounds] = cnt; }
         for (size_t i = 0; i < ns; i++) {
             if (!need[i]) continue;
             out[i] = decode_span(words, lm, g, in[i], subs[i].end_bit, &tot[i]);
