@@ -352,7 +352,8 @@ inline int batch_decode(bj_batch *b, cudaStream_t s) {
     b->last_stream = s;
     b->decoded = true; b->synced = false;
     if (b->n == 0) return BJ_OK;
-    b->rounds = c->sync_rounds > 0 ? c->sync_rounds : 3;
+    // round 0 cannot tell whether it settled everything (only rounds > 0 compare across CTAs): at least two
+    b->rounds = c->sync_rounds > 0 ? (c->sync_rounds < 2 ? 2 : c->sync_rounds) : 3;
     return batch_launch(b, s, 0, b->rounds);
 }
 

@@ -144,6 +144,36 @@ BJ_HD uint32_t lut_lookup(const LutMem &m, uint32_t tab, uint32_t win) {
 BJ_HD bool scan_keep(unsigned prev, unsigned b, unsigned next) { return b == 0xFFu ? next == 0x00u : prev != 0xFFu; }
 BJ_HD bool scan_is_rst(unsigned prev, unsigned b) { return prev == 0xFFu && b >= 0xD0u && b <= 0xD7u; }
 
+// The same rules on 16 bytes at once, four per 32-bit word (little-endian: byte i of the chunk sits in bits
+// 8*(i&3).. of w[1 + i/4]); w[0] is the word before the chunk (only its top byte matters), w[5] the word after
+// (only its low byte).  keep / rst: bit i = byte i survives / is the code byte of an RSTn marker.
+BJ_HD uint32_t bytes_eq(uint32_t a, uint32_t b) {                          // 0xFF in every byte where a == b
+#ifdef __CUDA_ARCH__
+    return __vcmpeq4(a, b);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xFFu) == ((b >> (8 * i)) & 0xFFu)) r |= 0xFFu << (8 * i);
+    return r;
+#endif
+}
+BJ_HD uint32_t movemask4(uint32_t m) { return (((m >> 7) & 0x01010101u) * 0x01020408u) >> 24; }   // bit 7 of each byte -> 4 bits
+BJ_HD void classify_words(const uint32_t w[6], uint32_t &keep, uint32_t &rst) {
+    keep = 0; rst = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++) {
+        const uint32_t x = w[k + 1];
+        const uint32_t before = (x << 8) | (w[k] >> 24);                   // byte i-1 under byte i
+        const uint32_t behind = (x >> 8) | (w[k + 2] << 24);               // byte i+1 under byte i
+        const uint32_t F = bytes_eq(x, 0xFFFFFFFFu), PF = bytes_eq(before, 0xFFFFFFFFu), Z = bytes_eq(behind, 0u);
+        const uint32_t km = (F & Z) | (~F & ~PF);                          // scan_keep
+        const uint32_t rm = PF & bytes_eq(x & 0xF8F8F8F8u, 0xD0D0D0D0u);   // scan_is_rst
+        keep |= movemask4(km) << (4 * k);
+        rst |= movemask4(rm) << (4 * k);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ bit reader
 // The un-stuffed stream is stored as 32-bit words whose most significant byte is the earliest byte (the
 // un-stuff kernel writes byte o to address o ^ 3), so a window is two aligned words and one funnel shift.

@@ -94,31 +94,30 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------ K0: un-stuff
-// One thread classifies 16 raw bytes (aligned 16-byte chunk of the file buffer).  keep: bit i = byte i survives;
-// rst: bit i = byte i is the code byte of an RSTn marker.
+// One thread classifies 16 raw bytes (aligned 16-byte chunk of the file buffer), branch-free and four bytes at a
+// time (per-byte compare masks on 32-bit words).  keep: bit i = byte i survives; rst: bit i = byte i is the code
+// byte of an RSTn marker.  The byte before the scan is the SOS header's Ah/Al byte (0 in a baseline file) and the
+// byte after it is the FF of the marker that ends the scan (parse.h: find_scan_end), so the rules "the first byte
+// has no FF before it" and "what follows the last byte is a marker" hold without special cases.
 __device__ __forceinline__ void classify16(const uint8_t *__restrict__ files, const HuffImg &im, uint32_t tile, uint32_t &keep,
                                            uint32_t &rst, uint4 &bytes) {
     const uint64_t a0 = (im.raw_off & ~(uint64_t)15) + (uint64_t)tile * kUnstuffTile + (uint64_t)threadIdx.x * 16;
     const int64_t r0 = (int64_t)a0 - (int64_t)im.raw_off;                  // scan-relative index of byte 0 (may be < 0)
-    keep = 0; rst = 0;
-    bytes = make_uint4(0, 0, 0, 0);
-    if (r0 >= (int64_t)im.raw_len || r0 + 16 <= 0) return;
-    bytes = __ldg(reinterpret_cast<const uint4 *>(files + a0));
-    unsigned prev = (r0 > 0) ? (unsigned)__ldg(files + a0 - 1) : 0u;
-    const unsigned after = (r0 + 16 < (int64_t)im.raw_len) ? (unsigned)__ldg(files + a0 + 16) : 0xFFu;
-    const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const unsigned b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-        unsigned next = i < 15 ? ((w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFFu) : after;
-        const int64_t r = r0 + i;
-        if (r + 1 >= (int64_t)im.raw_len) next = 0xFFu;                    // what follows the scan is the EOI's FF
-        const bool in = r >= 0 && r < (int64_t)im.raw_len;
-        const unsigned pv = r == 0 ? 0u : prev;
-        if (in && scan_keep(pv, b, next)) keep |= 1u << i;
-        if (in && scan_is_rst(pv, b)) rst |= 1u << i;
-        prev = b;
-    }
+    const bool live = r0 < (int64_t)im.raw_len && r0 + 16 > 0;
+    bytes = live ? __ldg(reinterpret_cast<const uint4 *>(files + a0)) : make_uint4(0, 0, 0, 0);
+    // neighbours' edge bytes: from the adjacent lanes, from memory at the warp's edges
+    const int lane = threadIdx.x & 31;
+    uint32_t prevw = __shfl_up_sync(0xFFFFFFFFu, bytes.w, 1), nextw = __shfl_down_sync(0xFFFFFFFFu, bytes.x, 1);
+    if (lane == 0) prevw = (live && a0 > 0) ? ((uint32_t)__ldg(files + a0 - 1) << 24) : 0u;
+    if (lane == 31) nextw = live ? (uint32_t)__ldg(files + a0 + 16) : 0u;
+    const uint32_t w[6] = {prevw, bytes.x, bytes.y, bytes.z, bytes.w, nextw};
+    classify_words(w, keep, rst);
+    // bytes outside the scan do not count
+    const int64_t lo64 = -r0, hi64 = (int64_t)im.raw_len - r0;
+    const uint32_t lo = lo64 <= 0 ? 0u : (lo64 >= 16 ? 16u : (uint32_t)lo64);
+    const uint32_t hi = hi64 <= 0 ? 0u : (hi64 >= 16 ? 16u : (uint32_t)hi64);
+    const uint32_t valid = live ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+    keep &= valid; rst &= valid;
 }
 
 __global__ void __launch_bounds__(kUnstuffThreads)
@@ -166,11 +165,15 @@ k_unstuff_scan(const HuffImg *__restrict__ imgs, int nimg, uint2 *__restrict__ t
     }
 }
 
+// The tile's surviving bytes are compacted in shared memory and leave as coalesced 32-bit words, byte-swapped so
+// that stream byte o lands at address o ^ 3 (huff_core.h "bit reader").  A tile's output starts at an arbitrary
+// byte, so the (at most two) words it shares with its neighbours are written bytewise.
 __global__ void __launch_bounds__(kUnstuffThreads)
 k_unstuff_write(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img,
                 const uint2 *__restrict__ tile_ex, const HuffImgState *__restrict__ st, uint32_t *__restrict__ clean,
                 uint32_t *__restrict__ seg_off) {
     __shared__ uint32_t s_tmp[2 * (kUnstuffThreads / 32) + 2];
+    __shared__ __align__(16) uint8_t s_out[kUnstuffTile + 16];
     const uint32_t img = tile_img[blockIdx.x];
     const HuffImg &im = imgs[img];
     uint32_t keep, rst;
@@ -178,16 +181,40 @@ k_unstuff_write(const uint8_t *__restrict__ files, const HuffImg *__restrict__ i
     classify16(files, im, blockIdx.x - im.tile_base, keep, rst, bytes);
     uint32_t ea, eb, ta, tb;
     block_excl_scan2<kUnstuffThreads>(__popc(keep), __popc(rst), ea, eb, ta, tb, s_tmp);
-    if ((keep | rst) == 0) return;
     const uint2 base = tile_ex[blockIdx.x];
-    uint32_t o = base.x + ea, sidx = base.y + eb + 1;
-    const uint32_t nseg = st[img].nseg;
-    uint8_t *cb = reinterpret_cast<uint8_t *>(clean + im.clean_word0);
-    const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
+    const uint32_t mis = base.x & 3u;                 // s_out[mis + k] = k-th surviving byte of the tile
+    {
+        const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
+        uint32_t pos = mis + ea;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        if (keep & (1u << i)) { cb[o ^ 3u] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8)); o++; }
-        if (rst & (1u << i)) { if (sidx < nseg) seg_off[im.seg_base + sidx] = o; sidx++; }
+        for (int i = 0; i < 16; i++) {
+            if (keep & (1u << i)) s_out[pos] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
+            pos += (keep >> i) & 1u;
+        }
+    }
+    if (rst) {                                        // restart markers: where the next segment starts (rare)
+        const uint32_t nseg = st[img].nseg;
+        uint32_t sidx = base.y + eb + 1;
+        for (uint32_t m = rst; m; m &= m - 1) {
+            const int i = __ffs(m) - 1;
+            if (sidx < nseg) seg_off[im.seg_base + sidx] = base.x + ea + __popc(keep & ((1u << i) - 1u));
+            sidx++;
+        }
+    }
+    __syncthreads();
+    if (ta == 0) return;
+    uint32_t *dstw = clean + im.clean_word0 + (base.x >> 2);
+    const uint32_t end = mis + ta;                    // staged bytes [mis, end)
+    const uint32_t nwords = (end + 3) >> 2;
+    for (uint32_t k = threadIdx.x; k < nwords; k += kUnstuffThreads) {
+        const uint32_t v = *reinterpret_cast<const uint32_t *>(s_out + 4 * k);
+        if (4 * k >= mis && 4 * k + 4 <= end) dstw[k] = __byte_perm(v, 0, 0x0123);
+        else {
+            uint8_t *db = reinterpret_cast<uint8_t *>(dstw + k);
+#pragma unroll
+            for (uint32_t b = 0; b < 4; b++)
+                if (4 * k + b >= mis && 4 * k + b < end) db[b ^ 3u] = (uint8_t)(v >> (8 * b));
+        }
     }
 }
 

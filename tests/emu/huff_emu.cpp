@@ -57,10 +57,22 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
     std::vector<uint8_t> clean(((rl + 3) / 4 + 4) * 4, 0);
     std::vector<uint32_t> seg_off(1, 0);
     size_t o = 0;
-    for (size_t i = 0; i < rl; i++) {
-        const unsigned prev = i ? raw[i - 1] : 0u, b = raw[i], next = i + 1 < rl ? raw[i + 1] : 0xFFu;
-        if (scan_keep(prev, b, next)) { clean[o ^ 3] = (uint8_t)b; o++; }
-        else if (scan_is_rst(prev, b) && seg_off.size() < nseg_expected) seg_off.push_back((uint32_t)o);
+    // the kernels' chunking: 16 bytes per thread, classified four bytes per word (classify_words); the byte before the
+    // scan is the SOS header's last byte and the byte after it the FF of the closing marker, as in the file
+    for (size_t i0 = 0; i0 < rl; i0 += 16) {
+        uint32_t w[6] = {0, 0, 0, 0, 0, 0};
+        auto at = [&](long long i) -> uint32_t { const long long a = (long long)d.scan_off + i; return (a >= 0 && (size_t)a < len) ? file[a] : 0u; };
+        w[0] = at((long long)i0 - 1) << 24;
+        for (int b = 0; b < 16; b++) w[1 + b / 4] |= at((long long)i0 + b) << (8 * (b & 3));
+        w[5] = at((long long)i0 + 16);
+        uint32_t keep, rst;
+        classify_words(w, keep, rst);
+        for (int b = 0; b < 16 && i0 + b < rl; b++) {
+            const unsigned prev = i0 + b ? raw[i0 + b - 1] : 0u, bb = raw[i0 + b], next = i0 + b + 1 < rl ? raw[i0 + b + 1] : 0xFFu;
+            if (((keep >> b) & 1u) != (scan_keep(prev, bb, next) ? 1u : 0u) || ((rst >> b) & 1u) != (scan_is_rst(prev, bb) ? 1u : 0u)) return -200;
+            if ((keep >> b) & 1u) { clean[o ^ 3] = (uint8_t)bb; o++; }
+            else if (((rst >> b) & 1u) && seg_off.size() < nseg_expected) seg_off.push_back((uint32_t)o);
+        }
     }
     const uint32_t clean_len = (uint32_t)o;
     const uint32_t nseg = (uint32_t)seg_off.size();

@@ -99,6 +99,23 @@ def test_stage_entropy_subsequence_sizes(dec, bits, golden, golden_dir):
         dec.set_option("subseq_bits", 1024)
 
 
+@pytest.mark.parametrize("rounds,bits", [(1, 128), (2, 256), (7, 128), (12, 1024)])
+def test_stage_entropy_few_blind_rounds(dec, rounds, bits, golden, golden_dir):
+    """Too few blind fix-up rounds for the chain to settle: the host's convergence check must add rounds (which walk
+    along unsettled chains without a limit) until the result is the fixed point - same coefficients."""
+    dec.set_option("sync_rounds", rounds)
+    dec.set_option("subseq_bits", bits)
+    try:
+        for name in ("ilsvrc_444", "p420_320x240", "p420_q100_64x64", "gray_ri3_64x48", "enc_420_100x60_ri4"):
+            data = _load(golden, golden_dir, name)
+            coef, status = dec.stage_entropy(data)
+            assert status == 0
+            assert np.array_equal(coef, ol.Restated(data, 0).coef_zz), (name, rounds, bits)
+    finally:
+        dec.set_option("sync_rounds", 0)
+        dec.set_option("subseq_bits", 1024)
+
+
 # ------------------------------------------------------------------ full path against the reference's BMPs
 
 @pytest.mark.parametrize("name", _names())
