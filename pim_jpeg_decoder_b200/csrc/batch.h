@@ -47,7 +47,7 @@ inline int batch_kernels_init(bj_ctx *c) {
 struct bj_batch {
     bj_ctx *ctx = nullptr;
     int n = 0, format = 0;
-    uint32_t sub_bytes = 128;
+    uint32_t slices_log2 = 2;            // slices (write pass) per sub-sequence (synchronisation pass), as a power of two
     int rounds = 3;
 
     std::vector<bj_image_desc> desc;
@@ -60,13 +60,13 @@ struct bj_batch {
     bj::PinBuf h_files, h_meta, h_res;
     size_t files_bytes = 0, meta_bytes = 0;
     // offsets inside the descriptor blob
-    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_utile = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0;
+    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_utile = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0, o_lutacs = 0;
     uint32_t n_idct_tiles = 0, n_blk = 0, n_utile = 0, n_dcc = 0, n_seg_entries = 0, n_sub_slots = 0, lut_smem = 0;
     size_t clean_words = 0, coef_units = 0, out_bytes = 0;
     uint64_t pixels = 0, scan_bytes = 0;
 
     // device
-    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_tilecnt, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
+    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_tilecnt, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels
     cudaStream_t last_stream = nullptr;
     bool uploaded = false, decoded = false, synced = false;
@@ -80,7 +80,7 @@ struct bj_batch {
     template <class T> T *hmeta(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(h_meta.p) + off); }
 
     void release() {
-        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_tilecnt, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
+        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_tilecnt, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
         h_files.release(); h_meta.release(); h_res.release();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     }
@@ -94,7 +94,8 @@ constexpr int kMaxRounds = 64;
 inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format) {
     if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
     b->ctx = c; b->n = n; b->format = format;
-    b->sub_bytes = c->subseq_bits ? (uint32_t)c->subseq_bits / 8 : 128u;
+    // slices per sub-sequence: option "slices" (1, 2, 4, 8), default 4
+    b->slices_log2 = c->slices == 1 ? 0u : c->slices == 2 ? 1u : c->slices == 8 ? 3u : 2u;
     b->uploaded = b->decoded = b->synced = false;
     b->desc.resize(n); b->parse_status.assign(n, BJ_OK);
     b->out_off.assign(n, 0); b->out_size.assign(n, 0); b->file_off.assign(n, 0);
@@ -108,12 +109,35 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
             b->parse_status[i] = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &b->desc[i]) : BJ_ERR_INVALID_JPEG;
     });
 
+    // ---- sub-sequence length of the synchronisation pass.  Explicit (option "subseq_bits"): the same for every
+    // image.  Automatic: nominally 4096 bits - a stream synchronises within about a thousand, so nearly every guess
+    // settles inside its own sub-sequence - but shorter when the whole batch would not fill the GPU with threads,
+    // and then adjusted per image so that its sub-sequences fill whole CTAs.
+    const uint32_t R = 1u << b->slices_log2;
+    uint32_t fixed_sub = c->subseq_bits ? (uint32_t)c->subseq_bits / 8u : 0u;
+    if (fixed_sub) while (b->slices_log2 && fixed_sub % (1u << b->slices_log2)) b->slices_log2--;
+    uint32_t nominal_sub = 512;
+    if (!fixed_sub) {
+        uint64_t total = 0;
+        for (int i = 0; i < n; i++) if (b->parse_status[i] == BJ_OK) total += b->desc[i].scan_len;
+        const uint64_t want_threads = (uint64_t)c->sm_count * 3072u;
+        nominal_sub = (uint32_t)std::min<uint64_t>(512u, std::max<uint64_t>(128u, total / want_threads));
+    }
+    auto sub_bytes_of = [&](uint32_t raw_len) -> uint32_t {
+        if (fixed_sub) return fixed_sub;
+        const uint32_t per_cta = nominal_sub * kHuffThreads;
+        const uint32_t m = std::max(1u, (raw_len + per_cta / 2) / per_cta);                  // CTAs for this image
+        uint32_t len = (raw_len + m * kHuffThreads - 1) / (m * kHuffThreads);
+        len = std::max(len, 64u);
+        return (len + 4 * R - 1) / (4 * R) * (4 * R);
+    };
+
     // ---- layout (serial: prefix sums over the batch)
     std::vector<HuffImg> himg(n);
     std::vector<ImgDev> idev(n);
     std::vector<TileDev> tiles;
     std::vector<uint32_t> blk_img, utile_img, dcc_img;
-    std::vector<uint32_t> luts_dc, luts_ac;
+    std::vector<uint32_t> luts_dc, luts_ac, luts_acs;     // acs: the synchronisation pass' grouped AC tables
     std::map<std::string, int> lut_index[2];
     std::vector<uint16_t> lut_n4[2];                // per pooled table: used size in 16-byte chunks
     size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
@@ -163,6 +187,10 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
                         pool.resize(pool.size() + cap);
                         const int used = build_lut(off, sym, ac != 0, &pool[(size_t)idx * cap]);
                         if (used < 0) rc = BJ_ERR_UNSUPPORTED;
+                        if (ac) {
+                            luts_acs.resize(pool.size());
+                            build_lut_sync(&pool[(size_t)idx * cap], std::max(used, 0), &luts_acs[(size_t)idx * cap]);
+                        }
                         lut_n4[ac].push_back((uint16_t)((std::max(used, 0) + 3) / 4));
                         lut_index[ac][key] = idx;
                         if (idx > 65535) rc = BJ_ERR_UNSUPPORTED;
@@ -205,7 +233,8 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         hi.nseg = hi.ri ? (g.nmcu + hi.ri - 1) / hi.ri : 1u;
         hi.bpm = (uint8_t)g.bpm; hi.ny = (uint8_t)(d.hs * d.vs); hi.ncomp = d.ncomp;
         hi.ndu = g.ndu;
-        const uint32_t sub_cap = (uint32_t)((hi.raw_len + b->sub_bytes - 1) / b->sub_bytes) + hi.nseg;
+        hi.sub_bytes = sub_bytes_of(hi.raw_len);
+        const uint32_t sub_cap = (uint32_t)((hi.raw_len + hi.sub_bytes - 1) / hi.sub_bytes) + hi.nseg;
         hi.nblk = (sub_cap + kHuffThreads - 1) / kHuffThreads;
         for (uint32_t k = 0; k < hi.nblk; k++) blk_img.push_back((uint32_t)i);
         nblk += hi.nblk;
@@ -239,6 +268,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     b->o_dcc = o;   o = align_up(o + dcc_img.size() * 4, 256);
     b->o_lutdc = o; o = align_up(o + luts_dc.size() * 4, 256);
     b->o_lutac = o; o = align_up(o + luts_ac.size() * 4, 256);
+    b->o_lutacs = o; o = align_up(o + luts_acs.size() * 4, 256);
     b->meta_bytes = o;
     if (b->h_meta.reserve(o) || b->h_files.reserve(b->files_bytes) ||
         b->h_res.reserve(align_up((size_t)n * sizeof(HuffImgState), 64) + kMaxRounds * 4 + 64)) return BJ_ERR_NOMEM;
@@ -249,6 +279,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     if (!dcc_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_dcc), dcc_img.data(), dcc_img.size() * 4);
     if (!luts_dc.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutdc), luts_dc.data(), luts_dc.size() * 4);
     if (!luts_ac.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutac), luts_ac.data(), luts_ac.size() * 4);
+    if (!luts_acs.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutacs), luts_acs.data(), luts_acs.size() * 4);
     // ---- pack the file bytes (per image, independent: worker pool)
     uint8_t *hf = reinterpret_cast<uint8_t *>(b->h_files.p);
     c->host_pool.parallel_for(n, 16, [&](int i0, int i1) {
@@ -263,6 +294,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         b->d_seg.reserve((size_t)(seg_entries + 2) * 4 * 2) || b->d_subseg.reserve((size_t)b->n_sub_slots * 4 + 16) ||
         b->d_stin.reserve((size_t)b->n_sub_slots * 8 + 16) || b->d_stout.reserve((size_t)b->n_sub_slots * 8 + 16) ||
         b->d_tot.reserve((size_t)b->n_sub_slots * 4 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 8 + 16) ||
+        b->d_slice.reserve(((size_t)b->n_sub_slots << b->slices_log2) * 16 + 16) ||
         b->d_dc.reserve(coef_units * 2 + 64) || b->d_dcagg.reserve((size_t)b->n_dcc * sizeof(DcAgg) + 16) ||
         b->d_tilecnt.reserve((size_t)b->n_utile * 8 + 16) || b->d_blkagg.reserve((size_t)nblk * sizeof(BlkAgg) + 16) ||
         b->d_state.reserve((size_t)n * sizeof(HuffImgState) + 16) || b->d_flags.reserve(kMaxRounds * 4) ||
@@ -290,7 +322,8 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     const uint32_t *blk_img = b->dmeta<uint32_t>(b->o_blk);
     const uint32_t *utile_img = b->dmeta<uint32_t>(b->o_utile);
     const uint32_t *dcc_img = b->dmeta<uint32_t>(b->o_dcc);
-    const uint32_t *luts_dc = b->dmeta<uint32_t>(b->o_lutdc), *luts_ac = b->dmeta<uint32_t>(b->o_lutac);
+    const uint32_t *luts_dc = b->dmeta<uint32_t>(b->o_lutdc), *luts_ac = b->dmeta<uint32_t>(b->o_lutac), *luts_acs = b->dmeta<uint32_t>(b->o_lutacs);
+    uint4 *slices = (uint4 *)b->d_slice.p;
     int16_t *dcp = (int16_t *)b->d_dc.p;
     DcAgg *dcagg = (DcAgg *)b->d_dcagg.p;
     HuffImgState *st = (HuffImgState *)b->d_state.p;
@@ -309,18 +342,18 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
         if (b->n_utile) k_unstuff_count<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_cnt);
         k_unstuff_scan<<<(n + 3) / 4, 128, 0, s>>>(himg, n, tile_cnt, st, seg_off);
         if (b->n_utile) k_unstuff_write<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_cnt, st, clean, seg_off);
-        k_subseq_table<<<n, 256, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg, b->sub_bytes);
+        k_subseq_table<<<n, 256, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg);
         b->launches = 2 + (b->n_utile ? 2 : 0);
         b->sync_rounds = 0;
         cudaEventRecord(b->ev[1], s);
     }
     if (b->n_blk) {
         for (int r = r0; r < r1; r++) {
-            k_huff_sync<<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_ac, st_in, st_out, tot, pre, agg, flags, r, b->sub_bytes);
+            k_huff_sync<<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, agg, flags, r, b->slices_log2);
             b->launches++; b->sync_rounds++;
         }
         cudaEventRecord(b->ev[2], s);
-        k_huff_write<<<b->n_blk, kHuffThreads, kSmemHuffStage + lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_ac, st_in, pre, agg, (int16_t *)b->d_coef.p, dcp, b->sub_bytes);
+        k_huff_write<<<b->n_blk << b->slices_log2, kHuffThreads, kSmemHuffStage + lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_ac, slices, pre, agg, (int16_t *)b->d_coef.p, dcp, b->slices_log2);
         b->launches++;
     }
     {

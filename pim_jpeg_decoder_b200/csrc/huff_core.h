@@ -112,15 +112,61 @@ inline int build_lut(const uint8_t offsets[17], const uint8_t symbols[162], bool
     return next;
 }
 
-// Where the staged tables live.  On the device: a 32-bit shared-memory address (loads are ld.shared with no
-// generic-address arithmetic in the decode loop); on the host: a pointer.  Table positions are BYTE offsets.
+// ------------------------------------------------------------------------------------------------ AC tables of the
+// synchronisation pass.  That pass tracks only the decoder STATE (no values), so one lookup may take several
+// symbols at once: every AC symbol (code + magnitude bits) that lies completely inside the kRootBits-bit window.
+//   bits 15..0   the step for ALL of them:  consumed bits << 8 | zig-zag advance   (added to the packed state S)
+//   bits 30..16  the same for the FIRST symbol alone
+//   bit  31      link (root only), as above; second-level entries describe one symbol (both halves equal)
+// End-of-block advances by 128 here (bit 7), a refused symbol is a plain step (the speculative decode never
+// stops), and a group never contains an end-of-block and never advances by more than 63.  After a step from
+// index z <= 63:   z' <= 63 the unit goes on;  z' == 64 its last coefficient was just read;  z' >= 128 end-of-block;
+// 65..127 means a symbol INSIDE the group ended the unit (or the single symbol is an over-long run): the decoder
+// takes the first symbol alone instead.
+constexpr uint32_t kSyncEob = 128u;
+inline uint32_t sync_half(int len, unsigned sym) {
+    const unsigned run = sym >> 4, size = sym & 15u;
+    const bool eob = sym == 0, bad = size > 10;
+    return (eob ? kSyncEob : run + 1u) | ((uint32_t)(len + (bad ? 0u : size)) << 8);
+}
+// `write_lut` = the table build_lut made for the same Huffman table (same root/second-level layout).
+inline void build_lut_sync(const uint32_t *write_lut, int used, uint32_t *lut) {
+    const int R = kRootBits;
+    auto half_of = [](uint32_t e) -> uint32_t {          // write-format leaf -> sync half
+        const uint32_t adv = (e & kLutEob) ? kSyncEob : (e & 0xFFu);
+        return adv | (e & 0xFF00u);
+    };
+    for (int i = 0; i < kLutCapAC; i++) lut[i] = 0;
+    for (int i = 1 << R; i < used; i++) { const uint32_t h = half_of(write_lut[i]); lut[i] = h | (h << 16); }
+    for (uint32_t w = 0; w < (1u << R); w++) {
+        const uint32_t e = write_lut[w];
+        if (e & kLutLink) { lut[w] = e; continue; }
+        const uint32_t first = half_of(e);
+        uint32_t bits = (first >> 8) & 0xFFu, adv = first & 0xFFu;
+        // more symbols from the rest of the window, while they fit completely
+        if (!(e & (kLutBad | kLutEob)) && bits <= (uint32_t)R) {
+            for (;;) {
+                const uint32_t rem = (uint32_t)R - bits;
+                if (rem == 0) break;
+                const uint32_t idx = (w << bits) & ((1u << R) - 1u);       // remaining bits, zero-padded
+                const uint32_t n = write_lut[idx];
+                if (n & (kLutLink | kLutBad | kLutEob)) break;
+                const uint32_t nb = (n >> 8) & 0xFFu, na = n & 0xFFu;
+                if (nb > rem || adv + na > 63u) break;
+                bits += nb; adv += na;
+            }
+        }
+        lut[w] = (adv | (bits << 8)) | (first << 16);
+    }
+}
+
+// Where the staged tables live.  Table positions are BYTE addresses: on the device absolute shared-memory
+// addresses (loads are ld.shared with no address arithmetic beyond the index), on the host offsets from `base`.
 struct LutMem {
 #ifdef __CUDA_ARCH__
-    uint32_t base;
-    __device__ __forceinline__ void attach(const uint32_t *smem) { base = (uint32_t)__cvta_generic_to_shared(smem); }
-    __device__ __forceinline__ uint32_t ld(uint32_t byte_off) const {
+    __device__ __forceinline__ uint32_t ld(uint32_t addr) const {
         uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
         return v;
     }
 #else
@@ -130,10 +176,34 @@ struct LutMem {
 #endif
 };
 
-// win = the next 32 bits of the stream, MSB first; tab = byte offset of the table.
+// Codes longer than the root (rare: ~0.4 % of symbols at q = 90).  Kept out of line on the device so that the hot
+// loops carry a branch to it instead of its predicated body.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+uint32_t lut_second(uint32_t tab, uint32_t e, uint32_t win
+#ifndef __CUDA_ARCH__
+                    , const LutMem &m
+#endif
+) {
+#ifdef __CUDA_ARCH__
+    const LutMem m{};
+#endif
+    return m.ld(tab + (e & 0xFFFFu) + (((win << kRootBits) >> (32u - ((e >> 16) & 15u))) << 2));
+}
+
+// win = the next 32 bits of the stream, MSB first; tab = position of the table.
 BJ_HD uint32_t lut_lookup(const LutMem &m, uint32_t tab, uint32_t win) {
     uint32_t e = m.ld(tab + ((win >> (32 - kRootBits)) << 2));
-    if (__builtin_expect((int32_t)e < 0, 0)) e = m.ld(tab + (e & 0xFFFFu) + (((win << kRootBits) >> (32u - ((e >> 16) & 15u))) << 2));
+    if (__builtin_expect((int32_t)e < 0, 0)) {
+#ifdef __CUDA_ARCH__
+        e = lut_second(tab, e, win);
+#else
+        e = lut_second(tab, e, win, m);
+#endif
+    }
     return e;
 }
 
@@ -195,21 +265,32 @@ struct BitStream {
     const uint32_t *w;            // -> word holding the current position
     uint32_t cur, nxt, nx2;       // that word and the two after it (the load runs one word ahead of its use)
     uint32_t word_end;            // S value of the first bit after `cur`
-    BJ_HD static uint32_t ld(const uint32_t *a) {
-#ifdef __CUDA_ARCH__
-        return __ldg(a);
-#else
-        return *a;
-#endif
-    }
     BJ_HD void open(const uint32_t *words, uint32_t p) {
         w = words + (p >> 5);
-        cur = ld(w); nxt = ld(w + 1); nx2 = ld(w + 2);
+#ifdef __CUDA_ARCH__
+        cur = __ldg(w); nxt = __ldg(w + 1); nx2 = __ldg(w + 2);
+#else
+        cur = w[0]; nxt = w[1]; nx2 = w[2];
+#endif
         word_end = kWordS;
     }
-    BJ_HD void advance() { cur = nxt; nxt = nx2; w++; nx2 = ld(w + 2); word_end += kWordS; }
+    // the next 32 bits at S, moving on to the next word first if S has left the current one
     BJ_HD uint32_t window(uint32_t S) {
-        if (S >= word_end) advance();
+#ifdef __CUDA_ARCH__
+        // predicated, no branch; the load writes nx2 directly (a select on the loaded value would stall on it)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ge.u32 p, %5, %4;\n\t"
+            "@p mov.b32 %0, %1;\n\t"
+            "@p mov.b32 %1, %2;\n\t"
+            "@p add.u64 %3, %3, 4;\n\t"
+            "@p add.u32 %4, %4, 8192;\n\t"
+            "@p ld.global.nc.u32 %2, [%3+8];\n\t}"
+            : "+r"(cur), "+r"(nxt), "+r"(nx2), "+l"(w), "+r"(word_end)
+            : "r"(S));
+#else
+        if (S >= word_end) { cur = nxt; nxt = nx2; w++; nx2 = w[2]; word_end += kWordS; }
+#endif
         return funnel_l(cur, nxt, S >> 8);
     }
 };
@@ -223,14 +304,15 @@ struct HuffState {
 };
 BJ_HD bool same_state(const HuffState &a, const HuffState &b) { return a.p == b.p && a.cz == b.cz; }
 
-// Per image: geometry of an MCU and where each component's tables sit.
+// Per image: geometry of an MCU and where each component's tables sit (LutMem positions).
 struct HuffGeom {
     uint32_t bpm;           // data units per MCU
     uint32_t ny;            // luma units per MCU (hs * vs); unit c belongs to component c < ny ? 0 : c - ny + 1
-    uint32_t tab[3];        // per component: DC table byte offset | AC table byte offset << 16 (from the staged base)
+    uint32_t dc[3], ac[3];  // per component: DC / AC table
 };
 BJ_HD uint32_t comp_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? 0u : c - g.ny + 1u; }
-BJ_HD uint32_t tabs_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.tab[0] : (c == g.ny ? g.tab[1] : g.tab[2]); }
+BJ_HD uint32_t dc_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.dc[0] : (c == g.ny ? g.dc[1] : g.dc[2]); }
+BJ_HD uint32_t ac_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.ac[0] : (c == g.ny ? g.ac[1] : g.ac[2]); }
 
 // Magnitude extension of the `size` bits that follow a `len`-bit code in the window
 // (src/jpeg_scanner.cpp:480-482 / :513-516: first bit 0 => negative).  size 0 gives 0.
@@ -248,44 +330,58 @@ BJ_HD int32_t extend_entry(uint32_t win, uint32_t e) {
 }
 
 // ------------------------------------------------------------------------------------------------ pass 1: synchronise
-// Decode from `st` until the position reaches end_bit (first symbol boundary at or after it).  Only the decoder
+// Decode from `st` until the position reaches end_bit (first step boundary at or after it).  Only the decoder
 // state is tracked - no values - plus the number of data units whose DC symbol starts inside the span (for the
 // prefix sum that tells every sub-sequence which unit it starts in).  Errors do not stop a speculative decode
 // (a wrong guess must not poison its successors): a refused symbol consumes its code bits (at least one) and the
 // unit simply continues; an over-long run ends the unit.  With the true entry state the result is the true exit
 // state up to the first real error, which the write pass detects and reports.
-// The inner loop runs to the end of the current stream word or of the span, whichever comes first, so a step is:
-// funnel shift, table load, add, unit-complete test, limit test.
-BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
-                            uint32_t *units_started) {
-    *units_started = 0;
-    if (st.p >= end_bit) return st;
+//
+// Slices.  The write pass works on finer pieces than this pass: a sub-sequence [start_bit, end_bit) is cut into
+// slices of slice_bits, and whenever the decode crosses the start of slice k >= 1 it reports the state there
+// (first step boundary at or after the slice's first bit) and the units started so far:  rec(k, p, cz, units).
+// Every slice of the sub-sequence is reported exactly once per call, in order.  The AC tables are the grouped ones
+// (build_lut_sync), so a "step" may be several symbols; they never span a unit boundary, so the units counted
+// between two reported states are exactly the units whose DC symbol starts between them.
+template <class Rec>
+BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t start_bit,
+                            uint32_t end_bit, uint32_t slice_bits, Rec &rec, uint32_t *units_started) {
     const uint32_t origin = st.p & ~31u;
     uint32_t c = st.cz >> 8;
     uint32_t S = ((st.p - origin) << 8) | (st.cz & 0xFFu);
-    const uint32_t endS = (end_bit - origin) << 8;
+    const uint32_t endS = end_bit > origin ? (end_bit - origin) << 8 : 0u;
     const uint32_t entered_mid = (S & 0xFFu) ? 1u : 0u;
+    const uint32_t nslices = end_bit > start_bit ? (end_bit - start_bit + slice_bits - 1u) / slice_bits : 1u;
+    uint32_t k = 1;
+    uint32_t ckS = start_bit + slice_bits > origin ? (start_bit + slice_bits - origin) << 8 : 0u;   // slice k starts here
+    uint32_t limS = (k < nslices && ckS < endS) ? ckS : endS;
     uint32_t ends = 0;
-    uint32_t tabs = tabs_of(g, c);
-    uint32_t tab = entered_mid ? (tabs >> 16) : (tabs & 0xFFFFu);
+    uint32_t ac = ac_of(g, c);
+    uint32_t tab = entered_mid ? ac : dc_of(g, c);
     BitStream bs;
     bs.open(words, st.p);
     for (;;) {
-        const uint32_t limit = endS < bs.word_end ? endS : bs.word_end;
-        while (S < limit) {
-            const uint32_t e = lut_lookup(luts, tab, funnel_l(bs.cur, bs.nxt, S >> 8));
-            S += e & 0xFFFFu;
-            tab = tabs >> 16;
-            if (S & 0x40u) {                                              // zig-zag index >= 64: unit complete
-                S &= ~0xFFu;
-                ends++;
-                c = (c + 1u == g.bpm) ? 0u : c + 1u;
-                tabs = tabs_of(g, c);
-                tab = tabs & 0xFFFFu;
+        if (S >= limS) {                                                  // once per slice
+            while (k < nslices && S >= ckS) {
+                rec(k, origin + (S >> 8), (c << 8) | (S & 0xFFu), ends + ((S & 0xFFu) ? 1u : 0u) - entered_mid);
+                k++;
+                ckS += slice_bits << 8;
             }
+            if (S >= endS) break;
+            limS = (k < nslices && ckS < endS) ? ckS : endS;
         }
-        if (S >= endS) break;
-        bs.advance();
+        const uint32_t e = lut_lookup(luts, tab, bs.window(S));
+        uint32_t Sn = S + (e & 0xFFFFu);
+        // 65..127: a symbol inside the group ended the unit (or an over-long run): the first symbol alone
+        if (__builtin_expect(((Sn & 0xFFu) - 65u) < 63u, 0)) Sn = S + ((e >> 16) & 0x7FFFu);
+        // zig-zag index >= 64: unit complete (also: over-long run).  Branch-free: most iterations of a warp see one.
+        const bool fin = (Sn & 0xC0u) != 0u;
+        const uint32_t c1 = (c + 1u == g.bpm) ? 0u : c + 1u;
+        c = fin ? c1 : c;
+        ends += fin ? 1u : 0u;
+        S = fin ? (Sn & ~0xFFu) : Sn;
+        ac = fin ? ac_of(g, c1) : ac;
+        tab = fin ? dc_of(g, c1) : ac;
     }
     // started = ended + (one still open at the exit) - (the one that was already open at the entry)
     *units_started = ends + ((S & 0xFFu) ? 1u : 0u) - entered_mid;
@@ -295,99 +391,91 @@ BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const Huf
 }
 
 // ------------------------------------------------------------------------------------------------ pass 2: write
-// Ownership rule: a data unit belongs to the sub-sequence in which its DC symbol starts; the owner decodes the
-// whole unit (running past its own end if necessary) and stores all 64 coefficients at once, so every unit is
-// written exactly once, by one thread, with no zero-fill pass.  A sub-sequence entered mid-unit first skips to
-// the end of that unit without storing anything.  DC DIFFERENCES go to a separate compact plane (2 bytes per
-// unit); the prediction sums over it are a separate, tiny scan (K1c) and slot 0 of every unit stays zero.
+// Ownership rule: a data unit belongs to the slice in which its DC symbol starts; the owner decodes the whole
+// unit (running past its own end if necessary) and stores all 64 coefficients at once, so every unit is written
+// exactly once, by one thread, with no zero-fill pass.  A slice entered mid-unit first skips to the end of that
+// unit without storing anything.  DC DIFFERENCES go to a separate compact plane (2 bytes per unit); the
+// prediction sums over it are a separate, tiny scan (K1c) and slot 0 of every unit stays zero.
 //
-// Sink concept:  void put(uint32_t zz, int16_t v);  void dc(uint32_t du, int16_t diff);  void flush(uint32_t du);
-// (flush also clears the staged unit)
-struct WriteResult {
-    uint32_t first_zero;    // first unit index that must read as zero because the reference stopped; UINT32_MAX if none
-};
+// The decode is a cursor that takes ONE symbol per step(), DC and AC alike, so the lanes of a warp stay together;
+// a step says when a unit is complete and the caller stores it (the kernel does that warp-cooperatively).
+// Sink concept:  void put(uint32_t zz, int16_t v)  - stage one non-zero AC coefficient of the current unit.
+constexpr uint32_t kEvDone = 2u;     // open(): nothing to do in this slice
 
-template <class Sink>
-BJ_HD WriteResult write_span(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
-                             uint32_t data_end_bit, uint32_t du, uint32_t du_end, bool last_of_segment, Sink &sink) {
-    WriteResult res;
-    res.first_zero = 0xFFFFFFFFu;
-    const uint32_t origin = st.p & ~31u;
-    uint32_t c = st.cz >> 8;
-    uint32_t S = ((st.p - origin) << 8) | (st.cz & 0xFFu);
-    const uint32_t endS = end_bit > origin ? (end_bit - origin) << 8 : 0u;
-    // S > dataS  <=>  the position is past the end of the segment's data: bits ran out inside the symbol
-    // (BitReader::read_bit returns -1 in the reference)
-    // (saturated: a position inside a span stays far below 2^24 bits from its origin)
-    const uint32_t data_rel = data_end_bit >= origin ? data_end_bit - origin : 0u;
-    const uint32_t dataS = ((data_rel < 0xFFFFFFu ? data_rel : 0xFFFFFFu) << 8) | 0xFFu;
-    uint32_t tabs = tabs_of(g, c);
+struct WriteCursor {
     BitStream bs;
-    bs.open(words, st.p);
-    bool stop = false;
-    if (S & 0xFFu) {                                      // entered inside a unit that belongs to a predecessor: skip it
-        for (;;) {
-            if (S >= endS) { stop = true; break; }
-            const uint32_t e = lut_lookup(luts, tabs >> 16, bs.window(S));
-            S += e & 0xFFFFu;
-            if (S & 0x40u) break;
-        }
-        if (!stop) {
+    uint32_t S, c, ac, tab, du;     // ac: AC table of the current unit; tab: table of the next symbol
+    uint32_t endS, dataS, du_end;
+    uint32_t first_zero;    // first unit index that must read as zero because the reference stopped; UINT32_MAX if none
+    int32_t dcv;            // DC difference of the unit being decoded (of the completed one right after its last step)
+
+    // Returns kEvDone if there is nothing to do.  Skips the unit a predecessor owns (no values).
+    BJ_HD uint32_t open(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
+                        uint32_t data_end_bit, uint32_t du0, uint32_t du_end_) {
+        first_zero = 0xFFFFFFFFu;
+        const uint32_t origin = st.p & ~31u;
+        c = st.cz >> 8;
+        S = ((st.p - origin) << 8) | (st.cz & 0xFFu);
+        endS = end_bit > origin ? (end_bit - origin) << 8 : 0u;
+        // S > dataS  <=>  the position is past the end of the segment's data: bits ran out inside the symbol
+        // (BitReader::read_bit returns -1 in the reference).  Saturated: positions stay far below 2^24 bits.
+        const uint32_t data_rel = data_end_bit >= origin ? data_end_bit - origin : 0u;
+        dataS = ((data_rel < 0xFFFFFFu ? data_rel : 0xFFFFFFu) << 8) | 0xFFu;
+        du = du0; du_end = du_end_;
+        dcv = 0;
+        ac = ac_of(g, c);
+        bs.open(words, st.p);
+        if (S & 0xFFu) {                                  // inside a unit that belongs to a predecessor: skip it
+            for (;;) {
+                if (S >= endS) return kEvDone;
+                const uint32_t e = lut_lookup(luts, ac, bs.window(S));
+                S += e & 0xFFFFu;
+                if (S & 0x40u) break;
+            }
             S &= ~0xFFu;
             c = (c + 1u == g.bpm) ? 0u : c + 1u;
-            tabs = tabs_of(g, c);
+            ac = ac_of(g, c);
         }
-    }
-    while (!stop) {
+        tab = dc_of(g, c);
         // a unit starts here: mine if it starts before my end and the segment still has units to give
-        if (S >= endS || du >= du_end) break;
-        {
-            const uint32_t win = bs.window(S);
-            const uint32_t e = lut_lookup(luts, tabs & 0xFFFFu, win);
-            const uint32_t Sn = S + (e & 0xFFFFu);
-            // a failed DC leaves the unit untouched (zero)
-            if ((e & kLutBad) || Sn > dataS) { res.first_zero = du; return res; }
-            sink.dc(du, (int16_t)extend_entry(win, e));                   // |diff| < 2^11
-            S = Sn;
+        return (S >= endS || du >= du_end) ? kEvDone : 0u;
+    }
+
+    // One symbol.  The reference's failure points: refused symbol, bits running out inside a symbol, run past the
+    // end of the unit ("i + run >= 64", src/jpeg_scanner.cpp:497-500).  A failed DC leaves the unit untouched
+    // (zero); a failed AC keeps what was stored before it.
+    // `unit` = unit du - 1 is complete (store the staged unit and its DC difference dcv, clear the stage);
+    // `done` = slice finished.
+    template <class Sink>
+    BJ_HD void step(const LutMem &luts, const HuffGeom &g, Sink &sink, bool &unit, bool &done) {
+        const uint32_t win = bs.window(S);
+        const uint32_t e = lut_lookup(luts, tab, win);
+        const uint32_t Sn = S + (e & 0xFFFFu);
+        const bool is_dc = (S & 0xFFu) == 0u;
+        if (__builtin_expect((e & kLutBad) || Sn > dataS, 0)) {
+            done = true;
+            first_zero = du;                                              // a failed DC: the unit stays zero
+            if (!is_dc) { first_zero = ++du; unit = true; }               // a failed AC: the unit keeps what it has
+            return;
         }
-        const uint32_t tab = tabs >> 16;
-        // AC symbols.  The reference's failure points: refused symbol, bits running out inside a symbol, run past
-        // the end of the unit ("i + run >= 64", src/jpeg_scanner.cpp:497-500).  A failed AC keeps what was stored
-        // before it.  The zig-zag index is >= 1 here, so an index above 64 means end-of-block or an over-long run.
-        bool open = true, failed = false;
-        while (open) {
-            while (S < bs.word_end) {
-                const uint32_t win = funnel_l(bs.cur, bs.nxt, S >> 8);
-                const uint32_t e = lut_lookup(luts, tab, win);
-                const uint32_t Sn = S + (e & 0xFFFFu);
-                if (__builtin_expect((e & kLutBad) || Sn > dataS, 0)) { failed = true; open = false; break; }
-                if (Sn & 0x40u) {                                         // index >= 64: the unit ends one way or another
-                    const uint32_t zn = Sn & 0xFFu;
-                    if (zn == 64u) {
-                        const int32_t v = extend_entry(win, e);
-                        if (v != 0) sink.put(63u, (int16_t)v);
-                    } else if (!(e & kLutEob)) failed = true;
-                    S = Sn;
-                    open = false;
-                    break;
-                }
-                const int32_t v = extend_entry(win, e);
-                if (v != 0) sink.put((Sn & 0xFFu) - 1u, (int16_t)v);    // size 0 (ZRL and friends) would store a literal 0: already there
-                S = Sn;
-            }
-            if (open) bs.advance();
-        }
-        sink.flush(du);
-        if (failed) { res.first_zero = du + 1; return res; }
+        const int32_t v = extend_entry(win, e);
+        const uint32_t zz = (Sn & 0xFFu) - 1u;            // index of the coefficient this symbol carries
+        dcv = is_dc ? v : dcv;                            // |diff| < 2^11
+        if (!is_dc && v != 0 && zz < 64u) sink.put(zz, (int16_t)v);   // size 0 (ZRL, EOB) stores nothing: zero is already there
+        tab = ac;
+        S = Sn;
+        if (!(Sn & 0x40u)) return;
+        // index >= 64: the unit ends one way or another
+        unit = true;
         du++;
+        if (__builtin_expect((Sn & 0xFFu) != 64u && !(e & kLutEob), 0)) { first_zero = du; done = true; return; }   // over-long run
         S &= ~0xFFu;
         c = (c + 1u == g.bpm) ? 0u : c + 1u;
-        tabs = tabs_of(g, c);
+        ac = ac_of(g, c);
+        tab = dc_of(g, c);
+        done = S >= endS || du >= du_end;
     }
-    // the last sub-sequence of a segment must have produced the segment's last unit
-    if (last_of_segment && du < du_end) res.first_zero = du;
-    return res;
-}
+};
 
 // ------------------------------------------------------------------------------------------------ K1c: DC prediction
 // Per MCU: turn the DC differences of its units (decode order: luma units, then Cb, then Cr) into predicted

@@ -5,10 +5,12 @@
 //                                                          restart-segment byte offsets
 //   k_subseq_table                                        (K0d) per image: split every segment into sub-sequences
 //   k_huff_sync                                           (K1b) speculative decode of every sub-sequence + fix-up
-//                                                          to the fixed point inside a CTA, block-level prefix sums
-//                                                          (unit counts and DC sums - K1c is folded in here)
-//   k_huff_write                                          (K1a) final decode from the synchronised entry states,
-//                                                          whole 128-byte units stored with 128-bit stores
+//                                                          to the fixed point inside a CTA (state only, several
+//                                                          symbols per table lookup), entry states of the finer
+//                                                          slices the write pass works on, block-level prefix sums
+//   k_huff_write                                          (K1a) final decode of every slice from its synchronised
+//                                                          entry state, one symbol per step for all lanes of a warp,
+//                                                          whole 128-byte units stored warp-cooperatively
 //   k_zero_tail                                                 units the reference never reached read as zero
 //
 // All arithmetic/semantics live in huff_core.h (shared with the CPU emulation used by the tests).
@@ -41,7 +43,7 @@ struct HuffImg {
     uint8_t dc_slot[3], ac_slot[3];  // per component: staged slot
     uint8_t pad_[2];
     uint16_t dc_n4[3], ac_n4[3];     // used size of each staged table in 16-byte chunks (tables are staged packed)
-    uint32_t pad2_;
+    uint32_t sub_bytes;      // length of this image's sub-sequences (synchronisation pass), a multiple of the slice count
 };
 
 // Per image, written by the kernels.
@@ -223,10 +225,11 @@ k_unstuff_write(const uint8_t *__restrict__ files, const HuffImg *__restrict__ i
 // max(1, ceil(len / sub_bytes)) sub-sequences; seg_sub0[s] = index of its first one, sub_seg[j] = owner segment.
 __global__ void __launch_bounds__(256)
 k_subseq_table(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ st, const uint32_t *__restrict__ seg_off,
-               uint32_t *__restrict__ seg_sub0, uint32_t *__restrict__ sub_seg, uint32_t sub_bytes) {
+               uint32_t *__restrict__ seg_sub0, uint32_t *__restrict__ sub_seg) {
     __shared__ uint32_t s_tmp[2 * 8 + 2];
     __shared__ uint32_t s_first[257];
     const HuffImg &im = imgs[blockIdx.x];
+    const uint32_t sub_bytes = im.sub_bytes;
     const uint32_t nseg = st[blockIdx.x].nseg;
     uint32_t carry = 0;
     for (uint32_t s0 = 0; s0 < nseg; s0 += 256) {
@@ -265,8 +268,9 @@ struct SubInfo {
 };
 
 __device__ __forceinline__ SubInfo sub_info(const HuffImg &im, const HuffImgState &is, uint32_t j, const uint32_t *__restrict__ seg_off,
-                                            const uint32_t *__restrict__ seg_sub0, const uint32_t *__restrict__ sub_seg, uint32_t sub_bytes) {
+                                            const uint32_t *__restrict__ seg_sub0, const uint32_t *__restrict__ sub_seg) {
     SubInfo u;
+    const uint32_t sub_bytes = im.sub_bytes;
     u.seg = is.nseg > 1 ? sub_seg[im.sub_base + j] : 0u;
     const uint32_t j0 = seg_sub0[im.seg_base + u.seg], j1 = seg_sub0[im.seg_base + u.seg + 1];
     u.k = j - j0;
@@ -306,12 +310,14 @@ __device__ __forceinline__ void stage_luts(const HuffImg &im, const uint32_t *__
         }
     }
     g.bpm = im.bpm; g.ny = im.ny;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_lut);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         const uint32_t ds = im.dc_slot[j], as = im.ac_slot[j];
-        g.tab[j] = (ds == 0 ? dc_off[0] : ds == 1 ? dc_off[1] : dc_off[2]) | (as == 0 ? ac_off[0] : as == 1 ? ac_off[1] : ac_off[2]) << 16;
+        g.dc[j] = sbase + (ds == 0 ? dc_off[0] : ds == 1 ? dc_off[1] : dc_off[2]);
+        g.ac[j] = sbase + (as == 0 ? ac_off[0] : as == 1 ? ac_off[1] : ac_off[2]);
     }
-    luts.attach(s_lut);
+    (void)luts;
 }
 
 __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (lo & 0xFFFFu) | (hi << 16); }
@@ -324,17 +330,24 @@ __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (l
 // round r>0: the first sub-sequence of the CTA takes the exit state of the previous CTA's last one; if that
 //          differs from what it used, the CTA re-converges.  flags[r] counts CTAs that changed in round r; the
 //          host launches rounds until a round reports 0.
+// Every decode also (re)writes the entry states of the sub-sequence's slices (slot 0 = the sub-sequence's own entry
+// state, written at the end); the last decode of a sub-sequence is the one from its final entry state.
+struct SliceStore {
+    uint4 *base;
+    __device__ __forceinline__ void operator()(uint32_t k, uint32_t p, uint32_t cz, uint32_t cnt) const { base[k] = make_uint4(p, cz, cnt, 0u); }
+};
+
 __global__ void __launch_bounds__(kHuffThreads, 6)
 k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
             const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
             const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
             uint2 *__restrict__ st_in, uint2 *__restrict__ st_out, uint32_t *__restrict__ sub_tot, uint2 *__restrict__ sub_pre,
-            BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round, uint32_t sub_bytes) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+            uint4 *__restrict__ slices, BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round, uint32_t slices_log2) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
     __shared__ uint32_t s_tot[kHuffThreads];
-    __shared__ uint32_t s_end[kHuffThreads];
+    __shared__ uint2 s_span[kHuffThreads];                                  // first bit, end bit
     __shared__ uint16_t s_work[2][kHuffThreads];
     __shared__ uint32_t s_nwork[2];
     __shared__ uint32_t s_flag;
@@ -353,7 +366,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
 
     SubInfo u;
     u.head = false; u.end_bit = 0; u.start_bit = 0;
-    if (active) u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg, sub_bytes);
+    if (active) u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg);
 
     if (tid == 0) { s_nwork[0] = 0; s_nwork[1] = 0; s_flag = 0; }
     __syncthreads();
@@ -367,7 +380,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
             if (prev.x != s_in[0].x || prev.y != s_in[0].y) { s_in[0] = prev; need = true; s_flag = 1; }
         }
     }
-    s_end[tid] = u.end_bit;
+    s_span[tid] = make_uint2(u.start_bit, u.end_bit);
     if (need) s_work[0][atomicAdd(&s_nwork[0], 1u)] = (uint16_t)tid;
     __syncthreads();
     if (round > 0 && s_flag == 0) return;                                   // nothing changed at this CTA's entry
@@ -376,6 +389,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     LutMem luts;
     stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g, luts);
     const uint32_t *__restrict__ words = clean + im.clean_word0;
+    const uint32_t slice_bits = (im.sub_bytes >> slices_log2) * 8u;
 
     int cur = 0;
     for (;;) {
@@ -387,7 +401,10 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
             HuffState in;
             in.p = s_in[item].x; in.cz = s_in[item].y;
             uint32_t started;
-            const HuffState o = decode_span(words, luts, g, in, s_end[item], &started);
+            SliceStore rec;
+            rec.base = slices + ((size_t)(im.sub_base + first_j + item) << slices_log2);
+            const uint2 span = s_span[item];
+            const HuffState o = decode_span(words, luts, g, in, span.x, span.y, slice_bits, rec, &started);
             s_out[item] = make_uint2(o.p, o.cz);
             s_tot[item] = started;
         }
@@ -433,6 +450,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
         if (!f) { v0 += s_w[warp]; hf = s_wf[warp]; }
         // exclusive: a head starts from zero; otherwise inclusive minus own
         st_in[gj] = s_in[tid];
+        slices[(size_t)gj << slices_log2] = make_uint4(s_in[tid].x, s_in[tid].y, 0u, 0u);
         st_out[gj] = s_out[tid];
         sub_tot[gj] = s_tot[tid];
         sub_pre[gj] = u.head ? make_uint2(0u, 1u) : make_uint2(v0 - own0, hf);   // .y: a head precedes inside this CTA
@@ -441,30 +459,18 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
 }
 
 // ------------------------------------------------------------------------------------------------ K1a: write
-// Per-thread unit staging in shared memory: thread t owns the 128 bytes at t * 128, its 16-byte chunk q stored
-// at chunk position q ^ (t & 7), so a finished unit leaves with eight 128-bit shared loads + eight 128-bit global
-// stores, and the 2-byte puts of a warp spread over the banks.
+// One thread = one slice; a CTA's 256 slices are consecutive (kHuffThreads >> slices_log2 sub-sequences of one CTA
+// of the synchronisation pass).  Every lane of a warp takes one symbol per iteration (WriteCursor::step), so the
+// warp stays converged; when lanes complete a unit, the warp stores those units together.
+// Unit staging in shared memory: thread t owns the 128 bytes at t * 128, its 16-byte chunk q stored at chunk
+// position q ^ (t & 7): the 2-byte puts of a warp spread over the banks, and a finished unit leaves as eight
+// 128-bit shared loads + eight 128-bit global stores issued by eight LANES (one 128-byte line per instruction).
 struct SmemUnitSink {
     uint32_t row;            // shared-memory address of stage + tid * 128
     uint32_t sw16;           // (tid & 7) << 4
-    int16_t *out;            // image's first unit
-    int16_t *dcp;            // image's first entry in the DC plane
-    uint32_t ndu;
-    __device__ __forceinline__ void dc(uint32_t du, int16_t diff) { if (du < ndu) dcp[du] = diff; }
     // chunk (zz >> 3) ^ sw, element zz & 7  ==  byte (zz * 2) ^ (sw << 4)
     __device__ __forceinline__ void put(uint32_t zz, int16_t v) {
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + ((zz << 1) ^ sw16)), "h"(v) : "memory");
-    }
-    __device__ __forceinline__ void flush(uint32_t du) {
-        uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)du * 64);
-#pragma unroll
-        for (uint32_t q = 0; q < 8; q++) {
-            const uint32_t a = row + ((q << 4) ^ sw16);
-            uint4 v;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
-            if (du < ndu) __stcs(dst + q, v);
-        }
     }
 };
 
@@ -474,22 +480,25 @@ __global__ void __launch_bounds__(kHuffThreads)
 k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
              const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
              const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
-             const uint2 *__restrict__ st_in, const uint2 *__restrict__ sub_pre, const BlkAgg *__restrict__ blk_agg,
-             int16_t *__restrict__ coef, int16_t *__restrict__ dc_plane, uint32_t sub_bytes) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+             const uint4 *__restrict__ slices, const uint2 *__restrict__ sub_pre, const BlkAgg *__restrict__ blk_agg,
+             int16_t *__restrict__ coef, int16_t *__restrict__ dc_plane, uint32_t slices_log2) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];                   // stage rows must be 128-byte aligned
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw + kSmemHuffStage);
     __shared__ uint32_t s_red[kHuffThreads / 32];
     __shared__ int s_h;
 
-    const uint32_t img = blk_img[blockIdx.x];
+    const uint32_t sblk = blockIdx.x >> slices_log2;                       // CTA of the synchronisation pass
+    const uint32_t img = blk_img[sblk];
     const HuffImg &im = imgs[img];
     const HuffImgState is = ist[img];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lb = blockIdx.x - im.blk_base;
-    const uint32_t j = lb * kHuffThreads + tid;
-    if (lb * kHuffThreads >= is.nsub) return;
-    const bool active = j < is.nsub;
+    const uint32_t lb = sblk - im.blk_base;
+    const uint32_t slot = (blockIdx.x & ((1u << slices_log2) - 1u)) * kHuffThreads + tid;   // slice slot within that CTA
+    const uint32_t j = lb * kHuffThreads + (slot >> slices_log2);          // image-local sub-sequence
+    const uint32_t k = slot & ((1u << slices_log2) - 1u);                  // slice of it
+    if (lb * kHuffThreads + ((slot - tid) >> slices_log2) >= is.nsub) return;   // whole CTA beyond the image's sub-sequences
+    bool active = j < is.nsub;
 
     // carry into this CTA: totals of the previous CTAs of the image back to the last one that contains a head
     if (tid == 0) s_h = 0;
@@ -515,25 +524,73 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
 #pragma unroll
     for (int w = 0; w < kHuffThreads / 32; w++) c0 += s_red[w];
 
-    if (!active) return;
-    const SubInfo u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg, sub_bytes);
-    const uint2 pre = sub_pre[im.sub_base + j];
-    const uint32_t n_ex = pre.x + (pre.y ? 0u : c0);
-    const uint32_t du0 = u.seg * im.ri * im.bpm;
-    const uint32_t du_end = (im.ri ? min(im.nmcu, (u.seg + 1u) * im.ri) : im.nmcu) * im.bpm;
-    const uint2 sin = st_in[im.sub_base + j];
-    HuffState in;
-    in.p = sin.x; in.cz = sin.y;
+    const uint32_t ndu = im.ndu;
+    uint4 *out = reinterpret_cast<uint4 *>(coef + (size_t)im.du_base * 64);
+    int16_t *dcp = dc_plane + im.du_base;
+    WriteCursor cur;
+    cur.first_zero = 0xFFFFFFFFu; cur.du = 0; cur.du_end = 0; cur.dcv = 0;
     SmemUnitSink sink;
-    sink.row = (uint32_t)__cvta_generic_to_shared(s_stage) + tid * 128;
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(s_stage);
+    sink.row = stage_addr + tid * 128;
     sink.sw16 = (tid & 7) << 4;
-    sink.out = coef + (size_t)im.du_base * 64;
-    sink.dcp = dc_plane + im.du_base;
-    sink.ndu = im.ndu;
-    const WriteResult r = write_span(clean + im.clean_word0, luts, g, in, u.end_bit, u.data_end_bit, du0 + n_ex, du_end, u.last, sink);
-    if (r.first_zero != 0xFFFFFFFFu) {
-        atomicMin(&ist[img].first_zero, r.first_zero);
-        ist[img].status = 1u;
+    // keep these in registers: recomputing them from the thread index in the symbol loop costs more than they do
+    asm volatile("mov.u32 %0, %0;" : "+r"(sink.row));
+    asm volatile("mov.u32 %0, %0;" : "+r"(sink.sw16));
+    bool done = true, last = false;
+    if (active) {
+        const SubInfo u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg);
+        const uint32_t slice_bits = (im.sub_bytes >> slices_log2) * 8u;
+        const uint32_t nsl = u.end_bit > u.start_bit ? (u.end_bit - u.start_bit + slice_bits - 1u) / slice_bits : 1u;
+        active = k < nsl;
+        if (active) {
+            const uint4 sl = slices[((size_t)(im.sub_base + j) << slices_log2) + k];
+            const uint2 pre = sub_pre[im.sub_base + j];
+            const uint32_t n_ex = pre.x + (pre.y ? 0u : c0) + sl.z;
+            const uint32_t du0 = u.seg * im.ri * im.bpm;
+            const uint32_t du_end = (im.ri ? min(im.nmcu, (u.seg + 1u) * im.ri) : im.nmcu) * im.bpm;
+            HuffState in;
+            in.p = sl.x; in.cz = sl.y;
+            last = u.last && k + 1u == nsl;
+            const uint32_t ev = cur.open(clean + im.clean_word0, luts, g, in, min(u.start_bit + (k + 1u) * slice_bits, u.end_bit),
+                                         u.data_end_bit, du0 + n_ex, du_end);
+            done = (ev & kEvDone) != 0u;
+        }
+    }
+
+    uint32_t warp_stage = stage_addr + (tid & ~31) * 128 + ((lane & 7) << 4);     // + this lane's chunk
+    asm volatile("mov.u32 %0, %0;" : "+r"(warp_stage));
+    uint4 *out_lane = out + (lane & 7);
+    for (;;) {
+        bool unit = false;
+        if (!done) cur.step(luts, g, sink, unit, done);
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, unit);
+        if (m) {                                                           // lanes in m completed unit du_done
+            const uint32_t du_mine = cur.du - 1u;
+            if (unit && du_mine < ndu) dcp[du_mine] = (int16_t)cur.dcv;
+            __syncwarp();
+            do {
+                const int l = __ffs(m) - 1;
+                m &= m - 1u;
+                const uint32_t du_l = __shfl_sync(0xFFFFFFFFu, du_mine, l);
+                if (lane < 8) {
+                    const uint32_t a = (warp_stage + l * 128) ^ ((l & 7) << 4);   // rows are 128-byte aligned
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
+                    if (du_l < ndu) __stcs(out_lane + (size_t)du_l * 8, v);
+                }
+            } while (m);
+            __syncwarp();
+        }
+        if (__all_sync(0xFFFFFFFFu, done)) break;
+    }
+    if (active) {
+        // the last slice of a segment must have produced the segment's last unit
+        if (cur.first_zero == 0xFFFFFFFFu && last && cur.du < cur.du_end) cur.first_zero = cur.du;
+        if (cur.first_zero != 0xFFFFFFFFu) {
+            atomicMin(&ist[img].first_zero, cur.first_zero);
+            ist[img].status = 1u;
+        }
     }
 }
 
@@ -570,7 +627,7 @@ k_dc_predict(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ 
     const uint32_t m = lc * kDcThreads + tid;
     const bool active = m < im.nmcu;
     HuffGeom g;
-    g.bpm = im.bpm; g.ny = im.ny; g.tab[0] = g.tab[1] = g.tab[2] = 0;
+    g.bpm = im.bpm; g.ny = im.ny;
     int16_t *p = dc_plane + im.du_base + (size_t)m * im.bpm;
     int16_t d[6] = {0, 0, 0, 0, 0, 0};
     uint32_t v0 = 0, v1 = 0, v2 = 0, f = 0;

@@ -20,30 +20,24 @@ using namespace bj;
 namespace {
 struct HostSink {
     int16_t unit[64];
-    int16_t *out;
-    int16_t *dcp;
-    uint32_t ndu;
-    std::vector<uint8_t> *written;
     HostSink() { memset(unit, 0, sizeof(unit)); }
     void put(uint32_t zz, int16_t v) { unit[zz] = v; }
-    void dc(uint32_t du, int16_t diff) { if (du < ndu) dcp[du] = diff; }
-    void flush(uint32_t du) {
-        if (du < ndu) { memcpy(out + (size_t)du * 64, unit, sizeof(unit)); (*written)[du]++; }
-        memset(unit, 0, sizeof(unit));
-    }
 };
+struct SliceRec { uint32_t p, cz, cnt; };
 }  // namespace
 
 // optional: per Jacobi round, how many sub-sequences were decoded (set by emu_set_round_hist; 64 entries)
 static uint32_t *g_round_hist = nullptr;
 extern "C" void emu_set_round_hist(uint32_t *hist) { g_round_hist = hist; }
 
+// slice_bytes = granularity of the write pass; a sub-sequence of the synchronisation pass is `slices` of them.
 // Returns 0 ok, <0 parse status.  info[0] = fix-up rounds, info[1] = first_zero (UINT32_MAX none), info[2] = nsub,
 // info[3] = number of units written more or less than once (must be 0 for a clean stream)
-extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16_t *coef_zz, uint32_t *info) {
+extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int slices, int16_t *coef_zz, uint32_t *info) {
     bj_image_desc d;
     int rc = parse_header(file, len, &d);
     if (rc != BJ_OK) return rc;
+    const uint32_t sub_bytes = (uint32_t)slice_bytes * (uint32_t)slices, slice_bits = (uint32_t)slice_bytes * 8u;
     const uint32_t nmx = (d.mcu_w + d.hs - 1) / d.hs, nmy = (d.mcu_h + d.vs - 1) / d.vs, nmcu = nmx * nmy;
     uint32_t bpm = 0;
     for (int j = 0; j < d.ncomp; j++) bpm += d.comp_h[j] * d.comp_v[j];
@@ -79,20 +73,24 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
     seg_off.push_back(clean_len);
     uint32_t first_zero = nseg < nseg_expected ? nseg * ri * bpm : 0xFFFFFFFFu;
 
-    // tables
-    std::vector<uint32_t> luts(3 * (kLutCapDC + kLutCapAC));
+    // tables: the write pass' single-symbol tables, and the synchronisation pass' grouped AC tables
+    const size_t lut_words = 3 * (kLutCapDC + kLutCapAC);
+    std::vector<uint32_t> luts(lut_words), luts_sync(lut_words);
     HuffGeom g;
     g.bpm = bpm; g.ny = (uint32_t)d.hs * d.vs;
     for (int j = 0; j < 3; j++) {
         const int jj = j < d.ncomp ? j : 0;
         const uint32_t odc = j * kLutCapDC, oac = 3 * kLutCapDC + j * kLutCapAC;
         if (build_lut(d.dc_offsets[d.dc_id[jj]], d.dc_symbols[d.dc_id[jj]], false, &luts[odc]) < 0) return -100;
-        if (build_lut(d.ac_offsets[d.ac_id[jj]], d.ac_symbols[d.ac_id[jj]], true, &luts[oac]) < 0) return -100;
-        g.tab[j] = (odc * 4) | ((oac * 4) << 16);
+        const int used = build_lut(d.ac_offsets[d.ac_id[jj]], d.ac_symbols[d.ac_id[jj]], true, &luts[oac]);
+        if (used < 0) return -100;
+        memcpy(&luts_sync[odc], &luts[odc], kLutCapDC * 4);
+        build_lut_sync(&luts[oac], used, &luts_sync[oac]);
+        g.dc[j] = odc * 4; g.ac[j] = oac * 4;
     }
-
-    LutMem lm;
+    LutMem lm, lm_sync;
     lm.attach(luts.data());
+    lm_sync.attach(luts_sync.data());
 
     // sub-sequence table
     struct Sub { uint32_t seg, start_bit, end_bit; bool head, last; };
@@ -111,18 +109,30 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
     const size_t ns = subs.size();
     const uint32_t *words = reinterpret_cast<const uint32_t *>(clean.data());
 
-    // pass 1: Jacobi rounds to the fixed point  in[i+1] == out[i]
+    // pass 1: Jacobi rounds to the fixed point  in[i+1] == out[i]; every decode (re)writes the sub-sequence's slices
     std::vector<HuffState> in(ns), out(ns);
     std::vector<uint32_t> tot(ns);
     std::vector<uint8_t> need(ns, 1);
+    std::vector<SliceRec> slice(ns * (size_t)slices);
+    std::vector<uint8_t> slice_seen(ns * (size_t)slices, 0);
     for (size_t i = 0; i < ns; i++) { in[i].p = subs[i].start_bit; in[i].cz = 0; }
     uint32_t rounds = 0;
+    int order_bad = 0;
     for (;;) {
         bool any = false;
         if (g_round_hist && rounds < 64) { uint32_t cnt = 0; for (size_t i = 0; i < ns; i++) cnt += need[i]; g_round_hist[rounds] = cnt; }
         for (size_t i = 0; i < ns; i++) {
             if (!need[i]) continue;
-            out[i] = decode_span(words, lm, g, in[i], subs[i].end_bit, &tot[i]);
+            uint32_t expect = 1;
+            auto rec = [&](uint32_t k, uint32_t p, uint32_t cz, uint32_t cnt) {
+                if (k != expect || k >= (uint32_t)slices) order_bad++;
+                expect = k + 1;
+                slice[i * slices + k] = SliceRec{p, cz, cnt};
+                slice_seen[i * slices + k] = 1;
+            };
+            out[i] = decode_span(words, lm_sync, g, in[i], subs[i].start_bit, subs[i].end_bit, slice_bits, rec, &tot[i]);
+            const uint32_t nsl = subs[i].end_bit > subs[i].start_bit ? (subs[i].end_bit - subs[i].start_bit + slice_bits - 1) / slice_bits : 1u;
+            if (expect != nsl) order_bad++;
             need[i] = 0; any = true;
         }
         if (!any) break;
@@ -132,8 +142,10 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
             if (!same_state(in[i], out[i - 1])) { in[i] = out[i - 1]; need[i] = 1; }
         }
     }
+    if (order_bad) return -300;
 
-    // prefix sum of the units started per segment, then the write pass (DC differences into their own plane)
+    // prefix sum of the units started per segment, then the write pass (DC differences into their own plane):
+    // one cursor per slice, one symbol per step, the finished unit stored when the step says so
     std::vector<uint8_t> written(ndu, 0);
     std::vector<int16_t> dcp(ndu, 0x5A5A);
     uint32_t n_ex = 0;
@@ -142,11 +154,28 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int sub_bytes, int16
         if (u.head) n_ex = 0;
         const uint32_t du0 = u.seg * ri * bpm;
         const uint32_t du_end = (ri ? std::min(nmcu, (u.seg + 1) * ri) : nmcu) * bpm;
-        HostSink sink;
-        sink.out = coef_zz; sink.dcp = dcp.data(); sink.ndu = ndu; sink.written = &written;
-        const WriteResult r = write_span(words, lm, g, in[i], u.end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex, du_end,
-                                         u.last, sink);
-        first_zero = std::min(first_zero, r.first_zero);
+        const uint32_t nsl = u.end_bit > u.start_bit ? (u.end_bit - u.start_bit + slice_bits - 1) / slice_bits : 1u;
+        for (uint32_t k = 0; k < nsl; k++) {
+            HuffState st = in[i];
+            uint32_t cnt = 0;
+            if (k) { st.p = slice[i * slices + k].p; st.cz = slice[i * slices + k].cz; cnt = slice[i * slices + k].cnt; }
+            const uint32_t end_bit = std::min(u.start_bit + (k + 1) * slice_bits, u.end_bit);
+            HostSink sink;
+            WriteCursor cur;
+            bool done = (cur.open(words, lm, g, st, end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex + cnt, du_end) & kEvDone) != 0;
+            while (!done) {
+                bool unit = false;
+                cur.step(lm, g, sink, unit, done);
+                if (unit) {
+                    const uint32_t du = cur.du - 1u;
+                    if (du < ndu) { memcpy(coef_zz + (size_t)du * 64, sink.unit, sizeof(sink.unit)); dcp[du] = (int16_t)cur.dcv; written[du]++; }
+                    memset(sink.unit, 0, sizeof(sink.unit));
+                }
+            }
+            // the last slice of a segment must have produced the segment's last unit
+            if (cur.first_zero == 0xFFFFFFFFu && u.last && k + 1 == nsl && cur.du < du_end) cur.first_zero = cur.du;
+            first_zero = std::min(first_zero, cur.first_zero);
+        }
         n_ex += tot[i];
     }
     // K1c: DC prediction over the plane, restarting at every restart interval; then merged into slot 0 for the comparison

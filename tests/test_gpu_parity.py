@@ -96,7 +96,24 @@ def test_stage_entropy_subsequence_sizes(dec, bits, golden, golden_dir):
             assert status == 0
             assert np.array_equal(coef, ol.Restated(data, 0).coef_zz), (name, bits)
     finally:
-        dec.set_option("subseq_bits", 1024)
+        dec.set_option("subseq_bits", 0)
+
+
+@pytest.mark.parametrize("slices,bits", [(1, 128), (2, 256), (8, 512), (8, 160), (4, 4096), (1, 4096), (2, 0), (8, 0)])
+def test_stage_entropy_slices(dec, slices, bits, golden, golden_dir):
+    """The write pass works on `slices` pieces of every sub-sequence of the synchronisation pass (entry states
+    recorded while synchronising); 160 bits = 20 bytes is not divisible by 8 (the slice count is lowered)."""
+    dec.set_option("slices", slices)
+    dec.set_option("subseq_bits", bits)
+    try:
+        for name in ("ilsvrc_444", "p420_320x240", "enc_444_100x60_ri1", "p420_q100_64x64", "gray_ri3_64x48", "enc_420_100x60_ri4"):
+            data = _load(golden, golden_dir, name)
+            coef, status = dec.stage_entropy(data)
+            assert status == 0
+            assert np.array_equal(coef, ol.Restated(data, 0).coef_zz), (name, slices, bits)
+    finally:
+        dec.set_option("slices", 0)
+        dec.set_option("subseq_bits", 0)
 
 
 @pytest.mark.parametrize("rounds,bits", [(1, 128), (2, 256), (7, 128), (12, 1024)])
@@ -113,7 +130,7 @@ def test_stage_entropy_few_blind_rounds(dec, rounds, bits, golden, golden_dir):
             assert np.array_equal(coef, ol.Restated(data, 0).coef_zz), (name, rounds, bits)
     finally:
         dec.set_option("sync_rounds", 0)
-        dec.set_option("subseq_bits", 1024)
+        dec.set_option("subseq_bits", 0)
 
 
 # ------------------------------------------------------------------ full path against the reference's BMPs
@@ -260,7 +277,7 @@ def test_large_image_properties(dec):
     try:
         o3, s3 = dec.decode([g, a], bj.BJ_OUT_RGB8)
     finally:
-        dec.set_option("subseq_bits", 1024)
+        dec.set_option("subseq_bits", 0)
     assert np.array_equal(o3[0], o2[1]) and np.array_equal(o3[1], o1[0])
     r = ol.Restated(a, 0)
     assert np.array_equal(o1[0].reshape(r.rgb.shape), r.rgb)

@@ -26,18 +26,18 @@ def emu():
     if not os.path.exists(EMU) or os.path.getmtime(EMU) < max(os.path.getmtime(src), os.path.getmtime(core)):
         subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", EMU, src], check=True)
     lib = C.CDLL(EMU)
-    lib.emu_entropy.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    lib.emu_entropy.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.emu_lut_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     return lib
 
 
-def run_emu(data, sub_bytes):
+def run_emu(data, sub_bytes, slices=4):
     r = ol.Restated(data, restart_mode=0)
     assert r.valid
     buf = np.frombuffer(data, dtype=np.uint8)
     got = np.full_like(r.coef_zz, 0x5A5A)          # poison: every unit must be written (or zero-filled)
     info = np.zeros(4, dtype=np.uint32)
-    rc = emu().emu_entropy(ol._ptr(buf), len(data), sub_bytes, ol._ptr(got), ol._ptr(info))
+    rc = emu().emu_entropy(ol._ptr(buf), len(data), sub_bytes, slices, ol._ptr(got), ol._ptr(info))
     assert rc == 0
     return r, got, info
 
@@ -49,11 +49,12 @@ def _golden_names():
     return sorted(k for k, v in g.items() if not v.get("invalid"))
 
 
-@pytest.mark.parametrize("sub_bytes", [4, 32, 128, 1024])
+@pytest.mark.parametrize("sub_bytes,slices", [(4, 1), (4, 4), (32, 2), (128, 4), (1024, 1), (16, 8)])
 @pytest.mark.parametrize("name", _golden_names())
-def test_emulated_entropy_stage_matches_oracle(name, sub_bytes, golden, golden_dir):
+def test_emulated_entropy_stage_matches_oracle(name, sub_bytes, slices, golden, golden_dir):
+    """sub_bytes = slice (write-pass) granularity; the synchronisation pass works on `slices` of them at a time."""
     data = open(os.path.join(golden_dir, golden[name]["file"]), "rb").read()
-    r, got, info = run_emu(data, sub_bytes)
+    r, got, info = run_emu(data, sub_bytes, slices)
     assert r.huff_rc == 0
     assert info[3] == 0, "a data unit was written twice or never"
     assert info[1] == 0xFFFFFFFF
