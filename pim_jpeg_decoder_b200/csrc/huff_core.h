@@ -399,7 +399,8 @@ BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const Huf
 //
 // The decode is a cursor that takes ONE symbol per step(), DC and AC alike, so the lanes of a warp stay together;
 // a step says when a unit is complete and the caller stores it (the kernel does that warp-cooperatively).
-// Sink concept:  void put(uint32_t zz, int16_t v)  - stage one non-zero AC coefficient of the current unit.
+// Sink concept:  void put(uint32_t zz, int16_t v)  - stage one non-zero value of the current unit (zz = 0: the DC
+// difference; the stored unit's slot 0 is zero, the difference goes to the DC plane).
 constexpr uint32_t kEvDone = 2u;     // open(): nothing to do in this slice
 
 struct WriteCursor {
@@ -407,7 +408,7 @@ struct WriteCursor {
     uint32_t S, c, ac, tab, du;     // ac: AC table of the current unit; tab: table of the next symbol
     uint32_t endS, dataS, du_end;
     uint32_t first_zero;    // first unit index that must read as zero because the reference stopped; UINT32_MAX if none
-    int32_t dcv;            // DC difference of the unit being decoded (of the completed one right after its last step)
+    uint32_t fail;          // 0, or why the slice stopped: 1 = refused symbol / bits ran out, 2 = over-long run
 
     // Returns kEvDone if there is nothing to do.  Skips the unit a predecessor owns (no values).
     BJ_HD uint32_t open(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
@@ -422,7 +423,7 @@ struct WriteCursor {
         const uint32_t data_rel = data_end_bit >= origin ? data_end_bit - origin : 0u;
         dataS = ((data_rel < 0xFFFFFFu ? data_rel : 0xFFFFFFu) << 8) | 0xFFu;
         du = du0; du_end = du_end_;
-        dcv = 0;
+        fail = 0u;
         ac = ac_of(g, c);
         bs.open(words, st.p);
         if (S & 0xFFu) {                                  // inside a unit that belongs to a predecessor: skip it
@@ -444,36 +445,37 @@ struct WriteCursor {
     // One symbol.  The reference's failure points: refused symbol, bits running out inside a symbol, run past the
     // end of the unit ("i + run >= 64", src/jpeg_scanner.cpp:497-500).  A failed DC leaves the unit untouched
     // (zero); a failed AC keeps what was stored before it.
-    // `unit` = unit du - 1 is complete (store the staged unit and its DC difference dcv, clear the stage);
-    // `done` = slice finished.
+    // One symbol.  `unit` = something for the caller to do: unit store_du() is complete (store the staged unit,
+    // whose slot 0 holds its DC difference, and clear the stage); `done` = slice finished (only ever set together
+    // with `unit`).  After a failure (`fail`), store_du() also settles first_zero.
     template <class Sink>
     BJ_HD void step(const LutMem &luts, const HuffGeom &g, Sink &sink, bool &unit, bool &done) {
         const uint32_t win = bs.window(S);
         const uint32_t e = lut_lookup(luts, tab, win);
         const uint32_t Sn = S + (e & 0xFFFFu);
-        const bool is_dc = (S & 0xFFu) == 0u;
-        if (__builtin_expect((e & kLutBad) || Sn > dataS, 0)) {
-            done = true;
-            first_zero = du;                                              // a failed DC: the unit stays zero
-            if (!is_dc) { first_zero = ++du; unit = true; }               // a failed AC: the unit keeps what it has
-            return;
-        }
+        if (__builtin_expect((e & kLutBad) || Sn > dataS, 0)) { fail = 1u; done = true; unit = true; return; }
         const int32_t v = extend_entry(win, e);
-        const uint32_t zz = (Sn & 0xFFu) - 1u;            // index of the coefficient this symbol carries
-        dcv = is_dc ? v : dcv;                            // |diff| < 2^11
-        if (!is_dc && v != 0 && zz < 64u) sink.put(zz, (int16_t)v);   // size 0 (ZRL, EOB) stores nothing: zero is already there
+        const uint32_t zz = (Sn & 0xFFu) - 1u;            // index of the coefficient this symbol carries; 0: the DC difference
+        if (v != 0 && zz < 64u) sink.put(zz, (int16_t)v); // size 0 (ZRL, EOB) stores nothing: zero is already there
         tab = ac;
         S = Sn;
         if (!(Sn & 0x40u)) return;
         // index >= 64: the unit ends one way or another
         unit = true;
+        if (__builtin_expect((Sn & 0xFFu) != 64u && !(e & kLutEob), 0)) { fail = 2u; done = true; return; }   // over-long run
         du++;
-        if (__builtin_expect((Sn & 0xFFu) != 64u && !(e & kLutEob), 0)) { first_zero = du; done = true; return; }   // over-long run
         S &= ~0xFFu;
         c = (c + 1u == g.bpm) ? 0u : c + 1u;
         ac = ac_of(g, c);
         tab = dc_of(g, c);
         done = S >= endS || du >= du_end;
+    }
+    // The unit to store after a step that said `unit` (UINT32_MAX: none).
+    BJ_HD uint32_t store_du() {
+        if (__builtin_expect(fail == 0u, 1)) return du - 1u;
+        if (fail == 1u && (S & 0xFFu) == 0u) { first_zero = du; return 0xFFFFFFFFu; }   // a failed DC: the unit stays zero
+        first_zero = du + 1u;                                                            // a failed AC keeps what was stored before it
+        return du;
     }
 };
 

@@ -466,11 +466,10 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
 // position q ^ (t & 7): the 2-byte puts of a warp spread over the banks, and a finished unit leaves as eight
 // 128-bit shared loads + eight 128-bit global stores issued by eight LANES (one 128-byte line per instruction).
 struct SmemUnitSink {
-    uint32_t row;            // shared-memory address of stage + tid * 128
-    uint32_t sw16;           // (tid & 7) << 4
+    uint32_t rowsw;          // shared-memory address of (stage + tid * 128) | ((tid & 7) << 4); rows are 128-byte aligned
     // chunk (zz >> 3) ^ sw, element zz & 7  ==  byte (zz * 2) ^ (sw << 4)
     __device__ __forceinline__ void put(uint32_t zz, int16_t v) {
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + ((zz << 1) ^ sw16)), "h"(v) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(rowsw ^ (zz << 1)), "h"(v) : "memory");
     }
 };
 
@@ -528,14 +527,12 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     uint4 *out = reinterpret_cast<uint4 *>(coef + (size_t)im.du_base * 64);
     int16_t *dcp = dc_plane + im.du_base;
     WriteCursor cur;
-    cur.first_zero = 0xFFFFFFFFu; cur.du = 0; cur.du_end = 0; cur.dcv = 0;
+    cur.first_zero = 0xFFFFFFFFu; cur.du = 0; cur.du_end = 0; cur.fail = 0u;
     SmemUnitSink sink;
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(s_stage);
-    sink.row = stage_addr + tid * 128;
-    sink.sw16 = (tid & 7) << 4;
-    // keep these in registers: recomputing them from the thread index in the symbol loop costs more than they do
-    asm volatile("mov.u32 %0, %0;" : "+r"(sink.row));
-    asm volatile("mov.u32 %0, %0;" : "+r"(sink.sw16));
+    sink.rowsw = (stage_addr + tid * 128) | ((tid & 7) << 4);
+    // keep it in a register: recomputing it from the thread index in the symbol loop costs more than it does
+    asm volatile("mov.u32 %0, %0;" : "+r"(sink.rowsw));
     bool done = true, last = false;
     if (active) {
         const SubInfo u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg);
@@ -560,33 +557,40 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     uint32_t warp_stage = stage_addr + (tid & ~31) * 128 + ((lane & 7) << 4);     // + this lane's chunk
     asm volatile("mov.u32 %0, %0;" : "+r"(warp_stage));
     uint4 *out_lane = out + (lane & 7);
-    for (;;) {
-        bool unit = false;
-        if (!done) cur.step(luts, g, sink, unit, done);
-        uint32_t m = __ballot_sync(0xFFFFFFFFu, unit);
-        if (m) {                                                           // lanes in m completed unit du_done
-            const uint32_t du_mine = cur.du - 1u;
-            if (unit && du_mine < ndu) dcp[du_mine] = (int16_t)cur.dcv;
+    uint32_t flusher = lane < 8 ? 1u : 0u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(flusher));
+    if (!__all_sync(0xFFFFFFFFu, done)) {
+        for (;;) {
+            bool unit = false;
+            if (!done) cur.step(luts, g, sink, unit, done);
+            uint32_t m = __ballot_sync(0xFFFFFFFFu, unit);
+            if (m == 0) continue;
+            // lanes in m completed unit du - 1 (or ended on a refused DC symbol: nothing to store)
+            const uint32_t du_mine = unit ? cur.store_du() : 0xFFFFFFFFu;
             __syncwarp();
             do {
                 const int l = __ffs(m) - 1;
                 m &= m - 1u;
                 const uint32_t du_l = __shfl_sync(0xFFFFFFFFu, du_mine, l);
-                if (lane < 8) {
-                    const uint32_t a = (warp_stage + l * 128) ^ ((l & 7) << 4);   // rows are 128-byte aligned
+                if (flusher) {
+                    const uint32_t x = (l & 7) << 4;
+                    const uint32_t a = (warp_stage + l * 128) ^ x;         // rows are 128-byte aligned
                     uint4 v;
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
                     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
-                    if (du_l < ndu) __stcs(out_lane + (size_t)du_l * 8, v);
+                    if (du_l < ndu) {                                      // this lane holds the unit's chunk `lane`
+                        if (lane == 0) { dcp[du_l] = (int16_t)v.x; v.x &= 0xFFFF0000u; }   // slot 0 = the DC difference
+                        __stcs(out_lane + (size_t)du_l * 8, v);
+                    }
                 }
             } while (m);
             __syncwarp();
+            if (__all_sync(0xFFFFFFFFu, done)) break;
         }
-        if (__all_sync(0xFFFFFFFFu, done)) break;
     }
     if (active) {
         // the last slice of a segment must have produced the segment's last unit
-        if (cur.first_zero == 0xFFFFFFFFu && last && cur.du < cur.du_end) cur.first_zero = cur.du;
+        if (cur.fail == 0u && last && cur.du < cur.du_end) cur.first_zero = cur.du;
         if (cur.first_zero != 0xFFFFFFFFu) {
             atomicMin(&ist[img].first_zero, cur.first_zero);
             ist[img].status = 1u;

@@ -16,7 +16,7 @@ namespace bj {
 
 constexpr int kSmemDu = kTileThreads * 128;              // 24576 B: coefficient units, then samples, in place
 constexpr int kSmemQ = 1024;                             // 3 * kQPitch words, padded
-constexpr int kRgbFront = 16;                            // slack so the misaligned copy-out may read 15 B early
+constexpr int kRgbFront = 16;                            // slack in front of the staging tile (the copy-out reads whole words)
 constexpr int kRgbMax = 1536 * 8 * 3;                    // widest tile: gray, 192 MCUs x 8 px x 8 rows x 3 B
 constexpr int kSmemIdctColor = kSmemDu + kSmemQ + kRgbFront + kRgbMax + 64;
 
@@ -27,6 +27,24 @@ __device__ __forceinline__ uint4 pack_row(const int (&X)[64], int r) {
     v.z = __byte_perm(X[r * 8 + 4], X[r * 8 + 5], 0x5410);
     v.w = __byte_perm(X[r * 8 + 6], X[r * 8 + 7], 0x5410);
     return v;
+}
+
+// Eight pixels of one row: luma words yv, the chroma words of the first / last output channel (fw / lw; with 2:1
+// horizontal subsampling every sample feeds two pixels) -> unclamped channel values (src/decoder_dpu.c:376-378).
+template <bool HS2>
+__device__ __forceinline__ void color8(const uint4 &yv, const unsigned *fw, const unsigned *lw, unsigned kF, unsigned kL, unsigned gF,
+                                       unsigned gL, int (&c0)[8], int (&c1)[8], int (&c2)[8]) {
+    const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int ci = HS2 ? (i >> 1) : i;                                 // chroma sample of pixel i
+        const int f = (ci & 1) ? sext_hi(fw[ci >> 1]) : sext_lo(fw[ci >> 1]);
+        const int l = (ci & 1) ? sext_hi(lw[ci >> 1]) : sext_lo(lw[ci >> 1]);
+        const int yy = ((i & 1) ? sext_hi(yw[i >> 1]) : sext_lo(yw[i >> 1])) + 128;
+        c0[i] = yy + ((int)(kF * (unsigned)f) >> 22);
+        c1[i] = yy - ((int)(gF * (unsigned)f) >> 22) - ((int)(gL * (unsigned)l) >> 22);
+        c2[i] = yy + ((int)(kL * (unsigned)l) >> 22);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ fast layout
@@ -104,7 +122,14 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
     {
         const unsigned inv = nseg > 1 ? (0xFFFFFFFFu / (unsigned)nseg + 1u) : 0u;
         const int items = rows * nseg;
+        // Output byte order R,G,B or B,G,R: instead of swapping per pixel, swap the roles of the two chroma planes
+        // and of their constants once (src/decoder_dpu.c:376-378):  first = y + 128 + ((kF * F) >> 22),
+        // last = y + 128 + ((kL * L) >> 22),  G = y + 128 - ((gF * F) >> 22) - ((gL * L) >> 22).
         const bool bgr = im->bgr != 0;
+        const unsigned kF = bgr ? 7432306u : 5880414u, kL = bgr ? 5880414u : 7432306u;
+        const unsigned gF = bgr ? 1442840u : 2994733u, gL = bgr ? 2994733u : 1442840u;
+        const int fdu = bgr ? 0 : 1, ldu = bgr ? 1 : 0;                    // unit offsets of F and L from the Cb unit
+        const bool has_f = bgr ? ncomp >= 2 : ncomp >= 3, has_l = bgr ? ncomp >= 3 : ncomp >= 2;
         for (int it = tid; it < items; it += kTileThreads) {
             const int py = nseg > 1 ? (int)__umulhi((unsigned)it, inv) : it;
             const int s = it - py * nseg;
@@ -112,37 +137,19 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
             const int by = py >> 3, r = py & 7;
             const int ydu = m * bpm + by * hs + bx;
             const uint4 yv = s_du[ydu * 8 + (r ^ (ydu & 7))];
-            int y[8] = {sext_lo(yv.x), sext_hi(yv.x), sext_lo(yv.y), sext_hi(yv.y),
-                        sext_lo(yv.z), sext_hi(yv.z), sext_lo(yv.w), sext_hi(yv.w)};
-            ChromaTerms ct[8];
-            if (ncomp >= 2) {
-                const int cdu = m * bpm + hs * vs;
-                const int rc = vs == 2 ? (by * 4 + (r >> 1)) : r;
-                const uint4 cbv = s_du[cdu * 8 + (rc ^ (cdu & 7))];
-                uint4 crv = make_uint4(0, 0, 0, 0);
-                if (ncomp >= 3) crv = s_du[(cdu + 1) * 8 + (rc ^ ((cdu + 1) & 7))];
-                if (hs == 2) {
-                    const unsigned cb0 = bx ? cbv.z : cbv.x, cb1 = bx ? cbv.w : cbv.y;
-                    const unsigned cr0 = bx ? crv.z : crv.x, cr1 = bx ? crv.w : crv.y;
-                    ct[0] = ct[1] = chroma_terms(sext_lo(cb0), sext_lo(cr0));
-                    ct[2] = ct[3] = chroma_terms(sext_hi(cb0), sext_hi(cr0));
-                    ct[4] = ct[5] = chroma_terms(sext_lo(cb1), sext_lo(cr1));
-                    ct[6] = ct[7] = chroma_terms(sext_hi(cb1), sext_hi(cr1));
-                } else {
-                    ct[0] = chroma_terms(sext_lo(cbv.x), sext_lo(crv.x)); ct[1] = chroma_terms(sext_hi(cbv.x), sext_hi(crv.x));
-                    ct[2] = chroma_terms(sext_lo(cbv.y), sext_lo(crv.y)); ct[3] = chroma_terms(sext_hi(cbv.y), sext_hi(crv.y));
-                    ct[4] = chroma_terms(sext_lo(cbv.z), sext_lo(crv.z)); ct[5] = chroma_terms(sext_hi(cbv.z), sext_hi(crv.z));
-                    ct[6] = chroma_terms(sext_lo(cbv.w), sext_lo(crv.w)); ct[7] = chroma_terms(sext_hi(cbv.w), sext_hi(crv.w));
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++) { ct[i].r = 128; ct[i].g = 128; ct[i].b = 128; }
-            }
+            const int cdu = m * bpm + hs * vs;
+            const int rc = vs == 2 ? (by * 4 + (r >> 1)) : r;
+            uint4 fv = make_uint4(0, 0, 0, 0), lv = make_uint4(0, 0, 0, 0);
+            if (has_f) fv = s_du[(cdu + fdu) * 8 + (rc ^ ((cdu + fdu) & 7))];
+            if (has_l) lv = s_du[(cdu + ldu) * 8 + (rc ^ ((cdu + ldu) & 7))];
             int c0[8], c1[8], c2[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int R = y[i] + ct[i].r, G = y[i] + ct[i].g, B = y[i] + ct[i].b;
-                c0[i] = bgr ? B : R; c1[i] = G; c2[i] = bgr ? R : B;
+            if (hs == 2) {
+                // one unit row feeds two segments (left half / right half), every chroma sample twice
+                const unsigned fw[2] = {bx ? fv.z : fv.x, bx ? fv.w : fv.y}, lw[2] = {bx ? lv.z : lv.x, bx ? lv.w : lv.y};
+                color8<true>(yv, fw, lw, kF, kL, gF, gL, c0, c1, c2);
+            } else {
+                const unsigned fw[4] = {fv.x, fv.y, fv.z, fv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+                color8<false>(yv, fw, lw, kF, kL, gF, gL, c0, c1, c2);
             }
             uint2 *dst = reinterpret_cast<uint2 *>(s_rgb + py * pitch + s * 24);
             dst[0] = make_uint2(pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]));
@@ -165,31 +172,39 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
         for (int r = warp; r < rows_valid; r += kTileThreads / 32) {
             const long long off = (long long)im->out_row0 + (long long)im->row_dir * (long long)(y0 + r) * (long long)im->out_pitch + (long long)x0 * 3;
             uint8_t *g = out + off;
-            const int mis = (int)((uintptr_t)g & 15);
-            uint8_t *a0 = g - mis;
-            const int nchunks = (mis + len + 15) >> 4;
             const uint8_t *sp = s_rgb + r * pitch;
-            for (int i = lane; i < nchunks; i += 32) {
-                const int so = i * 16 - mis;                       // staging byte offset of this chunk, >= -15
-                const uint8_t *p = sp + so;
-                const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+            // head: the bytes up to the first 16-byte boundary, one per lane
+            const int head = min((int)((16u - ((unsigned)(uintptr_t)g & 15u)) & 15u), len);
+            if (lane < head) g[lane] = lane < payload ? sp[lane] : (uint8_t)0;
+            // body: whole aligned 16-byte chunks
+            const int nfull = (len - head) >> 4;
+            {
+                const uint8_t *p0 = sp + head;
+                const unsigned a = (unsigned)__cvta_generic_to_shared(p0);
                 const unsigned sh = (a & 3u) * 8u;
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(p - (a & 3u));
-                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-                uint4 v;
-                v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
-                v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
-                if (so >= 0 && so + 16 <= payload) {
-                    __stcs(reinterpret_cast<uint4 *>(a0 + i * 16), v);
-                } else {
-                    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(p0 - (a & 3u));
+                uint4 *gp = reinterpret_cast<uint4 *>(g + head);
+                for (int i = lane; i < nfull; i += 32) {
+                    const uint32_t w0 = wp[4 * i], w1 = wp[4 * i + 1], w2 = wp[4 * i + 2], w3 = wp[4 * i + 3], w4 = wp[4 * i + 4];
+                    uint4 v;
+                    v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+                    v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+                    if (head + 16 * i + 16 > payload) {                    // BMP pad bytes (zero) inside this chunk
+                        const int keep = payload - head - 16 * i;          // data bytes in the chunk, < 16
+                        uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int b = 0; b < 16; b++) {
-                        const int idx = so + b;
-                        if (idx >= 0 && idx < len) a0[i * 16 + b] = idx < payload ? (uint8_t)(vv[b >> 2] >> ((b & 3) * 8)) : (uint8_t)0;
+                        for (int w = 0; w < 4; w++) {
+                            const int kb = keep - 4 * w;
+                            vv[w] = kb >= 4 ? vv[w] : (kb <= 0 ? 0u : (vv[w] & (0xFFFFFFFFu >> (32 - 8 * kb))));
+                        }
+                        v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
                     }
+                    __stcs(gp + i, v);
                 }
             }
+            // tail: what is left after the last whole chunk, one byte per lane
+            const int tail0 = head + 16 * nfull;
+            if (tail0 + lane < len) g[tail0 + lane] = tail0 + lane < payload ? sp[tail0 + lane] : (uint8_t)0;
         }
         // BMP file header (src/bmp_writer.cpp:26-41), written by the tile that owns the image's first MCU:
         // 'B','M', size(4), 0(4), 0x1A(4), 12(4), width(2), height(2), 1(2), 24(2)

@@ -167,13 +167,18 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int
                 bool unit = false;
                 cur.step(lm, g, sink, unit, done);
                 if (unit) {
-                    const uint32_t du = cur.du - 1u;
-                    if (du < ndu) { memcpy(coef_zz + (size_t)du * 64, sink.unit, sizeof(sink.unit)); dcp[du] = (int16_t)cur.dcv; written[du]++; }
+                    const uint32_t du = cur.store_du();
+                    if (du < ndu) {
+                        dcp[du] = sink.unit[0];
+                        sink.unit[0] = 0;
+                        memcpy(coef_zz + (size_t)du * 64, sink.unit, sizeof(sink.unit));
+                        written[du]++;
+                    }
                     memset(sink.unit, 0, sizeof(sink.unit));
                 }
             }
             // the last slice of a segment must have produced the segment's last unit
-            if (cur.first_zero == 0xFFFFFFFFu && u.last && k + 1 == nsl && cur.du < du_end) cur.first_zero = cur.du;
+            if (cur.fail == 0 && u.last && k + 1 == nsl && cur.du < du_end) cur.first_zero = cur.du;
             first_zero = std::min(first_zero, cur.first_zero);
         }
         n_ex += tot[i];
