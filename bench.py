@@ -216,6 +216,23 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 
+def bind_to_gpu_numa_node(index):
+    """Run this process (and what it allocates: the pinned staging buffers, first touch) on the cores next to its
+    GPU, so that the PCIe copies do not cross the socket interconnect.  Best effort: no NVML, no change."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        pynvml.nvmlShutdown()
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,7 +242,8 @@ def main():
     ap.add_argument("--workload", default="config2")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 4096 for config2/5, 16 for config3/4)")
     ap.add_argument("--unique", type=int, default=1024, help="distinct synthetic images generated per rank (cycled to fill the batch)")
-    ap.add_argument("--subseq-bits", type=int, default=0)
+    ap.add_argument("--subseq-bits", type=int, default=0, help="sub-sequence length of the Huffman synchronisation pass (0 = library default: per image, about 4096 bits)")
+    ap.add_argument("--slices", type=int, default=0, help="slices of a sub-sequence the Huffman write pass works on (0 = library default: 4)")
     ap.add_argument("--sync-rounds", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--sub-batch-mb", type=int, default=0, help="compressed MB per sub-batch of the one-call path (0 = library default)")
@@ -245,6 +263,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    bind_to_gpu_numa_node(local_rank)
     batch_n = args.batch or (4096 if args.workload in ("config2", "config5") else 16)
     specs, desc = workload_specs(args.workload, batch_n, args.unique, rank)
     workers = max(1, args.gen_workers // max(1, world))
@@ -256,6 +275,7 @@ def main():
     import pim_jpeg_decoder_b200 as bj
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -266,6 +286,8 @@ def main():
     dec = bj.Decoder(local_rank)                              # raises without a GPU: no CPU fallback exists
     if args.subseq_bits:
         dec.set_option("subseq_bits", args.subseq_bits)
+    if args.slices:
+        dec.set_option("slices", args.slices)
     if args.sync_rounds:
         dec.set_option("sync_rounds", args.sync_rounds)
     sampler = ClockSampler(local_rank)
@@ -343,6 +365,19 @@ def main():
             dec.set_option("sub_batch_bytes", args.sub_batch_mb << 20)
         if args.host_threads:
             dec.set_option("host_threads", args.host_threads)
+        # what the link gives this process: one large pinned copy each way (the e2e number is bounded by the D2H one)
+        pcie = {}
+        nb = min(o, 1 << 30)
+        dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        hview = torch.from_numpy(pin_out.array[:nb])
+        for name, dst, src in (("d2h_gbs", hview, dbuf), ("h2d_gbs", dbuf, hview)):
+            best = 0.0
+            for _ in range(3):
+                a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); dst.copy_(src, non_blocking=True); b2.record(); torch.cuda.synchronize()
+                best = max(best, nb / (a.elapsed_time(b2) * 1e-3) / 1e9)
+            pcie[name] = best
+        del dbuf
         k2 = args.e2e_steps or max(2, min(args.steps, 5))
         for _ in range(max(1, min(args.warmup, 2))):
             dec.decode_packed(pin_in.array, in_off, in_len, pin_out.array, out_off, bj.BJ_OUT_BMP)
@@ -368,6 +403,8 @@ def main():
                "h2d_bytes_per_step": int(dec.stat("decode_batch_h2d_bytes")), "d2h_bytes_per_step": int(dec.stat("decode_batch_d2h_bytes")),
                "sub_batches_per_step": int(dec.stat("decode_batch_sub_batches")), "host_threads": int(dec.stat("host_threads")),
                "host_prepare_ms_per_step": host_ms / k2, "host_wait_gpu_ms_per_step": wait_ms / k2,
+               "pcie_pinned_copy": pcie,
+               "d2h_floor_ms_per_step": 1e3 * dec.stat("decode_batch_d2h_bytes") / (pcie["d2h_gbs"] * 1e9) if pcie.get("d2h_gbs") else None,
                "timer": "host wall clock around the blocking bj_decode_batch call (pinned host buffers in and out), max over ranks"}
         pin_in.free()
         pin_out.free()
@@ -406,7 +443,7 @@ def main():
     nsub = float(info.subsequences)
     alg = {
         "unstuff": 2.0 * info.scan_bytes + clean,                     # raw bytes read by the count and the write kernel + clean bytes written
-        "sync": clean + 48.0 * nsub,                                  # stream read once + per-sub-sequence state/totals written
+        "sync": clean + (28.0 + 16.0 * (args.slices or 4)) * nsub,    # stream read once + per-sub-sequence states/totals + slice entry states written
         "write": clean + 128.0 * units,                               # stream read once + every coefficient unit written once
         "idct": 128.0 * units + float(info.out_bytes),                # coefficients read once + pixels written once
     }
@@ -437,7 +474,8 @@ def main():
         "images_per_s": batch_n * world * args.steps / total_s,
         "config": {"workload": desc, "images_per_gpu_per_step": batch_n, "output": "BMP bytes (bit-exact to the reference's write_BMP)",
                    "l2": "per-step working set (coefficients + pixels) is far larger than the 126 MB L2; no explicit flush",
-                   "subseq_bits": args.subseq_bits or 1024, "sharding": "by image, no collective on the data path"},
+                   "subseq_bits": args.subseq_bits or "per image, about 4096 (sub-sequences fill whole CTAs)", "slices": args.slices or 4,
+                   "sharding": "by image, no collective on the data path"},
         "roofline": roofline, "stages": stages,
         "entropy": {"ms": ent_ms, "compressed_gbs": info.scan_bytes / (ent_ms * 1e-3) / 1e9 if ent_ms else None},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
