@@ -61,6 +61,7 @@ struct bj_batch {
     size_t files_bytes = 0, meta_bytes = 0;
     // offsets inside the descriptor blob
     size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_utile = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0, o_lutacs = 0;
+    uint32_t idct_smem = 0;             // dynamic shared memory of k_idct_color: sized for the widest pixel tile of this batch
     uint32_t n_idct_tiles = 0, n_blk = 0, n_utile = 0, n_dcc = 0, n_seg_entries = 0, n_sub_slots = 0, lut_smem = 0;
     size_t clean_words = 0, coef_units = 0, out_bytes = 0;
     uint64_t pixels = 0, scan_bytes = 0;
@@ -144,6 +145,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     uint32_t seg_entries = 0, nblk = 0;
     int prev = -1;                                  // last valid image: its table slots are reused when the tables match
     b->pixels = 0; b->scan_bytes = 0; b->lut_smem = 0;
+    uint32_t rgb_max = 0;
     auto same_tables = [](const bj_image_desc &a, const bj_image_desc &q) {
         if (a.ncomp != q.ncomp || memcmp(a.dc_id, q.dc_id, 3) || memcmp(a.ac_id, q.ac_id, 3)) return false;
         for (int j = 0; j < a.ncomp; j++) {
@@ -250,10 +252,12 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         idev[i].dc_sep = 1;
         out_bytes += align_up(b->out_size[i], 16);
         append_tiles(g, (uint32_t)i, &tiles);
+        rgb_max = std::max<uint32_t>(rgb_max, std::min<uint32_t>(g.tile_mcus, g.nmx) * d.hs * 8u * d.vs * 8u * 3u);
         b->pixels += (uint64_t)d.width * d.height;
         b->scan_bytes += d.scan_len;
         if (coef_units > 0xFFFFFFF0ull || clean_words > 0xFFFFFFF0ull) return BJ_ERR_ARG;   // split the batch
     }
+    b->idct_smem = kSmemDu + kSmemQ + kRgbFront + std::min<uint32_t>(rgb_max, kRgbMax) + 64;
     b->files_bytes = fbytes + 64; b->clean_words = clean_words + 16; b->coef_units = coef_units; b->out_bytes = out_bytes;
     b->n_idct_tiles = (uint32_t)tiles.size(); b->n_blk = nblk; b->n_utile = (uint32_t)utile_img.size();
     b->n_dcc = (uint32_t)dcc_img.size(); b->n_seg_entries = seg_entries; b->n_sub_slots = nblk * kHuffThreads;
@@ -369,7 +373,7 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     if (!b->n_blk) cudaEventRecord(b->ev[2], s);
     cudaEventRecord(b->ev[3], s);
     if (b->n_idct_tiles) {
-        k_idct_color<<<b->n_idct_tiles, kTileThreads, kSmemIdctColor, s>>>((const int16_t *)b->d_coef.p, dcp, idev, tiles, (uint8_t *)b->d_out.p);
+        k_idct_color<<<b->n_idct_tiles, kTileThreads, b->idct_smem, s>>>((const int16_t *)b->d_coef.p, dcp, idev, tiles, (uint8_t *)b->d_out.p);
         b->launches++;
     }
     cudaEventRecord(b->ev[4], s);

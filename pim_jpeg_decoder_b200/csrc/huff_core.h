@@ -472,10 +472,13 @@ struct WriteCursor {
     }
     // The unit to store after a step that said `unit` (UINT32_MAX: none).
     BJ_HD uint32_t store_du() {
-        if (__builtin_expect(fail == 0u, 1)) return du - 1u;
-        if (fail == 1u && (S & 0xFFu) == 0u) { first_zero = du; return 0xFFFFFFFFu; }   // a failed DC: the unit stays zero
-        first_zero = du + 1u;                                                            // a failed AC keeps what was stored before it
-        return du;
+        uint32_t d = du - 1u;
+        if (__builtin_expect(fail != 0u, 0)) {
+            const bool dc = fail == 1u && (S & 0xFFu) == 0u;
+            first_zero = dc ? du : du + 1u;               // a failed DC: the unit stays zero; a failed AC keeps what was stored before it
+            d = dc ? 0xFFFFFFFFu : du;
+        }
+        return d;
     }
 };
 

@@ -559,6 +559,8 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     uint4 *out_lane = out + (lane & 7);
     uint32_t flusher = lane < 8 ? 1u : 0u;
     asm volatile("mov.u32 %0, %0;" : "+r"(flusher));
+    asm volatile("mov.u64 %0, %0;" : "+l"(out_lane));                      // (kept in registers, like warp_stage)
+    asm volatile("mov.u64 %0, %0;" : "+l"(dcp));
     if (!__all_sync(0xFFFFFFFFu, done)) {
         for (;;) {
             bool unit = false;

@@ -48,7 +48,7 @@ __device__ __forceinline__ void color8(const uint4 &yv, const unsigned *fw, cons
 }
 
 // ------------------------------------------------------------------------------------------------ fast layout
-__global__ void __launch_bounds__(kTileThreads, 3)
+__global__ void __launch_bounds__(kTileThreads, 4)
 k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_plane, const ImgDev *__restrict__ imgs,
              const TileDev *__restrict__ tiles, uint8_t *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem[];
