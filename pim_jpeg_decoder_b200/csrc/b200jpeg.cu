@@ -174,7 +174,7 @@ extern "C" int bj_stage_idct_color(bj_ctx *c, const bj_image_desc *desc, const i
     std::vector<TileDev> tiles;
     Geometry g = geometry_of(*desc);
     fill_imgdev(*desc, g, format, /*du_base=*/0, /*out_base=*/0, &im);
-    append_tiles(g, 0, &tiles);
+    append_tiles(g, 0, 0, &tiles);
     const size_t coef_bytes = (size_t)g.ndu * 128, out_bytes = bj_output_size(desc, format);
     DevBuf &dco = c->pool[POOL_COEF], &dout = c->pool[POOL_OUT], &dim = c->pool[POOL_IMGS], &dti = c->pool[POOL_TILES];
     if (dco.reserve(coef_bytes) || dout.reserve(out_bytes + 64) || dim.reserve(sizeof(im)) || dti.reserve(tiles.size() * sizeof(TileDev))) return BJ_ERR_NOMEM;

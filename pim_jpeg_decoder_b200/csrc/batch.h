@@ -251,7 +251,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         fill_imgdev(d, g, format, hi.du_base, out_bytes, &idev[i]);
         idev[i].dc_sep = 1;
         out_bytes += align_up(b->out_size[i], 16);
-        append_tiles(g, (uint32_t)i, &tiles);
+        append_tiles(g, (uint32_t)i, hi.du_base, &tiles);
         rgb_max = std::max<uint32_t>(rgb_max, std::min<uint32_t>(g.tile_mcus, g.nmx) * d.hs * 8u * d.vs * 8u * 3u);
         b->pixels += (uint64_t)d.width * d.height;
         b->scan_bytes += d.scan_len;

@@ -22,15 +22,19 @@ struct ImgDev {
     uint8_t  hs, vs, ncomp, bpm;  // luma sampling, components, data units per MCU
     uint8_t  bgr;                 // 1: B,G,R byte order (BMP)
     uint8_t  valid;
-    uint8_t  dc_sep;              // 1: slot 0 of every unit is unused, the DC value comes from the DC plane at du_base + unit
+    uint8_t  dc_sep;              // 1: slot 0 of every unit is unused, the DC value comes from the DC plane (informative: the kernel is told by its dc_plane argument)
     uint8_t  pad_[1];
     uint32_t q16[3][kQPitch];     // per component: (quantiser << 16) in ZIG-ZAG order (file order)
 };
 
 // One CTA of the fused dequant/IDCT/colour kernel: `nm` consecutive MCUs of MCU-row `my`, starting at `mx0`.
+// 16 bytes, one load; du0 / ndu let the CTA start fetching its coefficient units before it has seen the image record.
 struct TileDev {
     uint32_t img;
-    uint16_t my, mx0, nm, pad_;
+    uint16_t my, mx0, nm;
+    uint16_t ndu;                 // data units of the tile (nm * units per MCU), <= kTileThreads
+    uint32_t du0;                 // index of the tile's first data unit in the coefficient buffer / DC plane
 };
+static_assert(sizeof(TileDev) == 16, "TileDev is loaded as one uint4");
 
 }  // namespace bj

@@ -183,13 +183,14 @@ inline void fill_imgdev(const bj_image_desc &d, const Geometry &g, int format, u
             im->q16[j][k] = (j < d.ncomp && reachable[d.qt_id[j] & 3]) ? ((uint32_t)d.qt_zz[d.qt_id[j] & 3][k] << 16) : 0u;
 }
 
-inline void append_tiles(const Geometry &g, uint32_t img, std::vector<TileDev> *tiles) {
+inline void append_tiles(const Geometry &g, uint32_t img, uint32_t du_base, std::vector<TileDev> *tiles) {
     for (uint32_t my = 0; my < g.nmy; my++)
         for (uint32_t mx = 0; mx < g.nmx; mx += g.tile_mcus) {
             TileDev t;
             t.img = img; t.my = (uint16_t)my; t.mx0 = (uint16_t)mx;
             t.nm = (uint16_t)std::min<uint32_t>(g.tile_mcus, g.nmx - mx);
-            t.pad_ = 0;
+            t.ndu = (uint16_t)(t.nm * g.bpm);
+            t.du0 = du_base + (my * g.nmx + mx) * g.bpm;
             tiles->push_back(t);
         }
 }

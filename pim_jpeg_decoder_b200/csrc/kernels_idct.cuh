@@ -55,24 +55,42 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
     uint4 *s_du = reinterpret_cast<uint4 *>(smem);
     uint32_t *s_q = reinterpret_cast<uint32_t *>(smem + kSmemDu);
     uint8_t *s_rgb = smem + kSmemDu + kSmemQ + kRgbFront;
+    __shared__ uint16_t s_dc[kTileThreads];
 
     const int tid = threadIdx.x;
-    const TileDev t = tiles[blockIdx.x];
-    const ImgDev *__restrict__ im = imgs + t.img;
-    const int hs = im->hs, vs = im->vs, ncomp = im->ncomp, bpm = im->bpm;
-    const int nm = t.nm, ndu = nm * bpm;
-
-    // ---- stage 0: dequant tables + this tile's coefficient units (contiguous in HBM) -> smem, coalesced 16 B
-    for (int i = tid; i < 3 * kQPitch; i += kTileThreads) s_q[i] = (&im->q16[0][0])[i];
+    TileDev t;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(coef) +
-                           ((size_t)im->du_base + (size_t)(t.my * im->nmx + t.mx0) * bpm) * 8;
-        for (int q = tid; q < ndu * 8; q += kTileThreads) {
-            const uint4 v = __ldcs(src + q);
+        const uint4 tw = __ldg(reinterpret_cast<const uint4 *>(tiles) + blockIdx.x);     // the 16-byte record in one load
+        t.img = tw.x; t.my = (uint16_t)tw.y; t.mx0 = (uint16_t)(tw.y >> 16); t.nm = (uint16_t)tw.z; t.ndu = (uint16_t)(tw.z >> 16); t.du0 = tw.w;
+    }
+    const int ndu = t.ndu;
+
+    // ---- stage 0: this tile's coefficient units (contiguous in HBM) -> smem, coalesced 16 B.  All of a thread's
+    // loads are issued before the first store, and nothing here waits for the image record.
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(coef) + (size_t)t.du0 * 8;
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int q = tid + k * kTileThreads;
+            v[k] = q < ndu * 8 ? __ldcs(src + q) : make_uint4(0, 0, 0, 0);
+        }
+        // the entropy stage keeps predicted DC values in a separate plane (one short per unit): patched in here
+        unsigned dcv = 0;
+        const bool dc_sep = dc_plane != nullptr;
+        if (dc_sep && tid < ndu) dcv = (unsigned short)__ldg(dc_plane + (size_t)t.du0 + tid);
+        s_dc[tid] = (uint16_t)dcv;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int q = tid + k * kTileThreads;
             const int du = q >> 3, c = q & 7;
-            s_du[du * 8 + (c ^ (du & 7))] = v;
+            if (q < ndu * 8) s_du[du * 8 + (c ^ (du & 7))] = v[k];
         }
     }
+    const ImgDev *__restrict__ im = imgs + t.img;
+    const int hs = im->hs, vs = im->vs, ncomp = im->ncomp, bpm = im->bpm;
+    const int nm = t.nm;
+    for (int i = tid; i < 3 * kQPitch; i += kTileThreads) s_q[i] = (&im->q16[0][0])[i];
     __syncthreads();
 
     // ---- stage 1: one thread = one unit: de-zigzag (with the reference's 48/52 quirk), dequantise, IDCT
@@ -83,13 +101,12 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
         const uint4 *q4 = reinterpret_cast<const uint4 *>(s_q + comp * kQPitch);
         int X[64];
         unsigned raw48 = 0, raw52 = 0;
-        // the entropy stage keeps predicted DC values in a separate plane (one short per unit)
-        unsigned dcv = 0;
-        if (im->dc_sep) dcv = (unsigned short)__ldg(dc_plane + (size_t)im->du_base + (size_t)(t.my * im->nmx + t.mx0) * bpm + du);
+        const unsigned dcv = s_dc[du];
+        const bool dc_sep = dc_plane != nullptr;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             uint4 v = s_du[du * 8 + (c ^ sw)];
-            if (c == 0 && im->dc_sep) v.x = (v.x & 0xFFFF0000u) | dcv;
+            if (c == 0 && dc_sep) v.x = (v.x & 0xFFFF0000u) | dcv;
             const uint4 qa = q4[2 * c], qb = q4[2 * c + 1];
             // (w * (q<<16)) mod 2^32 only sees the low 16 bits of w: no unpack needed for the low halves
             X[zz2nat(8 * c + 0)] = (int)(v.x * qa.x);
