@@ -243,7 +243,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 4096 for config2/5, 16 for config3/4)")
     ap.add_argument("--unique", type=int, default=1024, help="distinct synthetic images generated per rank (cycled to fill the batch)")
     ap.add_argument("--subseq-bits", type=int, default=0, help="sub-sequence length of the Huffman synchronisation pass (0 = library default: per image, about 4096 bits)")
-    ap.add_argument("--slices", type=int, default=0, help="slices of a sub-sequence the Huffman write pass works on (0 = library default: 4)")
+    ap.add_argument("--slices", type=int, default=0, help="slices of a sub-sequence the Huffman write pass works on (0 = library default: 1)")
     ap.add_argument("--sync-rounds", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--sub-batch-mb", type=int, default=0, help="compressed MB per sub-batch of the one-call path (0 = library default)")
@@ -443,7 +443,7 @@ def main():
     nsub = float(info.subsequences)
     alg = {
         "unstuff": 2.0 * info.scan_bytes + clean,                     # raw bytes read by the count and the write kernel + clean bytes written
-        "sync": clean + (28.0 + 16.0 * (args.slices or 4)) * nsub,    # stream read once + per-sub-sequence states/totals + slice entry states written
+        "sync": clean + (28.0 + 16.0 * (args.slices or 1)) * nsub,    # stream read once + per-sub-sequence states/totals + slice entry states written
         "write": clean + 128.0 * units,                               # stream read once + every coefficient unit written once
         "idct": 128.0 * units + float(info.out_bytes),                # coefficients read once + pixels written once
     }
@@ -474,7 +474,7 @@ def main():
         "images_per_s": batch_n * world * args.steps / total_s,
         "config": {"workload": desc, "images_per_gpu_per_step": batch_n, "output": "BMP bytes (bit-exact to the reference's write_BMP)",
                    "l2": "per-step working set (coefficients + pixels) is far larger than the 126 MB L2; no explicit flush",
-                   "subseq_bits": args.subseq_bits or "per image, about 4096 (sub-sequences fill whole CTAs)", "slices": args.slices or 4,
+                   "subseq_bits": args.subseq_bits or "per image, 2400-4096 (sub-sequences fill whole CTAs)", "slices": args.slices or 1,
                    "sharding": "by image, no collective on the data path"},
         "roofline": roofline, "stages": stages,
         "entropy": {"ms": ent_ms, "compressed_gbs": info.scan_bytes / (ent_ms * 1e-3) / 1e9 if ent_ms else None},

@@ -152,8 +152,10 @@ int bj_stage_entropy(bj_ctx *ctx, const uint8_t *file, size_t len, int16_t *coef
 
 /* Tunables (0 = default):
  *   "subseq_bits"      sub-sequence size of the Huffman synchronisation pass in bits (multiple of 32, >= 128);
- *                      0 = chosen per image (about 4096 bits, so that an image's sub-sequences fill whole CTAs)
- *   "slices"           pieces of a sub-sequence the Huffman write pass works on (1, 2, 4 or 8; default 4)
+ *                      0 = chosen per image (2400-4096 bits, so that an image's sub-sequences fill whole CTAs;
+ *                      a typical restart segment in one piece)
+ *   "slices"           pieces of a sub-sequence the Huffman write pass works on (1, 2, 4 or 8; default 1: the write
+ *                      pass works on whole sub-sequences)
  *   "sync_rounds"      launches of the fix-up kernel before convergence is first checked
  *   "sub_batch_bytes"  compressed bytes per sub-batch of bj_decode_batch
  *   "packed_outputs"   1: output pointers that follow bj_batch_output_offset's layout (outs[i] = base + offset_i,

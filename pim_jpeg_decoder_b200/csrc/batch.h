@@ -47,7 +47,6 @@ inline int batch_kernels_init(bj_ctx *c) {
 struct bj_batch {
     bj_ctx *ctx = nullptr;
     int n = 0, format = 0;
-    uint32_t slices_log2 = 2;            // slices (write pass) per sub-sequence (synchronisation pass), as a power of two
     int rounds = 3;
 
     std::vector<bj_image_desc> desc;
@@ -60,8 +59,10 @@ struct bj_batch {
     bj::PinBuf h_files, h_meta, h_res;
     size_t files_bytes = 0, meta_bytes = 0;
     // offsets inside the descriptor blob
-    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_utile = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0, o_lutacs = 0;
+    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_wblk = 0, o_utile = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0, o_lutacs = 0;
     uint32_t idct_smem = 0;             // dynamic shared memory of k_idct_color: sized for the widest pixel tile of this batch
+    uint32_t n_wblk = 0;                // CTAs of the Huffman write pass
+    size_t n_slice_slots = 0;
     uint32_t n_idct_tiles = 0, n_blk = 0, n_utile = 0, n_dcc = 0, n_seg_entries = 0, n_sub_slots = 0, lut_smem = 0;
     size_t clean_words = 0, coef_units = 0, out_bytes = 0;
     uint64_t pixels = 0, scan_bytes = 0;
@@ -95,8 +96,6 @@ constexpr int kMaxRounds = 64;
 inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format) {
     if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
     b->ctx = c; b->n = n; b->format = format;
-    // slices per sub-sequence: option "slices" (1, 2, 4, 8), default 4
-    b->slices_log2 = c->slices == 1 ? 0u : c->slices == 2 ? 1u : c->slices == 8 ? 3u : 2u;
     b->uploaded = b->decoded = b->synced = false;
     b->desc.resize(n); b->parse_status.assign(n, BJ_OK);
     b->out_off.assign(n, 0); b->out_size.assign(n, 0); b->file_off.assign(n, 0);
@@ -110,34 +109,45 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
             b->parse_status[i] = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &b->desc[i]) : BJ_ERR_INVALID_JPEG;
     });
 
-    // ---- sub-sequence length of the synchronisation pass.  Explicit (option "subseq_bits"): the same for every
-    // image.  Automatic: nominally 4096 bits - a stream synchronises within about a thousand, so nearly every guess
-    // settles inside its own sub-sequence - but shorter when the whole batch would not fill the GPU with threads,
-    // and then adjusted per image so that its sub-sequences fill whole CTAs.
-    const uint32_t R = 1u << b->slices_log2;
-    uint32_t fixed_sub = c->subseq_bits ? (uint32_t)c->subseq_bits / 8u : 0u;
-    if (fixed_sub) while (b->slices_log2 && fixed_sub % (1u << b->slices_log2)) b->slices_log2--;
+    // ---- sub-sequence length and slices, per image.
+    // Explicit (options "subseq_bits", "slices"): the same for every image.  Automatic: nominally 4096 bits - a stream
+    // synchronises within about a thousand, so nearly every guess settles inside its own sub-sequence - but shorter
+    // when the whole batch would not fill the GPU with threads, and then adjusted per image so that its sub-sequences
+    // fill whole CTAs (a nearly empty second CTA costs a cross-CTA fix-up round); the write pass works on whole
+    // sub-sequences (1 slice).  An image with restart markers gets sub-sequences that hold a typical restart segment
+    // in one piece - segment heads need no speculation at all - and the write pass cuts them into 4 slices (8 when
+    // the batch is small), whose entry states the single synchronisation decode records.
+    const uint32_t fixed_sub = c->subseq_bits ? (uint32_t)c->subseq_bits / 8u : 0u;
+    uint32_t fixed_rl = c->slices == 2 ? 1u : c->slices == 4 ? 2u : c->slices == 8 ? 3u : 0u;
+    if (fixed_sub) while (fixed_rl && fixed_sub % (1u << fixed_rl)) fixed_rl--;
     uint32_t nominal_sub = 512;
-    if (!fixed_sub) {
-        uint64_t total = 0;
-        for (int i = 0; i < n; i++) if (b->parse_status[i] == BJ_OK) total += b->desc[i].scan_len;
-        const uint64_t want_threads = (uint64_t)c->sm_count * 3072u;
-        nominal_sub = (uint32_t)std::min<uint64_t>(512u, std::max<uint64_t>(128u, total / want_threads));
-    }
-    auto sub_bytes_of = [&](uint32_t raw_len) -> uint32_t {
+    uint64_t total_scan = 0;
+    for (int i = 0; i < n; i++) if (b->parse_status[i] == BJ_OK) total_scan += b->desc[i].scan_len;
+    if (!fixed_sub) nominal_sub = (uint32_t)std::min<uint64_t>(512u, std::max<uint64_t>(128u, total_scan / ((uint64_t)c->sm_count * 3072u)));
+    auto round_sub = [&](uint32_t len, uint32_t rl) { const uint32_t q = 4u << rl; return (std::max(len, 64u) + q - 1u) / q * q; };
+    auto sub_layout_of = [&](uint32_t raw_len, uint32_t nseg, uint32_t *rl) -> uint32_t {
+        *rl = c->slices ? fixed_rl : 0u;
         if (fixed_sub) return fixed_sub;
+        if (nseg > 1) {
+            const uint32_t avg = raw_len / nseg;
+            if (avg <= 1024) {
+                if (!c->slices) *rl = total_scan < ((uint64_t)16 << 20) ? 3u : 2u;
+                return round_sub(std::max(2 * avg, nominal_sub), *rl);
+            }
+        }
         const uint32_t per_cta = nominal_sub * kHuffThreads;
         const uint32_t m = std::max(1u, (raw_len + per_cta / 2) / per_cta);                  // CTAs for this image
-        uint32_t len = (raw_len + m * kHuffThreads - 1) / (m * kHuffThreads);
-        len = std::max(len, 64u);
-        return (len + 4 * R - 1) / (4 * R) * (4 * R);
+        const uint32_t slots = m * kHuffThreads;                                            // ceil(raw_len / len) + nseg must fit
+        if (slots <= nseg + 1) return round_sub(nominal_sub, *rl);
+        return round_sub((raw_len + slots - nseg - 1) / (slots - nseg), *rl);
     };
 
     // ---- layout (serial: prefix sums over the batch)
     std::vector<HuffImg> himg(n);
     std::vector<ImgDev> idev(n);
     std::vector<TileDev> tiles;
-    std::vector<uint32_t> blk_img, utile_img, dcc_img;
+    std::vector<uint32_t> blk_img, wblk_img, utile_img, dcc_img;
+    size_t slice_slots = 0;
     std::vector<uint32_t> luts_dc, luts_ac, luts_acs;     // acs: the synchronisation pass' grouped AC tables
     std::map<std::string, int> lut_index[2];
     std::vector<uint16_t> lut_n4[2];                // per pooled table: used size in 16-byte chunks
@@ -235,11 +245,19 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         hi.nseg = hi.ri ? (g.nmcu + hi.ri - 1) / hi.ri : 1u;
         hi.bpm = (uint8_t)g.bpm; hi.ny = (uint8_t)(d.hs * d.vs); hi.ncomp = d.ncomp;
         hi.ndu = g.ndu;
-        hi.sub_bytes = sub_bytes_of(hi.raw_len);
+        {
+            uint32_t rl = 0;
+            hi.sub_bytes = sub_layout_of(hi.raw_len, hi.nseg, &rl);
+            hi.slices_log2 = (uint8_t)rl;
+        }
         const uint32_t sub_cap = (uint32_t)((hi.raw_len + hi.sub_bytes - 1) / hi.sub_bytes) + hi.nseg;
         hi.nblk = (sub_cap + kHuffThreads - 1) / kHuffThreads;
         for (uint32_t k = 0; k < hi.nblk; k++) blk_img.push_back((uint32_t)i);
         nblk += hi.nblk;
+        hi.wblk_base = (uint32_t)wblk_img.size();
+        for (uint32_t k = 0; k < (hi.nblk << hi.slices_log2); k++) wblk_img.push_back((uint32_t)i);
+        hi.slice_base = (uint32_t)slice_slots;
+        slice_slots += ((size_t)hi.nblk * kHuffThreads) << hi.slices_log2;
         hi.ndcc = (g.nmcu + kDcThreads - 1) / kDcThreads;
         for (uint32_t k = 0; k < hi.ndcc; k++) dcc_img.push_back((uint32_t)i);
         seg_entries += hi.nseg + 1;
@@ -259,6 +277,8 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     }
     b->idct_smem = kSmemDu + kSmemQ + kRgbFront + std::min<uint32_t>(rgb_max, kRgbMax) + 64;
     b->files_bytes = fbytes + 64; b->clean_words = clean_words + 16; b->coef_units = coef_units; b->out_bytes = out_bytes;
+    b->n_wblk = (uint32_t)wblk_img.size(); b->n_slice_slots = slice_slots;
+    if (slice_slots > 0xFFFFFFF0ull) return BJ_ERR_ARG;
     b->n_idct_tiles = (uint32_t)tiles.size(); b->n_blk = nblk; b->n_utile = (uint32_t)utile_img.size();
     b->n_dcc = (uint32_t)dcc_img.size(); b->n_seg_entries = seg_entries; b->n_sub_slots = nblk * kHuffThreads;
 
@@ -268,6 +288,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     b->o_idev = o;  o = align_up(o + (size_t)n * sizeof(ImgDev), 256);
     b->o_tiles = o; o = align_up(o + tiles.size() * sizeof(TileDev), 256);
     b->o_blk = o;   o = align_up(o + blk_img.size() * 4, 256);
+    b->o_wblk = o;  o = align_up(o + wblk_img.size() * 4, 256);
     b->o_utile = o; o = align_up(o + utile_img.size() * 4, 256);
     b->o_dcc = o;   o = align_up(o + dcc_img.size() * 4, 256);
     b->o_lutdc = o; o = align_up(o + luts_dc.size() * 4, 256);
@@ -279,6 +300,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     if (n) { memcpy(b->hmeta<HuffImg>(b->o_himg), himg.data(), (size_t)n * sizeof(HuffImg)); memcpy(b->hmeta<ImgDev>(b->o_idev), idev.data(), (size_t)n * sizeof(ImgDev)); }
     if (!tiles.empty()) memcpy(b->hmeta<TileDev>(b->o_tiles), tiles.data(), tiles.size() * sizeof(TileDev));
     if (!blk_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_blk), blk_img.data(), blk_img.size() * 4);
+    if (!wblk_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_wblk), wblk_img.data(), wblk_img.size() * 4);
     if (!utile_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_utile), utile_img.data(), utile_img.size() * 4);
     if (!dcc_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_dcc), dcc_img.data(), dcc_img.size() * 4);
     if (!luts_dc.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutdc), luts_dc.data(), luts_dc.size() * 4);
@@ -298,7 +320,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         b->d_seg.reserve((size_t)(seg_entries + 2) * 4 * 2) || b->d_subseg.reserve((size_t)b->n_sub_slots * 4 + 16) ||
         b->d_stin.reserve((size_t)b->n_sub_slots * 8 + 16) || b->d_stout.reserve((size_t)b->n_sub_slots * 8 + 16) ||
         b->d_tot.reserve((size_t)b->n_sub_slots * 4 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 8 + 16) ||
-        b->d_slice.reserve(((size_t)b->n_sub_slots << b->slices_log2) * 16 + 16) ||
+        b->d_slice.reserve(b->n_slice_slots * 16 + 16) ||
         b->d_dc.reserve(coef_units * 2 + 64) || b->d_dcagg.reserve((size_t)b->n_dcc * sizeof(DcAgg) + 16) ||
         b->d_tilecnt.reserve((size_t)b->n_utile * 8 + 16) || b->d_blkagg.reserve((size_t)nblk * sizeof(BlkAgg) + 16) ||
         b->d_state.reserve((size_t)n * sizeof(HuffImgState) + 16) || b->d_flags.reserve(kMaxRounds * 4) ||
@@ -323,7 +345,7 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     const HuffImg *himg = b->dmeta<HuffImg>(b->o_himg);
     const ImgDev *idev = b->dmeta<ImgDev>(b->o_idev);
     const TileDev *tiles = b->dmeta<TileDev>(b->o_tiles);
-    const uint32_t *blk_img = b->dmeta<uint32_t>(b->o_blk);
+    const uint32_t *blk_img = b->dmeta<uint32_t>(b->o_blk), *wblk_img = b->dmeta<uint32_t>(b->o_wblk);
     const uint32_t *utile_img = b->dmeta<uint32_t>(b->o_utile);
     const uint32_t *dcc_img = b->dmeta<uint32_t>(b->o_dcc);
     const uint32_t *luts_dc = b->dmeta<uint32_t>(b->o_lutdc), *luts_ac = b->dmeta<uint32_t>(b->o_lutac), *luts_acs = b->dmeta<uint32_t>(b->o_lutacs);
@@ -353,11 +375,11 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     }
     if (b->n_blk) {
         for (int r = r0; r < r1; r++) {
-            k_huff_sync<<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, agg, flags, r, b->slices_log2);
+            k_huff_sync<<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, agg, flags, r);
             b->launches++; b->sync_rounds++;
         }
         cudaEventRecord(b->ev[2], s);
-        k_huff_write<<<b->n_blk << b->slices_log2, kHuffThreads, kSmemHuffStage + lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_ac, slices, pre, agg, (int16_t *)b->d_coef.p, dcp, b->slices_log2);
+        k_huff_write<<<b->n_wblk, kHuffThreads, kSmemHuffStage + lut_smem, s>>>(himg, st, wblk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_ac, slices, pre, agg, (int16_t *)b->d_coef.p, dcp);
         b->launches++;
     }
     {

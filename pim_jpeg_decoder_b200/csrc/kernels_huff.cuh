@@ -41,9 +41,12 @@ struct HuffImg {
     uint8_t ndc, nac;        // distinct DC / AC tables of this image = staged slots
     uint16_t dc_lut[3], ac_lut[3];   // pool index of each staged DC / AC slot
     uint8_t dc_slot[3], ac_slot[3];  // per component: staged slot
-    uint8_t pad_[2];
+    uint8_t slices_log2;     // the write pass works on 2^slices_log2 slices of every sub-sequence
+    uint8_t pad_[1];
     uint16_t dc_n4[3], ac_n4[3];     // used size of each staged table in 16-byte chunks (tables are staged packed)
     uint32_t sub_bytes;      // length of this image's sub-sequences (synchronisation pass), a multiple of the slice count
+    uint32_t wblk_base;      // first CTA of k_huff_write (nblk << slices_log2 of them)
+    uint32_t slice_base;     // first slot of this image in the slice table ((nblk * kHuffThreads) << slices_log2 slots)
 };
 
 // Per image, written by the kernels.
@@ -342,7 +345,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
             const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
             const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
             uint2 *__restrict__ st_in, uint2 *__restrict__ st_out, uint32_t *__restrict__ sub_tot, uint2 *__restrict__ sub_pre,
-            uint4 *__restrict__ slices, BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round, uint32_t slices_log2) {
+            uint4 *__restrict__ slices, BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
@@ -389,7 +392,9 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     LutMem luts;
     stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g, luts);
     const uint32_t *__restrict__ words = clean + im.clean_word0;
+    const uint32_t slices_log2 = im.slices_log2;
     const uint32_t slice_bits = (im.sub_bytes >> slices_log2) * 8u;
+    uint4 *img_slices = slices + im.slice_base;
 
     int cur = 0;
     for (;;) {
@@ -402,7 +407,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
             in.p = s_in[item].x; in.cz = s_in[item].y;
             uint32_t started;
             SliceStore rec;
-            rec.base = slices + ((size_t)(im.sub_base + first_j + item) << slices_log2);
+            rec.base = img_slices + ((size_t)(first_j + item) << slices_log2);
             const uint2 span = s_span[item];
             const HuffState o = decode_span(words, luts, g, in, span.x, span.y, slice_bits, rec, &started);
             s_out[item] = make_uint2(o.p, o.cz);
@@ -450,7 +455,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
         if (!f) { v0 += s_w[warp]; hf = s_wf[warp]; }
         // exclusive: a head starts from zero; otherwise inclusive minus own
         st_in[gj] = s_in[tid];
-        slices[(size_t)gj << slices_log2] = make_uint4(s_in[tid].x, s_in[tid].y, 0u, 0u);
+        img_slices[(size_t)j << slices_log2] = make_uint4(s_in[tid].x, s_in[tid].y, 0u, 0u);
         st_out[gj] = s_out[tid];
         sub_tot[gj] = s_tot[tid];
         sub_pre[gj] = u.head ? make_uint2(0u, 1u) : make_uint2(v0 - own0, hf);   // .y: a head precedes inside this CTA
@@ -476,24 +481,25 @@ struct SmemUnitSink {
 constexpr int kSmemHuffStage = kHuffThreads * 128;
 
 __global__ void __launch_bounds__(kHuffThreads)
-k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
+k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, const uint32_t *__restrict__ wblk_img,
              const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
              const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
              const uint4 *__restrict__ slices, const uint2 *__restrict__ sub_pre, const BlkAgg *__restrict__ blk_agg,
-             int16_t *__restrict__ coef, int16_t *__restrict__ dc_plane, uint32_t slices_log2) {
+             int16_t *__restrict__ coef, int16_t *__restrict__ dc_plane) {
     extern __shared__ __align__(128) uint8_t smem_raw[];                   // stage rows must be 128-byte aligned
     uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw + kSmemHuffStage);
     __shared__ uint32_t s_red[kHuffThreads / 32];
     __shared__ int s_h;
 
-    const uint32_t sblk = blockIdx.x >> slices_log2;                       // CTA of the synchronisation pass
-    const uint32_t img = blk_img[sblk];
+    const uint32_t img = wblk_img[blockIdx.x];
     const HuffImg &im = imgs[img];
     const HuffImgState is = ist[img];
+    const uint32_t slices_log2 = im.slices_log2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lb = sblk - im.blk_base;
-    const uint32_t slot = (blockIdx.x & ((1u << slices_log2) - 1u)) * kHuffThreads + tid;   // slice slot within that CTA
+    const uint32_t lw = blockIdx.x - im.wblk_base;                         // this image's write CTA
+    const uint32_t lb = lw >> slices_log2;                                 // ... which covers part of this CTA of the synchronisation pass
+    const uint32_t slot = (lw & ((1u << slices_log2) - 1u)) * kHuffThreads + tid;   // slice slot within that CTA
     const uint32_t j = lb * kHuffThreads + (slot >> slices_log2);          // image-local sub-sequence
     const uint32_t k = slot & ((1u << slices_log2) - 1u);                  // slice of it
     if (lb * kHuffThreads + ((slot - tid) >> slices_log2) >= is.nsub) return;   // whole CTA beyond the image's sub-sequences
@@ -540,7 +546,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
         const uint32_t nsl = u.end_bit > u.start_bit ? (u.end_bit - u.start_bit + slice_bits - 1u) / slice_bits : 1u;
         active = k < nsl;
         if (active) {
-            const uint4 sl = slices[((size_t)(im.sub_base + j) << slices_log2) + k];
+            const uint4 sl = slices[im.slice_base + ((size_t)j << slices_log2) + k];
             const uint2 pre = sub_pre[im.sub_base + j];
             const uint32_t n_ex = pre.x + (pre.y ? 0u : c0) + sl.z;
             const uint32_t du0 = u.seg * im.ri * im.bpm;
