@@ -442,7 +442,7 @@ def main():
     units = float(info.data_units)
     nsub = float(info.subsequences)
     alg = {
-        "unstuff": 2.0 * info.scan_bytes + clean,                     # raw bytes read by the count and the write kernel + clean bytes written
+        "unstuff": 1.0 * info.scan_bytes + clean,                     # raw bytes read once + clean bytes written
         "sync": clean + (28.0 + 16.0 * (args.slices or 1)) * nsub,    # stream read once + per-sub-sequence states/totals + slice entry states written
         "write": clean + 128.0 * units,                               # stream read once + every coefficient unit written once
         "idct": 128.0 * units + float(info.out_bytes),                # coefficients read once + pixels written once
@@ -461,7 +461,7 @@ def main():
             traffic = json.load(f).get(dom)
     except (OSError, ValueError):
         pass
-    kname = {"unstuff": "k_unstuff_count+k_unstuff_scan+k_unstuff_write+k_subseq_table", "sync": "k_huff_sync (all rounds)",
+    kname = {"unstuff": "k_unstuff+k_subseq_table", "sync": "k_huff_sync (all rounds)",
              "write": "k_huff_write (+k_zero_tail)", "idct": "k_idct_color"}
     roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,

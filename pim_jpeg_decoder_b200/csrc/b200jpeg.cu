@@ -326,7 +326,9 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
     while (rc == BJ_OK && i0 < n) {
         int i1 = i0;
         size_t bytes = 0;
-        while (i1 < n && (i1 == i0 || bytes + lens[i1] <= budget)) bytes += lens[i1++];
+        // the first sub-batches are small, so that the copy-out (the bound of this call) starts early
+        const size_t cap = k == 0 ? budget / 8 : (k == 1 ? budget / 3 : budget);
+        while (i1 < n && (i1 == i0 || bytes + lens[i1] <= cap)) bytes += lens[i1++];
         const int slot = k % kSlots;
         if (busy[slot]) rc = finish(slot);
         if (rc != BJ_OK) break;

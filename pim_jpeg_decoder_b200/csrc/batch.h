@@ -172,6 +172,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         memset(&idev[i], 0, sizeof(ImgDev));
         int rc = b->parse_status[i];
         Geometry g;
+        if (rc == BJ_OK && d.scan_len >= ((size_t)1 << 31)) rc = BJ_ERR_UNSUPPORTED;   // byte counts travel in 31 bits
         if (rc == BJ_OK) {
             g = geometry_of(d);
             if (prev >= 0 && same_tables(d, b->desc[prev])) {
@@ -239,7 +240,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         hi.raw_off = b->file_off[i] + d.scan_off;
         hi.raw_len = (uint32_t)d.scan_len;
         const uint64_t a0 = hi.raw_off & ~(uint64_t)15;
-        hi.ntile = (uint32_t)((hi.raw_off - a0 + hi.raw_len + kUnstuffTile - 1) / kUnstuffTile);
+        hi.ntile = std::max<uint32_t>(1u, (uint32_t)((hi.raw_off - a0 + hi.raw_len + kUnstuffTile - 1) / kUnstuffTile));
         for (uint32_t t = 0; t < hi.ntile; t++) utile_img.push_back((uint32_t)i);
         hi.nmcu = g.nmcu; hi.ri = d.restart_interval;
         hi.nseg = hi.ri ? (g.nmcu + hi.ri - 1) / hi.ri : 1u;
@@ -365,11 +366,11 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     if (r0 == 0) {
         cudaEventRecord(b->ev[0], s);
         cudaMemsetAsync(flags, 0, kMaxRounds * 4, s);
-        if (b->n_utile) k_unstuff_count<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_cnt);
-        k_unstuff_scan<<<(n + 3) / 4, 128, 0, s>>>(himg, n, tile_cnt, st, seg_off);
-        if (b->n_utile) k_unstuff_write<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_cnt, st, clean, seg_off);
+        cudaMemsetAsync(tile_cnt, 0, (size_t)b->n_utile * 8 + 8, s);                  // look-back status words
+        cudaMemsetAsync(st, 0, (size_t)n * sizeof(HuffImgState), s);                  // (rejected files keep an all-zero state)
+        if (b->n_utile) k_unstuff<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, (unsigned long long *)tile_cnt, st, clean, seg_off);
         k_subseq_table<<<n, 256, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg);
-        b->launches = 2 + (b->n_utile ? 2 : 0);
+        b->launches = 1 + (b->n_utile ? 1 : 0);
         b->sync_rounds = 0;
         cudaEventRecord(b->ev[1], s);
     }

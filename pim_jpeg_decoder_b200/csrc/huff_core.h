@@ -217,30 +217,30 @@ BJ_HD bool scan_is_rst(unsigned prev, unsigned b) { return prev == 0xFFu && b >=
 // The same rules on 16 bytes at once, four per 32-bit word (little-endian: byte i of the chunk sits in bits
 // 8*(i&3).. of w[1 + i/4]); w[0] is the word before the chunk (only its top byte matters), w[5] the word after
 // (only its low byte).  keep / rst: bit i = byte i survives / is the code byte of an RSTn marker.
-BJ_HD uint32_t bytes_eq(uint32_t a, uint32_t b) {                          // 0xFF in every byte where a == b
-#ifdef __CUDA_ARCH__
-    return __vcmpeq4(a, b);
-#else
-    uint32_t r = 0;
-    for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xFFu) == ((b >> (8 * i)) & 0xFFu)) r |= 0xFFu << (8 * i);
-    return r;
-#endif
-}
+// Per-byte tests are exact bit tricks that flag a byte in its bit 7 (no carries cross a byte):
+//   byte == FF  <=>  its low 7 bits + 1 carry into bit 7, and bit 7 is set
+//   byte == 00  <=>  its low 7 bits + 7F do not reach bit 7, and bit 7 is clear
+BJ_HD uint32_t flag_ff(uint32_t x) { return ((x & 0x7F7F7F7Fu) + 0x01010101u) & x & 0x80808080u; }
+BJ_HD uint32_t flag_00(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
 BJ_HD uint32_t movemask4(uint32_t m) { return (((m >> 7) & 0x01010101u) * 0x01020408u) >> 24; }   // bit 7 of each byte -> 4 bits
 BJ_HD void classify_words(const uint32_t w[6], uint32_t &keep, uint32_t &rst) {
     keep = 0; rst = 0;
+    uint32_t Fprev = flag_ff(w[0]);
+    uint32_t Z = flag_00(w[1]);
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int k = 0; k < 4; k++) {
         const uint32_t x = w[k + 1];
-        const uint32_t before = (x << 8) | (w[k] >> 24);                   // byte i-1 under byte i
-        const uint32_t behind = (x >> 8) | (w[k + 2] << 24);               // byte i+1 under byte i
-        const uint32_t F = bytes_eq(x, 0xFFFFFFFFu), PF = bytes_eq(before, 0xFFFFFFFFu), Z = bytes_eq(behind, 0u);
-        const uint32_t km = (F & Z) | (~F & ~PF);                          // scan_keep
-        const uint32_t rm = PF & bytes_eq(x & 0xF8F8F8F8u, 0xD0D0D0D0u);   // scan_is_rst
+        const uint32_t F = flag_ff(x), Znext = flag_00(w[k + 2]);
+        const uint32_t PF = (F << 8) | (Fprev >> 24);                      // flag of byte i-1 under byte i
+        const uint32_t ZN = (Z >> 8) | (Znext << 24);                      // flag of byte i+1 under byte i
+        const uint32_t R = flag_00((x ^ 0xD0D0D0D0u) & 0xF8F8F8F8u);       // D0..D7
+        const uint32_t km = (F & ZN) | (~(F | PF) & 0x80808080u);          // scan_keep
+        const uint32_t rm = PF & R;                                        // scan_is_rst
         keep |= movemask4(km) << (4 * k);
         rst |= movemask4(rm) << (4 * k);
+        Fprev = F; Z = Znext;
     }
 }
 

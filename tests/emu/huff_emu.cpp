@@ -228,3 +228,24 @@ extern "C" int emu_lut_check(const uint8_t *offsets, const uint8_t *symbols, int
     }
     return bad;
 }
+
+// Byte classification: the word-at-a-time rules (classify_words) against the per-byte ones on an arbitrary byte
+// string (16-byte chunks; bytes before / after the string read as 0).  Returns the number of mismatching bytes.
+extern "C" int emu_classify_check(const uint8_t *bytes, size_t n) {
+    int bad = 0;
+    auto at = [&](long long i) -> uint32_t { return (i >= 0 && (size_t)i < n) ? bytes[i] : 0u; };
+    for (size_t i0 = 0; i0 < n; i0 += 16) {
+        uint32_t w[6] = {0, 0, 0, 0, 0, 0};
+        w[0] = at((long long)i0 - 1) << 24;
+        for (int b = 0; b < 16; b++) w[1 + b / 4] |= at((long long)i0 + b) << (8 * (b & 3));
+        w[5] = at((long long)i0 + 16);
+        uint32_t keep, rst;
+        classify_words(w, keep, rst);
+        for (int b = 0; b < 16; b++) {
+            const unsigned prev = at((long long)i0 + b - 1), bb = at((long long)i0 + b), next = at((long long)i0 + b + 1);
+            bad += ((keep >> b) & 1u) != (scan_keep(prev, bb, next) ? 1u : 0u);
+            bad += ((rst >> b) & 1u) != (scan_is_rst(prev, bb) ? 1u : 0u);
+        }
+    }
+    return bad;
+}

@@ -232,6 +232,36 @@ def test_full_path_synthetic_vs_oracle(dec, w, h, sub, gray, ri):
     assert np.array_equal(outs[0], r.bmp)
 
 
+def test_large_mixed_batch_matches_single_image_decodes(dec):
+    """A batch big enough for the throughput layout (long sub-sequences, several CTAs per image, 4 slices for the
+    images with restart markers, 1 for the others - chosen per image): every image must come out exactly as when it
+    is decoded alone (small-batch layout), and a sample is checked against the oracle."""
+    import pim_jpeg_decoder_b200 as bj
+    uniq = []
+    for k in range(12):
+        uniq.append(js.synth_jpeg(500, 375, seed=100 + k, subsampling=2))
+        uniq.append(js.synth_jpeg(512, 384, seed=200 + k, subsampling=0, restart_blocks=4 + k))
+        uniq.append(js.synth_jpeg(1280, 720, seed=300 + k, subsampling=1 if k % 2 else 0, gray=(k % 3 == 0)))
+    files = (uniq * 5)[:170]
+    assert sum(len(f) for f in files) > (16 << 20)
+    dec.set_option("sub_batch_bytes", 64 << 20)          # one sub-batch
+    try:
+        outs, status = dec.decode(files, bj.BJ_OUT_BMP)
+    finally:
+        dec.set_option("sub_batch_bytes", 24 << 20)
+    assert all(st == 0 for st in status)
+    singles = {}
+    for i, f in enumerate(files):
+        key = i % len(uniq)
+        if key not in singles:
+            o, st = dec.decode([f], bj.BJ_OUT_BMP)
+            assert st == [0]
+            singles[key] = o[0]
+        assert np.array_equal(outs[i], singles[key]), i
+    for key in (0, 1, 2, 4, 17):
+        assert np.array_equal(singles[key], ol.Restated(uniq[key], 0).bmp), key
+
+
 def test_config3_restart_parity_rule(dec):
     """Config 3 shape (4:2:0 + restart interval 8), reduced size: GPU output == reference decode of the
     restart-free twin; the reference's own decode of the DRI file differs (its restart test is

@@ -93,6 +93,24 @@ def test_truncated_scan_zero_fills_like_the_reference():
     assert np.array_equal(got, r.coef_zz)
 
 
+def test_word_at_a_time_byte_classification():
+    """FF00 un-stuffing / RSTn / fill-byte rules four bytes per word (bit tricks) == the per-byte rules, on byte
+    strings dense in the special values and on every pair of adjacent byte values."""
+    lib = emu()
+    lib.emu_classify_check.argtypes = [C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(7)
+    special = np.array([0xFF, 0x00, 0xD0, 0xD3, 0xD7, 0xD8, 0xCF, 0x7F, 0x80, 0xFE, 0x01], dtype=np.uint8)
+    for dens in (0.1, 0.5, 0.9):
+        a = rng.integers(0, 256, 1 << 16, dtype=np.uint8)
+        m = rng.random(a.size) < dens
+        a[m] = special[rng.integers(0, special.size, int(m.sum()))]
+        assert lib.emu_classify_check(ol._ptr(a), a.size) == 0
+    pairs = np.stack(np.meshgrid(np.arange(256), np.arange(256), indexing="ij"), -1).reshape(-1).astype(np.uint8)
+    for shift in range(4):                      # every pair at every alignment inside a word
+        b = np.concatenate([np.full(shift, 0x55, np.uint8), pairs])
+        assert lib.emu_classify_check(ol._ptr(b), b.size) == 0
+
+
 def test_lut_matches_bit_serial_search():
     lib = emu()
     dht, _ = js.std_tables()
