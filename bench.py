@@ -248,6 +248,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--sub-batch-mb", type=int, default=0, help="compressed MB per sub-batch of the one-call path (0 = library default)")
     ap.add_argument("--host-threads", type=int, default=0, help="host worker threads of the one-call path (0 = library default)")
+    ap.add_argument("--no-ramp", action="store_true", help="one-call path: all sub-batches the same size")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--gen-workers", type=int, default=min(32, os.cpu_count() or 1))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -365,6 +366,8 @@ def main():
             dec.set_option("sub_batch_bytes", args.sub_batch_mb << 20)
         if args.host_threads:
             dec.set_option("host_threads", args.host_threads)
+        if args.no_ramp:
+            dec.set_option("sub_batch_ramp", 0)
         # what the link gives this process: one large pinned copy each way (the e2e number is bounded by the D2H one)
         pcie = {}
         nb = min(o, 1 << 30)

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200jpeg.so")
+LIB_PATH = os.environ.get("B200JPEG_LIB") or os.path.join(HERE, "libb200jpeg.so")   # (the override is for A/B measurements)
 
 BJ_OK = 0
 BJ_ERR_ARG = -1

@@ -89,6 +89,7 @@ extern "C" void bj_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
     if (!c || !name) return BJ_ERR_ARG;
     if (!strcmp(name, "subseq_bits")) { if (value != 0 && (value < 128 || value % 32 || value > (1 << 18))) return BJ_ERR_ARG; c->subseq_bits = (int)value; return BJ_OK; }
+    if (!strcmp(name, "sub_batch_ramp")) { c->sub_batch_ramp = value != 0; return BJ_OK; }
     if (!strcmp(name, "slices")) { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return BJ_ERR_ARG; c->slices = (int)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_bytes = (size_t)value; return BJ_OK; }
     if (!strcmp(name, "packed_outputs")) { c->packed_outputs = value != 0; return BJ_OK; }
@@ -310,10 +311,25 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
     bool busy[kSlots] = {};
     double nsub = 0, launches = 0, h2d = 0, d2h = 0, host_ms = 0, wait_ms = 0;
     int rc = BJ_OK;
+    // B200JPEG_TRACE=1: one line per sub-batch on stderr - when its kernels ran and its copy-out ended (ms since the
+    // first sub-batch was enqueued) - to see whether the copy-out engine is kept busy.  (No event is recorded in front
+    // of the upload: on a stream whose last operation was a copy-out it waits for the copy-out engine.)
+    static const bool trace = getenv("B200JPEG_TRACE") != nullptr;
+    cudaEvent_t ev_base = nullptr;
+    double host_t[kSlots][2] = {};
+    const double wall0 = wall_ms();
     auto finish = [&](int slot) -> int {
         bj_batch *b = c->slots[slot];
         const double t0 = wall_ms();
         int r = batch_sync(b);
+        if (trace && r == BJ_OK && ev_base) {
+            float k0 = 0, k1 = 0, out = 0;
+            cudaEventSynchronize(b->ev[5]);
+            cudaEventElapsedTime(&k0, ev_base, b->ev[0]);
+            cudaEventElapsedTime(&k1, ev_base, b->ev[4]); cudaEventElapsedTime(&out, ev_base, b->ev[5]);
+            fprintf(stderr, "b200jpeg trace: sub-batch of %4d images (%6.1f MB out)  host prepare %6.2f..%6.2f  kernels %6.2f..%6.2f  copied out %6.2f\n",
+                    b->n, b->d2h_bytes / 1e6, host_t[slot][0], host_t[slot][1], k0, k1, out);
+        }
         if (r == BJ_OK && b->n_blk && b->h_flags()[b->rounds - 1] != 0)   // extra rounds ran: the early copy-out is stale
             r = batch_download(b, outs + first[slot], c->streams[slot]);
         wait_ms += wall_ms() - t0;
@@ -327,7 +343,7 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
         int i1 = i0;
         size_t bytes = 0;
         // the first sub-batches are small, so that the copy-out (the bound of this call) starts early
-        const size_t cap = k == 0 ? budget / 8 : (k == 1 ? budget / 3 : budget);
+        const size_t cap = !c->sub_batch_ramp ? budget : (k == 0 ? budget / 8 : (k == 1 ? budget / 3 : budget));
         while (i1 < n && (i1 == i0 || bytes + lens[i1] <= cap)) bytes += lens[i1++];
         const int slot = k % kSlots;
         if (busy[slot]) rc = finish(slot);
@@ -337,12 +353,17 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
         const double t0 = wall_ms();
         rc = batch_assign(b, c, files + i0, lens + i0, i1 - i0, format);
         host_ms += wall_ms() - t0;
+        host_t[slot][0] = t0 - wall0; host_t[slot][1] = wall_ms() - wall0;
+        if (rc == BJ_OK && trace) {
+            if (!ev_base) { cudaEventCreate(&ev_base); cudaEventRecord(ev_base, s); }
+        }
         if (rc == BJ_OK) rc = batch_upload(b, s);
         if (rc == BJ_OK) rc = batch_decode(b, s);
         if (rc == BJ_OK) {                                            // enqueue the copy-out behind the kernels, no host wait
             b->synced = true;                                         // (checked for real in finish())
             rc = batch_download_async(b, outs + i0, s);
             b->synced = false;
+            if (trace) cudaEventRecord(b->ev[5], s);
         }
         first[slot] = i0; count[slot] = i1 - i0; busy[slot] = true;
         nsub += 1;
@@ -350,6 +371,7 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
     }
     // drain in submission order
     for (int j = 0; j < kSlots; j++) { const int slot = (k + j) % kSlots; if (busy[slot]) { const int r = finish(slot); if (rc == BJ_OK) rc = r; } }
+    if (ev_base) cudaEventDestroy(ev_base);
     c->stats[0] = nsub; c->stats[1] = launches; c->stats[2] = h2d; c->stats[3] = d2h; c->stats[4] = host_ms; c->stats[5] = wait_ms;
     return rc;
 }

@@ -69,7 +69,7 @@ struct bj_batch {
 
     // device
     bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_tilecnt, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels, copied out
     cudaStream_t last_stream = nullptr;
     bool uploaded = false, decoded = false, synced = false;
     uint32_t launches = 0, sync_rounds = 0;

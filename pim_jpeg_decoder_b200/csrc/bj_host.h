@@ -114,6 +114,7 @@ struct bj_ctx {
     int subseq_bits = 0;                 // sub-sequence length of the synchronisation pass; 0 = automatic (per image)
     int slices = 0;                      // slices (write pass) per sub-sequence: 1, 2, 4, 8; 0 = default (1)
     size_t sub_batch_bytes = 0;          // 0 = default
+    int sub_batch_ramp = 1;              // the first two sub-batches of a call are smaller (the copy-out starts earlier)
     int packed_outputs = 0;              // see batch_download_async
     int sync_rounds = 0;                 // 0 = default (3 launches of the fix-up kernel before the first check)
     struct bj_batch *slots[bj::kSlots] = {};          // sub-batches of bj_decode_batch in flight (one stream each)
