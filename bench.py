@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--sub-batch-mb", type=int, default=0, help="compressed MB per sub-batch of the one-call path (0 = library default)")
     ap.add_argument("--host-threads", type=int, default=0, help="host worker threads of the one-call path (0 = library default)")
     ap.add_argument("--no-ramp", action="store_true", help="one-call path: all sub-batches the same size")
+    ap.add_argument("--staged-inputs", action="store_true", help="one-call path: copy the files into the library's pinned staging first (for callers whose inputs are not page-locked)")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--gen-workers", type=int, default=min(32, os.cpu_count() or 1))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -362,6 +363,7 @@ def main():
         pin_out = bj.PinnedBuffer(o)
         out_off = np.array(offs, dtype=np.uint64)
         dec.set_option("packed_outputs", 1)
+        dec.set_option("packed_inputs", 0 if args.staged_inputs else 1)     # pin_in is one pinned allocation
         if args.sub_batch_mb:
             dec.set_option("sub_batch_bytes", args.sub_batch_mb << 20)
         if args.host_threads:

@@ -158,6 +158,9 @@ int bj_stage_entropy(bj_ctx *ctx, const uint8_t *file, size_t len, int16_t *coef
  *                      pass works on whole sub-sequences)
  *   "sync_rounds"      launches of the fix-up kernel before convergence is first checked
  *   "sub_batch_bytes"  compressed bytes per sub-batch of bj_decode_batch
+ *   "packed_inputs"    1: all input files of a bj_decode_batch call lie in ONE page-locked allocation (bj_host_alloc /
+ *                      cudaHostAlloc), close together: they are uploaded straight from there, nothing is copied on
+ *                      the host.  Only set it when that is true - pageable memory would make the upload synchronous
  *   "packed_outputs"   1: output pointers that follow bj_batch_output_offset's layout (outs[i] = base + offset_i,
  *                      for the one-call path: offsets restart at 0 in every sub-batch) belong to ONE allocation,
  *                      so runs of images are copied out in one transfer, padding bytes included */

@@ -93,6 +93,7 @@ extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
     if (!strcmp(name, "slices")) { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return BJ_ERR_ARG; c->slices = (int)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_bytes = (size_t)value; return BJ_OK; }
     if (!strcmp(name, "packed_outputs")) { c->packed_outputs = value != 0; return BJ_OK; }
+    if (!strcmp(name, "packed_inputs")) { c->packed_inputs = value != 0; return BJ_OK; }
     if (!strcmp(name, "host_threads")) { if (value < 1 || value > 256) return BJ_ERR_ARG; c->host_pool.resize((int)value); return BJ_OK; }
     if (!strcmp(name, "sync_rounds")) { if (value < 0 || value > kMaxRounds) return BJ_ERR_ARG; c->sync_rounds = (int)value; return BJ_OK; }
     return BJ_ERR_ARG;
@@ -351,7 +352,7 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
         bj_batch *b = c->slots[slot];
         cudaStream_t s = c->streams[slot];
         const double t0 = wall_ms();
-        rc = batch_assign(b, c, files + i0, lens + i0, i1 - i0, format);
+        rc = batch_assign(b, c, files + i0, lens + i0, i1 - i0, format, c->packed_inputs != 0);
         host_ms += wall_ms() - t0;
         host_t[slot][0] = t0 - wall0; host_t[slot][1] = wall_ms() - wall0;
         if (rc == BJ_OK && trace) {

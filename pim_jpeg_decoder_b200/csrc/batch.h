@@ -58,6 +58,7 @@ struct bj_batch {
     // host staging (pinned): file bytes; descriptor blob; results
     bj::PinBuf h_files, h_meta, h_res;
     size_t files_bytes = 0, meta_bytes = 0;
+    const uint8_t *direct_src = nullptr;   // set: the files are uploaded straight from the caller's (pinned) memory, files_bytes from here
     // offsets inside the descriptor blob
     size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_wblk = 0, o_utile = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0, o_lutacs = 0;
     uint32_t idct_smem = 0;             // dynamic shared memory of k_idct_color: sized for the widest pixel tile of this batch
@@ -93,7 +94,7 @@ namespace bj {
 constexpr int kMaxRounds = 64;
 
 // (Re)fill a batch object from a list of files: parse, lay out, pack.  Host work only (plus buffer growth).
-inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format) {
+inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, bool direct = false) {
     if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
     b->ctx = c; b->n = n; b->format = format;
     b->uploaded = b->decoded = b->synced = false;
@@ -108,6 +109,24 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         for (int i = i0; i < i1; i++)
             b->parse_status[i] = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &b->desc[i]) : BJ_ERR_INVALID_JPEG;
     });
+
+    // ---- where the file bytes are uploaded from.  Normally they are packed into this batch's pinned staging buffer
+    // (one copy on the worker pool).  With option "packed_inputs" the caller states that all files of the call lie in
+    // ONE pinned allocation: then the span from the first to the last file goes up as it is, straight from the
+    // caller's memory, and nothing is copied on the host.
+    b->direct_src = nullptr;
+    uint64_t span_lo = ~0ull, span_hi = 0, span_sum = 0;
+    if (direct) {
+        for (int i = 0; i < n; i++) {
+            if (b->parse_status[i] != BJ_OK) continue;
+            const uint64_t a = (uint64_t)(uintptr_t)files[i];
+            span_lo = std::min(span_lo, a); span_hi = std::max(span_hi, a + lens[i]); span_sum += lens[i];
+        }
+        if (span_hi > span_lo && span_hi - span_lo <= 2 * span_sum + (1u << 16)) {
+            span_lo &= ~(uint64_t)15;
+            b->direct_src = reinterpret_cast<const uint8_t *>((uintptr_t)span_lo);
+        }
+    }
 
     // ---- sub-sequence length and slices, per image.
     // Explicit (options "subseq_bits", "slices"): the same for every image.  Automatic: nominally 4096 bits - a stream
@@ -226,7 +245,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
             if (smem > b->lut_smem) b->lut_smem = smem;
         }
         b->parse_status[i] = rc;
-        b->file_off[i] = fbytes;
+        b->file_off[i] = b->direct_src ? (uint64_t)(uintptr_t)files[i] - span_lo : fbytes;
         hi.seg_base = seg_entries;
         hi.blk_base = nblk;
         hi.sub_base = nblk * kHuffThreads;
@@ -277,7 +296,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         if (coef_units > 0xFFFFFFF0ull || clean_words > 0xFFFFFFF0ull) return BJ_ERR_ARG;   // split the batch
     }
     b->idct_smem = kSmemDu + kSmemQ + kRgbFront + std::min<uint32_t>(rgb_max, kRgbMax) + 64;
-    b->files_bytes = fbytes + 64; b->clean_words = clean_words + 16; b->coef_units = coef_units; b->out_bytes = out_bytes;
+    b->files_bytes = b->direct_src ? (size_t)(span_hi - span_lo) : fbytes + 64; b->clean_words = clean_words + 16; b->coef_units = coef_units; b->out_bytes = out_bytes;
     b->n_wblk = (uint32_t)wblk_img.size(); b->n_slice_slots = slice_slots;
     if (slice_slots > 0xFFFFFFF0ull) return BJ_ERR_ARG;
     b->n_idct_tiles = (uint32_t)tiles.size(); b->n_blk = nblk; b->n_utile = (uint32_t)utile_img.size();
@@ -296,7 +315,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     b->o_lutac = o; o = align_up(o + luts_ac.size() * 4, 256);
     b->o_lutacs = o; o = align_up(o + luts_acs.size() * 4, 256);
     b->meta_bytes = o;
-    if (b->h_meta.reserve(o) || b->h_files.reserve(b->files_bytes) ||
+    if (b->h_meta.reserve(o) || (!b->direct_src && b->h_files.reserve(b->files_bytes)) ||
         b->h_res.reserve(align_up((size_t)n * sizeof(HuffImgState), 64) + kMaxRounds * 4 + 64)) return BJ_ERR_NOMEM;
     if (n) { memcpy(b->hmeta<HuffImg>(b->o_himg), himg.data(), (size_t)n * sizeof(HuffImg)); memcpy(b->hmeta<ImgDev>(b->o_idev), idev.data(), (size_t)n * sizeof(ImgDev)); }
     if (!tiles.empty()) memcpy(b->hmeta<TileDev>(b->o_tiles), tiles.data(), tiles.size() * sizeof(TileDev));
@@ -308,16 +327,18 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     if (!luts_ac.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutac), luts_ac.data(), luts_ac.size() * 4);
     if (!luts_acs.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutacs), luts_acs.data(), luts_acs.size() * 4);
     // ---- pack the file bytes (per image, independent: worker pool)
-    uint8_t *hf = reinterpret_cast<uint8_t *>(b->h_files.p);
-    c->host_pool.parallel_for(n, 16, [&](int i0, int i1) {
-        for (int i = i0; i < i1; i++) {
-            if (b->parse_status[i] != BJ_OK) continue;
-            memcpy(hf + b->file_off[i], files[i], lens[i]);
-            memset(hf + b->file_off[i] + lens[i], 0, align_up(lens[i] + 16, 16) - lens[i]);
-        }
-    });
+    if (!b->direct_src) {
+        uint8_t *hf = reinterpret_cast<uint8_t *>(b->h_files.p);
+        c->host_pool.parallel_for(n, 16, [&](int i0, int i1) {
+            for (int i = i0; i < i1; i++) {
+                if (b->parse_status[i] != BJ_OK) continue;
+                memcpy(hf + b->file_off[i], files[i], lens[i]);
+                memset(hf + b->file_off[i] + lens[i], 0, align_up(lens[i] + 16, 16) - lens[i]);
+            }
+        });
+    }
     // ---- device buffers
-    if (b->d_files.reserve(b->files_bytes) || b->d_meta.reserve(b->meta_bytes) || b->d_clean.reserve(b->clean_words * 4) ||
+    if (b->d_files.reserve(b->files_bytes + 4096) || b->d_meta.reserve(b->meta_bytes) || b->d_clean.reserve(b->clean_words * 4) ||
         b->d_seg.reserve((size_t)(seg_entries + 2) * 4 * 2) || b->d_subseg.reserve((size_t)b->n_sub_slots * 4 + 16) ||
         b->d_stin.reserve((size_t)b->n_sub_slots * 8 + 16) || b->d_stout.reserve((size_t)b->n_sub_slots * 8 + 16) ||
         b->d_tot.reserve((size_t)b->n_sub_slots * 4 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 8 + 16) ||
@@ -334,7 +355,7 @@ inline int batch_upload(bj_batch *b, cudaStream_t s) {
     if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
     b->last_stream = s;
     if (b->n == 0) { b->uploaded = true; return BJ_OK; }
-    int rc = c->check(cudaMemcpyAsync(b->d_files.p, b->h_files.p, b->files_bytes, cudaMemcpyHostToDevice, s));
+    int rc = c->check(cudaMemcpyAsync(b->d_files.p, b->direct_src ? (const void *)b->direct_src : b->h_files.p, b->files_bytes, cudaMemcpyHostToDevice, s));
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(b->d_meta.p, b->h_meta.p, b->meta_bytes, cudaMemcpyHostToDevice, s));
     b->uploaded = rc == BJ_OK;
     return rc;

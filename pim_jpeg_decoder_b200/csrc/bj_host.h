@@ -116,6 +116,7 @@ struct bj_ctx {
     size_t sub_batch_bytes = 0;          // 0 = default
     int sub_batch_ramp = 1;              // the first two sub-batches of a call are smaller (the copy-out starts earlier)
     int packed_outputs = 0;              // see batch_download_async
+    int packed_inputs = 0;               // see batch_assign: upload straight from the caller's pinned memory
     int sync_rounds = 0;                 // 0 = default (3 launches of the fix-up kernel before the first check)
     struct bj_batch *slots[bj::kSlots] = {};          // sub-batches of bj_decode_batch in flight (one stream each)
     bj::HostPool host_pool;

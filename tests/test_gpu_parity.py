@@ -180,8 +180,8 @@ def test_full_path_sub_batching(dec, golden, golden_dir):
         assert st == 0 and sha(o) == golden[golden[n]["expect"]]["bmp_sha256"], n
 
 
-@pytest.mark.parametrize("threads", [1, 5])
-def test_decode_packed_host_threads(dec, threads, golden, golden_dir):
+@pytest.mark.parametrize("threads,direct", [(1, 0), (5, 0), (3, 1)])
+def test_decode_packed_host_threads(dec, threads, direct, golden, golden_dir):
     """The batch-pipeline form of the one-call path (all files in one pinned buffer, outputs in another), with the
     host parse/pack work on 1 and on 5 worker threads, over 3 slots of small sub-batches."""
     import pim_jpeg_decoder_b200 as bj
@@ -203,12 +203,14 @@ def test_decode_packed_host_threads(dec, threads, golden, golden_dir):
     dec.set_option("host_threads", threads)
     dec.set_option("sub_batch_bytes", 1 << 16)
     dec.set_option("packed_outputs", 1)
+    dec.set_option("packed_inputs", direct)           # upload straight from the pinned source buffer
     try:
         status = dec.decode_packed(src.array, src_off, [len(f) for f in files], dst.array, dst_off, bj.BJ_OUT_BMP)
         assert dec.stat("host_threads") == threads and dec.stat("decode_batch_sub_batches") > 6
     finally:
         dec.set_option("sub_batch_bytes", 24 << 20)
         dec.set_option("packed_outputs", 0)
+        dec.set_option("packed_inputs", 0)
         dec.set_option("host_threads", 4)
     for n, st, off, size in zip(names, status, dst_off, sizes):
         if golden[n].get("invalid"):
