@@ -309,10 +309,21 @@ struct HuffGeom {
     uint32_t bpm;           // data units per MCU
     uint32_t ny;            // luma units per MCU (hs * vs); unit c belongs to component c < ny ? 0 : c - ny + 1
     uint32_t dc[3], ac[3];  // per component: DC / AC table
+    uint32_t unit_tab;      // device, optional: shared-memory address of {DC table, AC table} per unit of the MCU (0: none)
 };
 BJ_HD uint32_t comp_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? 0u : c - g.ny + 1u; }
 BJ_HD uint32_t dc_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.dc[0] : (c == g.ny ? g.dc[1] : g.dc[2]); }
 BJ_HD uint32_t ac_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.ac[0] : (c == g.ny ? g.ac[1] : g.ac[2]); }
+// both tables of unit c: one 64-bit shared load where the per-unit table exists (rarely-taken, divergent code paths)
+BJ_HD void tables_of(const HuffGeom &g, uint32_t c, uint32_t &dc, uint32_t &ac) {
+#ifdef __CUDA_ARCH__
+    if (g.unit_tab) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(dc), "=r"(ac) : "r"(g.unit_tab + c * 8u));
+        return;
+    }
+#endif
+    dc = dc_of(g, c); ac = ac_of(g, c);
+}
 
 // Magnitude extension of the `size` bits that follow a `len`-bit code in the window
 // (src/jpeg_scanner.cpp:480-482 / :513-516: first bit 0 => negative).  size 0 gives 0.
@@ -466,8 +477,7 @@ struct WriteCursor {
         du++;
         S &= ~0xFFu;
         c = (c + 1u == g.bpm) ? 0u : c + 1u;
-        ac = ac_of(g, c);
-        tab = dc_of(g, c);
+        tables_of(g, c, tab, ac);
         done = S >= endS || du >= du_end;
     }
     // The unit to store after a step that said `unit` (UINT32_MAX: none).

@@ -336,7 +336,7 @@ __device__ __forceinline__ void stage_luts(const HuffImg &im, const uint32_t *__
             off += n4;
         }
     }
-    g.bpm = im.bpm; g.ny = im.ny;
+    g.bpm = im.bpm; g.ny = im.ny; g.unit_tab = 0;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_lut);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -515,6 +515,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw + kSmemHuffStage);
     __shared__ uint32_t s_red[kHuffThreads / 32];
     __shared__ int s_h;
+    __shared__ uint2 s_units[16];                                          // per unit of the MCU: DC table, AC table
 
     const uint32_t img = wblk_img[blockIdx.x];
     const HuffImg &im = imgs[img];
@@ -548,6 +549,8 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     HuffGeom g;
     LutMem luts;
     stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g, luts);
+    if (tid < 16) s_units[tid] = (uint32_t)tid < g.bpm ? make_uint2(dc_of(g, tid), ac_of(g, tid)) : make_uint2(0u, 0u);
+    if (g.bpm <= 16u) g.unit_tab = (uint32_t)__cvta_generic_to_shared(s_units);
     __syncthreads();
     c0 = 0;
 #pragma unroll
@@ -587,7 +590,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     uint32_t warp_stage = stage_addr + (tid & ~31) * 128 + ((lane & 7) << 4);     // + this lane's chunk
     asm volatile("mov.u32 %0, %0;" : "+r"(warp_stage));
     uint4 *out_lane = out + (lane & 7);
-    uint32_t flusher = lane < 8 ? 1u : 0u;
+    uint32_t flusher = lane < 8 ? 1u : (lane < 16 ? 2u : 0u);              // which of the two units of a flush pass this lane moves
     asm volatile("mov.u32 %0, %0;" : "+r"(flusher));
     asm volatile("mov.u64 %0, %0;" : "+l"(out_lane));                      // (kept in registers, like warp_stage)
     asm volatile("mov.u64 %0, %0;" : "+l"(dcp));
@@ -600,18 +603,20 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
             // lanes in m completed unit du - 1 (or ended on a refused DC symbol: nothing to store)
             const uint32_t du_mine = unit ? cur.store_du() : 0xFFFFFFFFu;
             __syncwarp();
-            do {
-                const int l = __ffs(m) - 1;
-                m &= m - 1u;
-                const uint32_t du_l = __shfl_sync(0xFFFFFFFFu, du_mine, l);
-                if (flusher) {
+            do {                                                           // two units per pass: lanes 0-7 and 8-15
+                const uint32_t m1 = m & (m - 1u);
+                const int l0 = __ffs(m) - 1, l1 = __ffs(m1) - 1;           // l1 = -1: no second unit in this pass
+                const int l = flusher == 2u ? l1 : l0;                     // (selects, no branch: the shuffle is warp-wide)
+                m = m1 & (m1 - 1u);
+                const uint32_t du_l = __shfl_sync(0xFFFFFFFFu, du_mine, l & 31);
+                if (flusher != 0u && l >= 0) {
                     const uint32_t x = (l & 7) << 4;
                     const uint32_t a = (warp_stage + l * 128) ^ x;         // rows are 128-byte aligned
                     uint4 v;
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
                     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
-                    if (du_l < ndu) {                                      // this lane holds the unit's chunk `lane`
-                        if (lane == 0) { dcp[du_l] = (int16_t)v.x; v.x &= 0xFFFF0000u; }   // slot 0 = the DC difference
+                    if (du_l < ndu) {                                      // this lane holds the unit's chunk `lane & 7`
+                        if ((lane & 7) == 0) { dcp[du_l] = (int16_t)v.x; v.x &= 0xFFFF0000u; }   // slot 0 = the DC difference
                         __stcs(out_lane + (size_t)du_l * 8, v);
                     }
                 }
@@ -663,7 +668,7 @@ k_dc_predict(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ 
     const uint32_t m = lc * kDcThreads + tid;
     const bool active = m < im.nmcu;
     HuffGeom g;
-    g.bpm = im.bpm; g.ny = im.ny;
+    g.bpm = im.bpm; g.ny = im.ny; g.unit_tab = 0;
     int16_t *p = dc_plane + im.du_base + (size_t)m * im.bpm;
     int16_t d[6] = {0, 0, 0, 0, 0, 0};
     uint32_t v0 = 0, v1 = 0, v2 = 0, f = 0;

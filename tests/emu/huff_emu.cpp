@@ -77,7 +77,7 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int
     const size_t lut_words = 3 * (kLutCapDC + kLutCapAC);
     std::vector<uint32_t> luts(lut_words), luts_sync(lut_words);
     HuffGeom g;
-    g.bpm = bpm; g.ny = (uint32_t)d.hs * d.vs;
+    g.bpm = bpm; g.ny = (uint32_t)d.hs * d.vs; g.unit_tab = 0;
     for (int j = 0; j < 3; j++) {
         const int jj = j < d.ncomp ? j : 0;
         const uint32_t odc = j * kLutCapDC, oac = 3 * kLutCapDC + j * kLutCapAC;
