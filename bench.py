@@ -483,6 +483,10 @@ def main():
                    "sharding": "by image, no collective on the data path"},
         "roofline": roofline, "stages": stages,
         "entropy": {"ms": ent_ms, "compressed_gbs": info.scan_bytes / (ent_ms * 1e-3) / 1e9 if ent_ms else None},
+        # the whole decode as one box: compressed bytes in + 3 B/px out; the coefficient round trip is overhead, not credit
+        "whole_decode": {"alg_bytes": float(info.scan_bytes) + float(info.out_bytes),
+                         "achieved_gbs": (float(info.scan_bytes) + float(info.out_bytes)) / (ms_max / args.steps * 1e-3) / 1e9,
+                         "frac": (float(info.scan_bytes) + float(info.out_bytes)) / (ms_max / args.steps * 1e-3) / 1e9 / peak},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(windows),
         "first_bmp_sha256": first_hash,
