@@ -366,8 +366,12 @@ def main():
         dec.set_option("packed_inputs", 0 if args.staged_inputs else 1)     # pin_in is one pinned allocation
         if args.sub_batch_mb:
             dec.set_option("sub_batch_bytes", args.sub_batch_mb << 20)
-        if args.host_threads:
-            dec.set_option("host_threads", args.host_threads)
+        # host worker threads of this rank: its share of the box's cores (the library's own default, min(4, cores/2),
+        # does not know about the other ranks), one core left to the calling thread
+        share = len(os.sched_getaffinity(0)) // max(1, world)
+        host_threads = args.host_threads or (max(1, min(4, share - 1)) if world > 1 else 0)
+        if host_threads:
+            dec.set_option("host_threads", host_threads)
         if args.no_ramp:
             dec.set_option("sub_batch_ramp", 0)
         # what the link gives this process: one large pinned copy each way (the e2e number is bounded by the D2H one)
