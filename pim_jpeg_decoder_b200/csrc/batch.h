@@ -73,6 +73,7 @@ struct bj_batch {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels, copied out
     cudaStream_t last_stream = nullptr;
     bool uploaded = false, decoded = false, synced = false;
+    bool multi_blk = false;              // some image's sub-sequences span more than one CTA of the synchronisation pass
     uint32_t launches = 0, sync_rounds = 0;
     float ms_entropy = 0.f, ms_idct = 0.f, ms_unstuff = 0.f, ms_sync = 0.f, ms_write = 0.f;
     uint64_t d2h_bytes = 0;
@@ -173,7 +174,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
     uint32_t seg_entries = 0, nblk = 0;
     int prev = -1;                                  // last valid image: its table slots are reused when the tables match
-    b->pixels = 0; b->scan_bytes = 0; b->lut_smem = 0;
+    b->pixels = 0; b->scan_bytes = 0; b->lut_smem = 0; b->multi_blk = false;
     uint32_t rgb_max = 0;
     auto same_tables = [](const bj_image_desc &a, const bj_image_desc &q) {
         if (a.ncomp != q.ncomp || memcmp(a.dc_id, q.dc_id, 3) || memcmp(a.ac_id, q.ac_id, 3)) return false;
@@ -274,6 +275,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         hi.nblk = (sub_cap + kHuffThreads - 1) / kHuffThreads;
         for (uint32_t k = 0; k < hi.nblk; k++) blk_img.push_back((uint32_t)i);
         nblk += hi.nblk;
+        if (hi.nblk > 1) b->multi_blk = true;
         hi.wblk_base = (uint32_t)wblk_img.size();
         for (uint32_t k = 0; k < (hi.nblk << hi.slices_log2); k++) wblk_img.push_back((uint32_t)i);
         hi.slice_base = (uint32_t)slice_slots;
@@ -433,8 +435,10 @@ inline int batch_decode(bj_batch *b, cudaStream_t s) {
     b->last_stream = s;
     b->decoded = true; b->synced = false;
     if (b->n == 0) return BJ_OK;
-    // round 0 cannot tell whether it settled everything (only rounds > 0 compare across CTAs): at least two
+    // round 0 cannot tell whether it settled everything (only rounds > 0 compare across CTAs): at least two - unless no
+    // image has more than one CTA: then round 0 is all there is to do (every CTA starts at an image head)
     b->rounds = c->sync_rounds > 0 ? (c->sync_rounds < 2 ? 2 : c->sync_rounds) : 3;
+    if (!b->multi_blk) b->rounds = 1;
     return batch_launch(b, s, 0, b->rounds);
 }
 
