@@ -309,20 +309,25 @@ struct HuffGeom {
     uint32_t bpm;           // data units per MCU
     uint32_t ny;            // luma units per MCU (hs * vs); unit c belongs to component c < ny ? 0 : c - ny + 1
     uint32_t dc[3], ac[3];  // per component: DC / AC table
-    uint32_t unit_tab;      // device, optional: shared-memory address of {DC table, AC table} per unit of the MCU (0: none)
+    uint32_t unit_tab;      // device, optional: shared-memory address of one uint2 per unit of the MCU:
+                            // {DC table | index << 24, AC table} of the unit that FOLLOWS it (0: none)
 };
 BJ_HD uint32_t comp_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? 0u : c - g.ny + 1u; }
 BJ_HD uint32_t dc_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.dc[0] : (c == g.ny ? g.dc[1] : g.dc[2]); }
 BJ_HD uint32_t ac_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.ac[0] : (c == g.ny ? g.ac[1] : g.ac[2]); }
-// both tables of unit c: one 64-bit shared load where the per-unit table exists (rarely-taken, divergent code paths)
-BJ_HD void tables_of(const HuffGeom &g, uint32_t c, uint32_t &dc, uint32_t &ac) {
+// The unit after unit c of the MCU: its index and both its tables - one 64-bit shared load where the per-unit
+// table exists (the hot loops hand over from unit to unit in most iterations of a warp), selects otherwise.
+BJ_HD void next_unit(const HuffGeom &g, uint32_t c, uint32_t &c1, uint32_t &dc, uint32_t &ac) {
 #ifdef __CUDA_ARCH__
     if (g.unit_tab) {
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(dc), "=r"(ac) : "r"(g.unit_tab + c * 8u));
+        uint32_t x;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(ac) : "r"(g.unit_tab + c * 8u));
+        dc = x & 0xFFFFFFu; c1 = x >> 24;
         return;
     }
 #endif
-    dc = dc_of(g, c); ac = ac_of(g, c);
+    c1 = (c + 1u == g.bpm) ? 0u : c + 1u;
+    dc = dc_of(g, c1); ac = ac_of(g, c1);
 }
 
 // Magnitude extension of the `size` bits that follow a `len`-bit code in the window
@@ -387,12 +392,13 @@ BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const Huf
         if (__builtin_expect(((Sn & 0xFFu) - 65u) < 63u, 0)) Sn = S + ((e >> 16) & 0x7FFFu);
         // zig-zag index >= 64: unit complete (also: over-long run).  Branch-free: most iterations of a warp see one.
         const bool fin = (Sn & 0xC0u) != 0u;
-        const uint32_t c1 = (c + 1u == g.bpm) ? 0u : c + 1u;
+        uint32_t c1, dcn, acn;
+        next_unit(g, c, c1, dcn, acn);
         c = fin ? c1 : c;
         ends += fin ? 1u : 0u;
         S = fin ? (Sn & ~0xFFu) : Sn;
-        ac = fin ? ac_of(g, c1) : ac;
-        tab = fin ? dc_of(g, c1) : ac;
+        ac = fin ? acn : ac;
+        tab = fin ? dcn : ac;
     }
     // started = ended + (one still open at the exit) - (the one that was already open at the entry)
     *units_started = ends + ((S & 0xFFu) ? 1u : 0u) - entered_mid;
@@ -476,8 +482,7 @@ struct WriteCursor {
         if (__builtin_expect((Sn & 0xFFu) != 64u && !(e & kLutEob), 0)) { fail = 2u; done = true; return; }   // over-long run
         du++;
         S &= ~0xFFu;
-        c = (c + 1u == g.bpm) ? 0u : c + 1u;
-        tables_of(g, c, tab, ac);
+        next_unit(g, c, c, tab, ac);
         done = S >= endS || du >= du_end;
     }
     // The unit to store after a step that said `unit` (UINT32_MAX: none).

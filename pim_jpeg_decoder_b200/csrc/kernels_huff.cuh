@@ -313,7 +313,8 @@ __device__ __forceinline__ SubInfo sub_info(const HuffImg &im, const HuffImgStat
 // stage the image's tables into shared memory, packed (DC slots first, then AC slots; only the used part of every
 // table), 16 bytes per thread per step.  Returns where they are through `g` (byte offsets) and `luts`.
 __device__ __forceinline__ void stage_luts(const HuffImg &im, const uint32_t *__restrict__ lut_dc_pool,
-                                           const uint32_t *__restrict__ lut_ac_pool, uint32_t *s_lut, HuffGeom &g, LutMem &luts) {
+                                           const uint32_t *__restrict__ lut_ac_pool, uint32_t *s_lut, uint2 *s_units /* [16] */,
+                                           HuffGeom &g, LutMem &luts) {
     uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
     uint32_t off = 0, dc_off[3] = {0, 0, 0}, ac_off[3] = {0, 0, 0};
 #pragma unroll
@@ -343,6 +344,14 @@ __device__ __forceinline__ void stage_luts(const HuffImg &im, const uint32_t *__
         const uint32_t ds = im.dc_slot[j], as = im.ac_slot[j];
         g.dc[j] = sbase + (ds == 0 ? dc_off[0] : ds == 1 ? dc_off[1] : dc_off[2]);
         g.ac[j] = sbase + (as == 0 ? ac_off[0] : as == 1 ? ac_off[1] : ac_off[2]);
+    }
+    // per unit of the MCU: tables and index of the unit that follows it (huff_core.h: next_unit)
+    if (g.bpm <= 16u) {
+        if (threadIdx.x < g.bpm) {
+            const uint32_t c1 = threadIdx.x + 1u == g.bpm ? 0u : threadIdx.x + 1u;
+            s_units[threadIdx.x] = make_uint2(dc_of(g, c1) | (c1 << 24), ac_of(g, c1));
+        }
+        g.unit_tab = (uint32_t)__cvta_generic_to_shared(s_units);
     }
     (void)luts;
 }
@@ -375,6 +384,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
     __shared__ uint32_t s_tot[kHuffThreads];
     __shared__ uint2 s_span[kHuffThreads];                                  // first bit, end bit
+    __shared__ uint2 s_units[16];
     __shared__ uint16_t s_work[2][kHuffThreads];
     __shared__ uint32_t s_nwork[2];
     __shared__ uint32_t s_flag;
@@ -414,7 +424,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
 
     HuffGeom g;
     LutMem luts;
-    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g, luts);
+    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, s_units, g, luts);
     const uint32_t *__restrict__ words = clean + im.clean_word0;
     const uint32_t slices_log2 = im.slices_log2;
     const uint32_t slice_bits = (im.sub_bytes >> slices_log2) * 8u;
@@ -515,7 +525,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw + kSmemHuffStage);
     __shared__ uint32_t s_red[kHuffThreads / 32];
     __shared__ int s_h;
-    __shared__ uint2 s_units[16];                                          // per unit of the MCU: DC table, AC table
+    __shared__ uint2 s_units[16];
 
     const uint32_t img = wblk_img[blockIdx.x];
     const HuffImg &im = imgs[img];
@@ -548,9 +558,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     for (int i = tid; i < 32 * kHuffThreads; i += kHuffThreads) s_stage[i] = 0;
     HuffGeom g;
     LutMem luts;
-    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, g, luts);
-    if (tid < 16) s_units[tid] = (uint32_t)tid < g.bpm ? make_uint2(dc_of(g, tid), ac_of(g, tid)) : make_uint2(0u, 0u);
-    if (g.bpm <= 16u) g.unit_tab = (uint32_t)__cvta_generic_to_shared(s_units);
+    stage_luts(im, lut_dc_pool, lut_ac_pool, s_lut, s_units, g, luts);
     __syncthreads();
     c0 = 0;
 #pragma unroll
