@@ -60,7 +60,7 @@ struct bj_batch {
     size_t files_bytes = 0, meta_bytes = 0;
     const uint8_t *direct_src = nullptr;   // set: the files are uploaded straight from the caller's (pinned) memory, files_bytes from here
     // offsets inside the descriptor blob
-    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_wblk = 0, o_utile = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0, o_lutacs = 0;
+    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_wblk = 0, o_utile = 0, o_tileex = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0, o_lutacs = 0;
     uint32_t idct_smem = 0;             // dynamic shared memory of k_idct_color: sized for the widest pixel tile of this batch
     uint32_t n_wblk = 0;                // CTAs of the Huffman write pass
     size_t n_slice_slots = 0;
@@ -69,7 +69,7 @@ struct bj_batch {
     uint64_t pixels = 0, scan_bytes = 0;
 
     // device
-    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_tilecnt, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
+    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels, copied out
     cudaStream_t last_stream = nullptr;
     bool uploaded = false, decoded = false, synced = false;
@@ -84,7 +84,7 @@ struct bj_batch {
     template <class T> T *hmeta(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(h_meta.p) + off); }
 
     void release() {
-        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_tilecnt, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
+        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
         h_files.release(); h_meta.release(); h_res.release();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     }
@@ -105,12 +105,6 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
     for (auto &e : b->ev) if (!e && c->check(cudaEventCreate(&e)) != BJ_OK) return BJ_ERR_CUDA;
 
-    // ---- parse (per image, independent: worker pool)
-    c->host_pool.parallel_for(n, 32, [&](int i0, int i1) {
-        for (int i = i0; i < i1; i++)
-            b->parse_status[i] = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &b->desc[i]) : BJ_ERR_INVALID_JPEG;
-    });
-
     // ---- where the file bytes are uploaded from.  Normally they are packed into this batch's pinned staging buffer
     // (one copy on the worker pool).  With option "packed_inputs" the caller states that all files of the call lie in
     // ONE pinned allocation: then the span from the first to the last file goes up as it is, straight from the
@@ -119,7 +113,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     uint64_t span_lo = ~0ull, span_hi = 0, span_sum = 0;
     if (direct) {
         for (int i = 0; i < n; i++) {
-            if (b->parse_status[i] != BJ_OK) continue;
+            if (!files[i] || !lens[i]) continue;
             const uint64_t a = (uint64_t)(uintptr_t)files[i];
             span_lo = std::min(span_lo, a); span_hi = std::max(span_hi, a + lens[i]); span_sum += lens[i];
         }
@@ -128,6 +122,23 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
             b->direct_src = reinterpret_cast<const uint8_t *>((uintptr_t)span_lo);
         }
     }
+
+    // ---- parse (per image, independent: worker pool).  The walk over the scan also counts, per un-stuff tile, the
+    // bytes that will not survive and the restart markers (parse.h: ScanTiles), so K0 needs no counting pass.
+    std::vector<uint32_t> tile_cap(n + 1, 0);
+    for (int i = 0; i < n; i++) tile_cap[i + 1] = tile_cap[i] + (uint32_t)((lens[i] + 15 + kScanTile - 1) / kScanTile + 1);
+    std::vector<uint32_t> tile_dropped(tile_cap[n], 0), tile_rst(tile_cap[n], 0);
+    std::vector<uint32_t> scan_mis(n, 0);
+    c->host_pool.parallel_for(n, 32, [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++) {
+            ScanTiles st;
+            st.dropped = tile_dropped.data() + tile_cap[i]; st.rst = tile_rst.data() + tile_cap[i];
+            st.ntile = tile_cap[i + 1] - tile_cap[i];
+            st.mis = b->direct_src ? (uint32_t)((uintptr_t)files[i] & 15u) : 0u;       // staged files start 16-byte aligned
+            b->parse_status[i] = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &b->desc[i], &st) : BJ_ERR_INVALID_JPEG;
+            scan_mis[i] = st.mis;
+        }
+    });
 
     // ---- sub-sequence length and slices, per image.
     // Explicit (options "subseq_bits", "slices"): the same for every image.  Automatic: nominally 4096 bits - a stream
@@ -167,6 +178,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     std::vector<ImgDev> idev(n);
     std::vector<TileDev> tiles;
     std::vector<uint32_t> blk_img, wblk_img, utile_img, dcc_img;
+    std::vector<uint2> tile_ex;                      // per un-stuff tile: surviving bytes / restart markers of the image before it
     size_t slice_slots = 0;
     std::vector<uint32_t> luts_dc, luts_ac, luts_acs;     // acs: the synchronisation pass' grouped AC tables
     std::map<std::string, int> lut_index[2];
@@ -261,7 +273,18 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         hi.raw_len = (uint32_t)d.scan_len;
         const uint64_t a0 = hi.raw_off & ~(uint64_t)15;
         hi.ntile = std::max<uint32_t>(1u, (uint32_t)((hi.raw_off - a0 + hi.raw_len + kUnstuffTile - 1) / kUnstuffTile));
-        for (uint32_t t = 0; t < hi.ntile; t++) utile_img.push_back((uint32_t)i);
+        {
+            const uint32_t mis = (uint32_t)(hi.raw_off - a0);
+            if (mis != scan_mis[i] || hi.ntile > tile_cap[i + 1] - tile_cap[i]) return BJ_ERR_ARG;      // (cannot happen)
+            uint32_t kept = 0, rst = 0;
+            for (uint32_t t = 0; t < hi.ntile; t++) {
+                utile_img.push_back((uint32_t)i);
+                tile_ex.push_back(make_uint2(kept, rst));
+                const uint64_t lo = std::max<uint64_t>(mis, (uint64_t)t * kScanTile), hi_ = std::min<uint64_t>((uint64_t)mis + hi.raw_len, (uint64_t)(t + 1) * kScanTile);
+                kept += (uint32_t)(hi_ > lo ? hi_ - lo : 0) - tile_dropped[tile_cap[i] + t];
+                rst += tile_rst[tile_cap[i] + t];
+            }
+        }
         hi.nmcu = g.nmcu; hi.ri = d.restart_interval;
         hi.nseg = hi.ri ? (g.nmcu + hi.ri - 1) / hi.ri : 1u;
         hi.bpm = (uint8_t)g.bpm; hi.ny = (uint8_t)(d.hs * d.vs); hi.ncomp = d.ncomp;
@@ -312,6 +335,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     b->o_blk = o;   o = align_up(o + blk_img.size() * 4, 256);
     b->o_wblk = o;  o = align_up(o + wblk_img.size() * 4, 256);
     b->o_utile = o; o = align_up(o + utile_img.size() * 4, 256);
+    b->o_tileex = o; o = align_up(o + tile_ex.size() * 8, 256);
     b->o_dcc = o;   o = align_up(o + dcc_img.size() * 4, 256);
     b->o_lutdc = o; o = align_up(o + luts_dc.size() * 4, 256);
     b->o_lutac = o; o = align_up(o + luts_ac.size() * 4, 256);
@@ -324,6 +348,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     if (!blk_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_blk), blk_img.data(), blk_img.size() * 4);
     if (!wblk_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_wblk), wblk_img.data(), wblk_img.size() * 4);
     if (!utile_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_utile), utile_img.data(), utile_img.size() * 4);
+    if (!tile_ex.empty()) memcpy(b->hmeta<uint2>(b->o_tileex), tile_ex.data(), tile_ex.size() * 8);
     if (!dcc_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_dcc), dcc_img.data(), dcc_img.size() * 4);
     if (!luts_dc.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutdc), luts_dc.data(), luts_dc.size() * 4);
     if (!luts_ac.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutac), luts_ac.data(), luts_ac.size() * 4);
@@ -346,7 +371,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         b->d_tot.reserve((size_t)b->n_sub_slots * 4 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 8 + 16) ||
         b->d_slice.reserve(b->n_slice_slots * 16 + 16) ||
         b->d_dc.reserve(coef_units * 2 + 64) || b->d_dcagg.reserve((size_t)b->n_dcc * sizeof(DcAgg) + 16) ||
-        b->d_tilecnt.reserve((size_t)b->n_utile * 8 + 16) || b->d_blkagg.reserve((size_t)nblk * sizeof(BlkAgg) + 16) ||
+        b->d_blkagg.reserve((size_t)nblk * sizeof(BlkAgg) + 16) ||
         b->d_state.reserve((size_t)n * sizeof(HuffImgState) + 16) || b->d_flags.reserve(kMaxRounds * 4) ||
         b->d_coef.reserve(coef_units * 128 + 16) || b->d_out.reserve(out_bytes + 64)) return BJ_ERR_NOMEM;
     return BJ_OK;
@@ -380,7 +405,7 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     uint32_t *seg_off = (uint32_t *)b->d_seg.p, *seg_sub0 = seg_off + b->n_seg_entries + 2;
     uint32_t *sub_seg = (uint32_t *)b->d_subseg.p, *flags = (uint32_t *)b->d_flags.p;
     uint32_t *clean = (uint32_t *)b->d_clean.p;
-    uint2 *st_in = (uint2 *)b->d_stin.p, *st_out = (uint2 *)b->d_stout.p, *tile_cnt = (uint2 *)b->d_tilecnt.p;
+    uint2 *st_in = (uint2 *)b->d_stin.p, *st_out = (uint2 *)b->d_stout.p;
     uint32_t *tot = (uint32_t *)b->d_tot.p;
     uint2 *pre = (uint2 *)b->d_pre.p;
     BlkAgg *agg = (BlkAgg *)b->d_blkagg.p;
@@ -389,9 +414,8 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     if (r0 == 0) {
         cudaEventRecord(b->ev[0], s);
         cudaMemsetAsync(flags, 0, kMaxRounds * 4, s);
-        cudaMemsetAsync(tile_cnt, 0, (size_t)b->n_utile * 8 + 8, s);                  // look-back status words
         cudaMemsetAsync(st, 0, (size_t)n * sizeof(HuffImgState), s);                  // (rejected files keep an all-zero state)
-        if (b->n_utile) k_unstuff<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, (unsigned long long *)tile_cnt, st, clean, seg_off);
+        if (b->n_utile) k_unstuff<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, b->dmeta<uint2>(b->o_tileex), st, clean, seg_off);
         k_subseq_table<<<n, 256, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg);
         b->launches = 1 + (b->n_utile ? 1 : 0);
         b->sync_rounds = 0;

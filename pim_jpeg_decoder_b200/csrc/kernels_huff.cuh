@@ -2,7 +2,7 @@
 // reference (src/jpeg_scanner.cpp:405-520, 707-756) with data-parallel kernels:
 //
 //   k_unstuff                                             (K0)  raw scan bytes -> un-stuffed big-endian words,
-//                                                          restart-segment byte offsets; one pass (decoupled look-back)
+//                                                          restart-segment byte offsets; one pass (tile offsets from the host's scan walk)
 //   k_subseq_table                                        (K0d) per image: split every segment into sub-sequences
 //   k_huff_sync                                           (K1b) speculative decode of every sub-sequence + fix-up
 //                                                          to the fixed point inside a CTA (state only, several
@@ -17,12 +17,14 @@
 #pragma once
 #include "bj_dev.h"
 #include "huff_core.h"
+#include "parse.h"
 
 namespace bj {
 
 constexpr int kHuffThreads = 256;          // sub-sequences per CTA
 constexpr int kUnstuffThreads = 256;
 constexpr int kUnstuffTile = kUnstuffThreads * 16;   // raw bytes per CTA of K0
+static_assert(kUnstuffTile == (int)kScanTile, "the host counts dropped bytes per tile of this size (parse.h)");
 
 // Per image, written by the host.
 struct HuffImg {
@@ -143,74 +145,40 @@ __device__ __forceinline__ uint32_t block_excl_scan_packed(uint32_t v, uint32_t 
     return inc - v + s_tmp[warp];
 }
 
-// One pass: classify, count, chain the tile's counts to those of the image's earlier tiles (decoupled look-back:
-// every tile publishes  state | restart markers | surviving bytes  as ONE 64-bit word - first its own counts, then,
-// once it has walked back to a tile that already knows its prefix, the inclusive prefix), compact the surviving
-// bytes in shared memory and store them as coalesced 32-bit words, byte-swapped so that stream byte o lands at
-// address o ^ 3 (huff_core.h "bit reader").  A tile's output starts at an arbitrary byte, so the (at most two) words
-// it shares with its neighbours are written bytewise.  The image's last tile also writes the image's state.
-// tile_status is zeroed before the launch; CTAs are dispatched in index order, so a predecessor is always running
-// or done.
-constexpr unsigned long long kTileAgg = 1ull << 62, kTilePrefix = 2ull << 62;
-__device__ __forceinline__ unsigned long long tile_pack(unsigned long long state, uint32_t kept, uint32_t rst) {
-    return state | ((unsigned long long)rst << 31) | kept;
-}
-
+// One pass: classify, count, compact the surviving bytes in shared memory and store them as coalesced 32-bit words,
+// byte-swapped so that stream byte o lands at address o ^ 3 (huff_core.h "bit reader").  Where the tile's bytes go
+// (surviving bytes and restart markers of the image before this tile) comes from the host: its walk over the scan
+// visits every FF anyway and counts per tile what will be dropped (parse.h: ScanTiles) - so there is no counting
+// pass and no chaining between CTAs.  A tile's output starts at an arbitrary byte, so the (at most two) words it
+// shares with its neighbours are written bytewise.  The image's last tile also writes the image's state.
 __global__ void __launch_bounds__(kUnstuffThreads)
 k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img,
-          unsigned long long *tile_status, HuffImgState *__restrict__ st, uint32_t *__restrict__ clean, uint32_t *__restrict__ seg_off) {
+          const uint2 *__restrict__ tile_ex, HuffImgState *__restrict__ st, uint32_t *__restrict__ clean, uint32_t *__restrict__ seg_off) {
     __shared__ uint32_t s_tmp[kUnstuffThreads / 32 + 1];
-    __shared__ uint2 s_base;
     __shared__ __align__(16) uint8_t s_out[kUnstuffTile + 16];
     const uint32_t img = tile_img[blockIdx.x];
     const HuffImg &im = imgs[img];
+    const uint2 base = __ldg(tile_ex + blockIdx.x);
     uint32_t keep, rst;
     uint4 bytes;
     classify16(files, im, blockIdx.x - im.tile_base, keep, rst, bytes);
     uint32_t tot;
     const uint32_t ex = block_excl_scan_packed<kUnstuffThreads>(__popc(keep) | (__popc(rst) << 16), tot, s_tmp);
     const uint32_t ea = ex & 0xFFFFu, eb = ex >> 16, ta = tot & 0xFFFFu, tb = tot >> 16;
-    if (threadIdx.x < 32) {                                                // warp 0: look back 32 tiles at a time
-        const uint32_t lt = blockIdx.x - im.tile_base, lane = threadIdx.x;
-        uint32_t pa = 0, pb = 0;                                           // surviving bytes / markers before this tile
-        volatile unsigned long long *status = tile_status;
-        if (lt != 0) {
-            if (lane == 0) status[blockIdx.x] = tile_pack(kTileAgg, ta, tb);
-            for (uint32_t newest = blockIdx.x - 1;; newest -= 32) {
-                const bool valid = newest >= im.tile_base + lane;          // tile newest - lane belongs to this image
-                unsigned long long v = 0;
-                if (valid) do { v = status[newest - lane]; } while ((v >> 62) == 0);
-                // the nearest tile that already knows its prefix ends the walk (the image's first tile always does)
-                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, valid && (v >> 62) == 2);
-                const bool take = valid && (pm == 0 || lane <= (uint32_t)(__ffs(pm) - 1));
-                uint32_t a = take ? (uint32_t)(v & 0x7FFFFFFFu) : 0u, c = take ? (uint32_t)((v >> 31) & 0x7FFFFFFFu) : 0u;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, d); c += __shfl_xor_sync(0xFFFFFFFFu, c, d); }
-                pa += a; pb += c;
-                if (pm) break;
-            }
-        }
-        if (lane == 0) {
-            status[blockIdx.x] = tile_pack(kTilePrefix, pa + ta, pb + tb);
-            s_base = make_uint2(pa, pb);
-            if (lt + 1 == im.ntile) {                                      // the image's totals
-                const uint32_t ca = pa + ta, cb = pb + tb;
-                HuffImgState s;
-                s.clean_len = ca; s.nrst = cb;
-                s.nseg = min(cb + 1u, im.nseg);
-                s.nsub = 0;
-                // segments whose marker is missing are never decoded: everything from their first unit on reads as zero
-                s.first_zero = (s.nseg < im.nseg) ? s.nseg * im.ri * im.bpm : 0xFFFFFFFFu;
-                s.status = (im.ri != 0 && cb + 1u != im.nseg) ? 1u : 0u;
-                s.pad_[0] = s.pad_[1] = 0;
-                st[img] = s;
-                seg_off[im.seg_base] = 0;
-                seg_off[im.seg_base + s.nseg] = ca;
-            }
-        }
+    if (threadIdx.x == 0 && blockIdx.x - im.tile_base + 1 == im.ntile) {   // the image's totals
+        const uint32_t ca = base.x + ta, cb = base.y + tb;
+        HuffImgState s;
+        s.clean_len = ca; s.nrst = cb;
+        s.nseg = min(cb + 1u, im.nseg);
+        s.nsub = 0;
+        // segments whose marker is missing are never decoded: everything from their first unit on reads as zero
+        s.first_zero = (s.nseg < im.nseg) ? s.nseg * im.ri * im.bpm : 0xFFFFFFFFu;
+        s.status = (im.ri != 0 && cb + 1u != im.nseg) ? 1u : 0u;
+        s.pad_[0] = s.pad_[1] = 0;
+        st[img] = s;
+        seg_off[im.seg_base] = 0;
+        seg_off[im.seg_base + s.nseg] = ca;
     }
-    __syncthreads();
-    const uint2 base = s_base;
     const uint32_t mis = base.x & 3u;                 // s_out[mis + k] = k-th surviving byte of the tile
     {
         const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};

@@ -35,7 +35,12 @@ extern "C" void emu_set_round_hist(uint32_t *hist) { g_round_hist = hist; }
 // info[3] = number of units written more or less than once (must be 0 for a clean stream)
 extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int slices, int16_t *coef_zz, uint32_t *info) {
     bj_image_desc d;
-    int rc = parse_header(file, len, &d);
+    // the parser's per-tile counts of dropped bytes / restart markers (what K0 is told instead of counting itself)
+    const uint32_t tile_cap = (uint32_t)((len + 15 + kScanTile - 1) / kScanTile + 1);
+    std::vector<uint32_t> host_dropped(tile_cap, 0), host_rst(tile_cap, 0);
+    ScanTiles tiles;
+    tiles.dropped = host_dropped.data(); tiles.rst = host_rst.data(); tiles.ntile = tile_cap; tiles.mis = 0;
+    int rc = parse_header(file, len, &d, &tiles);
     if (rc != BJ_OK) return rc;
     const uint32_t sub_bytes = (uint32_t)slice_bytes * (uint32_t)slices, slice_bits = (uint32_t)slice_bytes * 8u;
     const uint32_t nmx = (d.mcu_w + d.hs - 1) / d.hs, nmy = (d.mcu_h + d.vs - 1) / d.vs, nmcu = nmx * nmy;
@@ -67,6 +72,17 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int
             if ((keep >> b) & 1u) { clean[o ^ 3] = (uint8_t)bb; o++; }
             else if (((rst >> b) & 1u) && seg_off.size() < nseg_expected) seg_off.push_back((uint32_t)o);
         }
+    }
+    {   // ... and the same counts from the kernels' own classification, tile by tile
+        std::vector<uint32_t> dev_dropped(tile_cap, 0), dev_rst(tile_cap, 0);
+        if (tiles.mis != (d.scan_off & 15u)) return -201;
+        for (size_t i = 0; i < rl; i++) {
+            const unsigned prev = i ? raw[i - 1] : 0u, bb = raw[i], next = i + 1 < rl ? raw[i + 1] : 0xFFu;
+            const size_t t = (i + tiles.mis) / kScanTile;
+            if (!scan_keep(prev, bb, next)) dev_dropped[t]++;
+            if (scan_is_rst(prev, bb)) dev_rst[t]++;
+        }
+        if (dev_dropped != host_dropped || dev_rst != host_rst) return -202;
     }
     const uint32_t clean_len = (uint32_t)o;
     const uint32_t nseg = (uint32_t)seg_off.size();
