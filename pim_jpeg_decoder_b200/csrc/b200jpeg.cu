@@ -319,9 +319,13 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
     cudaEvent_t ev_base = nullptr;
     double host_t[kSlots][2] = {};
     const double wall0 = wall_ms();
+    static const bool blocking_wait = getenv("B200JPEG_SPIN_WAIT") == nullptr;
     auto finish = [&](int slot) -> int {
         bj_batch *b = c->slots[slot];
         const double t0 = wall_ms();
+        // sleep until the sub-batch's copy-out is done instead of polling for it (cudaStreamSynchronize spins by
+        // default, and a polling host thread takes bandwidth from the copy-out it is waiting for)
+        if (blocking_wait && b->ev_done) cudaEventSynchronize(b->ev_done);
         int r = batch_sync(b);
         if (trace && r == BJ_OK && ev_base) {
             float k0 = 0, k1 = 0, out = 0;
@@ -365,6 +369,8 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
             rc = batch_download_async(b, outs + i0, s);
             b->synced = false;
             if (trace) cudaEventRecord(b->ev[5], s);
+            if (!b->ev_done) cudaEventCreateWithFlags(&b->ev_done, cudaEventBlockingSync | cudaEventDisableTiming);
+            if (b->ev_done) cudaEventRecord(b->ev_done, s);
         }
         first[slot] = i0; count[slot] = i1 - i0; busy[slot] = true;
         nsub += 1;
