@@ -265,3 +265,24 @@ extern "C" int emu_classify_check(const uint8_t *bytes, size_t n) {
     }
     return bad;
 }
+
+// The parser's per-tile counts (dropped bytes, restart markers) against the per-byte rules, for a file whose first
+// byte sits at `base_mis` (mod 16) in the device buffer.  Returns 0, a parse status < 0, or 1 on a mismatch.
+extern "C" int emu_scan_tiles_check(const uint8_t *file, size_t len, int base_mis) {
+    bj_image_desc d;
+    const uint32_t tile_cap = (uint32_t)((len + 15 + kScanTile - 1) / kScanTile + 1);
+    std::vector<uint32_t> host_dropped(tile_cap, 0), host_rst(tile_cap, 0), dev_dropped(tile_cap, 0), dev_rst(tile_cap, 0);
+    ScanTiles tiles;
+    tiles.dropped = host_dropped.data(); tiles.rst = host_rst.data(); tiles.ntile = tile_cap; tiles.mis = (uint32_t)base_mis;
+    const int rc = parse_header(file, len, &d, &tiles);
+    if (rc != BJ_OK) return rc;
+    if (tiles.mis != ((uint32_t)base_mis + d.scan_off) % 16u) return 1;
+    const uint8_t *raw = file + d.scan_off;
+    for (size_t i = 0; i < d.scan_len; i++) {
+        const unsigned prev = i ? raw[i - 1] : 0u, bb = raw[i], next = i + 1 < d.scan_len ? raw[i + 1] : 0xFFu;
+        const size_t t = (i + tiles.mis) / kScanTile;
+        if (!scan_keep(prev, bb, next)) dev_dropped[t]++;
+        if (scan_is_rst(prev, bb)) dev_rst[t]++;
+    }
+    return (dev_dropped == host_dropped && dev_rst == host_rst) ? 0 : 1;
+}

@@ -111,6 +111,37 @@ def test_word_at_a_time_byte_classification():
         assert lib.emu_classify_check(ol._ptr(b), b.size) == 0
 
 
+def test_parser_counts_dropped_bytes_per_tile():
+    """The un-stuff kernel is told by the host where every 4 KB tile's surviving bytes go: the header parse counts, per
+    tile, the bytes the scan-byte rules drop and the RSTn markers while it looks for the end of the scan.  Checked
+    against the per-byte rules on scans dense in stuffed FFs, restart markers and fill bytes, at every alignment."""
+    lib = emu()
+    lib.emu_scan_tiles_check.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    base = js.synth_jpeg(64, 48, seed=1, subsampling=2)
+    h = ol.Restated(base, 0).h
+    head = base[:h.scan_off]
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        parts = []
+        n = 0
+        while n < 3 * 4096 + 500 * trial:
+            k = int(rng.integers(0, 6))
+            if k == 0:
+                piece = bytes([0xFF, 0x00])
+            elif k == 1:
+                piece = bytes([0xFF, 0xD0 + int(rng.integers(0, 8))])
+            elif k == 2:
+                piece = bytes([0xFF] * int(rng.integers(1, 4)) + [0xFF, 0xD0 + int(rng.integers(0, 8))])   # fill bytes before a marker
+            else:
+                piece = bytes(int(x) for x in rng.integers(0, 255, int(rng.integers(1, 40))))            # no FF
+            parts.append(piece)
+            n += len(piece)
+        data = head + b"".join(parts) + b"\xFF\xD9"
+        buf = np.frombuffer(data, dtype=np.uint8)
+        for mis in (0, 1, 7, 15):
+            assert lib.emu_scan_tiles_check(ol._ptr(buf), len(data), mis) == 0, (trial, mis)
+
+
 def test_lut_matches_bit_serial_search():
     lib = emu()
     dht, _ = js.std_tables()
