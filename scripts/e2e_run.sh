@@ -4,6 +4,6 @@ mkdir -p gpurun_out
 for i in 1 2; do
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_sleep_direct_$i.json 2> gpurun_out/${T}.err
 B200JPEG_SPIN_WAIT=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_spin_direct_$i.json 2>> gpurun_out/${T}.err
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --staged-inputs > gpurun_out/${T}_sleep_staged_$i.json 2>> gpurun_out/${T}.err
-B200JPEG_SPIN_WAIT=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --staged-inputs > gpurun_out/${T}_spin_staged_$i.json 2>> gpurun_out/${T}.err
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --direct-inputs > gpurun_out/${T}_sleep_staged_$i.json 2>> gpurun_out/${T}.err
+B200JPEG_SPIN_WAIT=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --direct-inputs > gpurun_out/${T}_spin_staged_$i.json 2>> gpurun_out/${T}.err
 done
