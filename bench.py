@@ -78,14 +78,17 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=100):
         self.index = index
         self.rows = []
         self.proc = None
+        self.interval_ms = interval_ms
 
     def start(self):
+        if self.interval_ms <= 0:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -254,6 +257,7 @@ def main():
     ap.add_argument("--gen-workers", type=int, default=min(32, os.cpu_count() or 1))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--clock-sample-ms", type=int, default=100, help="nvidia-smi polling interval while the timed regions run (0 = no sampling: for A/B only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -292,7 +296,7 @@ def main():
         dec.set_option("slices", args.slices)
     if args.sync_rounds:
         dec.set_option("sync_rounds", args.sync_rounds)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_sample_ms)
     sampler.start()
     windows = []
 
@@ -413,7 +417,7 @@ def main():
         e2e = {"value": px * world * k2 / e2e_s / 1e6, "unit": UNIT, "images_per_s": batch_n * world * k2 / e2e_s,
                "ms_per_step": 1e3 * e2e_s / k2, "steps": k2,
                "h2d_bytes_per_step": int(dec.stat("decode_batch_h2d_bytes")), "d2h_bytes_per_step": int(dec.stat("decode_batch_d2h_bytes")),
-               "sub_batches_per_step": int(dec.stat("decode_batch_sub_batches")), "host_threads": int(dec.stat("host_threads")),
+               "sub_batches_per_step": int(dec.stat("decode_batch_sub_batches")), "d2h_copies_per_step": int(dec.stat("decode_batch_d2h_copies")), "host_threads": int(dec.stat("host_threads")),
                "host_prepare_ms_per_step": host_ms / k2, "host_wait_gpu_ms_per_step": wait_ms / k2,
                "pcie_pinned_copy": pcie,
                "d2h_floor_ms_per_step": 1e3 * dec.stat("decode_batch_d2h_bytes") / (pcie["d2h_gbs"] * 1e9) if pcie.get("d2h_gbs") else None,

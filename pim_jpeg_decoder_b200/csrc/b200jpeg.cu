@@ -108,6 +108,7 @@ extern "C" int bj_get_stat(const bj_ctx *c, const char *name, double *value) {
     if (!strcmp(name, "decode_batch_d2h_bytes")) { *value = c->stats[3]; return BJ_OK; }
     if (!strcmp(name, "decode_batch_host_ms")) { *value = c->stats[4]; return BJ_OK; }        // parse + layout + pack, summed
     if (!strcmp(name, "decode_batch_wait_ms")) { *value = c->stats[5]; return BJ_OK; }        // host blocked on the GPU, summed
+    if (!strcmp(name, "decode_batch_d2h_copies")) { *value = c->stats[6]; return BJ_OK; }
     if (!strcmp(name, "host_threads")) { *value = c->host_pool.threads(); return BJ_OK; }
     return BJ_ERR_ARG;
 }
@@ -310,7 +311,7 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
     for (auto &b : c->slots) if (!b) { b = new (std::nothrow) bj_batch(); if (!b) return BJ_ERR_NOMEM; }
     int first[kSlots] = {}, count[kSlots] = {};
     bool busy[kSlots] = {};
-    double nsub = 0, launches = 0, h2d = 0, d2h = 0, host_ms = 0, wait_ms = 0;
+    double nsub = 0, launches = 0, h2d = 0, d2h = 0, host_ms = 0, wait_ms = 0, d2h_copies = 0;
     int rc = BJ_OK;
     // B200JPEG_TRACE=1: one line per sub-batch on stderr - when its kernels ran and its copy-out ended (ms since the
     // first sub-batch was enqueued) - to see whether the copy-out engine is kept busy.  (No event is recorded in front
@@ -339,7 +340,7 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
             r = batch_download(b, outs + first[slot], c->streams[slot]);
         wait_ms += wall_ms() - t0;
         if (r == BJ_OK && status) for (int i = 0; i < count[slot]; i++) status[first[slot] + i] = batch_image_status(b, i);
-        launches += b->launches; h2d += (double)(b->files_bytes + b->meta_bytes); d2h += (double)b->d2h_bytes;
+        launches += b->launches; h2d += (double)(b->files_bytes + b->meta_bytes); d2h += (double)b->d2h_bytes; d2h_copies += b->d2h_copies;
         busy[slot] = false;
         return r;
     };
@@ -379,6 +380,6 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
     // drain in submission order
     for (int j = 0; j < kSlots; j++) { const int slot = (k + j) % kSlots; if (busy[slot]) { const int r = finish(slot); if (rc == BJ_OK) rc = r; } }
     if (ev_base) cudaEventDestroy(ev_base);
-    c->stats[0] = nsub; c->stats[1] = launches; c->stats[2] = h2d; c->stats[3] = d2h; c->stats[4] = host_ms; c->stats[5] = wait_ms;
+    c->stats[0] = nsub; c->stats[1] = launches; c->stats[2] = h2d; c->stats[3] = d2h; c->stats[4] = host_ms; c->stats[5] = wait_ms; c->stats[6] = d2h_copies;
     return rc;
 }

@@ -78,6 +78,7 @@ struct bj_batch {
     uint32_t launches = 0, sync_rounds = 0;
     float ms_entropy = 0.f, ms_idct = 0.f, ms_unstuff = 0.f, ms_sync = 0.f, ms_write = 0.f;
     uint64_t d2h_bytes = 0;
+    uint32_t d2h_copies = 0;
 
     bj::HuffImgState *h_state() { return reinterpret_cast<bj::HuffImgState *>(h_res.p); }
     uint32_t *h_flags() { return reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(h_res.p) + bj::align_up((size_t)n * sizeof(bj::HuffImgState), 64)); }
@@ -498,7 +499,7 @@ inline int batch_sync(bj_batch *b) {
 inline int batch_download_async(bj_batch *b, uint8_t *const *outs, cudaStream_t s) {
     bj_ctx *c = b->ctx;
     int rc = BJ_OK;
-    b->d2h_bytes = 0;
+    b->d2h_bytes = 0; b->d2h_copies = 0;
     // option "packed_outputs": the caller states that host buffers laid out like the device buffer (see
     // bj_batch_output_offset) are one allocation, so runs of images go out as one copy (the <= 15 padding bytes
     // between them are overwritten).  Never inferred from pointer values alone: two separate heap blocks can
@@ -511,7 +512,7 @@ inline int batch_download_async(bj_batch *b, uint8_t *const *outs, cudaStream_t 
         while (c->packed_outputs && k + 1 < b->n && b->parse_status[k + 1] == BJ_OK && outs[k + 1] &&
                outs[k + 1] == outs[i] + (b->out_off[k + 1] - b->out_off[i])) { k++; end = b->out_off[k] + b->out_size[k]; }
         rc = c->check(cudaMemcpyAsync(outs[i], (const uint8_t *)b->d_out.p + b->out_off[i], end - b->out_off[i], cudaMemcpyDeviceToHost, s));
-        b->d2h_bytes += end - b->out_off[i];
+        b->d2h_bytes += end - b->out_off[i]; b->d2h_copies++;
         i = k + 1;
     }
     return rc;

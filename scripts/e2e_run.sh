@@ -2,8 +2,7 @@
 T=${1:-e2e}
 mkdir -p gpurun_out
 for i in 1 2; do
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_sleep_direct_$i.json 2> gpurun_out/${T}.err
-B200JPEG_SPIN_WAIT=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_spin_direct_$i.json 2>> gpurun_out/${T}.err
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --direct-inputs > gpurun_out/${T}_sleep_staged_$i.json 2>> gpurun_out/${T}.err
-B200JPEG_SPIN_WAIT=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --direct-inputs > gpurun_out/${T}_spin_staged_$i.json 2>> gpurun_out/${T}.err
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_smi100_$i.json 2> gpurun_out/${T}.err
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --clock-sample-ms 0 > gpurun_out/${T}_nosmi_$i.json 2>> gpurun_out/${T}.err
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --clock-sample-ms 1000 > gpurun_out/${T}_smi1000_$i.json 2>> gpurun_out/${T}.err
 done
