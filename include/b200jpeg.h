@@ -158,6 +158,9 @@ int bj_stage_entropy(bj_ctx *ctx, const uint8_t *file, size_t len, int16_t *coef
  *                      pass works on whole sub-sequences)
  *   "sync_rounds"      launches of the fix-up kernel before convergence is first checked
  *   "sub_batch_bytes"  compressed bytes per sub-batch of bj_decode_batch
+ *   "sub_batch_ramp"   0: all sub-batches the same size (default 1: the first two are 1/8 and 1/3 of it, so that the
+ *                      copy-out starts early)
+ *   "host_threads"     worker threads for the per-image host work of bj_decode_batch, the caller included
  *   "packed_inputs"    1: all input files of a bj_decode_batch call lie in ONE page-locked allocation (bj_host_alloc /
  *                      cudaHostAlloc), close together: they are uploaded straight from there, nothing is copied on
  *                      the host.  Only set it when that is true - pageable memory would make the upload synchronous
@@ -167,7 +170,9 @@ int bj_stage_entropy(bj_ctx *ctx, const uint8_t *file, size_t len, int16_t *coef
 int bj_set_option(bj_ctx *ctx, const char *name, long value);
 /* Counters of the last call: "exec_ms" (kernel time of bj_exec_mcus - the reference's "DPU execution" profile line,
  * src/decoder_host.cpp:291-294), "decode_batch_sub_batches", "decode_batch_launches", "decode_batch_h2d_bytes",
- * "decode_batch_d2h_bytes". */
+ * "decode_batch_d2h_bytes", "decode_batch_d2h_copies", "decode_batch_host_ms" (parse + layout + pack),
+ * "decode_batch_wait_ms" (caller blocked on the GPU), "host_threads".
+ * Environment: B200JPEG_TRACE=1 prints one line per sub-batch of bj_decode_batch (host prepare, kernels, copy-out). */
 int bj_get_stat(const bj_ctx *ctx, const char *name, double *value);
 
 /* Version / build info. */
