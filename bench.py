@@ -370,6 +370,7 @@ def main():
         # pin_in is one pinned allocation, so the files could go up straight from it (option "packed_inputs": half the
         # host work); measured on these boxes the copy-out then runs a little slower (the staged copy leaves the bytes
         # in the CPU's cache for the upload to pick up), so the default stays the staging copy
+        # (also with 4 ranks on one host, where it halves a host time of 70 ms per step: 112 ms per call against 97)
         dec.set_option("packed_inputs", 1 if args.direct_inputs else 0)
         if args.sub_batch_mb:
             dec.set_option("sub_batch_bytes", args.sub_batch_mb << 20)
