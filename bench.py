@@ -248,6 +248,7 @@ def main():
     ap.add_argument("--subseq-bits", type=int, default=0, help="sub-sequence length of the Huffman synchronisation pass (0 = library default: per image, about 4096 bits)")
     ap.add_argument("--slices", type=int, default=0, help="slices of a sub-sequence the Huffman write pass works on (0 = library default: 1)")
     ap.add_argument("--sync-rounds", type=int, default=0)
+    ap.add_argument("--sync-phased", type=int, default=-1, help="1/0: Huffman synchronisation pass with / without early stop of re-decodes (-1 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--sub-batch-mb", type=int, default=0, help="compressed MB per sub-batch of the one-call path (0 = library default)")
     ap.add_argument("--host-threads", type=int, default=0, help="host worker threads of the one-call path (0 = library default)")
@@ -296,6 +297,8 @@ def main():
         dec.set_option("slices", args.slices)
     if args.sync_rounds:
         dec.set_option("sync_rounds", args.sync_rounds)
+    if args.sync_phased >= 0:
+        dec.set_option("sync_phased", args.sync_phased)
     sampler = ClockSampler(local_rank, args.clock_sample_ms)
     sampler.start()
     windows = []
@@ -464,7 +467,7 @@ def main():
     nsub = float(info.subsequences)
     alg = {
         "unstuff": 1.0 * info.scan_bytes + clean,                     # raw bytes read once + clean bytes written
-        "sync": clean + (28.0 + 16.0 * (args.slices or 1)) * nsub,    # stream read once + per-sub-sequence states/totals + slice entry states written
+        "sync": clean + (28.0 + 16.0 * (args.slices or 1) + 64.0) * nsub,    # stream read once + per-sub-sequence states/totals + slice entry states + 4 quarter records written
         "write": clean + 128.0 * units,                               # stream read once + every coefficient unit written once
         "idct": 128.0 * units + float(info.out_bytes),                # coefficients read once + pixels written once
     }

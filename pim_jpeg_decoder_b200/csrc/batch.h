@@ -38,7 +38,8 @@ constexpr int kSmemHuffSyncMax = kSmemLutMax;
 
 inline int batch_kernels_init(bj_ctx *c) {
     if (c->check(cudaFuncSetAttribute(k_huff_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffWriteMax)) != BJ_OK) return BJ_ERR_CUDA;
-    if (c->check(cudaFuncSetAttribute(k_huff_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
+    if (c->check(cudaFuncSetAttribute(k_huff_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
+    if (c->check(cudaFuncSetAttribute(k_huff_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
     return BJ_OK;
 }
 
@@ -69,11 +70,12 @@ struct bj_batch {
     uint64_t pixels = 0, scan_bytes = 0;
 
     // device
-    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
+    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_quarter, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels, copied out
     cudaEvent_t ev_done = nullptr;       // one-call path: recorded behind the copy-out, created for a sleeping wait
     cudaStream_t last_stream = nullptr;
     bool uploaded = false, decoded = false, synced = false;
+    bool phased = true;                  // which variant of the synchronisation kernel this batch was laid out for
     bool multi_blk = false;              // some image's sub-sequences span more than one CTA of the synchronisation pass
     uint32_t launches = 0, sync_rounds = 0;
     float ms_entropy = 0.f, ms_idct = 0.f, ms_unstuff = 0.f, ms_sync = 0.f, ms_write = 0.f;
@@ -86,7 +88,7 @@ struct bj_batch {
     template <class T> T *hmeta(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(h_meta.p) + off); }
 
     void release() {
-        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
+        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_quarter, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
         h_files.release(); h_meta.release(); h_res.release();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (ev_done) { cudaEventDestroy(ev_done); ev_done = nullptr; }
@@ -189,7 +191,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
     uint32_t seg_entries = 0, nblk = 0;
     int prev = -1;                                  // last valid image: its table slots are reused when the tables match
-    b->pixels = 0; b->scan_bytes = 0; b->lut_smem = 0; b->multi_blk = false;
+    b->pixels = 0; b->scan_bytes = 0; b->lut_smem = 0; b->multi_blk = false; b->phased = c->sync_phased != 0;
     uint32_t rgb_max = 0;
     auto same_tables = [](const bj_image_desc &a, const bj_image_desc &q) {
         if (a.ncomp != q.ncomp || memcmp(a.dc_id, q.dc_id, 3) || memcmp(a.ac_id, q.ac_id, 3)) return false;
@@ -372,7 +374,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         b->d_seg.reserve((size_t)(seg_entries + 2) * 4 * 2) || b->d_subseg.reserve((size_t)b->n_sub_slots * 4 + 16) ||
         b->d_stin.reserve((size_t)b->n_sub_slots * 8 + 16) || b->d_stout.reserve((size_t)b->n_sub_slots * 8 + 16) ||
         b->d_tot.reserve((size_t)b->n_sub_slots * 4 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 8 + 16) ||
-        b->d_slice.reserve(b->n_slice_slots * 16 + 16) ||
+        b->d_slice.reserve(b->n_slice_slots * 16 + 16) || (b->phased && b->d_quarter.reserve((size_t)b->n_sub_slots * 8 * 16 + 16)) ||
         b->d_dc.reserve(coef_units * 2 + 64) || b->d_dcagg.reserve((size_t)b->n_dcc * sizeof(DcAgg) + 16) ||
         b->d_blkagg.reserve((size_t)nblk * sizeof(BlkAgg) + 16) ||
         b->d_state.reserve((size_t)n * sizeof(HuffImgState) + 16) || b->d_flags.reserve(kMaxRounds * 4) ||
@@ -426,7 +428,10 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     }
     if (b->n_blk) {
         for (int r = r0; r < r1; r++) {
-            k_huff_sync<<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, agg, flags, r);
+            if (b->phased)
+                k_huff_sync<true><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, (uint4 *)b->d_quarter.p, agg, flags, r);
+            else
+                k_huff_sync<false><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, nullptr, agg, flags, r);
             b->launches++; b->sync_rounds++;
         }
         cudaEventRecord(b->ev[2], s);

@@ -112,6 +112,7 @@ struct bj_ctx {
     int device = 0;
     int sm_count = 0;
     int subseq_bits = 0;                 // sub-sequence length of the synchronisation pass; 0 = automatic (per image)
+    int sync_phased = 1;                 // synchronisation pass: re-decodes stop where they meet the previous decode (kernels_huff.cuh)
     int slices = 0;                      // slices (write pass) per sub-sequence: 1, 2, 4, 8; 0 = default (1)
     size_t sub_batch_bytes = 0;          // 0 = default
     int sub_batch_ramp = 1;              // the first two sub-batches of a call are smaller (the copy-out starts earlier)

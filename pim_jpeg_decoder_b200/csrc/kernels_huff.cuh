@@ -341,12 +341,23 @@ struct SliceStore {
     __device__ __forceinline__ void operator()(uint32_t k, uint32_t p, uint32_t cz, uint32_t cnt) const { base[k] = make_uint4(p, cz, cnt, 0u); }
 };
 
+struct NoRec {
+    __device__ __forceinline__ void operator()(uint32_t, uint32_t, uint32_t, uint32_t) const {}
+};
+// PHASED: from the second decode of a sub-sequence on, a decode stops as soon as it meets the trajectory of the
+// previous one.  Every decode runs quarter by quarter (eighth by eighth for images with 8 slices) and keeps, per
+// quarter, the state at its end and the units started in it (`quarters`, 8 entries per sub-sequence); a re-decode whose
+// state at the end of a quarter equals the recorded one is done - the rest of its trajectory, its exit state and the
+// later quarters' counts are those of the previous decode.  Between quarters the sub-sequences still running are
+// compacted onto the first threads, like between the iterations.  The write pass' slice table is filled from the
+// quarter records at the end (a slice always starts at a quarter boundary).
+template <bool PHASED>
 __global__ void __launch_bounds__(kHuffThreads, 6)
 k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
             const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
             const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
             uint2 *__restrict__ st_in, uint2 *__restrict__ st_out, uint32_t *__restrict__ sub_tot, uint2 *__restrict__ sub_pre,
-            uint4 *__restrict__ slices, BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round) {
+            uint4 *__restrict__ slices, uint4 *__restrict__ quarters, BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
@@ -356,6 +367,9 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     __shared__ uint16_t s_work[2][kHuffThreads];
     __shared__ uint32_t s_nwork[2];
     __shared__ uint32_t s_flag;
+    __shared__ uint2 s_cur[PHASED ? kHuffThreads : 1];                      // PHASED: state at the end of the last quarter done
+    __shared__ uint16_t s_plist[2][PHASED ? kHuffThreads : 1];              // PHASED: sub-sequences still running in this iteration
+    __shared__ uint32_t s_pn[2];
     __shared__ uint32_t s_w[kHuffThreads / 32 + 1];
     __shared__ uint32_t s_wf[kHuffThreads / 32 + 1];
 
@@ -398,22 +412,64 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     const uint32_t slice_bits = (im.sub_bytes >> slices_log2) * 8u;
     uint4 *img_slices = slices + im.slice_base;
 
+    const uint32_t ql2 = slices_log2 > 2u ? slices_log2 : 2u;               // PHASED: quarters (or eighths) per sub-sequence
+    const uint32_t qbits = (im.sub_bytes >> ql2) * 8u;
+    uint4 *img_quarters = quarters + ((size_t)im.sub_base << 3);
+
     int cur = 0;
-    for (;;) {
+    for (uint32_t iter = 0;; iter++) {
         __syncthreads();
         const uint32_t nw = s_nwork[cur];
         if (nw == 0) break;
-        for (uint32_t w = tid; w < nw; w += kHuffThreads) {
-            const uint32_t item = s_work[cur][w];
-            HuffState in;
-            in.p = s_in[item].x; in.cz = s_in[item].y;
-            uint32_t started;
-            SliceStore rec;
-            rec.base = img_slices + ((size_t)(first_j + item) << slices_log2);
-            const uint2 span = s_span[item];
-            const HuffState o = decode_span(words, luts, g, in, span.x, span.y, slice_bits, rec, &started);
-            s_out[item] = make_uint2(o.p, o.cz);
-            s_tot[item] = started;
+        if (!PHASED) {
+            for (uint32_t w = tid; w < nw; w += kHuffThreads) {
+                const uint32_t item = s_work[cur][w];
+                HuffState in;
+                in.p = s_in[item].x; in.cz = s_in[item].y;
+                uint32_t started;
+                SliceStore rec;
+                rec.base = img_slices + ((size_t)(first_j + item) << slices_log2);
+                const uint2 span = s_span[item];
+                const HuffState o = decode_span(words, luts, g, in, span.x, span.y, slice_bits, rec, &started);
+                s_out[item] = make_uint2(o.p, o.cz);
+                s_tot[item] = started;
+            }
+        } else {
+            const bool has_prev = round > 0 || iter > 0;                    // every sub-sequence on the list has been decoded before
+            for (uint32_t w = tid; w < nw; w += kHuffThreads) s_plist[0][w] = s_work[cur][w];
+            if (tid == 0) { s_pn[0] = nw; s_pn[1] = 0; }
+            int pc = 0;
+            for (uint32_t q = 0; q < (1u << ql2); q++) {
+                __syncthreads();
+                const uint32_t pn = s_pn[pc];
+                if (pn == 0) break;
+                for (uint32_t w = tid; w < pn; w += kHuffThreads) {
+                    const uint32_t item = s_plist[pc][w];
+                    const uint2 span = s_span[item];
+                    const uint32_t qs = span.x + q * qbits, qe = min(qs + qbits, span.y);
+                    const bool last = qe >= span.y;
+                    const uint2 e = q == 0 ? s_in[item] : s_cur[item];
+                    HuffState in;
+                    in.p = e.x; in.cz = e.y;
+                    uint32_t n;
+                    NoRec rec;
+                    const HuffState o = decode_span(words, luts, g, in, qs, qe, qbits, rec, &n);
+                    uint4 *qr = img_quarters + ((size_t)(first_j + item) << 3) + q;
+                    uint4 old = make_uint4(0u, 0u, 0u, 0u);
+                    if (has_prev) old = *qr;
+                    *qr = make_uint4(o.p, o.cz, n, 0u);
+                    s_tot[item] = (q == 0 && !has_prev ? 0u : s_tot[item]) + n - old.z;
+                    if (last) s_out[item] = make_uint2(o.p, o.cz);
+                    else if (!(has_prev && old.x == o.p && old.y == o.cz)) {        // not yet on the old trajectory: go on
+                        s_cur[item] = make_uint2(o.p, o.cz);
+                        s_plist[pc ^ 1][atomicAdd(&s_pn[pc ^ 1], 1u)] = (uint16_t)item;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) s_pn[pc] = 0;
+                pc ^= 1;
+            }
+            __syncthreads();
         }
         if (tid == 0) s_nwork[cur ^ 1] = 0;
         __syncthreads();
@@ -458,6 +514,17 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
         // exclusive: a head starts from zero; otherwise inclusive minus own
         st_in[gj] = s_in[tid];
         img_slices[(size_t)j << slices_log2] = make_uint4(s_in[tid].x, s_in[tid].y, 0u, 0u);
+        if (PHASED && slices_log2) {                                       // slice k starts where quarter k * step - 1 ended
+            const uint32_t step = 1u << (ql2 - slices_log2);
+            const uint4 *qr = img_quarters + ((size_t)j << 3);
+            const uint32_t nsl = u.end_bit > u.start_bit ? (u.end_bit - u.start_bit + slice_bits - 1u) / slice_bits : 1u;
+            uint32_t cnt = 0;
+            for (uint32_t k = 1; k < nsl; k++) {
+                uint4 e = qr[0];
+                for (uint32_t q = (k - 1u) * step; q < k * step; q++) { e = qr[q]; cnt += e.z; }
+                img_slices[((size_t)j << slices_log2) + k] = make_uint4(e.x, e.y, cnt, 0u);
+            }
+        }
         st_out[gj] = s_out[tid];
         sub_tot[gj] = s_tot[tid];
         sub_pre[gj] = u.head ? make_uint2(0u, 1u) : make_uint2(v0 - own0, hf);   // .y: a head precedes inside this CTA
