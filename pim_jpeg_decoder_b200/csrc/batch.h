@@ -40,6 +40,16 @@ inline int batch_kernels_init(bj_ctx *c) {
     if (c->check(cudaFuncSetAttribute(k_huff_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffWriteMax)) != BJ_OK) return BJ_ERR_CUDA;
     if (c->check(cudaFuncSetAttribute(k_huff_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
     if (c->check(cudaFuncSetAttribute(k_huff_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
+#ifndef BJ_SYNC_CARVEOUT
+#define BJ_SYNC_CARVEOUT 72            // % of 228 KB: 164 KB of shared memory for 5 CTAs, the rest is L1 (kernels_huff.cuh: BJ_SYNC_CTAS)
+#endif
+#if BJ_SYNC_CARVEOUT > 0
+    if (c->check(cudaFuncSetAttribute(k_huff_sync<true>, cudaFuncAttributePreferredSharedMemoryCarveout, BJ_SYNC_CARVEOUT)) != BJ_OK) return BJ_ERR_CUDA;
+    if (c->check(cudaFuncSetAttribute(k_huff_sync<false>, cudaFuncAttributePreferredSharedMemoryCarveout, BJ_SYNC_CARVEOUT)) != BJ_OK) return BJ_ERR_CUDA;
+#endif
+#ifdef BJ_WRITE_CARVEOUT
+    if (c->check(cudaFuncSetAttribute(k_huff_write, cudaFuncAttributePreferredSharedMemoryCarveout, BJ_WRITE_CARVEOUT)) != BJ_OK) return BJ_ERR_CUDA;
+#endif
     return BJ_OK;
 }
 

@@ -261,6 +261,9 @@ BJ_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, uint32_t s) {      // top 32 b
 // table entry.  The zig-zag index never exceeds 127 (63 + 64), so bit 6 set means "unit complete" and the byte
 // never carries into the position.  A symbol consumes at most 27 bits, so the word index grows by at most one.
 constexpr uint32_t kWordS = 32u << 8;
+#ifndef BJ_STREAM_LD
+#define BJ_STREAM_LD "ld.global.nc.u32"
+#endif
 struct BitStream {
     const uint32_t *w;            // -> word holding the current position
     uint32_t cur, nxt, nx2;       // that word and the two after it (the load runs one word ahead of its use)
@@ -277,15 +280,18 @@ struct BitStream {
     // the next 32 bits at S, moving on to the next word first if S has left the current one
     BJ_HD uint32_t window(uint32_t S) {
 #ifdef __CUDA_ARCH__
-        // predicated, no branch; the load writes nx2 directly (a select on the loaded value would stall on it)
+        // predicated, no branch; the load writes nx2 directly (a select on the loaded value would stall on it).
+        // The pointer moves by a 0-or-1 select folded into a multiply-add: a predicated 64-bit add comes out of
+        // ptxas as an add, a carry add, two selects and two moves.
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
+            "{\n\t.reg .pred p;\n\t.reg .u32 a;\n\t"
             "setp.ge.u32 p, %5, %4;\n\t"
+            "selp.u32 a, 1, 0, p;\n\t"
             "@p mov.b32 %0, %1;\n\t"
             "@p mov.b32 %1, %2;\n\t"
-            "@p add.u64 %3, %3, 4;\n\t"
+            "mad.wide.u32 %3, a, 4, %3;\n\t"
             "@p add.u32 %4, %4, 8192;\n\t"
-            "@p ld.global.nc.u32 %2, [%3+8];\n\t}"
+            "@p " BJ_STREAM_LD " %2, [%3+8];\n\t}"
             : "+r"(cur), "+r"(nxt), "+r"(nx2), "+l"(w), "+r"(word_end)
             : "r"(S));
 #else
@@ -309,26 +315,58 @@ struct HuffGeom {
     uint32_t bpm;           // data units per MCU
     uint32_t ny;            // luma units per MCU (hs * vs); unit c belongs to component c < ny ? 0 : c - ny + 1
     uint32_t dc[3], ac[3];  // per component: DC / AC table
-    uint32_t unit_tab;      // device, optional: shared-memory address of one uint2 per unit of the MCU:
-                            // {DC table | index << 24, AC table} of the unit that FOLLOWS it (0: none)
+    uint32_t unit_tab;      // device: shared-memory address (256-byte aligned) of one uint4 per unit c of the MCU, about
+                            // the unit c1 that FOLLOWS it: {DC table, AC table, UnitWalk step from c to c1, c1}
 };
 BJ_HD uint32_t comp_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? 0u : c - g.ny + 1u; }
 BJ_HD uint32_t dc_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.dc[0] : (c == g.ny ? g.dc[1] : g.dc[2]); }
 BJ_HD uint32_t ac_of(const HuffGeom &g, uint32_t c) { return c < g.ny ? g.ac[0] : (c == g.ny ? g.ac[1] : g.ac[2]); }
-// The unit after unit c of the MCU: its index and both its tables - one 64-bit shared load where the per-unit
-// table exists (the hot loops hand over from unit to unit in most iterations of a warp), selects otherwise.
+// The unit after unit c of the MCU: its index and both its tables - one 128-bit shared load on the device (the
+// Huffman kernels always stage the table: stage_luts), selects on the host.
 BJ_HD void next_unit(const HuffGeom &g, uint32_t c, uint32_t &c1, uint32_t &dc, uint32_t &ac) {
 #ifdef __CUDA_ARCH__
-    if (g.unit_tab) {
-        uint32_t x;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(ac) : "r"(g.unit_tab + c * 8u));
-        dc = x & 0xFFFFFFu; c1 = x >> 24;
-        return;
-    }
-#endif
+    [[maybe_unused]] uint32_t step;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dc), "=r"(ac), "=r"(step), "=r"(c1) : "r"(g.unit_tab + c * 16u));
+#else
     c1 = (c + 1u == g.bpm) ? 0u : c + 1u;
     dc = dc_of(g, c1); ac = ac_of(g, c1);
+#endif
 }
+
+// Where the synchronisation pass is: unit c of the MCU, and how many units it has completed.  On the device both
+// live in one register, completed << 8 | c << 4, so that the hand-over to the next unit is one predicated add of
+// the table's step (0x100 + 16 * (c1 - c)) and the table entry's address is one logic operation.
+struct UnitWalk {
+#ifdef __CUDA_ARCH__
+    uint32_t cu;
+    BJ_HD void start(uint32_t c) { cu = c << 4; }
+    BJ_HD uint32_t unit() const { return (cu >> 4) & 15u; }
+    BJ_HD uint32_t ended() const { return cu >> 8; }
+    // `fin`: the unit is complete - move on to the next one.  tab = table of the next symbol, ac = AC table of the unit.
+    BJ_HD void advance(const HuffGeom &g, bool fin, uint32_t &tab, uint32_t &ac) {
+        uint32_t dcn, acn, step;
+        [[maybe_unused]] uint32_t c1;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dcn), "=r"(acn), "=r"(step), "=r"(c1) : "r"(g.unit_tab | (cu & 0xF0u)));
+        cu += fin ? step : 0u;
+        ac = fin ? acn : ac;
+        tab = fin ? dcn : ac;
+    }
+#else
+    uint32_t c, n;
+    void start(uint32_t c0) { c = c0; n = 0; }
+    uint32_t unit() const { return c; }
+    uint32_t ended() const { return n; }
+    void advance(const HuffGeom &g, bool fin, uint32_t &tab, uint32_t &ac) {
+        uint32_t c1, dcn, acn;
+        next_unit(g, c, c1, dcn, acn);
+        c = fin ? c1 : c;
+        n += fin ? 1u : 0u;
+        ac = fin ? acn : ac;
+        tab = fin ? dcn : ac;
+    }
+#endif
+};
+BJ_HD constexpr uint32_t unit_walk_step(uint32_t c, uint32_t c1) { return 0x100u + 16u * (c1 - c); }
 
 // Magnitude extension of the `size` bits that follow a `len`-bit code in the window
 // (src/jpeg_scanner.cpp:480-482 / :513-516: first bit 0 => negative).  size 0 gives 0.
@@ -363,7 +401,8 @@ template <class Rec>
 BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t start_bit,
                             uint32_t end_bit, uint32_t slice_bits, Rec &rec, uint32_t *units_started) {
     const uint32_t origin = st.p & ~31u;
-    uint32_t c = st.cz >> 8;
+    UnitWalk u;
+    u.start(st.cz >> 8);
     uint32_t S = ((st.p - origin) << 8) | (st.cz & 0xFFu);
     const uint32_t endS = end_bit > origin ? (end_bit - origin) << 8 : 0u;
     const uint32_t entered_mid = (S & 0xFFu) ? 1u : 0u;
@@ -371,39 +410,33 @@ BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const Huf
     uint32_t k = 1;
     uint32_t ckS = start_bit + slice_bits > origin ? (start_bit + slice_bits - origin) << 8 : 0u;   // slice k starts here
     uint32_t limS = (k < nslices && ckS < endS) ? ckS : endS;
-    uint32_t ends = 0;
-    uint32_t ac = ac_of(g, c);
-    uint32_t tab = entered_mid ? ac : dc_of(g, c);
+    uint32_t ac = ac_of(g, st.cz >> 8);
+    uint32_t tab = entered_mid ? ac : dc_of(g, st.cz >> 8);
     BitStream bs;
     bs.open(words, st.p);
     for (;;) {
-        if (S >= limS) {                                                  // once per slice
-            while (k < nslices && S >= ckS) {
-                rec(k, origin + (S >> 8), (c << 8) | (S & 0xFFu), ends + ((S & 0xFFu) ? 1u : 0u) - entered_mid);
-                k++;
-                ckS += slice_bits << 8;
-            }
-            if (S >= endS) break;
-            limS = (k < nslices && ckS < endS) ? ckS : endS;
+        while (S < limS) {
+            const uint32_t e = lut_lookup(luts, tab, bs.window(S));
+            uint32_t Sn = S + (e & 0xFFFFu);
+            // 65..127: a symbol inside the group ended the unit (or an over-long run): the first symbol alone
+            if (__builtin_expect(((Sn & 0xFFu) - 65u) < 63u, 0)) Sn = S + ((e >> 16) & 0x7FFFu);
+            // zig-zag index >= 64: unit complete (also: over-long run).  Branch-free: most iterations of a warp see one.
+            const bool fin = (Sn & 0xC0u) != 0u;
+            u.advance(g, fin, tab, ac);
+            S = fin ? (Sn & ~0xFFu) : Sn;
         }
-        const uint32_t e = lut_lookup(luts, tab, bs.window(S));
-        uint32_t Sn = S + (e & 0xFFFFu);
-        // 65..127: a symbol inside the group ended the unit (or an over-long run): the first symbol alone
-        if (__builtin_expect(((Sn & 0xFFu) - 65u) < 63u, 0)) Sn = S + ((e >> 16) & 0x7FFFu);
-        // zig-zag index >= 64: unit complete (also: over-long run).  Branch-free: most iterations of a warp see one.
-        const bool fin = (Sn & 0xC0u) != 0u;
-        uint32_t c1, dcn, acn;
-        next_unit(g, c, c1, dcn, acn);
-        c = fin ? c1 : c;
-        ends += fin ? 1u : 0u;
-        S = fin ? (Sn & ~0xFFu) : Sn;
-        ac = fin ? acn : ac;
-        tab = fin ? dcn : ac;
+        while (k < nslices && S >= ckS) {                                 // once per slice
+            rec(k, origin + (S >> 8), (u.unit() << 8) | (S & 0xFFu), u.ended() + ((S & 0xFFu) ? 1u : 0u) - entered_mid);
+            k++;
+            ckS += slice_bits << 8;
+        }
+        if (S >= endS) break;
+        limS = (k < nslices && ckS < endS) ? ckS : endS;
     }
     // started = ended + (one still open at the exit) - (the one that was already open at the entry)
-    *units_started = ends + ((S & 0xFFu) ? 1u : 0u) - entered_mid;
+    *units_started = u.ended() + ((S & 0xFFu) ? 1u : 0u) - entered_mid;
     HuffState o;
-    o.p = origin + (S >> 8); o.cz = (c << 8) | (S & 0xFFu);
+    o.p = origin + (S >> 8); o.cz = (u.unit() << 8) | (S & 0xFFu);
     return o;
 }
 
@@ -462,9 +495,9 @@ struct WriteCursor {
     // One symbol.  The reference's failure points: refused symbol, bits running out inside a symbol, run past the
     // end of the unit ("i + run >= 64", src/jpeg_scanner.cpp:497-500).  A failed DC leaves the unit untouched
     // (zero); a failed AC keeps what was stored before it.
-    // One symbol.  `unit` = something for the caller to do: unit store_du() is complete (store the staged unit,
-    // whose slot 0 holds its DC difference, and clear the stage); `done` = slice finished (only ever set together
-    // with `unit`).  After a failure (`fail`), store_du() also settles first_zero.
+    // `unit` = something for the caller to do: unit store_du() is complete (store the staged unit, whose slot 0
+    // holds its DC difference, and clear the stage); `done` = slice finished (only ever set together with `unit`).
+    // After a failure (`fail`), store_du() also settles first_zero.
     template <class Sink>
     BJ_HD void step(const LutMem &luts, const HuffGeom &g, Sink &sink, bool &unit, bool &done) {
         const uint32_t win = bs.window(S);

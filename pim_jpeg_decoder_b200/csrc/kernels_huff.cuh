@@ -281,7 +281,7 @@ __device__ __forceinline__ SubInfo sub_info(const HuffImg &im, const HuffImgStat
 // stage the image's tables into shared memory, packed (DC slots first, then AC slots; only the used part of every
 // table), 16 bytes per thread per step.  Returns where they are through `g` (byte offsets) and `luts`.
 __device__ __forceinline__ void stage_luts(const HuffImg &im, const uint32_t *__restrict__ lut_dc_pool,
-                                           const uint32_t *__restrict__ lut_ac_pool, uint32_t *s_lut, uint2 *s_units /* [16] */,
+                                           const uint32_t *__restrict__ lut_ac_pool, uint32_t *s_lut, uint4 *s_units /* [16], 256-byte aligned */,
                                            HuffGeom &g, LutMem &luts) {
     uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
     uint32_t off = 0, dc_off[3] = {0, 0, 0}, ac_off[3] = {0, 0, 0};
@@ -314,13 +314,12 @@ __device__ __forceinline__ void stage_luts(const HuffImg &im, const uint32_t *__
         g.ac[j] = sbase + (as == 0 ? ac_off[0] : as == 1 ? ac_off[1] : ac_off[2]);
     }
     // per unit of the MCU: tables and index of the unit that follows it (huff_core.h: next_unit)
-    if (g.bpm <= 16u) {
-        if (threadIdx.x < g.bpm) {
-            const uint32_t c1 = threadIdx.x + 1u == g.bpm ? 0u : threadIdx.x + 1u;
-            s_units[threadIdx.x] = make_uint2(dc_of(g, c1) | (c1 << 24), ac_of(g, c1));
-        }
-        g.unit_tab = (uint32_t)__cvta_generic_to_shared(s_units);
+    if (threadIdx.x < g.bpm && threadIdx.x < 16u) {
+        const uint32_t c1 = threadIdx.x + 1u == g.bpm ? 0u : threadIdx.x + 1u;
+        s_units[threadIdx.x] = make_uint4(dc_of(g, c1), ac_of(g, c1), unit_walk_step(threadIdx.x, c1), c1);
     }
+    g.unit_tab = (uint32_t)__cvta_generic_to_shared(s_units);
+    asm volatile("mov.u32 %0, %0;" : "+r"(g.unit_tab));                   // a register, not an address rebuilt in the symbol loops
     (void)luts;
 }
 
@@ -352,7 +351,14 @@ struct NoRec {
 // compacted onto the first threads, like between the iterations.  The write pass' slice table is filled from the
 // quarter records at the end (a slice always starts at a quarter boundary).
 template <bool PHASED>
-__global__ void __launch_bounds__(kHuffThreads, 6)
+// CTAs per SM the synchronisation pass is compiled for.  Every thread walks its own 128-byte lines of the stream, so
+// the L1 has to hold about one line per resident thread or the lines are evicted before their 32 words are used:
+// 5 CTAs with the shared-memory carve-out limited to 164 KB (92 KB of L1, batch.h) beat 6 CTAs with 56 KB of L1 by
+// a quarter (measured: 6: 2.09 ms, 5: 1.53 ms, 4: 2.16 ms, 3: 2.44 ms on config 2).
+#ifndef BJ_SYNC_CTAS
+#define BJ_SYNC_CTAS 5
+#endif
+__global__ void __launch_bounds__(kHuffThreads, BJ_SYNC_CTAS)
 k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
             const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
             const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
@@ -363,7 +369,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
     __shared__ uint32_t s_tot[kHuffThreads];
     __shared__ uint2 s_span[kHuffThreads];                                  // first bit, end bit
-    __shared__ uint2 s_units[16];
+    __shared__ __align__(256) uint4 s_units[16];
     __shared__ uint16_t s_work[2][kHuffThreads];
     __shared__ uint32_t s_nwork[2];
     __shared__ uint32_t s_flag;
@@ -549,7 +555,10 @@ struct SmemUnitSink {
 
 constexpr int kSmemHuffStage = kHuffThreads * 128;
 
-__global__ void __launch_bounds__(kHuffThreads)
+#ifndef BJ_WRITE_CTAS
+#define BJ_WRITE_CTAS 4                // shared memory allows 4; telling the compiler buys 52 registers instead of 40 (-2 %)
+#endif
+__global__ void __launch_bounds__(kHuffThreads, BJ_WRITE_CTAS)
 k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, const uint32_t *__restrict__ wblk_img,
              const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
              const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
@@ -560,7 +569,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw + kSmemHuffStage);
     __shared__ uint32_t s_red[kHuffThreads / 32];
     __shared__ int s_h;
-    __shared__ uint2 s_units[16];
+    __shared__ __align__(256) uint4 s_units[16];
 
     const uint32_t img = wblk_img[blockIdx.x];
     const HuffImg &im = imgs[img];
