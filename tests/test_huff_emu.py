@@ -93,6 +93,64 @@ def test_truncated_scan_zero_fills_like_the_reference():
     assert np.array_equal(got, r.coef_zz)
 
 
+def _corrupt_scan(data, rng, flips):
+    """Flip `flips` random bits inside the entropy-coded data; bytes that become FF are set to FE so that no marker
+    or stuffing pair appears (the damage stays inside the Huffman data: refused codes, over-long runs, bits running
+    out, wrong unit counts).  Returns the damaged file and the restart segment of the first damaged byte."""
+    h = ol.Restated(data, 0).h
+    a = bytearray(data)
+    lo, hi = h.scan_off + 4, h.scan_off + h.scan_len - 4
+    first = None
+    for pos in rng.integers(lo, hi, flips):
+        if a[pos] == 0xFF or a[pos - 1] == 0xFF:
+            continue                                    # leave stuffed pairs and markers alone
+        a[pos] ^= 1 << int(rng.integers(0, 8))
+        if a[pos] == 0xFF:
+            a[pos] = 0xFE
+        first = int(pos) if first is None else min(first, int(pos))
+    seg = 0
+    if first is not None:
+        scan = bytes(a[h.scan_off:first])
+        seg = sum(1 for i in range(len(scan) - 1) if scan[i] == 0xFF and 0xD0 <= scan[i + 1] <= 0xD7)
+    return bytes(a), seg
+
+
+@pytest.mark.parametrize("sub,sub_bytes,slices", [(2, 128, 4), (0, 32, 2), (2, 64, 1), (0, 16, 8), (1, 1024, 1)])
+def test_corrupted_scans_stop_where_the_reference_stops(sub, sub_bytes, slices):
+    """Damaged Huffman data (no restart markers): the reference stops at the first refused code / over-long run /
+    missing bit and leaves every later coefficient zero (src/jpeg_scanner.cpp:467-520, result ignored at
+    src/decoder_host.cpp:181); units before the failure keep their values, the failing unit keeps what was stored
+    before the failing symbol.  Bit-exact, including which unit is the first zero one."""
+    rng = np.random.default_rng(1000 * sub + slices)
+    base = js.synth_jpeg(200, 152, seed=40 + sub, subsampling=sub)
+    failed = 0
+    for trial in range(24):
+        bad, _ = _corrupt_scan(base, rng, 1 + trial % 8)
+        r, got, info = run_emu(bad, sub_bytes, slices)
+        failed += r.huff_rc != 0
+        assert (info[1] != 0xFFFFFFFF) == (r.huff_rc != 0), trial
+        assert np.array_equal(got, r.coef_zz), trial
+    assert failed >= 2                                   # the damage does make the reference fail
+
+
+@pytest.mark.parametrize("sub,ri,sub_bytes,slices", [(2, 4, 64, 1), (0, 3, 16, 8), (0, 7, 128, 2)])
+def test_corrupted_scans_with_restart_markers_agree_up_to_the_damaged_segment(sub, ri, sub_bytes, slices):
+    """With restart markers a damaged file is where this back end and the reference part ways ON PURPOSE: the reference's
+    scanner has thrown the marker positions away, so after damage inside a segment its bit
+    position drifts and everything that follows is garbage or zero; here every segment starts at its marker.  What
+    must hold: every unit of the segments before the damaged one is the reference's, bit for bit."""
+    rng = np.random.default_rng(1000 * sub + 10 * ri + slices)
+    base = js.synth_jpeg(200, 152, seed=40 + sub + ri, subsampling=sub, restart_blocks=ri)
+    good = ol.Restated(base, 0)
+    bpm = {0: 3, 1: 4, 2: 6}[sub]                        # data units per MCU
+    for trial in range(12):
+        bad, seg = _corrupt_scan(base, rng, 1 + trial % 4)
+        r, got, info = run_emu(bad, sub_bytes, slices)
+        n = seg * ri * bpm
+        assert np.array_equal(got[:n], r.coef_zz[:n]), trial
+        assert np.array_equal(got[:n], good.coef_zz[:n]), trial
+
+
 def test_word_at_a_time_byte_classification():
     """FF00 un-stuffing / RSTn / fill-byte rules four bytes per word (bit tricks) == the per-byte rules, on byte
     strings dense in the special values and on every pair of adjacent byte values."""
