@@ -336,7 +336,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         if (coef_units > 0xFFFFFFF0ull || clean_words > 0xFFFFFFF0ull) return BJ_ERR_ARG;   // split the batch
     }
     b->idct_smem = kSmemDu + kSmemQ + kRgbFront + std::min<uint32_t>(rgb_max, kRgbMax) + 64;
-    b->files_bytes = b->direct_src ? (size_t)(span_hi - span_lo) : fbytes + 64; b->clean_words = clean_words + 16; b->coef_units = coef_units; b->out_bytes = out_bytes;
+    b->files_bytes = b->direct_src ? (size_t)(span_hi - span_lo) : fbytes + 64; b->clean_words = clean_words + 96; b->coef_units = coef_units; b->out_bytes = out_bytes;   // (96 words of slack: a damaged unit is read to its end, up to 63 symbols of 27 bits past the data)
     b->n_wblk = (uint32_t)wblk_img.size(); b->n_slice_slots = slice_slots;
     if (slice_slots > 0xFFFFFFF0ull) return BJ_ERR_ARG;
     b->n_idct_tiles = (uint32_t)tiles.size(); b->n_blk = nblk; b->n_utile = (uint32_t)utile_img.size();

@@ -277,6 +277,16 @@ struct BitStream {
 #endif
         word_end = kWordS;
     }
+    // back to an earlier position of the same span (the write pass re-reads a unit that did not end well)
+    BJ_HD void seek(uint32_t S) {
+        w -= ((word_end >> 13) - 1u) - (S >> 13);
+#ifdef __CUDA_ARCH__
+        cur = __ldg(w); nxt = __ldg(w + 1); nx2 = __ldg(w + 2);
+#else
+        cur = w[0]; nxt = w[1]; nx2 = w[2];
+#endif
+        word_end = ((S >> 13) + 1u) << 13;
+    }
     // the next 32 bits at S, moving on to the next word first if S has left the current one
     BJ_HD uint32_t window(uint32_t S) {
 #ifdef __CUDA_ARCH__
@@ -456,6 +466,7 @@ constexpr uint32_t kEvDone = 2u;     // open(): nothing to do in this slice
 struct WriteCursor {
     BitStream bs;
     uint32_t S, c, ac, tab, du;     // ac: AC table of the current unit; tab: table of the next symbol
+    uint32_t S0, bad;               // where the current unit starts; OR of its symbols' table entries (kLutBad is sticky)
     uint32_t endS, dataS, du_end;
     uint32_t first_zero;    // first unit index that must read as zero because the reference stopped; UINT32_MAX if none
     uint32_t fail;          // 0, or why the slice stopped: 1 = refused symbol / bits ran out, 2 = over-long run
@@ -488,6 +499,7 @@ struct WriteCursor {
             ac = ac_of(g, c);
         }
         tab = dc_of(g, c);
+        S0 = S; bad = 0u;
         // a unit starts here: mine if it starts before my end and the segment still has units to give
         return (S >= endS || du >= du_end) ? kEvDone : 0u;
     }
@@ -498,24 +510,61 @@ struct WriteCursor {
     // `unit` = something for the caller to do: unit store_du() is complete (store the staged unit, whose slot 0
     // holds its DC difference, and clear the stage); `done` = slice finished (only ever set together with `unit`).
     // After a failure (`fail`), store_du() also settles first_zero.
+    //
+    // The symbol loop does not look for failures: it decodes on (a refused code is a table entry like any other,
+    // with no value; a coefficient index past 63 wraps inside the staged unit) and looks back when the unit ends -
+    // did any symbol carry kLutBad, does the unit end past the segment's data, did it end on an over-long run.
+    // A unit that did not end well is decoded again from its first symbol by redo_unit(), which stops exactly where
+    // the reference stops.  (Damaged data only; at most 63 further symbols are read before the unit ends.)
     template <class Sink>
     BJ_HD void step(const LutMem &luts, const HuffGeom &g, Sink &sink, bool &unit, bool &done) {
         const uint32_t win = bs.window(S);
         const uint32_t e = lut_lookup(luts, tab, win);
         const uint32_t Sn = S + (e & 0xFFFFu);
-        if (__builtin_expect((e & kLutBad) || Sn > dataS, 0)) { fail = 1u; done = true; unit = true; return; }
+        bad |= e;
         const int32_t v = extend_entry(win, e);
-        const uint32_t zz = (Sn & 0xFFu) - 1u;            // index of the coefficient this symbol carries; 0: the DC difference
-        if (v != 0 && zz < 64u) sink.put(zz, (int16_t)v); // size 0 (ZRL, EOB) stores nothing: zero is already there
+        // index of the coefficient this symbol carries (0: the DC difference).  size 0 (ZRL, EOB, refused) stores nothing.
+        if (v != 0) sink.put(((Sn & 0xFFu) - 1u) & 63u, (int16_t)v);
         tab = ac;
         S = Sn;
         if (!(Sn & 0x40u)) return;
         // index >= 64: the unit ends one way or another
         unit = true;
-        if (__builtin_expect((Sn & 0xFFu) != 64u && !(e & kLutEob), 0)) { fail = 2u; done = true; return; }   // over-long run
+        if (__builtin_expect((bad & kLutBad) || Sn > dataS || ((Sn & 0xFFu) != 64u && !(e & kLutEob)), 0)) {
+            redo_unit(luts, g, sink, done);
+            return;
+        }
         du++;
         S &= ~0xFFu;
         next_unit(g, c, c, tab, ac);
+        S0 = S; bad = 0u;
+        done = S >= endS || du >= du_end;
+    }
+    // The current unit again, from its first symbol, symbol by symbol with the reference's checks.
+    template <class Sink>
+    BJ_HD void redo_unit(const LutMem &luts, const HuffGeom &g, Sink &sink, bool &done) {
+        sink.reset();
+        S = S0;
+        bs.seek(S0);
+        tab = dc_of(g, c);
+        for (;;) {
+            const uint32_t win = bs.window(S);
+            const uint32_t e = lut_lookup(luts, tab, win);
+            const uint32_t Sn = S + (e & 0xFFFFu);
+            if ((e & kLutBad) || Sn > dataS) { fail = 1u; done = true; return; }
+            const int32_t v = extend_entry(win, e);
+            const uint32_t zz = (Sn & 0xFFu) - 1u;
+            if (v != 0 && zz < 64u) sink.put(zz, (int16_t)v);
+            tab = ac;
+            S = Sn;
+            if (!(Sn & 0x40u)) continue;
+            if ((Sn & 0xFFu) != 64u && !(e & kLutEob)) { fail = 2u; done = true; return; }   // over-long run
+            break;                                        // (not reached: a unit is only decoded again if one of the checks fires)
+        }
+        du++;
+        S &= ~0xFFu;
+        next_unit(g, c, c, tab, ac);
+        S0 = S; bad = 0u;
         done = S >= endS || du >= du_end;
     }
     // The unit to store after a step that said `unit` (UINT32_MAX: none).

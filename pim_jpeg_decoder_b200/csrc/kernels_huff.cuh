@@ -551,6 +551,10 @@ struct SmemUnitSink {
     __device__ __forceinline__ void put(uint32_t zz, int16_t v) {
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(rowsw ^ (zz << 1)), "h"(v) : "memory");
     }
+    __device__ __forceinline__ void reset() {            // zero the thread's 128-byte row (rare: a unit is decoded again)
+        const uint32_t row = rowsw & ~0x7Fu;
+        for (uint32_t k = 0; k < 128u; k += 16u) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(row + k), "r"(0u) : "memory");
+    }
 };
 
 constexpr int kSmemHuffStage = kHuffThreads * 128;

@@ -22,6 +22,7 @@ struct HostSink {
     int16_t unit[64];
     HostSink() { memset(unit, 0, sizeof(unit)); }
     void put(uint32_t zz, int16_t v) { unit[zz] = v; }
+    void reset() { memset(unit, 0, sizeof(unit)); }
 };
 struct SliceRec { uint32_t p, cz, cnt; };
 }  // namespace

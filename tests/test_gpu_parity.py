@@ -332,6 +332,36 @@ def test_truncated_scan_matches_reference_partial_image(dec):
     assert np.array_equal(outs[1], ol.Restated(data, 0).bmp)
 
 
+@pytest.mark.parametrize("sub,bits,slices", [(2, 0, 0), (0, 256, 2), (1, 1024, 0), (2, 128, 8), (0, 4096, 4)])
+def test_damaged_scans_stop_where_the_reference_stops(dec, sub, bits, slices):
+    """Bits flipped inside the Huffman data (no restart markers): refused codes, over-long runs, bits running out.  The
+    write pass decodes such a unit to its end and then again, exactly (huff_core.h: WriteCursor::redo_unit); the
+    coefficients - which unit is the last one with values, and what the failing unit keeps - must be the reference's."""
+    import pim_jpeg_decoder_b200 as bj
+    from test_huff_emu import _corrupt_scan
+    rng = np.random.default_rng(500 + 10 * sub + slices)
+    base = js.synth_jpeg(200, 152, seed=40 + sub, subsampling=sub)
+    dec.set_option("subseq_bits", bits)
+    dec.set_option("slices", slices)
+    failed = 0
+    try:
+        for trial in range(24):
+            bad, _ = _corrupt_scan(base, rng, 1 + trial % 8)
+            r = ol.Restated(bad, 0)
+            coef, status = dec.stage_entropy(bad)
+            failed += r.huff_rc != 0
+            assert (status != 0) == (r.huff_rc != 0), trial
+            assert np.array_equal(coef, r.coef_zz), trial
+        bads = [_corrupt_scan(base, rng, 3)[0] for _ in range(8)]
+        outs, status = dec.decode(bads + [base], bj.BJ_OUT_BMP)
+        for b, o in zip(bads + [base], outs):
+            assert np.array_equal(o, ol.Restated(b, 0).bmp)
+    finally:
+        dec.set_option("subseq_bits", 0)
+        dec.set_option("slices", 0)
+    assert failed >= 2
+
+
 def test_large_image_properties(dec):
     """Full-size config-4 shapes (3840x2160 4:4:4 and gray, no restart markers): checked through size-independent
     properties - the image decodes identically alone, inside a batch, and at another sub-sequence size - plus an
