@@ -470,6 +470,10 @@ struct WriteCursor {
     uint32_t endS, dataS, du_end;
     uint32_t first_zero;    // first unit index that must read as zero because the reference stopped; UINT32_MAX if none
     uint32_t fail;          // 0, or why the slice stopped: 1 = refused symbol / bits ran out, 2 = over-long run
+    uint32_t done;          // the slice is finished (set by the step that completes its last unit, or by a failure)
+    uint32_t st_du;         // after a step that returned true: the unit to store from the stage (UINT32_MAX: none)
+    uint32_t idle;          // device: position of an all-zero word.  A finished lane keeps stepping with its warp on a
+                            // zero window and this "table": the entry is 0, the position does not move, nothing is staged
 
     // Returns kEvDone if there is nothing to do.  Skips the unit a predecessor owns (no values).
     BJ_HD uint32_t open(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t end_bit,
@@ -484,7 +488,7 @@ struct WriteCursor {
         const uint32_t data_rel = data_end_bit >= origin ? data_end_bit - origin : 0u;
         dataS = ((data_rel < 0xFFFFFFu ? data_rel : 0xFFFFFFu) << 8) | 0xFFu;
         du = du0; du_end = du_end_;
-        fail = 0u;
+        fail = 0u; done = 0u; st_du = 0xFFFFFFFFu;
         ac = ac_of(g, c);
         bs.open(words, st.p);
         if (S & 0xFFu) {                                  // inside a unit that belongs to a predecessor: skip it
@@ -504,12 +508,13 @@ struct WriteCursor {
         return (S >= endS || du >= du_end) ? kEvDone : 0u;
     }
 
-    // One symbol.  The reference's failure points: refused symbol, bits running out inside a symbol, run past the
-    // end of the unit ("i + run >= 64", src/jpeg_scanner.cpp:497-500).  A failed DC leaves the unit untouched
-    // (zero); a failed AC keeps what was stored before it.
-    // `unit` = something for the caller to do: unit store_du() is complete (store the staged unit, whose slot 0
-    // holds its DC difference, and clear the stage); `done` = slice finished (only ever set together with `unit`).
-    // After a failure (`fail`), store_du() also settles first_zero.
+    // One symbol.  Returns true when there is something for the caller to do: the unit st_du is complete - store the
+    // staged unit (slot 0 holds its DC difference) and clear the stage; st_du = UINT32_MAX: nothing to store.  `done`
+    // is only ever set by a step that returns true.
+    //
+    // The reference's failure points: refused symbol, bits running out inside a symbol, run past the end of the unit
+    // ("i + run >= 64", src/jpeg_scanner.cpp:497-500).  A failed DC leaves the unit untouched (zero); a failed AC
+    // keeps what was stored before it; first_zero = the first unit the reference never reached.
     //
     // The symbol loop does not look for failures: it decodes on (a refused code is a table entry like any other,
     // with no value; a coefficient index past 63 wraps inside the staged unit) and looks back when the unit ends -
@@ -517,7 +522,7 @@ struct WriteCursor {
     // A unit that did not end well is decoded again from its first symbol by redo_unit(), which stops exactly where
     // the reference stops.  (Damaged data only; at most 63 further symbols are read before the unit ends.)
     template <class Sink>
-    BJ_HD void step(const LutMem &luts, const HuffGeom &g, Sink &sink, bool &unit, bool &done) {
+    BJ_HD bool step(const LutMem &luts, const HuffGeom &g, Sink &sink) {
         const uint32_t win = bs.window(S);
         const uint32_t e = lut_lookup(luts, tab, win);
         const uint32_t Sn = S + (e & 0xFFFFu);
@@ -527,22 +532,35 @@ struct WriteCursor {
         if (v != 0) sink.put(((Sn & 0xFFu) - 1u) & 63u, (int16_t)v);
         tab = ac;
         S = Sn;
-        if (!(Sn & 0x40u)) return;
+        if (!(Sn & 0x40u)) return false;
         // index >= 64: the unit ends one way or another
-        unit = true;
-        if (__builtin_expect((bad & kLutBad) || Sn > dataS || ((Sn & 0xFFu) != 64u && !(e & kLutEob)), 0)) {
-            redo_unit(luts, g, sink, done);
-            return;
-        }
-        du++;
+        if (__builtin_expect((bad & kLutBad) || Sn > dataS || ((Sn & 0xFFu) != 64u && !(e & kLutEob)), 0)) redo_unit(luts, g, sink);
+        else unit_done(g);
+        return true;
+    }
+    BJ_HD void unit_done(const HuffGeom &g) {
+        st_du = du++;
         S &= ~0xFFu;
         next_unit(g, c, c, tab, ac);
         S0 = S; bad = 0u;
-        done = S >= endS || du >= du_end;
+        if (S >= endS || du >= du_end) finish();
+    }
+    BJ_HD void finish() {
+        done = 1u;
+#ifdef __CUDA_ARCH__
+        S = 0u; bs.cur = 0u; bs.nxt = 0u; tab = idle; ac = idle;     // (S stays below bs.word_end: no further loads)
+#endif
+    }
+    BJ_HD void failed(uint32_t why) {
+        fail = why;
+        const bool dc = why == 1u && (S & 0xFFu) == 0u;
+        first_zero = dc ? du : du + 1u;                   // a failed DC: the unit stays zero; a failed AC keeps what was stored before it
+        st_du = dc ? 0xFFFFFFFFu : du;
+        finish();
     }
     // The current unit again, from its first symbol, symbol by symbol with the reference's checks.
     template <class Sink>
-    BJ_HD void redo_unit(const LutMem &luts, const HuffGeom &g, Sink &sink, bool &done) {
+    BJ_HD void redo_unit(const LutMem &luts, const HuffGeom &g, Sink &sink) {
         sink.reset();
         S = S0;
         bs.seek(S0);
@@ -551,31 +569,17 @@ struct WriteCursor {
             const uint32_t win = bs.window(S);
             const uint32_t e = lut_lookup(luts, tab, win);
             const uint32_t Sn = S + (e & 0xFFFFu);
-            if ((e & kLutBad) || Sn > dataS) { fail = 1u; done = true; return; }
+            if ((e & kLutBad) || Sn > dataS) { failed(1u); return; }
             const int32_t v = extend_entry(win, e);
             const uint32_t zz = (Sn & 0xFFu) - 1u;
             if (v != 0 && zz < 64u) sink.put(zz, (int16_t)v);
             tab = ac;
             S = Sn;
             if (!(Sn & 0x40u)) continue;
-            if ((Sn & 0xFFu) != 64u && !(e & kLutEob)) { fail = 2u; done = true; return; }   // over-long run
+            if ((Sn & 0xFFu) != 64u && !(e & kLutEob)) { failed(2u); return; }   // over-long run
             break;                                        // (not reached: a unit is only decoded again if one of the checks fires)
         }
-        du++;
-        S &= ~0xFFu;
-        next_unit(g, c, c, tab, ac);
-        S0 = S; bad = 0u;
-        done = S >= endS || du >= du_end;
-    }
-    // The unit to store after a step that said `unit` (UINT32_MAX: none).
-    BJ_HD uint32_t store_du() {
-        uint32_t d = du - 1u;
-        if (__builtin_expect(fail != 0u, 0)) {
-            const bool dc = fail == 1u && (S & 0xFFu) == 0u;
-            first_zero = dc ? du : du + 1u;               // a failed DC: the unit stays zero; a failed AC keeps what was stored before it
-            d = dc ? 0xFFFFFFFFu : du;
-        }
-        return d;
+        unit_done(g);
     }
 };
 

@@ -574,6 +574,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     __shared__ uint32_t s_red[kHuffThreads / 32];
     __shared__ int s_h;
     __shared__ __align__(256) uint4 s_units[16];
+    __shared__ uint32_t s_zero;                                            // what a finished lane reads as its table (WriteCursor::idle)
 
     const uint32_t img = wblk_img[blockIdx.x];
     const HuffImg &im = imgs[img];
@@ -589,7 +590,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     bool active = j < is.nsub;
 
     // carry into this CTA: totals of the previous CTAs of the image back to the last one that contains a head
-    if (tid == 0) s_h = 0;
+    if (tid == 0) { s_h = 0; s_zero = 0u; }
     __syncthreads();
     {
         int h = -1;
@@ -616,7 +617,9 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     uint4 *out = reinterpret_cast<uint4 *>(coef + (size_t)im.du_base * 64);
     int16_t *dcp = dc_plane + im.du_base;
     WriteCursor cur;
-    cur.first_zero = 0xFFFFFFFFu; cur.du = 0; cur.du_end = 0; cur.fail = 0u;
+    cur.first_zero = 0xFFFFFFFFu; cur.du = 0; cur.du_end = 0; cur.fail = 0u; cur.st_du = 0xFFFFFFFFu;
+    cur.idle = (uint32_t)__cvta_generic_to_shared(&s_zero);
+    asm volatile("mov.u32 %0, %0;" : "+r"(cur.idle));
     SmemUnitSink sink;
     const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(s_stage);
     sink.rowsw = (stage_addr + tid * 128) | ((tid & 7) << 4);
@@ -650,14 +653,18 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     asm volatile("mov.u32 %0, %0;" : "+r"(flusher));
     asm volatile("mov.u64 %0, %0;" : "+l"(out_lane));                      // (kept in registers, like warp_stage)
     asm volatile("mov.u64 %0, %0;" : "+l"(dcp));
+    // a lane with nothing to do idles like one that has finished; every lane of the warp takes every step
+    if (done) {
+        if (!active) { cur.bs.w = clean + im.clean_word0; cur.bs.nx2 = 0u; cur.bs.word_end = kWordS; cur.endS = 0u; cur.dataS = 0xFFFFFFFFu; cur.c = 0u; cur.S0 = 0u; cur.bad = 0u; }
+        cur.finish();
+    }
     if (!__all_sync(0xFFFFFFFFu, done)) {
         for (;;) {
-            bool unit = false;
-            if (!done) cur.step(luts, g, sink, unit, done);
+            const bool unit = cur.step(luts, g, sink);
             uint32_t m = __ballot_sync(0xFFFFFFFFu, unit);
             if (m == 0) continue;
-            // lanes in m completed unit du - 1 (or ended on a refused DC symbol: nothing to store)
-            const uint32_t du_mine = unit ? cur.store_du() : 0xFFFFFFFFu;
+            // lanes in m completed unit st_du (or ended on a refused DC symbol: nothing to store)
+            const uint32_t du_mine = unit ? cur.st_du : 0xFFFFFFFFu;
             __syncwarp();
             do {                                                           // two units per pass: lanes 0-7 and 8-15
                 const uint32_t m1 = m & (m - 1u);
@@ -678,7 +685,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
                 }
             } while (m);
             __syncwarp();
-            if (__all_sync(0xFFFFFFFFu, done)) break;
+            if (__all_sync(0xFFFFFFFFu, cur.done != 0u)) break;
         }
     }
     if (active) {

@@ -179,12 +179,13 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int
             const uint32_t end_bit = std::min(u.start_bit + (k + 1) * slice_bits, u.end_bit);
             HostSink sink;
             WriteCursor cur;
+            cur.idle = 0;
             bool done = (cur.open(words, lm, g, st, end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex + cnt, du_end) & kEvDone) != 0;
             while (!done) {
-                bool unit = false;
-                cur.step(lm, g, sink, unit, done);
+                const bool unit = cur.step(lm, g, sink);
+                done = cur.done != 0;
                 if (unit) {
-                    const uint32_t du = cur.store_du();
+                    const uint32_t du = cur.st_du;
                     if (du < ndu) {
                         dcp[du] = sink.unit[0];
                         sink.unit[0] = 0;
