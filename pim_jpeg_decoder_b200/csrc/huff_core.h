@@ -460,7 +460,8 @@ BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const Huf
 // The decode is a cursor that takes ONE symbol per step(), DC and AC alike, so the lanes of a warp stay together;
 // a step says when a unit is complete and the caller stores it (the kernel does that warp-cooperatively).
 // Sink concept:  void put(uint32_t zz, int16_t v)  - stage one non-zero value of the current unit (zz = 0: the DC
-// difference; the stored unit's slot 0 is zero, the difference goes to the DC plane).
+// difference; the stored unit's slot 0 is zero, the difference goes to the DC plane);  void reset()  - forget what
+// has been staged for the current unit (it is decoded again: redo_unit).
 constexpr uint32_t kEvDone = 2u;     // open(): nothing to do in this slice
 
 struct WriteCursor {
