@@ -288,3 +288,36 @@ extern "C" int emu_scan_tiles_check(const uint8_t *file, size_t len, int base_mi
     }
     return (dev_dropped == host_dropped && dev_rst == host_rst) ? 0 : 1;
 }
+
+// The device form of UnitWalk keeps (completed units << 8 | unit index << 4) in one register and advances it by the
+// table's step (unit_walk_step); the BitStream can be moved back inside its span (seek).  Both are device-side
+// shortcuts of what the host code above does with separate variables: check the arithmetic here.
+extern "C" int emu_unit_walk_check(void) {
+    for (uint32_t bpm = 1; bpm <= 10; bpm++) {
+        for (uint32_t c0 = 0; c0 < bpm; c0++) {
+            uint32_t cu = c0 << 4, c = c0, n = 0;
+            for (int i = 0; i < 5000; i++) {
+                const uint32_t c1 = c + 1 == bpm ? 0 : c + 1;
+                if (((cu & 0xF0u) >> 4) != c || (cu >> 4 & 15u) != c || (cu >> 8) != n) return 1;
+                cu += unit_walk_step(c, c1);
+                c = c1; n++;
+            }
+        }
+    }
+    // seek: read windows going forward, jump back, the windows repeat
+    uint32_t words[64];
+    for (int i = 0; i < 64; i++) words[i] = 0x9E3779B9u * (uint32_t)(i + 1);
+    for (uint32_t p0 = 0; p0 < 96; p0 += 7) {
+        BitStream bs;
+        bs.open(words, p0);
+        const uint32_t origin = p0 & ~31u;
+        uint32_t S = (p0 - origin) << 8, seen[40], at[40];
+        for (int i = 0; i < 40; i++) { at[i] = S; seen[i] = bs.window(S); S += (uint32_t)(1 + (i * 5) % 27) << 8; }
+        for (int back = 39; back >= 0; back -= 3) {
+            bs.seek(at[back]);
+            uint32_t T = at[back];
+            for (int i = back; i < 40; i++) { if (bs.window(T) != seen[i]) return 2; T += (uint32_t)(1 + (i * 5) % 27) << 8; }
+        }
+    }
+    return 0;
+}

@@ -216,3 +216,9 @@ def test_lut_matches_bit_serial_search():
     sy = np.arange(162, dtype=np.uint8)
     assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy), 0) == 0
     assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy), 1) == 0
+
+
+def test_unit_walk_and_stream_seek_arithmetic():
+    """The packed unit counter of the synchronisation pass (completed << 8 | unit << 4, advanced by the table's step)
+    and the bit reader's seek (the write pass re-reads a damaged unit) against the plain forms."""
+    assert emu().emu_unit_walk_check() == 0
