@@ -362,6 +362,33 @@ def test_damaged_scans_stop_where_the_reference_stops(dec, sub, bits, slices):
     assert failed >= 2
 
 
+def test_random_images_sizes_and_damage(dec):
+    """Random geometry / sampling / quality / restart interval / sub-sequence length / slice count, and for the files
+    without restart markers a damaged twin: coefficients against the oracle, bit for bit."""
+    from test_huff_emu import _corrupt_scan
+    rng = np.random.default_rng(2024)
+    try:
+        for trial in range(48):
+            w, h = int(rng.integers(8, 400)), int(rng.integers(8, 300))
+            sub, gray = int(rng.integers(0, 3)), bool(rng.integers(0, 5) == 0)
+            ri = int(rng.choice([0, 0, 0, 1, 3, 8]))
+            dec.set_option("subseq_bits", int(rng.choice([0, 128, 160, 256, 1024, 4096])))
+            dec.set_option("slices", int(rng.choice([0, 1, 2, 4, 8])))
+            data = js.synth_jpeg(w, h, seed=trial, subsampling=sub, gray=gray, restart_blocks=ri)
+            coef, status = dec.stage_entropy(data)
+            assert status == 0 and np.array_equal(coef, ol.Restated(data, 0).coef_zz), trial
+            if ri == 0:
+                bad, _ = _corrupt_scan(data, rng, int(rng.integers(1, 6)))
+                r = ol.Restated(bad, 0)
+                if r.valid:
+                    coef, status = dec.stage_entropy(bad)
+                    assert (status != 0) == (r.huff_rc != 0), trial
+                    assert np.array_equal(coef, r.coef_zz), trial
+    finally:
+        dec.set_option("subseq_bits", 0)
+        dec.set_option("slices", 0)
+
+
 def test_large_image_properties(dec):
     """Full-size config-4 shapes (3840x2160 4:4:4 and gray, no restart markers): checked through size-independent
     properties - the image decodes identically alone, inside a batch, and at another sub-sequence size - plus an
