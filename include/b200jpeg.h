@@ -6,7 +6,8 @@
  * and there is NO CPU fallback: without a CUDA device every compute entry fails with BJ_ERR_CUDA.
  *
  * Threading: a bj_ctx is single-owner (one consumer thread per context, like the reference's `offloading`
- * thread, src/decoder_host.cpp:213-350).  One context drives one GPU; one process per GPU.
+ * thread, src/decoder_host.cpp:213-350).  bj_create: one context drives one GPU (one process per GPU, e.g. under
+ * torchrun); bj_create_multi: one context drives several GPUs of the box from one process, one host thread each.
  * Ownership: the caller owns every host pointer it passes; the library owns device and pinned staging memory.
  */
 #ifndef B200JPEG_H
@@ -34,6 +35,13 @@ typedef struct bj_ctx bj_ctx;
  * Context.  Replaces: `auto pim = DpuSet::allocate(DPU_ALLOCATE_ALL)` + `pim.load(DPU_BINARY)`
  * (src/decoder_host.cpp:32,268).  `device` is the CUDA ordinal (LOCAL_RANK in a one-process-per-GPU job). */
 int bj_create(bj_ctx **ctx, int device);
+/* All GPUs from ONE process, like `DpuSet::allocate(DPU_ALLOCATE_ALL)` takes every DPU of the machine
+ * (src/decoder_host.cpp:32-33).  devices == NULL: devices 0..ndev-1; ndev <= 0: every visible device.  bj_decode_batch /
+ * bj_submit on such a context deal the image list to the GPUs sub-batch by sub-batch from one shared cursor (images are
+ * independent: no collective); bj_exec_mcus splits its DPUs into equal contiguous shares; the staged and stage-level
+ * entries run on the first device. */
+int bj_create_multi(bj_ctx **ctx, const int *devices, int ndev);
+int bj_device_count(const bj_ctx *ctx);
 void bj_destroy(bj_ctx *ctx);
 const char *bj_status_string(int status);
 const char *bj_last_error(const bj_ctx *ctx);   /* text of the last CUDA error seen by this context */
@@ -43,6 +51,10 @@ int bj_device_sm_count(const bj_ctx *ctx);
  * std::vector, src/decoder_host.cpp:25-30); optional. */
 void *bj_host_alloc(size_t bytes);
 void bj_host_free(void *p);
+/* Page-lock memory the caller already owns (cudaHostRegister) and tell the library about it.  Input files that lie
+ * inside memory from bj_host_alloc / bj_host_register are uploaded straight from there (no staging copy on the host). */
+int bj_host_register(void *p, size_t bytes);
+int bj_host_unregister(void *p);
 
 /* ---------------------------------------------------------------------------------------------------------
  * COMPAT ENTRY = the DPU program.  Replaces the sequence
@@ -106,6 +118,17 @@ size_t bj_output_size(const bj_image_desc *desc, int format);
 int bj_decode_batch(bj_ctx *ctx, const uint8_t *const *files, const size_t *lens, int n, int format,
                     uint8_t *const *outs, int *status);
 
+/* FULL PATH, asynchronous.  bj_submit hands the batch to the context's worker thread and returns at once; bj_wait blocks
+ * until that batch's outputs are in host memory, returns what bj_decode_batch would have returned and releases the job.
+ * Jobs run in submission order.  All arrays (files, lens, outs, status) must stay valid until bj_wait returns.  This is
+ * the reference's producer / consumer overlap (two threads and a queue, src/decoder_host.cpp:25-38,364-365): submit
+ * batch k+1 - or read its files - while batch k decodes, write batch k-1's BMPs meanwhile.  While jobs are pending the
+ * context may only be used through bj_submit / bj_wait. */
+typedef struct bj_job bj_job;
+int bj_submit(bj_ctx *ctx, const uint8_t *const *files, const size_t *lens, int n, int format,
+              uint8_t *const *outs, int *status, bj_job **job);
+int bj_wait(bj_job *job);
+
 /* FULL PATH, staged (device-resident batch) - what bj_decode_batch is made of, and what bench.py times with the
  * inputs already in HBM. */
 typedef struct bj_batch bj_batch;
@@ -161,17 +184,27 @@ int bj_stage_entropy(bj_ctx *ctx, const uint8_t *file, size_t len, int16_t *coef
  *   "sub_batch_ramp"   0: all sub-batches the same size (default 1: the first two are 1/8 and 1/3 of it, so that the
  *                      copy-out starts early)
  *   "host_threads"     worker threads for the per-image host work of bj_decode_batch, the caller included
- *   "packed_inputs"    1: all input files of a bj_decode_batch call lie in ONE page-locked allocation (bj_host_alloc /
- *                      cudaHostAlloc), close together: they are uploaded straight from there, nothing is copied on
- *                      the host.  Only set it when that is true - pageable memory would make the upload synchronous
+ *   "packed_inputs"    where the file bytes are uploaded from.  0 (default): straight from the caller's memory when the
+ *                      files of a sub-batch lie close together inside memory from bj_host_alloc / bj_host_register,
+ *                      through a pinned staging copy otherwise;  1: the caller states that the files lie in ONE
+ *                      page-locked allocation the library does not know (e.g. cudaHostAlloc) - only set it when that
+ *                      is true, pageable memory would make the upload synchronous;  -1: always stage
+ *   "max_image_pixels" images with more pixels get BJ_ERR_UNSUPPORTED (default 2^28), like the reference's "Too high
+ *                      resolution" (src/decoder_host.cpp:146-149): a tiny file cannot claim tens of GB of buffers
+ *   "sub_batch_out_bytes"  decoded bytes per sub-batch of bj_decode_batch (default 1 GiB)
+ *   "debug_poison"     1: coefficient, DC, stream and output buffers are filled with 0xA5 before every decode (tests:
+ *                      every byte that is read or returned must have been written by that decode)
  *   "packed_outputs"   1: output pointers that follow bj_batch_output_offset's layout (outs[i] = base + offset_i,
  *                      for the one-call path: offsets restart at 0 in every sub-batch) belong to ONE allocation,
  *                      so runs of images are copied out in one transfer, padding bytes included */
 int bj_set_option(bj_ctx *ctx, const char *name, long value);
 /* Counters of the last call: "exec_ms" (kernel time of bj_exec_mcus - the reference's "DPU execution" profile line,
  * src/decoder_host.cpp:291-294), "decode_batch_sub_batches", "decode_batch_launches", "decode_batch_h2d_bytes",
- * "decode_batch_d2h_bytes", "decode_batch_d2h_copies", "decode_batch_host_ms" (parse + layout + pack),
- * "decode_batch_wait_ms" (caller blocked on the GPU), "host_threads".
+ * "decode_batch_d2h_bytes", "decode_batch_d2h_copies", "decode_batch_host_ms" (header parse + layout [+ staging copy]),
+ * "decode_batch_wait_ms" (caller blocked on the GPU), "host_threads", "devices", and the kernel time per stage summed
+ * over the sub-batches - the reference's per-stage "Profiles" lines (src/decoder_host.cpp:379-394) -
+ * "decode_batch_ms_unstuff", "decode_batch_ms_sync", "decode_batch_ms_write", "decode_batch_ms_idct".
+ * For a multi-GPU context: byte and launch counts are sums, times the maximum over the devices.
  * Environment: B200JPEG_TRACE=1 prints one line per sub-batch of bj_decode_batch (host prepare, kernels, copy-out). */
 int bj_get_stat(const bj_ctx *ctx, const char *name, double *value);
 

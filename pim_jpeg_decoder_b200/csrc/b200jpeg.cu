@@ -4,11 +4,13 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stddef.h>
 #include <string.h>
 
 #include <algorithm>
 #include <time.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200jpeg.h"
@@ -37,6 +39,8 @@ extern "C" const char *bj_status_string(int s) {
 
 extern "C" const char *bj_build_info(void) { return "b200jpeg sm_100a (CUDA " BJ_STR(CUDART_VERSION) "), built " __DATE__; }
 
+extern "C" void bj_destroy(bj_ctx *c);
+
 extern "C" int bj_create(bj_ctx **out, int device) {
     if (!out) return BJ_ERR_ARG;
     *out = nullptr;
@@ -50,29 +54,78 @@ extern "C" int bj_create(bj_ctx **out, int device) {
     bj_ctx *c = new (std::nothrow) bj_ctx();
     if (!c) return BJ_ERR_NOMEM;
     c->device = device;
-    if (c->check(cudaSetDevice(device)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
+    int rc = c->check(cudaSetDevice(device));
     cudaDeviceProp prop;
-    if (c->check(cudaGetDeviceProperties(&prop, device)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
-    c->sm_count = prop.multiProcessorCount;
-    if (c->check(cudaFuncSetAttribute(k_idct_color, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemIdctColor)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
-    if (batch_kernels_init(c) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
-    for (int i = 0; i < kSlots; i++)
-        if (c->check(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) != BJ_OK) { delete c; return BJ_ERR_CUDA; }
+    if (rc == BJ_OK) rc = c->check(cudaGetDeviceProperties(&prop, device));
+    if (rc == BJ_OK) c->sm_count = prop.multiProcessorCount;
+    if (rc == BJ_OK) rc = c->check(cudaFuncSetAttribute(k_idct_color, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemIdctColor));
+    if (rc == BJ_OK) rc = batch_kernels_init(c);
+    for (int i = 0; i < kSlots && rc == BJ_OK; i++) rc = c->check(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 2 && rc == BJ_OK; i++) rc = c->check(cudaEventCreate(&c->ev_exec[i]));
+    if (rc != BJ_OK) { bj_destroy(c); return BJ_ERR_CUDA; }                   // (releases whatever was created)
     {
-        const unsigned hw = std::thread::hardware_concurrency();
-        c->host_pool.resize(std::max(1, std::min(4, (int)hw / 2)));   // measured on the 16-core B200 box: 4 is the knee, more only contends with the copy engines
+        // worker threads for the per-image host work (header parse; staging copies for pageable inputs): a few are
+        // enough - the host reads some hundred bytes per file - and more only take memory bandwidth from the copy
+        // engines.  Never more than this process may run on (cgroup / affinity), the caller included.
+        const int avail = std::max(1, (int)std::thread::hardware_concurrency());
+        c->host_pool.resize(std::max(1, std::min(4, avail / 2)));
     }
     *out = c;
     return BJ_OK;
 }
 
+// All the GPUs of one process: replaces `DpuSet::allocate(DPU_ALLOCATE_ALL)` (src/decoder_host.cpp:32-33) - the
+// reference's single process spreads its work over every DPU of the machine; here one context drives `ndev` GPUs,
+// one host thread each.  devices == NULL: the first ndev devices; ndev <= 0: all of them.
+extern "C" int bj_create_multi(bj_ctx **out, const int *devices, int ndev) {
+    if (!out) return BJ_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fprintf(stderr, "b200jpeg: no CUDA device (%s) - this library has no CPU fallback\n", cudaGetErrorString(e));
+        return BJ_ERR_CUDA;
+    }
+    if (ndev <= 0) { ndev = count; devices = nullptr; }
+    if (ndev > count && !devices) return BJ_ERR_ARG;
+    bj_ctx *c = new (std::nothrow) bj_ctx();
+    if (!c) return BJ_ERR_NOMEM;
+    for (int i = 0; i < ndev; i++) {
+        bj_ctx *ch = nullptr;
+        const int rc = bj_create(&ch, devices ? devices[i] : i);
+        if (rc != BJ_OK) { bj_destroy(c); return rc; }
+        c->children.push_back(ch);
+    }
+    c->device = c->children[0]->device;
+    c->sm_count = c->children[0]->sm_count;
+    // the host threads of all devices together stay within the process' cores
+    const int avail = std::max(1, (int)std::thread::hardware_concurrency());
+    const int per = std::max(1, std::min(4, avail / (2 * ndev)));
+    for (bj_ctx *ch : c->children) ch->host_pool.resize(per);
+    *out = c;
+    return BJ_OK;
+}
+
+extern "C" int bj_device_count(const bj_ctx *c) { return !c ? 0 : (c->children.empty() ? 1 : (int)c->children.size()); }
+
 extern "C" void bj_destroy(bj_ctx *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
-    cudaDeviceSynchronize();
-    for (auto &p : c->pool) p.release();
-    for (auto &b : c->slots) if (b) { b->release(); delete b; b = nullptr; }
-    for (int i = 0; i < kSlots; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    if (c->async) {
+        { std::lock_guard<std::mutex> l(c->async->m); c->async->stop = true; }
+        c->async->cv.notify_all();
+        if (c->async->th.joinable()) c->async->th.join();                      // (finishes the queued jobs first)
+        delete c->async;
+        c->async = nullptr;
+    }
+    for (bj_ctx *ch : c->children) bj_destroy(ch);
+    if (c->children.empty()) {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        for (auto &p : c->pool) p.release();
+        for (auto &b : c->slots) if (b) { b->release(); delete b; b = nullptr; }
+        for (int i = 0; i < kSlots; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+        for (auto &ev : c->ev_exec) if (ev) cudaEventDestroy(ev);
+    }
     delete c;
 }
 
@@ -81,20 +134,43 @@ extern "C" int bj_device_sm_count(const bj_ctx *c) { return c ? c->sm_count : 0;
 
 extern "C" void *bj_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    pinned_ranges().add(p, bytes ? bytes : 1);
     return p;
 }
-extern "C" void bj_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void bj_host_free(void *p) { if (p) { pinned_ranges().remove(p); cudaFreeHost(p); } }
+
+extern "C" int bj_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return BJ_ERR_ARG;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return BJ_ERR_CUDA; }
+    if (e != cudaSuccess) cudaGetLastError();
+    pinned_ranges().add(p, bytes);
+    return BJ_OK;
+}
+extern "C" int bj_host_unregister(void *p) {
+    if (!p) return BJ_ERR_ARG;
+    pinned_ranges().remove(p);
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return BJ_ERR_CUDA; }
+    return BJ_OK;
+}
 
 extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
     if (!c || !name) return BJ_ERR_ARG;
+    if (!c->children.empty()) {                                   // a multi-GPU context: the same for every device
+        for (bj_ctx *ch : c->children) { const int rc = bj_set_option(ch, name, value); if (rc != BJ_OK) return rc; }
+        if (strcmp(name, "sub_batch_bytes") && strcmp(name, "sub_batch_ramp")) return BJ_OK;    // (these two also steer the dealing)
+    }
     if (!strcmp(name, "subseq_bits")) { if (value != 0 && (value < 128 || value % 32 || value > (1 << 18))) return BJ_ERR_ARG; c->subseq_bits = (int)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_ramp")) { c->sub_batch_ramp = value != 0; return BJ_OK; }
     if (!strcmp(name, "sync_phased")) { c->sync_phased = value != 0; return BJ_OK; }
     if (!strcmp(name, "slices")) { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return BJ_ERR_ARG; c->slices = (int)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_bytes = (size_t)value; return BJ_OK; }
     if (!strcmp(name, "packed_outputs")) { c->packed_outputs = value != 0; return BJ_OK; }
-    if (!strcmp(name, "packed_inputs")) { c->packed_inputs = value != 0; return BJ_OK; }
+    if (!strcmp(name, "packed_inputs")) { if (value < -1 || value > 1) return BJ_ERR_ARG; c->packed_inputs = (int)value; return BJ_OK; }
+    if (!strcmp(name, "debug_poison")) { c->debug_poison = value != 0; return BJ_OK; }
+    if (!strcmp(name, "max_image_pixels")) { if (value < 1) return BJ_ERR_ARG; c->max_image_pixels = (size_t)value; return BJ_OK; }
+    if (!strcmp(name, "sub_batch_out_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_out_bytes = (size_t)value; return BJ_OK; }
     if (!strcmp(name, "host_threads")) { if (value < 1 || value > 256) return BJ_ERR_ARG; c->host_pool.resize((int)value); return BJ_OK; }
     if (!strcmp(name, "sync_rounds")) { if (value < 0 || value > kMaxRounds) return BJ_ERR_ARG; c->sync_rounds = (int)value; return BJ_OK; }
     return BJ_ERR_ARG;
@@ -110,14 +186,21 @@ extern "C" int bj_get_stat(const bj_ctx *c, const char *name, double *value) {
     if (!strcmp(name, "decode_batch_host_ms")) { *value = c->stats[4]; return BJ_OK; }        // parse + layout + pack, summed
     if (!strcmp(name, "decode_batch_wait_ms")) { *value = c->stats[5]; return BJ_OK; }        // host blocked on the GPU, summed
     if (!strcmp(name, "decode_batch_d2h_copies")) { *value = c->stats[6]; return BJ_OK; }
-    if (!strcmp(name, "host_threads")) { *value = c->host_pool.threads(); return BJ_OK; }
+    // kernel time per stage, summed over the sub-batches (CUDA events): the reference's per-stage "Profiles" lines
+    // (src/decoder_host.cpp:379-394; DPU cycle counters src/decoder_dpu.c:52-55) for the one-call path
+    if (!strcmp(name, "decode_batch_ms_unstuff")) { *value = c->stats[7]; return BJ_OK; }
+    if (!strcmp(name, "decode_batch_ms_sync")) { *value = c->stats[8]; return BJ_OK; }
+    if (!strcmp(name, "decode_batch_ms_write")) { *value = c->stats[9]; return BJ_OK; }
+    if (!strcmp(name, "decode_batch_ms_idct")) { *value = c->stats[10]; return BJ_OK; }
+    if (!strcmp(name, "devices")) { *value = c->children.empty() ? 1 : (double)c->children.size(); return BJ_OK; }
+    if (!strcmp(name, "host_threads")) { *value = (c->children.empty() ? c : c->children[0])->host_pool.threads(); return BJ_OK; }
     return BJ_ERR_ARG;
 }
 
 // ------------------------------------------------------------------------------------------------ compat entry
 
 extern "C" int bj_exec_mcus_device(bj_ctx *c, const uint32_t *d_md, int16_t *d_mcus, int nchunk, int M, void *stream) {
-    if (!c || !d_md || !d_mcus || nchunk < 0 || M < 4) return BJ_ERR_ARG;
+    if (!c || !d_md || !d_mcus || nchunk < 0 || M < 4 || M % 4 || !c->children.empty()) return BJ_ERR_ARG;
     if (nchunk == 0) return BJ_OK;
     const int blk_per_chunk = M / 4;
     const long long nblk = (long long)nchunk * blk_per_chunk;
@@ -126,30 +209,47 @@ extern "C" int bj_exec_mcus_device(bj_ctx *c, const uint32_t *d_md, int16_t *d_m
     return c->check(cudaGetLastError());
 }
 
+static int exec_mcus_one(bj_ctx *c, const uint32_t *metadata, int16_t *mcus, int nchunk, int M) {
+    if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
+    const size_t md_bytes = (size_t)nchunk * 276 * 4, mc_bytes = (size_t)nchunk * 64 * M * 3 * 2;
+    DevBuf &dmd = c->pool[POOL_COMPAT_MD], &dmc = c->pool[POOL_COMPAT_MCUS];
+    if (dmd.reserve(md_bytes) != BJ_OK || dmc.reserve(mc_bytes) != BJ_OK) return BJ_ERR_NOMEM;
+    cudaStream_t s = c->streams[0];
+    // the three pim.copy calls + pim.exec of src/decoder_host.cpp:276-308
+    int rc = c->check(cudaMemcpyAsync(dmd.p, metadata, md_bytes, cudaMemcpyHostToDevice, s));
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dmc.p, mcus, mc_bytes, cudaMemcpyHostToDevice, s));
+    cudaEventRecord(c->ev_exec[0], s);
+    if (rc == BJ_OK) rc = bj_exec_mcus_device(c, (const uint32_t *)dmd.p, (int16_t *)dmc.p, nchunk, M, s);
+    cudaEventRecord(c->ev_exec[1], s);
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(mcus, dmc.p, mc_bytes, cudaMemcpyDeviceToHost, s));
+    if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
+    if (rc == BJ_OK) cudaEventElapsedTime(&c->last_exec_ms, c->ev_exec[0], c->ev_exec[1]);
+    return rc;
+}
+
 extern "C" int bj_exec_mcus(bj_ctx *c, const uint32_t *metadata, int16_t *mcus, int nchunk) {
     if (!c || !metadata || !mcus || nchunk < 0) return BJ_ERR_ARG;
     if (nchunk == 0) return BJ_OK;
     int M = 0;                                   // MAX_MCU_PER_DPU as the host compiled it (metadata[19], decoder_host.cpp:172)
     for (int i = 0; i < nchunk && M == 0; i++) M = (int)metadata[(size_t)i * 276 + 19];
     if (M == 0) return BJ_OK;                    // only idle DPUs: the program touches nothing
-    if (M < 4) return BJ_ERR_ARG;
-    if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
-    const size_t md_bytes = (size_t)nchunk * 276 * 4, mc_bytes = (size_t)nchunk * 64 * M * 3 * 2;
-    DevBuf &dmd = c->pool[POOL_COMPAT_MD], &dmc = c->pool[POOL_COMPAT_MCUS];
-    if (dmd.reserve(md_bytes) != BJ_OK || dmc.reserve(mc_bytes) != BJ_OK) return BJ_ERR_NOMEM;
-    cudaStream_t s = c->streams[0];
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    // the three pim.copy calls + pim.exec of src/decoder_host.cpp:276-308
-    int rc = c->check(cudaMemcpyAsync(dmd.p, metadata, md_bytes, cudaMemcpyHostToDevice, s));
-    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dmc.p, mcus, mc_bytes, cudaMemcpyHostToDevice, s));
-    cudaEventRecord(e0, s);
-    if (rc == BJ_OK) rc = bj_exec_mcus_device(c, (const uint32_t *)dmd.p, (int16_t *)dmc.p, nchunk, M, s);
-    cudaEventRecord(e1, s);
-    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(mcus, dmc.p, mc_bytes, cudaMemcpyDeviceToHost, s));
-    if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
-    if (rc == BJ_OK) cudaEventElapsedTime(&c->last_exec_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (M < 4 || M % 4) return BJ_ERR_ARG;       // the DPU program works on whole blocks of 4 positions (src/decoder_dpu.c:130)
+    for (int i = 0; i < nchunk; i++) { const uint32_t m = metadata[(size_t)i * 276 + 19]; if (m != 0 && m != (uint32_t)M) return BJ_ERR_ARG; }
+    if (c->children.empty()) return exec_mcus_one(c, metadata, mcus, nchunk, M);
+    // multi-GPU context: the DPUs are dealt to the GPUs in equal contiguous shares, one host thread per GPU
+    const int nd = (int)c->children.size();
+    std::vector<int> rcs(nd, BJ_OK);
+    std::vector<std::thread> th;
+    auto share = [&](int d) {
+        const int lo = (int)((long long)nchunk * d / nd), hi = (int)((long long)nchunk * (d + 1) / nd);
+        if (hi > lo) rcs[d] = exec_mcus_one(c->children[d], metadata + (size_t)lo * 276, mcus + (size_t)lo * 64 * M * 3, hi - lo, M);
+    };
+    for (int d = 1; d < nd; d++) th.emplace_back(share, d);
+    share(0);
+    for (auto &t : th) t.join();
+    c->last_exec_ms = 0.f;
+    int rc = BJ_OK;
+    for (int d = 0; d < nd; d++) { if (rc == BJ_OK) rc = rcs[d]; c->last_exec_ms = std::max(c->last_exec_ms, c->children[d]->last_exec_ms); }
     return rc;
 }
 
@@ -172,22 +272,27 @@ extern "C" size_t bj_output_size(const bj_image_desc *d, int format) {
 
 extern "C" int bj_stage_idct_color(bj_ctx *c, const bj_image_desc *desc, const int16_t *coef_zz, int format, uint8_t *out) {
     if (!c || !desc || !coef_zz || !out) return BJ_ERR_ARG;
+    if (!c->children.empty()) c = c->children[0];                // (stage entries run on the first device of a multi-GPU context)
     if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+    if (!desc_is_sane(*desc)) return BJ_ERR_ARG;                 // a caller-made descriptor: checked before it sizes anything
     if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
-    ImgDev im;
+    struct StageRec { ImgDev im; QTab q; } rec;                  // one upload: the image record and its quantiser set
     std::vector<TileDev> tiles;
     Geometry g = geometry_of(*desc);
-    fill_imgdev(*desc, g, format, /*du_base=*/0, /*out_base=*/0, &im);
+    fill_imgdev(*desc, g, format, /*du_base=*/0, /*out_base=*/0, &rec.im);
+    fill_qtab(*desc, &rec.q);
     append_tiles(g, 0, 0, &tiles);
     const size_t coef_bytes = (size_t)g.ndu * 128, out_bytes = bj_output_size(desc, format);
     DevBuf &dco = c->pool[POOL_COEF], &dout = c->pool[POOL_OUT], &dim = c->pool[POOL_IMGS], &dti = c->pool[POOL_TILES];
-    if (dco.reserve(coef_bytes) || dout.reserve(out_bytes + 64) || dim.reserve(sizeof(im)) || dti.reserve(tiles.size() * sizeof(TileDev))) return BJ_ERR_NOMEM;
+    if (dco.reserve(coef_bytes) || dout.reserve(out_bytes + 64) || dim.reserve(sizeof(rec)) || dti.reserve(tiles.size() * sizeof(TileDev))) return BJ_ERR_NOMEM;
     cudaStream_t s = c->streams[0];
     int rc = c->check(cudaMemcpyAsync(dco.p, coef_zz, coef_bytes, cudaMemcpyHostToDevice, s));
-    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dim.p, &im, sizeof(im), cudaMemcpyHostToDevice, s));
+    if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dim.p, &rec, sizeof(rec), cudaMemcpyHostToDevice, s));
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dti.p, tiles.data(), tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
     if (rc == BJ_OK) {
-        k_idct_color<<<(unsigned)tiles.size(), kTileThreads, kSmemIdctColor, s>>>((const int16_t *)dco.p, nullptr, (const ImgDev *)dim.p, (const TileDev *)dti.p, (uint8_t *)dout.p);
+        const uint8_t *base = (const uint8_t *)dim.p;
+        k_idct_color<<<(unsigned)tiles.size(), kTileThreads, kSmemIdctColor, s>>>((const int16_t *)dco.p, nullptr, (const ImgDev *)base, (const QTab *)(base + offsetof(StageRec, q)),
+                                                                                 (const TileDev *)dti.p, (uint8_t *)dout.p);
         rc = c->check(cudaGetLastError());
     }
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(out, dout.p, out_bytes, cudaMemcpyDeviceToHost, s));
@@ -199,6 +304,7 @@ extern "C" int bj_stage_idct_color(bj_ctx *c, const bj_image_desc *desc, const i
 
 extern "C" int bj_batch_create(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, bj_batch **out) {
     if (!c || !out || n < 0 || (n > 0 && (!files || !lens))) return BJ_ERR_ARG;
+    if (!c->children.empty()) c = c->children[0];                // a staged batch lives on one device
     *out = nullptr;
     bj_batch *b = new (std::nothrow) bj_batch();
     if (!b) return BJ_ERR_NOMEM;
@@ -235,7 +341,11 @@ extern "C" int bj_batch_status(const bj_batch *b, int *status) {
 extern "C" int bj_batch_get_info(const bj_batch *b, bj_batch_info *info) {
     if (!b || !info) return BJ_ERR_ARG;
     memset(info, 0, sizeof(*info));
-    info->pixels = b->pixels; info->scan_bytes = b->scan_bytes; info->data_units = b->coef_units; info->out_bytes = b->out_bytes;
+    info->pixels = b->pixels; info->scan_bytes = b->scan_bytes_max; info->data_units = b->coef_units; info->out_bytes = b->out_bytes;
+    if (b->synced) {                                             // the scans' true lengths are found on the device
+        info->scan_bytes = 0;
+        for (int i = 0; i < b->n; i++) info->scan_bytes += const_cast<bj_batch *>(b)->h_state()[i].raw_len;
+    }
     info->h2d_bytes = b->files_bytes + b->meta_bytes; info->d2h_bytes = b->d2h_bytes;
     uint32_t nsub = 0;
     if (b->synced) for (int i = 0; i < b->n; i++) nsub += const_cast<bj_batch *>(b)->h_state()[i].nsub;
@@ -272,6 +382,7 @@ extern "C" int bj_batch_device_coefficients(const bj_batch *b, int i, void **dpt
 // Stage-level entry for known-answer tests: K0 + K1 only; coefficients (zig-zag, DC un-differenced) back to the host.
 extern "C" int bj_stage_entropy(bj_ctx *c, const uint8_t *file, size_t len, int16_t *coef_zz, size_t capacity_bytes, int *status) {
     if (!c || !file || !coef_zz) return BJ_ERR_ARG;
+    if (!c->children.empty()) c = c->children[0];
     bj_batch *b = nullptr;
     const uint8_t *files[1] = {file};
     const size_t lens[1] = {len};
@@ -295,24 +406,46 @@ extern "C" int bj_stage_entropy(bj_ctx *c, const uint8_t *file, size_t len, int1
 
 // ------------------------------------------------------------------------------------------------ full path, one call
 // Sub-batches rotate over kSlots batch objects, each with its own stream: while sub-batch k copies out (PCIe D2H is
-// the bound of this call: 3 bytes per pixel), sub-batch k+1 decodes and the host parses and packs sub-batch k+2
-// on the worker pool.
+// the bound of this call: 3 bytes per pixel), sub-batch k+1 decodes and the host reads the headers of sub-batch k+2.
+// The image list is cut into sub-batches by a RangeSource; the devices of a multi-GPU context (bj_create_multi) pull
+// from ONE source, so the list is dealt dynamically - by sub-batch, in list order, no collective - like the reference
+// deals its images over all DPUs of the machine (src/decoder_host.cpp:32-33,125-149).
 static double wall_ms() {
     struct timespec t;
     clock_gettime(CLOCK_MONOTONIC, &t);
     return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
 }
 
-extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format,
-                               uint8_t *const *outs, int *status) {
-    if (!c || n < 0 || (n > 0 && (!files || !lens || !outs))) return BJ_ERR_ARG;
-    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+namespace {
+struct RangeSource {
+    std::mutex m;
+    const size_t *lens;
+    int n, next = 0;
+    size_t budget;
+    bool ramp;
+    // k = how many ranges the asking device has had: its first two are small, so that its copy-out starts early
+    bool take(int k, int *i0, int *i1) {
+        std::lock_guard<std::mutex> l(m);
+        if (next >= n) return false;
+        const size_t cap = !ramp ? budget : (k == 0 ? budget / 8 : (k == 1 ? budget / 3 : budget));
+        int j = next;
+        size_t bytes = 0;
+        while (j < n && (j == next || bytes + lens[j] <= cap)) bytes += lens[j++];
+        *i0 = next; *i1 = j; next = j;
+        return true;
+    }
+};
+enum { ST_SUB = 0, ST_LAUNCH, ST_H2D, ST_D2H, ST_HOST_MS, ST_WAIT_MS, ST_D2H_COPIES, ST_MS_UNSTUFF, ST_MS_SYNC, ST_MS_WRITE, ST_MS_IDCT, ST_COUNT };
+}  // namespace
+
+// One device's share of a call: pull ranges from `src` until it runs dry.
+static int decode_worker(bj_ctx *c, RangeSource *src, const uint8_t *const *files, const size_t *lens, int format,
+                         uint8_t *const *outs, int *status) {
     if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
-    const size_t budget = c->sub_batch_bytes ? c->sub_batch_bytes : ((size_t)24 << 20);    // compressed bytes per sub-batch
     for (auto &b : c->slots) if (!b) { b = new (std::nothrow) bj_batch(); if (!b) return BJ_ERR_NOMEM; }
     int first[kSlots] = {}, count[kSlots] = {};
     bool busy[kSlots] = {};
-    double nsub = 0, launches = 0, h2d = 0, d2h = 0, host_ms = 0, wait_ms = 0, d2h_copies = 0;
+    double st[ST_COUNT] = {};
     int rc = BJ_OK;
     // B200JPEG_TRACE=1: one line per sub-batch on stderr - when its kernels ran and its copy-out ended (ms since the
     // first sub-batch was enqueued) - to see whether the copy-out engine is kept busy.  (No event is recorded in front
@@ -334,53 +467,150 @@ extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const siz
             cudaEventSynchronize(b->ev[5]);
             cudaEventElapsedTime(&k0, ev_base, b->ev[0]);
             cudaEventElapsedTime(&k1, ev_base, b->ev[4]); cudaEventElapsedTime(&out, ev_base, b->ev[5]);
-            fprintf(stderr, "b200jpeg trace: sub-batch of %4d images (%6.1f MB out)  host prepare %6.2f..%6.2f  kernels %6.2f..%6.2f  copied out %6.2f\n",
-                    b->n, b->d2h_bytes / 1e6, host_t[slot][0], host_t[slot][1], k0, k1, out);
+            fprintf(stderr, "b200jpeg trace: dev %d sub-batch of %4d images (%6.1f MB out, %s)  host prepare %6.2f..%6.2f  kernels %6.2f..%6.2f  copied out %6.2f\n",
+                    c->device, b->n, b->d2h_bytes / 1e6, b->direct_src ? "direct upload" : "staged upload", host_t[slot][0], host_t[slot][1], k0, k1, out);
         }
-        if (r == BJ_OK && b->n_blk && b->h_flags()[b->rounds - 1] != 0)   // extra rounds ran: the early copy-out is stale
+        if (r == BJ_OK && b->redone)                                   // extra fix-up rounds ran: the early copy-out is stale
             r = batch_download(b, outs + first[slot], c->streams[slot]);
-        wait_ms += wall_ms() - t0;
-        if (r == BJ_OK && status) for (int i = 0; i < count[slot]; i++) status[first[slot] + i] = batch_image_status(b, i);
-        launches += b->launches; h2d += (double)(b->files_bytes + b->meta_bytes); d2h += (double)b->d2h_bytes; d2h_copies += b->d2h_copies;
+        st[ST_WAIT_MS] += wall_ms() - t0;
+        if (status) for (int i = 0; i < count[slot]; i++) status[first[slot] + i] = r == BJ_OK ? batch_image_status(b, i) : r;
+        st[ST_LAUNCH] += b->launches; st[ST_H2D] += (double)(b->files_bytes + b->meta_bytes); st[ST_D2H] += (double)b->d2h_bytes; st[ST_D2H_COPIES] += b->d2h_copies;
+        if (r == BJ_OK) { st[ST_MS_UNSTUFF] += b->ms_unstuff; st[ST_MS_SYNC] += b->ms_sync; st[ST_MS_WRITE] += b->ms_write; st[ST_MS_IDCT] += b->ms_idct; }
         busy[slot] = false;
         return r;
     };
-    int i0 = 0, k = 0;
-    while (rc == BJ_OK && i0 < n) {
-        int i1 = i0;
-        size_t bytes = 0;
-        // the first sub-batches are small, so that the copy-out (the bound of this call) starts early
-        const size_t cap = !c->sub_batch_ramp ? budget : (k == 0 ? budget / 8 : (k == 1 ? budget / 3 : budget));
-        while (i1 < n && (i1 == i0 || bytes + lens[i1] <= cap)) bytes += lens[i1++];
-        const int slot = k % kSlots;
-        if (busy[slot]) rc = finish(slot);
-        if (rc != BJ_OK) break;
-        bj_batch *b = c->slots[slot];
-        cudaStream_t s = c->streams[slot];
-        const double t0 = wall_ms();
-        rc = batch_assign(b, c, files + i0, lens + i0, i1 - i0, format, c->packed_inputs != 0);
-        host_ms += wall_ms() - t0;
-        host_t[slot][0] = t0 - wall0; host_t[slot][1] = wall_ms() - wall0;
-        if (rc == BJ_OK && trace) {
-            if (!ev_base) { cudaEventCreate(&ev_base); cudaEventRecord(ev_base, s); }
+    int k = 0, r0 = 0, r1 = 0, nranges = 0;
+    while (rc == BJ_OK && src->take(nranges, &r0, &r1)) {
+        nranges++;
+        int i0 = r0;
+        while (rc == BJ_OK && i0 < r1) {
+            const int slot = k % kSlots;
+            if (busy[slot]) rc = finish(slot);
+            if (rc != BJ_OK) break;
+            bj_batch *b = c->slots[slot];
+            cudaStream_t s = c->streams[slot];
+            const double t0 = wall_ms();
+            rc = batch_assign(b, c, files + i0, lens + i0, r1 - i0, format, c->sub_batch_out_bytes);
+            const int m = rc == BJ_OK ? b->n : 0;
+            st[ST_HOST_MS] += wall_ms() - t0;
+            host_t[slot][0] = t0 - wall0; host_t[slot][1] = wall_ms() - wall0;
+            if (rc == BJ_OK && trace && !ev_base) { cudaEventCreate(&ev_base); cudaEventRecord(ev_base, s); }
+            if (rc == BJ_OK) rc = batch_upload(b, s);
+            if (rc == BJ_OK) rc = batch_decode(b, s);
+            if (rc == BJ_OK) {                                            // enqueue the copy-out behind the kernels, no host wait
+                b->synced = true;                                         // (checked for real in finish())
+                rc = batch_download_async(b, outs + i0, s);
+                b->synced = false;
+                if (trace) cudaEventRecord(b->ev[5], s);
+                if (!b->ev_done) cudaEventCreateWithFlags(&b->ev_done, cudaEventBlockingSync | cudaEventDisableTiming);
+                if (b->ev_done) cudaEventRecord(b->ev_done, s);
+            }
+            if (rc != BJ_OK) {                                            // nothing (complete) was enqueued for this range: report it, do not wait for it
+                cudaStreamSynchronize(s);
+                if (status) for (int i = i0; i < r1; i++) status[i] = rc;
+                break;
+            }
+            first[slot] = i0; count[slot] = m; busy[slot] = true;
+            st[ST_SUB] += 1;
+            i0 += m; k++;
         }
-        if (rc == BJ_OK) rc = batch_upload(b, s);
-        if (rc == BJ_OK) rc = batch_decode(b, s);
-        if (rc == BJ_OK) {                                            // enqueue the copy-out behind the kernels, no host wait
-            b->synced = true;                                         // (checked for real in finish())
-            rc = batch_download_async(b, outs + i0, s);
-            b->synced = false;
-            if (trace) cudaEventRecord(b->ev[5], s);
-            if (!b->ev_done) cudaEventCreateWithFlags(&b->ev_done, cudaEventBlockingSync | cudaEventDisableTiming);
-            if (b->ev_done) cudaEventRecord(b->ev_done, s);
-        }
-        first[slot] = i0; count[slot] = i1 - i0; busy[slot] = true;
-        nsub += 1;
-        i0 = i1; k++;
     }
     // drain in submission order
     for (int j = 0; j < kSlots; j++) { const int slot = (k + j) % kSlots; if (busy[slot]) { const int r = finish(slot); if (rc == BJ_OK) rc = r; } }
     if (ev_base) cudaEventDestroy(ev_base);
-    c->stats[0] = nsub; c->stats[1] = launches; c->stats[2] = h2d; c->stats[3] = d2h; c->stats[4] = host_ms; c->stats[5] = wait_ms; c->stats[6] = d2h_copies;
+    for (int i = 0; i < ST_COUNT; i++) c->stats[i] = st[i];
+    return rc;
+}
+
+static int decode_batch_now(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, uint8_t *const *outs, int *status) {
+    RangeSource src;
+    src.lens = lens; src.n = n;
+    src.budget = c->sub_batch_bytes ? c->sub_batch_bytes : ((size_t)24 << 20);    // compressed bytes per sub-batch
+    src.ramp = c->sub_batch_ramp != 0;
+    if (c->children.empty()) return decode_worker(c, &src, files, lens, format, outs, status);
+    // multi-GPU context: one host thread per device, all pulling sub-batches from the same source
+    if (status) for (int i = 0; i < n; i++) status[i] = BJ_ERR_CUDA;                // (overwritten by whoever decodes the image)
+    std::vector<int> rcs(c->children.size(), BJ_OK);
+    std::vector<std::thread> th;
+    for (size_t d = 1; d < c->children.size(); d++)
+        th.emplace_back([&, d] { rcs[d] = decode_worker(c->children[d], &src, files, lens, format, outs, status); });
+    rcs[0] = decode_worker(c->children[0], &src, files, lens, format, outs, status);
+    for (auto &t : th) t.join();
+    int rc = BJ_OK;
+    for (int i = 0; i < ST_COUNT; i++) c->stats[i] = 0;
+    for (size_t d = 0; d < c->children.size(); d++) {
+        if (rc == BJ_OK) rc = rcs[d];
+        if (rcs[d] != BJ_OK) c->last_error = c->children[d]->last_error;
+        for (int i = 0; i < ST_COUNT; i++) {
+            const bool is_time = i == ST_HOST_MS || i == ST_WAIT_MS || i >= ST_MS_UNSTUFF;
+            c->stats[i] = is_time ? std::max(c->stats[i], c->children[d]->stats[i]) : c->stats[i] + c->children[d]->stats[i];   // devices work side by side
+        }
+    }
+    return rc;
+}
+
+extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format,
+                               uint8_t *const *outs, int *status) {
+    if (!c || n < 0 || (n > 0 && (!files || !lens || !outs))) return BJ_ERR_ARG;
+    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+    if (c->async && c->async->pending()) return BJ_ERR_ARG;                          // jobs of bj_submit are still running on this context
+    return decode_batch_now(c, files, lens, n, format, outs, status);
+}
+
+// ------------------------------------------------------------------------------------------------ full path, asynchronous
+// bj_submit hands a batch to the context's worker thread and returns; bj_wait blocks until that batch's outputs are
+// in host memory.  Jobs run in submission order.  What the reference does with its producer / consumer threads and
+// the queue between them (src/decoder_host.cpp:25-38,364-365) a caller gets by submitting batch k+1 (or reading its
+// files) while batch k decodes, and writing batch k-1's outputs meanwhile (host/decoder_b200.cpp does exactly that).
+struct bj_job {
+    const uint8_t *const *files; const size_t *lens; int n, format; uint8_t *const *outs; int *status;
+    int rc = BJ_OK;
+    bool done = false;
+    bj_ctx *ctx = nullptr;
+};
+
+void bj::AsyncWorker::run() {
+    for (;;) {
+        bj_job *j = nullptr;
+        {
+            std::unique_lock<std::mutex> l(m);
+            cv.wait(l, [&] { return stop || !q.empty(); });
+            if (q.empty()) return;
+            j = q.front();
+        }
+        const int rc = decode_batch_now(j->ctx, j->files, j->lens, j->n, j->format, j->outs, j->status);
+        {
+            std::lock_guard<std::mutex> l(m);
+            q.pop_front();
+            j->rc = rc; j->done = true;
+        }
+        done_cv.notify_all();
+    }
+}
+
+extern "C" int bj_submit(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, uint8_t *const *outs, int *status, bj_job **job) {
+    if (!c || !job || n < 0 || (n > 0 && (!files || !lens || !outs))) return BJ_ERR_ARG;
+    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+    *job = nullptr;
+    bj_job *j = new (std::nothrow) bj_job{files, lens, n, format, outs, status};
+    if (!j) return BJ_ERR_NOMEM;
+    j->ctx = c;
+    if (!c->async) {
+        c->async = new (std::nothrow) AsyncWorker();
+        if (!c->async) { delete j; return BJ_ERR_NOMEM; }
+        c->async->th = std::thread([w = c->async] { w->run(); });
+    }
+    { std::lock_guard<std::mutex> l(c->async->m); c->async->q.push_back(j); }
+    c->async->cv.notify_one();
+    *job = j;
+    return BJ_OK;
+}
+
+extern "C" int bj_wait(bj_job *j) {
+    if (!j || !j->ctx || !j->ctx->async) return BJ_ERR_ARG;
+    AsyncWorker *w = j->ctx->async;
+    { std::unique_lock<std::mutex> l(w->m); w->done_cv.wait(l, [&] { return j->done; }); }
+    const int rc = j->rc;
+    delete j;
     return rc;
 }

@@ -1,8 +1,11 @@
 // Host orchestration of the full path: a batch of JPEG files -> kernels K0..K3 -> pixels.
 // Replaces, per image, the producer half of the reference's pipeline (read_JPEG's scan copy + decode_Huffman_data,
 // src/decoder_host.cpp:119-181) and its consumer half (pim.copy / pim.exec / pim.copy, :268-312) with one
-// asynchronous sequence of kernel launches on a CUDA stream.  Nothing here decodes on the CPU: the host parses
-// headers (parse.h), builds the per-image descriptors and lookup tables, and packs bytes for one H2D copy.
+// asynchronous sequence of kernel launches on a CUDA stream.  Nothing here decodes on the CPU, and the host never
+// touches the entropy-coded bytes: it reads the file HEADERS (parse.h, a few hundred bytes per file), builds one small
+// record per image and the lookup tables, and hands the file bytes to the GPU - straight from the caller's memory when
+// that is page-locked, through a pinned staging copy otherwise.  Where a scan ends, what survives un-stuffing, and
+// every per-CTA table are worked out on the device (kernels_huff.cuh: k_scan_count / k_scan_tiles / k_expand_maps).
 #pragma once
 #include <map>
 #include <string>
@@ -65,28 +68,33 @@ struct bj_batch {
     std::vector<size_t> out_off, out_size;
     std::vector<uint64_t> file_off;
     std::vector<uint32_t> du_base, ndu;
+    std::vector<bj::HuffImg> himg;       // per-image records (kept here between calls: no reallocation in steady state)
+    std::vector<bj::ImgDev> idev;
 
     // host staging (pinned): file bytes; descriptor blob; results
     bj::PinBuf h_files, h_meta, h_res;
     size_t files_bytes = 0, meta_bytes = 0;
     const uint8_t *direct_src = nullptr;   // set: the files are uploaded straight from the caller's (pinned) memory, files_bytes from here
-    // offsets inside the descriptor blob
-    size_t o_himg = 0, o_idev = 0, o_tiles = 0, o_blk = 0, o_wblk = 0, o_utile = 0, o_tileex = 0, o_dcc = 0, o_lutdc = 0, o_lutac = 0, o_lutacs = 0;
+    // offsets inside the descriptor blob (host -> device)
+    size_t o_himg = 0, o_idev = 0, o_qtab = 0, o_lutdc = 0, o_lutac = 0, o_lutacs = 0;
+    // offsets inside the map buffer (written on the device by k_expand_maps)
+    size_t m_tiles = 0, m_blk = 0, m_wblk = 0, m_utile = 0, m_dcc = 0, maps_bytes = 0;
     uint32_t idct_smem = 0;             // dynamic shared memory of k_idct_color: sized for the widest pixel tile of this batch
     uint32_t n_wblk = 0;                // CTAs of the Huffman write pass
     size_t n_slice_slots = 0;
     uint32_t n_idct_tiles = 0, n_blk = 0, n_utile = 0, n_dcc = 0, n_seg_entries = 0, n_sub_slots = 0, lut_smem = 0;
     size_t clean_words = 0, coef_units = 0, out_bytes = 0;
-    uint64_t pixels = 0, scan_bytes = 0;
+    uint64_t pixels = 0, scan_bytes_max = 0;
 
     // device
-    bj::DevBuf d_files, d_meta, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_quarter, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
+    bj::DevBuf d_files, d_meta, d_maps, d_tilecnt, d_tileex, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_quarter, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels, copied out
     cudaEvent_t ev_done = nullptr;       // one-call path: recorded behind the copy-out, created for a sleeping wait
     cudaStream_t last_stream = nullptr;
     bool uploaded = false, decoded = false, synced = false;
     bool phased = true;                  // which variant of the synchronisation kernel this batch was laid out for
     bool multi_blk = false;              // some image's sub-sequences span more than one CTA of the synchronisation pass
+    bool redone = false;                 // batch_sync had to run extra fix-up rounds: everything after them was computed again
     uint32_t launches = 0, sync_rounds = 0;
     float ms_entropy = 0.f, ms_idct = 0.f, ms_unstuff = 0.f, ms_sync = 0.f, ms_write = 0.f;
     uint64_t d2h_bytes = 0;
@@ -96,9 +104,10 @@ struct bj_batch {
     uint32_t *h_flags() { return reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(h_res.p) + bj::align_up((size_t)n * sizeof(bj::HuffImgState), 64)); }
     template <class T> T *dmeta(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(d_meta.p) + off); }
     template <class T> T *hmeta(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(h_meta.p) + off); }
+    template <class T> T *dmap(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(d_maps.p) + off); }
 
     void release() {
-        for (bj::DevBuf *b : {&d_files, &d_meta, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_quarter, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
+        for (bj::DevBuf *b : {&d_files, &d_meta, &d_maps, &d_tilecnt, &d_tileex, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_quarter, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
         h_files.release(); h_meta.release(); h_res.release();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (ev_done) { cudaEventDestroy(ev_done); ev_done = nullptr; }
@@ -109,51 +118,65 @@ namespace bj {
 
 constexpr int kMaxRounds = 64;
 
-// (Re)fill a batch object from a list of files: parse, lay out, pack.  Host work only (plus buffer growth).
-inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, bool direct = false) {
+// (Re)fill a batch object from a list of files: parse the headers, lay out, (stage).  Host work only (plus buffer growth).
+//   out_cap   the batch takes images from the front of the list until their decoded bytes pass this (at least one):
+//             b->n tells how many.  A few hostile headers (a 1 KB file that declares 65535 x 65535) cannot make a
+//             sub-batch of the one-call path arbitrarily large, and an image above ctx->max_image_pixels is refused
+//             on its own (BJ_ERR_UNSUPPORTED) like the reference's "Too high resolution" (src/decoder_host.cpp:146-149).
+inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, size_t out_cap = ~(size_t)0) {
     if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
     b->ctx = c; b->n = n; b->format = format;
     b->uploaded = b->decoded = b->synced = false;
     b->desc.resize(n); b->parse_status.assign(n, BJ_OK);
-    b->out_off.assign(n, 0); b->out_size.assign(n, 0); b->file_off.assign(n, 0);
-    b->du_base.assign(n, 0); b->ndu.assign(n, 0);
     if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
     for (auto &e : b->ev) if (!e && c->check(cudaEventCreate(&e)) != BJ_OK) return BJ_ERR_CUDA;
 
-    // ---- where the file bytes are uploaded from.  Normally they are packed into this batch's pinned staging buffer
-    // (one copy on the worker pool).  With option "packed_inputs" the caller states that all files of the call lie in
-    // ONE pinned allocation: then the span from the first to the last file goes up as it is, straight from the
-    // caller's memory, and nothing is copied on the host.
+    // ---- headers (per image, independent: worker pool).  Nothing behind the SOS header is read.
+    std::vector<Geometry> geo(n);
+    c->host_pool.parallel_for(n, 64, [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++) {
+            bj_image_desc &d = b->desc[i];
+            int rc = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &d, /*walk_scan=*/false) : BJ_ERR_INVALID_JPEG;
+            if (rc == BJ_OK && d.scan_len >= ((size_t)1 << 31)) rc = BJ_ERR_UNSUPPORTED;   // byte counts travel in 31 bits
+            if (rc == BJ_OK && (size_t)d.width * d.height > c->max_image_pixels) rc = BJ_ERR_UNSUPPORTED;
+            if (rc == BJ_OK) geo[i] = geometry_of(d);
+            b->parse_status[i] = rc;
+        }
+    });
+    // ---- how many of the candidates this batch takes
+    if (out_cap != ~(size_t)0) {
+        size_t acc = 0;
+        int m = 0;
+        while (m < n) {
+            const size_t sz = b->parse_status[m] == BJ_OK ? align_up(bj_output_size(&b->desc[m], format), 16) : 0;
+            if (m > 0 && acc + sz > out_cap) break;
+            acc += sz; m++;
+        }
+        n = m; b->n = n;
+        b->desc.resize(n); b->parse_status.resize(n);
+    }
+    b->out_off.assign(n, 0); b->out_size.assign(n, 0); b->file_off.assign(n, 0);
+    b->du_base.assign(n, 0); b->ndu.assign(n, 0);
+    b->himg.resize(n); b->idev.resize(n);
+
+    // ---- where the file bytes are uploaded from.  If the span from the first to the last file lies inside page-locked
+    // memory this library knows about (bj_host_alloc / bj_host_register), or the caller says so (option "packed_inputs"
+    // = 1), and the files lie close together, the span goes up as it is, straight from the caller's memory: nothing is
+    // copied on the host.  Otherwise the files are packed into this batch's pinned staging buffer (worker pool).
     b->direct_src = nullptr;
     uint64_t span_lo = ~0ull, span_hi = 0, span_sum = 0;
-    if (direct) {
+    if (c->packed_inputs >= 0) {
         for (int i = 0; i < n; i++) {
-            if (!files[i] || !lens[i]) continue;
+            if (b->parse_status[i] != BJ_OK) continue;
             const uint64_t a = (uint64_t)(uintptr_t)files[i];
             span_lo = std::min(span_lo, a); span_hi = std::max(span_hi, a + lens[i]); span_sum += lens[i];
         }
-        if (span_hi > span_lo && span_hi - span_lo <= 2 * span_sum + (1u << 16)) {
+        if (span_hi > span_lo && span_hi - span_lo <= 2 * span_sum + (1u << 16) &&
+            (c->packed_inputs == 1 || pinned_ranges().contains((uintptr_t)span_lo, (uintptr_t)span_hi))) {
             span_lo &= ~(uint64_t)15;
             b->direct_src = reinterpret_cast<const uint8_t *>((uintptr_t)span_lo);
         }
     }
-
-    // ---- parse (per image, independent: worker pool).  The walk over the scan also counts, per un-stuff tile, the
-    // bytes that will not survive and the restart markers (parse.h: ScanTiles), so K0 needs no counting pass.
-    std::vector<uint32_t> tile_cap(n + 1, 0);
-    for (int i = 0; i < n; i++) tile_cap[i + 1] = tile_cap[i] + (uint32_t)((lens[i] + 15 + kScanTile - 1) / kScanTile + 1);
-    std::vector<uint32_t> tile_dropped(tile_cap[n], 0), tile_rst(tile_cap[n], 0);
-    std::vector<uint32_t> scan_mis(n, 0);
-    c->host_pool.parallel_for(n, 32, [&](int i0, int i1) {
-        for (int i = i0; i < i1; i++) {
-            ScanTiles st;
-            st.dropped = tile_dropped.data() + tile_cap[i]; st.rst = tile_rst.data() + tile_cap[i];
-            st.ntile = tile_cap[i + 1] - tile_cap[i];
-            st.mis = b->direct_src ? (uint32_t)((uintptr_t)files[i] & 15u) : 0u;       // staged files start 16-byte aligned
-            b->parse_status[i] = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &b->desc[i], &st) : BJ_ERR_INVALID_JPEG;
-            scan_mis[i] = st.mis;
-        }
-    });
 
     // ---- sub-sequence length and slices, per image.
     // Explicit (options "subseq_bits", "slices"): the same for every image.  Automatic: nominally 4096 bits - a stream
@@ -188,20 +211,18 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         return round_sub((raw_len + slots - nseg - 1) / (slots - nseg), *rl);
     };
 
-    // ---- layout (serial: prefix sums over the batch)
-    std::vector<HuffImg> himg(n);
-    std::vector<ImgDev> idev(n);
-    std::vector<TileDev> tiles;
-    std::vector<uint32_t> blk_img, wblk_img, utile_img, dcc_img;
-    std::vector<uint2> tile_ex;                      // per un-stuff tile: surviving bytes / restart markers of the image before it
+    // ---- layout (serial: prefix sums over the batch, O(images))
+    std::vector<HuffImg> &himg = b->himg;
+    std::vector<ImgDev> &idev = b->idev;
+    std::vector<QTab> qtabs;
     size_t slice_slots = 0;
     std::vector<uint32_t> luts_dc, luts_ac, luts_acs;     // acs: the synchronisation pass' grouped AC tables
     std::map<std::string, int> lut_index[2];
     std::vector<uint16_t> lut_n4[2];                // per pooled table: used size in 16-byte chunks
     size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
-    uint32_t seg_entries = 0, nblk = 0;
+    uint32_t seg_entries = 0, nblk = 0, n_utile = 0, n_wblk = 0, n_dcc = 0, n_tiles = 0;
     int prev = -1;                                  // last valid image: its table slots are reused when the tables match
-    b->pixels = 0; b->scan_bytes = 0; b->lut_smem = 0; b->multi_blk = false; b->phased = c->sync_phased != 0;
+    b->pixels = 0; b->scan_bytes_max = 0; b->lut_smem = 0; b->multi_blk = false; b->phased = c->sync_phased != 0;
     uint32_t rgb_max = 0;
     auto same_tables = [](const bj_image_desc &a, const bj_image_desc &q) {
         if (a.ncomp != q.ncomp || memcmp(a.dc_id, q.dc_id, 3) || memcmp(a.ac_id, q.ac_id, 3)) return false;
@@ -218,10 +239,8 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         memset(&hi, 0, sizeof(hi));
         memset(&idev[i], 0, sizeof(ImgDev));
         int rc = b->parse_status[i];
-        Geometry g;
-        if (rc == BJ_OK && d.scan_len >= ((size_t)1 << 31)) rc = BJ_ERR_UNSUPPORTED;   // byte counts travel in 31 bits
+        const Geometry &g = geo[i];
         if (rc == BJ_OK) {
-            g = geometry_of(d);
             if (prev >= 0 && same_tables(d, b->desc[prev])) {
                 const HuffImg &hp = himg[prev];
                 hi.ndc = hp.ndc; hi.nac = hp.nac;
@@ -266,7 +285,6 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
                     (ac ? hi.ac_n4 : hi.dc_n4)[s] = lut_n4[ac][slots[s]];
                 }
             }
-            if (rc == BJ_OK) prev = i;
             uint32_t smem = 0;
             for (int s = 0; s < hi.ndc; s++) smem += hi.dc_n4[s] * 16u;
             for (int s = 0; s < hi.nac; s++) smem += hi.ac_n4[s] * 16u;
@@ -277,29 +295,17 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         hi.seg_base = seg_entries;
         hi.blk_base = nblk;
         hi.sub_base = nblk * kHuffThreads;
-        hi.tile_base = (uint32_t)utile_img.size();
+        hi.tile_base = n_utile;
         hi.clean_word0 = (uint32_t)clean_words;
         hi.du_base = (uint32_t)coef_units;
-        hi.dcc_base = (uint32_t)dcc_img.size();
+        hi.dcc_base = n_dcc;
         if (rc != BJ_OK) { seg_entries += 2; hi.ndc = hi.nac = 0; continue; }
         fbytes += align_up(lens[i] + 16, 16);
         hi.valid = 1;
         hi.raw_off = b->file_off[i] + d.scan_off;
-        hi.raw_len = (uint32_t)d.scan_len;
-        const uint64_t a0 = hi.raw_off & ~(uint64_t)15;
-        hi.ntile = std::max<uint32_t>(1u, (uint32_t)((hi.raw_off - a0 + hi.raw_len + kUnstuffTile - 1) / kUnstuffTile));
-        {
-            const uint32_t mis = (uint32_t)(hi.raw_off - a0);
-            if (mis != scan_mis[i] || hi.ntile > tile_cap[i + 1] - tile_cap[i]) return BJ_ERR_ARG;      // (cannot happen)
-            uint32_t kept = 0, rst = 0;
-            for (uint32_t t = 0; t < hi.ntile; t++) {
-                utile_img.push_back((uint32_t)i);
-                tile_ex.push_back(make_uint2(kept, rst));
-                const uint64_t lo = std::max<uint64_t>(mis, (uint64_t)t * kScanTile), hi_ = std::min<uint64_t>((uint64_t)mis + hi.raw_len, (uint64_t)(t + 1) * kScanTile);
-                kept += (uint32_t)(hi_ > lo ? hi_ - lo : 0) - tile_dropped[tile_cap[i] + t];
-                rst += tile_rst[tile_cap[i] + t];
-            }
-        }
+        hi.raw_len = (uint32_t)d.scan_len;                                   // upper bound: up to the end of the file
+        hi.ntile = std::max<uint32_t>(1u, (uint32_t)(((hi.raw_off & 15u) + hi.raw_len + kUnstuffTile - 1) / kUnstuffTile));
+        n_utile += hi.ntile;
         hi.nmcu = g.nmcu; hi.ri = d.restart_interval;
         hi.nseg = hi.ri ? (g.nmcu + hi.ri - 1) / hi.ri : 1u;
         hi.bpm = (uint8_t)g.bpm; hi.ny = (uint8_t)(d.hs * d.vs); hi.ncomp = d.ncomp;
@@ -311,15 +317,14 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         }
         const uint32_t sub_cap = (uint32_t)((hi.raw_len + hi.sub_bytes - 1) / hi.sub_bytes) + hi.nseg;
         hi.nblk = (sub_cap + kHuffThreads - 1) / kHuffThreads;
-        for (uint32_t k = 0; k < hi.nblk; k++) blk_img.push_back((uint32_t)i);
         nblk += hi.nblk;
         if (hi.nblk > 1) b->multi_blk = true;
-        hi.wblk_base = (uint32_t)wblk_img.size();
-        for (uint32_t k = 0; k < (hi.nblk << hi.slices_log2); k++) wblk_img.push_back((uint32_t)i);
+        hi.wblk_base = n_wblk;
+        n_wblk += hi.nblk << hi.slices_log2;
         hi.slice_base = (uint32_t)slice_slots;
         slice_slots += ((size_t)hi.nblk * kHuffThreads) << hi.slices_log2;
         hi.ndcc = (g.nmcu + kDcThreads - 1) / kDcThreads;
-        for (uint32_t k = 0; k < hi.ndcc; k++) dcc_img.push_back((uint32_t)i);
+        n_dcc += hi.ndcc;
         seg_entries += hi.nseg + 1;
         clean_words += hi.raw_len / 4 + 4;
         b->du_base[i] = (uint32_t)coef_units; b->ndu[i] = g.ndu;
@@ -328,47 +333,48 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         b->out_off[i] = out_bytes;
         fill_imgdev(d, g, format, hi.du_base, out_bytes, &idev[i]);
         idev[i].dc_sep = 1;
+        idev[i].tile0 = n_tiles;
+        n_tiles += idct_tile_count(g);
+        if (prev >= 0 && same_qtab(d, b->desc[prev])) idev[i].qslot = idev[prev].qslot;
+        else { idev[i].qslot = (uint32_t)qtabs.size(); qtabs.emplace_back(); fill_qtab(d, &qtabs.back()); }
+        prev = i;
         out_bytes += align_up(b->out_size[i], 16);
-        append_tiles(g, (uint32_t)i, hi.du_base, &tiles);
         rgb_max = std::max<uint32_t>(rgb_max, std::min<uint32_t>(g.tile_mcus, g.nmx) * d.hs * 8u * d.vs * 8u * 3u);
         b->pixels += (uint64_t)d.width * d.height;
-        b->scan_bytes += d.scan_len;
-        if (coef_units > 0xFFFFFFF0ull || clean_words > 0xFFFFFFF0ull) return BJ_ERR_ARG;   // split the batch
+        b->scan_bytes_max += d.scan_len;
+        if (coef_units > 0xFFFFFFF0ull || clean_words > 0xFFFFFFF0ull || slice_slots > 0xFFFFFFF0ull) return BJ_ERR_ARG;   // split the batch
     }
     b->idct_smem = kSmemDu + kSmemQ + kRgbFront + std::min<uint32_t>(rgb_max, kRgbMax) + 64;
     b->files_bytes = b->direct_src ? (size_t)(span_hi - span_lo) : fbytes + 64; b->clean_words = clean_words + 96; b->coef_units = coef_units; b->out_bytes = out_bytes;   // (96 words of slack: a damaged unit is read to its end, up to 63 symbols of 27 bits past the data)
-    b->n_wblk = (uint32_t)wblk_img.size(); b->n_slice_slots = slice_slots;
-    if (slice_slots > 0xFFFFFFF0ull) return BJ_ERR_ARG;
-    b->n_idct_tiles = (uint32_t)tiles.size(); b->n_blk = nblk; b->n_utile = (uint32_t)utile_img.size();
-    b->n_dcc = (uint32_t)dcc_img.size(); b->n_seg_entries = seg_entries; b->n_sub_slots = nblk * kHuffThreads;
+    b->n_wblk = n_wblk; b->n_slice_slots = slice_slots;
+    b->n_idct_tiles = n_tiles; b->n_blk = nblk; b->n_utile = n_utile;
+    b->n_dcc = n_dcc; b->n_seg_entries = seg_entries; b->n_sub_slots = nblk * kHuffThreads;
 
-    // ---- descriptor blob
+    // ---- descriptor blob (host -> device): one record per image, the table pools
     size_t o = 0;
     b->o_himg = o;  o = align_up(o + (size_t)n * sizeof(HuffImg), 256);
     b->o_idev = o;  o = align_up(o + (size_t)n * sizeof(ImgDev), 256);
-    b->o_tiles = o; o = align_up(o + tiles.size() * sizeof(TileDev), 256);
-    b->o_blk = o;   o = align_up(o + blk_img.size() * 4, 256);
-    b->o_wblk = o;  o = align_up(o + wblk_img.size() * 4, 256);
-    b->o_utile = o; o = align_up(o + utile_img.size() * 4, 256);
-    b->o_tileex = o; o = align_up(o + tile_ex.size() * 8, 256);
-    b->o_dcc = o;   o = align_up(o + dcc_img.size() * 4, 256);
+    b->o_qtab = o;  o = align_up(o + qtabs.size() * sizeof(QTab), 256);
     b->o_lutdc = o; o = align_up(o + luts_dc.size() * 4, 256);
     b->o_lutac = o; o = align_up(o + luts_ac.size() * 4, 256);
     b->o_lutacs = o; o = align_up(o + luts_acs.size() * 4, 256);
     b->meta_bytes = o;
-    if (b->h_meta.reserve(o) || (!b->direct_src && b->h_files.reserve(b->files_bytes)) ||
+    // ---- map buffer (device only: k_expand_maps)
+    o = 0;
+    b->m_tiles = o; o = align_up(o + (size_t)n_tiles * sizeof(TileDev), 256);
+    b->m_blk = o;   o = align_up(o + (size_t)nblk * 4, 256);
+    b->m_wblk = o;  o = align_up(o + (size_t)n_wblk * 4, 256);
+    b->m_utile = o; o = align_up(o + (size_t)n_utile * 4, 256);
+    b->m_dcc = o;   o = align_up(o + (size_t)n_dcc * 4, 256);
+    b->maps_bytes = o;
+    if (b->h_meta.reserve(b->meta_bytes) || (!b->direct_src && b->h_files.reserve(b->files_bytes)) ||
         b->h_res.reserve(align_up((size_t)n * sizeof(HuffImgState), 64) + kMaxRounds * 4 + 64)) return BJ_ERR_NOMEM;
     if (n) { memcpy(b->hmeta<HuffImg>(b->o_himg), himg.data(), (size_t)n * sizeof(HuffImg)); memcpy(b->hmeta<ImgDev>(b->o_idev), idev.data(), (size_t)n * sizeof(ImgDev)); }
-    if (!tiles.empty()) memcpy(b->hmeta<TileDev>(b->o_tiles), tiles.data(), tiles.size() * sizeof(TileDev));
-    if (!blk_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_blk), blk_img.data(), blk_img.size() * 4);
-    if (!wblk_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_wblk), wblk_img.data(), wblk_img.size() * 4);
-    if (!utile_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_utile), utile_img.data(), utile_img.size() * 4);
-    if (!tile_ex.empty()) memcpy(b->hmeta<uint2>(b->o_tileex), tile_ex.data(), tile_ex.size() * 8);
-    if (!dcc_img.empty()) memcpy(b->hmeta<uint32_t>(b->o_dcc), dcc_img.data(), dcc_img.size() * 4);
+    if (!qtabs.empty()) memcpy(b->hmeta<QTab>(b->o_qtab), qtabs.data(), qtabs.size() * sizeof(QTab));
     if (!luts_dc.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutdc), luts_dc.data(), luts_dc.size() * 4);
     if (!luts_ac.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutac), luts_ac.data(), luts_ac.size() * 4);
     if (!luts_acs.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutacs), luts_acs.data(), luts_acs.size() * 4);
-    // ---- pack the file bytes (per image, independent: worker pool)
+    // ---- stage the file bytes (only when they cannot go up from where they are; per image, independent: worker pool)
     if (!b->direct_src) {
         uint8_t *hf = reinterpret_cast<uint8_t *>(b->h_files.p);
         c->host_pool.parallel_for(n, 16, [&](int i0, int i1) {
@@ -380,7 +386,8 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         });
     }
     // ---- device buffers
-    if (b->d_files.reserve(b->files_bytes + 4096) || b->d_meta.reserve(b->meta_bytes) || b->d_clean.reserve(b->clean_words * 4) ||
+    if (b->d_files.reserve(b->files_bytes + 4096) || b->d_meta.reserve(b->meta_bytes) || b->d_maps.reserve(b->maps_bytes + 16) ||
+        b->d_tilecnt.reserve((size_t)n_utile * 8 + 16) || b->d_tileex.reserve((size_t)n_utile * 8 + 16) || b->d_clean.reserve(b->clean_words * 4) ||
         b->d_seg.reserve((size_t)(seg_entries + 2) * 4 * 2) || b->d_subseg.reserve((size_t)b->n_sub_slots * 4 + 16) ||
         b->d_stin.reserve((size_t)b->n_sub_slots * 8 + 16) || b->d_stout.reserve((size_t)b->n_sub_slots * 8 + 16) ||
         b->d_tot.reserve((size_t)b->n_sub_slots * 4 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 8 + 16) ||
@@ -392,6 +399,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     return BJ_OK;
 }
 
+// H2D of the file bytes and the per-image records; the per-CTA maps are then expanded on the device.
 inline int batch_upload(bj_batch *b, cudaStream_t s) {
     bj_ctx *c = b->ctx;
     if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
@@ -399,6 +407,11 @@ inline int batch_upload(bj_batch *b, cudaStream_t s) {
     if (b->n == 0) { b->uploaded = true; return BJ_OK; }
     int rc = c->check(cudaMemcpyAsync(b->d_files.p, b->direct_src ? (const void *)b->direct_src : b->h_files.p, b->files_bytes, cudaMemcpyHostToDevice, s));
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(b->d_meta.p, b->h_meta.p, b->meta_bytes, cudaMemcpyHostToDevice, s));
+    if (rc == BJ_OK) {
+        k_expand_maps<<<b->n, 256, 0, s>>>(b->dmeta<HuffImg>(b->o_himg), b->dmeta<ImgDev>(b->o_idev), b->dmap<uint32_t>(b->m_utile), b->dmap<uint32_t>(b->m_blk),
+                                          b->dmap<uint32_t>(b->m_wblk), b->dmap<uint32_t>(b->m_dcc), b->dmap<TileDev>(b->m_tiles));
+        rc = c->check(cudaGetLastError());
+    }
     b->uploaded = rc == BJ_OK;
     return rc;
 }
@@ -408,10 +421,11 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     bj_ctx *c = b->ctx;
     const HuffImg *himg = b->dmeta<HuffImg>(b->o_himg);
     const ImgDev *idev = b->dmeta<ImgDev>(b->o_idev);
-    const TileDev *tiles = b->dmeta<TileDev>(b->o_tiles);
-    const uint32_t *blk_img = b->dmeta<uint32_t>(b->o_blk), *wblk_img = b->dmeta<uint32_t>(b->o_wblk);
-    const uint32_t *utile_img = b->dmeta<uint32_t>(b->o_utile);
-    const uint32_t *dcc_img = b->dmeta<uint32_t>(b->o_dcc);
+    const QTab *qtabs = b->dmeta<QTab>(b->o_qtab);
+    const TileDev *tiles = b->dmap<TileDev>(b->m_tiles);
+    const uint32_t *blk_img = b->dmap<uint32_t>(b->m_blk), *wblk_img = b->dmap<uint32_t>(b->m_wblk);
+    const uint32_t *utile_img = b->dmap<uint32_t>(b->m_utile);
+    const uint32_t *dcc_img = b->dmap<uint32_t>(b->m_dcc);
     const uint32_t *luts_dc = b->dmeta<uint32_t>(b->o_lutdc), *luts_ac = b->dmeta<uint32_t>(b->o_lutac), *luts_acs = b->dmeta<uint32_t>(b->o_lutacs);
     uint4 *slices = (uint4 *)b->d_slice.p;
     int16_t *dcp = (int16_t *)b->d_dc.p;
@@ -428,13 +442,30 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     const size_t lut_smem = b->lut_smem;
     if (r0 == 0) {
         cudaEventRecord(b->ev[0], s);
+        if (c->debug_poison) {                                                        // tests: whatever is read later must have been written by this decode
+            cudaMemsetAsync(b->d_coef.p, 0xA5, b->coef_units * 128, s);
+            cudaMemsetAsync(b->d_dc.p, 0xA5, b->coef_units * 2, s);
+            cudaMemsetAsync(b->d_out.p, 0xA5, b->out_bytes, s);
+            cudaMemsetAsync(b->d_clean.p, 0xA5, b->clean_words * 4, s);
+        }
         cudaMemsetAsync(flags, 0, kMaxRounds * 4, s);
         cudaMemsetAsync(st, 0, (size_t)n * sizeof(HuffImgState), s);                  // (rejected files keep an all-zero state)
-        if (b->n_utile) k_unstuff<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, b->dmeta<uint2>(b->o_tileex), st, clean, seg_off);
+        b->launches = 0;
+        if (b->n_utile) {
+            uint2 *tile_cnt = (uint2 *)b->d_tilecnt.p, *tile_ex = (uint2 *)b->d_tileex.p;
+            k_scan_count<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_cnt);
+            k_scan_tiles<<<n, kScanTilesThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, tile_cnt, tile_ex, st, seg_off);
+            k_unstuff<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_ex, st, clean, seg_off);
+            b->launches += 3;
+        }
         k_subseq_table<<<n, 256, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg);
-        b->launches = 1 + (b->n_utile ? 1 : 0);
+        b->launches++;
         b->sync_rounds = 0;
         cudaEventRecord(b->ev[1], s);
+    } else {
+        // the write pass ran on entry states that had not settled: what it made of the images' states does not count
+        k_reset_state<<<(n + 255) / 256, 256, 0, s>>>(st, n);
+        b->launches++;
     }
     if (b->n_blk) {
         for (int r = r0; r < r1; r++) {
@@ -461,7 +492,7 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     if (!b->n_blk) cudaEventRecord(b->ev[2], s);
     cudaEventRecord(b->ev[3], s);
     if (b->n_idct_tiles) {
-        k_idct_color<<<b->n_idct_tiles, kTileThreads, b->idct_smem, s>>>((const int16_t *)b->d_coef.p, dcp, idev, tiles, (uint8_t *)b->d_out.p);
+        k_idct_color<<<b->n_idct_tiles, kTileThreads, b->idct_smem, s>>>((const int16_t *)b->d_coef.p, dcp, idev, qtabs, tiles, (uint8_t *)b->d_out.p);
         b->launches++;
     }
     cudaEventRecord(b->ev[4], s);
@@ -493,12 +524,15 @@ inline int batch_sync(bj_batch *b) {
     cudaStream_t s = b->last_stream;
     int rc = c->check(cudaStreamSynchronize(s));
     int r = b->rounds;
-    while (rc == BJ_OK && b->n_blk && b->h_flags()[r - 1] != 0) {
+    b->redone = false;
+    while (rc == BJ_OK && b->n_blk && b->multi_blk && b->h_flags()[r - 1] != 0) {
+        b->redone = true;
         if (r + 2 > kMaxRounds) { c->last_error = "entropy stage did not converge"; return BJ_ERR_CUDA; }
         rc = batch_launch(b, s, r, r + 2);
         if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
         r += 2;
     }
+    b->rounds = r;
     if (rc == BJ_OK) {
         cudaEventElapsedTime(&b->ms_entropy, b->ev[0], b->ev[3]);
         cudaEventElapsedTime(&b->ms_unstuff, b->ev[0], b->ev[1]);
@@ -544,7 +578,11 @@ inline int batch_download(bj_batch *b, uint8_t *const *outs, cudaStream_t s) {
 
 inline int batch_image_status(const bj_batch *b, int i) {
     if (b->parse_status[i] != BJ_OK) return b->parse_status[i];
-    if (b->synced && const_cast<bj_batch *>(b)->h_state()[i].status) return BJ_ERR_CORRUPT_SCAN;
+    if (b->synced) {
+        const uint32_t st = const_cast<bj_batch *>(b)->h_state()[i].status;
+        if (st == kStatusInvalid) return BJ_ERR_INVALID_JPEG;     // the scan does not end in EOI: read_JPEG sets valid = false
+        if (st) return BJ_ERR_CORRUPT_SCAN;
+    }
     return BJ_OK;
 }
 

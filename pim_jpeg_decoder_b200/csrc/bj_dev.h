@@ -24,7 +24,13 @@ struct ImgDev {
     uint8_t  valid;
     uint8_t  dc_sep;              // 1: slot 0 of every unit is unused, the DC value comes from the DC plane (informative: the kernel is told by its dc_plane argument)
     uint8_t  pad_[1];
-    uint32_t q16[3][kQPitch];     // per component: (quantiser << 16) in ZIG-ZAG order (file order)
+    uint32_t qslot;               // this image's quantiser set in the batch's pool of QTab (deduplicated across the batch)
+    uint32_t tile0;               // index of this image's first K2/K3 tile in the batch's tile list
+};
+
+// One set of quantisation tables as the K2 kernel stages it: per component (quantiser << 16) in ZIG-ZAG (file) order.
+struct QTab {
+    uint32_t q16[3][kQPitch];
 };
 
 // One CTA of the fused dequant/IDCT/colour kernel: `nm` consecutive MCUs of MCU-row `my`, starting at `mx0`.

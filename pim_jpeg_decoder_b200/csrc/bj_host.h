@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -102,10 +103,44 @@ public:
     }
 };
 
+// Page-locked host ranges this library knows about (bj_host_alloc, bj_host_register): files that lie inside one of
+// them are uploaded straight from the caller's memory, without a staging copy.
+class PinnedRanges {
+    std::mutex m_;
+    std::vector<std::pair<uintptr_t, uintptr_t>> r_;
+public:
+    void add(const void *p, size_t bytes) { std::lock_guard<std::mutex> l(m_); r_.emplace_back((uintptr_t)p, (uintptr_t)p + bytes); }
+    void remove(const void *p) {
+        std::lock_guard<std::mutex> l(m_);
+        for (size_t i = 0; i < r_.size(); i++) if (r_[i].first == (uintptr_t)p) { r_[i] = r_.back(); r_.pop_back(); return; }
+    }
+    bool contains(uintptr_t lo, uintptr_t hi) {
+        std::lock_guard<std::mutex> l(m_);
+        for (auto &r : r_) if (lo >= r.first && hi <= r.second) return true;
+        return false;
+    }
+};
+inline PinnedRanges &pinned_ranges() { static PinnedRanges r; return r; }
+
 constexpr int kSlots = 3;             // sub-batches in flight inside bj_decode_batch
 
 enum { POOL_COMPAT_MD = 0, POOL_COMPAT_MCUS, POOL_COEF, POOL_OUT, POOL_IMGS, POOL_TILES, POOL_COUNT };
 
+}  // namespace bj
+
+struct bj_job;
+
+namespace bj {
+// The thread behind bj_submit / bj_wait: runs the submitted batches one after the other (b200jpeg.cu).
+struct AsyncWorker {
+    std::mutex m;
+    std::condition_variable cv, done_cv;
+    std::deque<bj_job *> q;              // front = the job that is running
+    bool stop = false;
+    std::thread th;
+    void run();
+    bool pending() { std::lock_guard<std::mutex> l(m); return !q.empty(); }
+};
 }  // namespace bj
 
 struct bj_ctx {
@@ -117,13 +152,20 @@ struct bj_ctx {
     size_t sub_batch_bytes = 0;          // 0 = default
     int sub_batch_ramp = 1;              // the first two sub-batches of a call are smaller (the copy-out starts earlier)
     int packed_outputs = 0;              // see batch_download_async
-    int packed_inputs = 0;               // see batch_assign: upload straight from the caller's pinned memory
+    int packed_inputs = 0;               // see batch_assign: 0 = upload straight from the caller's memory when it is known to be page-locked
+                                         // (bj_host_alloc / bj_host_register), 1 = the caller says it is, -1 = always stage
+    int debug_poison = 0;                // fill coefficient / DC / output buffers with 0xA5 before every decode (tests: every byte must be written)
+    size_t max_image_pixels = (size_t)1 << 28;   // larger images are refused (BJ_ERR_UNSUPPORTED), like the reference's "Too high resolution"
+    size_t sub_batch_out_bytes = (size_t)1 << 30; // decoded bytes per sub-batch of bj_decode_batch
     int sync_rounds = 0;                 // 0 = default (3 launches of the fix-up kernel before the first check)
     struct bj_batch *slots[bj::kSlots] = {};          // sub-batches of bj_decode_batch in flight (one stream each)
     bj::HostPool host_pool;
     int host_threads = 0;                // 0 = default: min(4, hardware threads / 2)
-    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double stats[16] = {};
     cudaStream_t streams[bj::kSlots] = {};
+    cudaEvent_t ev_exec[2] = {nullptr, nullptr};      // bj_exec_mcus: around the kernel ("DPU execution" profile line)
+    std::vector<bj_ctx *> children;      // bj_create_multi: one single-device context per GPU; this one only deals the work
+    bj::AsyncWorker *async = nullptr;    // bj_submit / bj_wait
     bj::DevBuf pool[bj::POOL_COUNT];
     std::string last_error;
     float last_exec_ms = 0.f;
@@ -176,6 +218,11 @@ inline void fill_imgdev(const bj_image_desc &d, const Geometry &g, int format, u
         im->row_dir = 1;
         im->bgr = 0;
     }
+}
+
+// The image's quantiser set as the K2 kernel stages it.
+inline void fill_qtab(const bj_image_desc &d, QTab *q) {
+    memset(q, 0, sizeof(*q));
     // The reference forwards quantisation tables to the DPUs only up to the first unset table id
     // (src/decoder_host.cpp:173-178): a table behind a gap reads as zeros.
     bool reachable[4];
@@ -183,8 +230,28 @@ inline void fill_imgdev(const bj_image_desc &d, const Geometry &g, int format, u
     for (int t = 0; t < 4; t++) { ok = ok && d.qt_set[t]; reachable[t] = ok; }
     for (int j = 0; j < 3; j++)
         for (int k = 0; k < 64; k++)
-            im->q16[j][k] = (j < d.ncomp && reachable[d.qt_id[j] & 3]) ? ((uint32_t)d.qt_zz[d.qt_id[j] & 3][k] << 16) : 0u;
+            q->q16[j][k] = (j < d.ncomp && reachable[d.qt_id[j] & 3]) ? ((uint32_t)d.qt_zz[d.qt_id[j] & 3][k] << 16) : 0u;
 }
+// Same quantiser set?  (what fill_qtab reads of the two descriptors)
+inline bool same_qtab(const bj_image_desc &a, const bj_image_desc &b) {
+    return a.ncomp == b.ncomp && !memcmp(a.qt_id, b.qt_id, 3) && !memcmp(a.qt_set, b.qt_set, 4) && !memcmp(a.qt_zz, b.qt_zz, sizeof(a.qt_zz));
+}
+
+// Descriptors that do not come from parse_header (bj_stage_idct_color, bj_decode_batch_desc) are checked before they
+// reach a kernel: the tile and shared-memory sizes assume what the reference's parser enforces
+// (src/jpeg_scanner.cpp:187-285: 1..3 components, luma sampling 1 or 2, chroma 1x1, table ids below 4).
+inline bool desc_is_sane(const bj_image_desc &d) {
+    if (d.width == 0 || d.height == 0 || d.width > 65535u || d.height > 65535u) return false;
+    if (d.ncomp < 1 || d.ncomp > 3) return false;
+    if ((d.hs != 1 && d.hs != 2) || (d.vs != 1 && d.vs != 2)) return false;
+    if (d.comp_h[0] != d.hs || d.comp_v[0] != d.vs) return false;
+    for (int j = 1; j < d.ncomp; j++) if (d.comp_h[j] != 1 || d.comp_v[j] != 1) return false;
+    for (int j = 0; j < d.ncomp; j++) if (d.qt_id[j] > 3 || d.dc_id[j] > 3 || d.ac_id[j] > 3) return false;
+    if (d.mcu_w != (d.width + 7) / 8 || d.mcu_h != (d.height + 7) / 8) return false;
+    return true;
+}
+
+inline uint32_t idct_tile_count(const Geometry &g) { return g.nmy * ((g.nmx + g.tile_mcus - 1) / g.tile_mcus); }
 
 inline void append_tiles(const Geometry &g, uint32_t img, uint32_t du_base, std::vector<TileDev> *tiles) {
     for (uint32_t my = 0; my < g.nmy; my++)

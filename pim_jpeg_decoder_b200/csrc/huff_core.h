@@ -244,6 +244,56 @@ BJ_HD void classify_words(const uint32_t w[6], uint32_t &keep, uint32_t &rst) {
     }
 }
 
+// Where the entropy-coded segment ends (src/jpeg_scanner.cpp:405-433): at the first FF that is followed by something
+// other than 00 (stuffing), FF (a fill byte) or RSTn.  EOI (D9) there is the regular end; any other marker makes the
+// file invalid ("Invalid marker during compressed data scan").
+BJ_HD bool scan_is_end(unsigned b, unsigned next) { return b == 0xFFu && next != 0x00u && next != 0xFFu && !(next >= 0xD0u && next <= 0xD7u); }
+// The counting pass of K0 (which finds that FF on the device, so that the host never walks the scan): the same on 16
+// bytes at once, plus  end: bit i = byte i is such an FF.
+BJ_HD void classify_words_end(const uint32_t w[6], uint32_t &keep, uint32_t &rst, uint32_t &end) {
+    keep = 0; rst = 0; end = 0;
+    uint32_t Fprev = flag_ff(w[0]);
+    uint32_t F = flag_ff(w[1]), Z = flag_00(w[1]), R = flag_00((w[1] ^ 0xD0D0D0D0u) & 0xF8F8F8F8u);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++) {
+        const uint32_t xn = w[k + 2];
+        const uint32_t Fn = flag_ff(xn), Zn = flag_00(xn), Rn = flag_00((xn ^ 0xD0D0D0D0u) & 0xF8F8F8F8u);
+        const uint32_t PF = (F << 8) | (Fprev >> 24);                      // flag of byte i-1 under byte i
+        const uint32_t ZN = (Z >> 8) | (Zn << 24);                         // flags of byte i+1 under byte i
+        const uint32_t FN = (F >> 8) | (Fn << 24);
+        const uint32_t RN = (R >> 8) | (Rn << 24);
+        const uint32_t km = (F & ZN) | (~(F | PF) & 0x80808080u);          // scan_keep
+        const uint32_t rm = PF & R;                                        // scan_is_rst
+        const uint32_t em = F & ~(ZN | FN | RN);                           // scan_is_end
+        keep |= movemask4(km) << (4 * k);
+        rst |= movemask4(rm) << (4 * k);
+        end |= movemask4(em) << (4 * k);
+        Fprev = F; F = Fn; Z = Zn; R = Rn;
+    }
+}
+
+// A 16-byte chunk whose first byte has scan-relative index r0 (negative in front of the scan), clipped to the scan
+// [0, raw_len): bytes outside do not count, and the FF that ends the scan must have its marker code inside, too.
+BJ_HD void clip_chunk(int64_t r0, uint32_t raw_len, uint32_t &keep, uint32_t &rst, uint32_t &end) {
+    const int64_t lo64 = -r0, hi64 = (int64_t)raw_len - r0;
+    const uint32_t lo = lo64 <= 0 ? 0u : (lo64 >= 16 ? 16u : (uint32_t)lo64);
+    const uint32_t hi = hi64 <= 0 ? 0u : (hi64 >= 16 ? 16u : (uint32_t)hi64);
+    const uint32_t valid = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+    keep &= valid; rst &= valid;
+    end &= valid & (hi64 > 16 ? 0xFFFFu : (valid >> 1));
+}
+// The bytes of that chunk in front of scan-relative position e (the scan's end; kNoScanEnd: all of them).
+constexpr uint32_t kNoScanEnd = 0xFFFFFFFFu;
+BJ_HD uint32_t chunk_mask_before(int64_t r0, uint32_t e) {
+    const int64_t lim = e == kNoScanEnd ? 16 : (int64_t)e - r0;
+    return lim >= 16 ? 0xFFFFu : (lim <= 0 ? 0u : ((1u << (uint32_t)lim) - 1u));
+}
+// The tile (of tile_bytes raw bytes, aligned in the file buffer) that holds scan-relative position e, for a scan whose
+// first byte sits `mis` bytes into its first tile.
+BJ_HD uint32_t tile_of_pos(uint32_t mis, uint32_t e, uint32_t tile_bytes) { return (uint32_t)(((uint64_t)mis + e) / tile_bytes); }
+
 // ------------------------------------------------------------------------------------------------ bit reader
 // The un-stuffed stream is stored as 32-bit words whose most significant byte is the earliest byte (the
 // un-stuff kernel writes byte o to address o ^ 3), so a window is two aligned words and one funnel shift.

@@ -1,8 +1,11 @@
 // K0/K1: entropy stage on sm_100a.  Replaces the host-side, single-threaded, bit-serial Huffman decode of the
 // reference (src/jpeg_scanner.cpp:405-520, 707-756) with data-parallel kernels:
 //
-//   k_unstuff                                             (K0)  raw scan bytes -> un-stuffed big-endian words,
-//                                                          restart-segment byte offsets; one pass (tile offsets from the host's scan walk)
+//   k_scan_count, k_scan_tiles, k_unstuff                 (K0)  raw scan bytes -> un-stuffed big-endian words,
+//                                                          restart-segment byte offsets, and WHERE THE SCAN ENDS: count per
+//                                                          tile -> per-image scan over the tiles -> compact.  The host reads
+//                                                          only the file headers; it never walks the entropy-coded bytes
+//   k_expand_maps                                               CTA -> image maps and the K2/K3 tile list, from per-image records
 //   k_subseq_table                                        (K0d) per image: split every segment into sub-sequences
 //   k_huff_sync                                           (K1b) speculative decode of every sub-sequence + fix-up
 //                                                          to the fixed point inside a CTA (state only, several
@@ -24,12 +27,12 @@ namespace bj {
 constexpr int kHuffThreads = 256;          // sub-sequences per CTA
 constexpr int kUnstuffThreads = 256;
 constexpr int kUnstuffTile = kUnstuffThreads * 16;   // raw bytes per CTA of K0
-static_assert(kUnstuffTile == (int)kScanTile, "the host counts dropped bytes per tile of this size (parse.h)");
 
 // Per image, written by the host.
 struct HuffImg {
     uint64_t raw_off;        // offset of the first scan byte in the batch's file buffer
-    uint32_t raw_len;        // raw scan bytes (stuffed, with RSTn)
+    uint32_t raw_len;        // UPPER BOUND of the raw scan bytes: everything from the first scan byte to the end of the file
+                             // (the scan's true length is found on the device: HuffImgState::raw_len)
     uint32_t clean_word0;    // first word of this image's un-stuffed stream
     uint32_t tile_base, ntile;
     uint32_t seg_base;       // index into seg_off / seg_sub0 (nseg + 1 entries each)
@@ -55,12 +58,18 @@ struct HuffImg {
 struct HuffImgState {
     uint32_t clean_len;      // un-stuffed bytes
     uint32_t nrst;           // RSTn markers found
-    uint32_t nseg;           // segments actually decoded: min(nrst + 1, expected)
+    uint32_t nseg;           // segments actually decoded: min(nrst + 1, expected); 0 for a file whose scan does not end in EOI
     uint32_t nsub;           // sub-sequences
     uint32_t first_zero;     // first unit (image-local) the reference never reached; >= ndu if none
-    uint32_t status;         // 0 ok, 1 corrupt entropy-coded data
+    uint32_t status;         // 0 ok, 1 corrupt entropy-coded data, 2 invalid file (kStatusInvalid)
+    uint32_t raw_len;        // raw scan bytes (stuffed, with RSTn) up to the FF that ends the scan
+    uint32_t end_code;       // the byte after that FF (D9 = EOI: the only valid one); 0x100: the file ended first
+    uint32_t first_zero0, status0;   // first_zero / status as K0 left them: the write pass updates the two above, and a
+                                     // re-launch of the write pass (batch.h: batch_sync) starts from these again
     uint32_t pad_[2];
 };
+constexpr uint32_t kStatusInvalid = 2u;    // read_JPEG's scan-byte loop would set valid = false (src/jpeg_scanner.cpp:405-433)
+constexpr uint32_t kNoEnd = kNoScanEnd;
 
 struct BlkAgg {              // units started in one CTA since its last segment head (or since its start)
     uint32_t n, has_head;
@@ -101,30 +110,111 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------ K0: un-stuff
-// One thread classifies 16 raw bytes (aligned 16-byte chunk of the file buffer), branch-free and four bytes at a
-// time (per-byte compare masks on 32-bit words).  keep: bit i = byte i survives; rst: bit i = byte i is the code
-// byte of an RSTn marker.  The byte before the scan is the SOS header's Ah/Al byte (0 in a baseline file) and the
-// byte after it is the FF of the marker that ends the scan (parse.h: find_scan_end), so the rules "the first byte
-// has no FF before it" and "what follows the last byte is a marker" hold without special cases.
-__device__ __forceinline__ void classify16(const uint8_t *__restrict__ files, const HuffImg &im, uint32_t tile, uint32_t &keep,
-                                           uint32_t &rst, uint4 &bytes) {
+// Three small kernels, all over aligned tiles of kUnstuffTile raw bytes (one thread = one aligned 16-byte chunk of the
+// file buffer = one 128-bit load, classified branch-free four bytes per 32-bit word):
+//   k_scan_count   per tile: where the scan ends if it ends inside the tile (the first FF followed by something other
+//                  than 00 / FF / RSTn, src/jpeg_scanner.cpp:405-433), and how many bytes survive / how many RSTn
+//                  markers lie before that point
+//   k_scan_tiles   per image: scan over its tiles -> every tile's output position, the image's totals, the scan's true
+//                  length and whether it ends in EOI (a file the reference rejects is flagged here: kStatusInvalid)
+//   k_unstuff      per tile: compact the surviving bytes in shared memory, store them as big-endian words
+// The host passes only an upper bound of the scan (first scan byte .. end of file): it never touches the
+// entropy-coded bytes.  The byte before the scan is the SOS header's Ah/Al byte (0 in a baseline file), so the rule
+// "the first byte has no FF before it" holds without a special case.
+struct Chunk16 {
+    uint4 bytes;
+    uint32_t keep, rst, end;   // bit i = byte i survives / is the code byte of an RSTn marker / is the FF that ends the scan
+    int64_t r0;                // scan-relative index of byte 0 (may be < 0)
+};
+
+template <bool WITH_END>
+__device__ __forceinline__ Chunk16 classify16(const uint8_t *__restrict__ files, const HuffImg &im, uint32_t tile, uint32_t raw_len) {
+    Chunk16 c;
     const uint64_t a0 = (im.raw_off & ~(uint64_t)15) + (uint64_t)tile * kUnstuffTile + (uint64_t)threadIdx.x * 16;
-    const int64_t r0 = (int64_t)a0 - (int64_t)im.raw_off;                  // scan-relative index of byte 0 (may be < 0)
-    const bool live = r0 < (int64_t)im.raw_len && r0 + 16 > 0;
-    bytes = live ? __ldg(reinterpret_cast<const uint4 *>(files + a0)) : make_uint4(0, 0, 0, 0);
+    c.r0 = (int64_t)a0 - (int64_t)im.raw_off;
+    const bool live = c.r0 < (int64_t)raw_len && c.r0 + 16 > 0;
+    c.bytes = live ? __ldg(reinterpret_cast<const uint4 *>(files + a0)) : make_uint4(0, 0, 0, 0);
     // neighbours' edge bytes: from the adjacent lanes, from memory at the warp's edges
     const int lane = threadIdx.x & 31;
-    uint32_t prevw = __shfl_up_sync(0xFFFFFFFFu, bytes.w, 1), nextw = __shfl_down_sync(0xFFFFFFFFu, bytes.x, 1);
+    uint32_t prevw = __shfl_up_sync(0xFFFFFFFFu, c.bytes.w, 1), nextw = __shfl_down_sync(0xFFFFFFFFu, c.bytes.x, 1);
     if (lane == 0) prevw = (live && a0 > 0) ? ((uint32_t)__ldg(files + a0 - 1) << 24) : 0u;
     if (lane == 31) nextw = live ? (uint32_t)__ldg(files + a0 + 16) : 0u;
-    const uint32_t w[6] = {prevw, bytes.x, bytes.y, bytes.z, bytes.w, nextw};
-    classify_words(w, keep, rst);
-    // bytes outside the scan do not count
-    const int64_t lo64 = -r0, hi64 = (int64_t)im.raw_len - r0;
-    const uint32_t lo = lo64 <= 0 ? 0u : (lo64 >= 16 ? 16u : (uint32_t)lo64);
-    const uint32_t hi = hi64 <= 0 ? 0u : (hi64 >= 16 ? 16u : (uint32_t)hi64);
-    const uint32_t valid = live ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
-    keep &= valid; rst &= valid;
+    const uint32_t w[6] = {prevw, c.bytes.x, c.bytes.y, c.bytes.z, c.bytes.w, nextw};
+    if (WITH_END) classify_words_end(w, c.keep, c.rst, c.end);
+    else { classify_words(w, c.keep, c.rst); c.end = 0u; }
+    clip_chunk(c.r0, raw_len, c.keep, c.rst, c.end);                       // bytes outside [0, raw_len) do not count
+    return c;
+}
+
+// Per tile: x = surviving bytes | RSTn markers << 16 (both counted only in front of the scan's end), y = scan-relative
+// position of the FF that ends the scan if it lies in this tile, else kNoEnd.
+__global__ void __launch_bounds__(kUnstuffThreads)
+k_scan_count(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img, uint2 *__restrict__ tile_cnt) {
+    __shared__ uint32_t s_end, s_cnt;
+    const uint32_t img = tile_img[blockIdx.x];
+    const HuffImg &im = imgs[img];
+    if (threadIdx.x == 0) { s_end = kNoEnd; s_cnt = 0u; }
+    const Chunk16 c = classify16<true>(files, im, blockIdx.x - im.tile_base, im.raw_len);
+    __syncthreads();
+    if (c.end) atomicMin(&s_end, (uint32_t)(c.r0 + (__ffs(c.end) - 1)));
+    __syncthreads();
+    const uint32_t e = s_end;
+    const uint32_t m = chunk_mask_before(c.r0, e);                         // bytes of this chunk in front of the end
+    uint32_t v = __popc(c.keep & m) | (__popc(c.rst & m) << 16);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt, v);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = make_uint2(s_cnt, e);
+}
+
+// One CTA per image: exclusive scan of the per-tile counts up to the tile in which the scan ends -> tile_ex (surviving
+// bytes / RSTn markers of the image in front of each tile); then the image's state.
+constexpr int kScanTilesThreads = 1024;
+__global__ void __launch_bounds__(kScanTilesThreads)
+k_scan_tiles(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint2 *__restrict__ tile_cnt, uint2 *__restrict__ tile_ex,
+             HuffImgState *__restrict__ st, uint32_t *__restrict__ seg_off) {
+    __shared__ uint32_t s_tmp[2 * (kScanTilesThreads / 32) + 2];
+    __shared__ uint32_t s_end;
+    const uint32_t img = blockIdx.x;
+    const HuffImg &im = imgs[img];
+    if (!im.valid) return;                                                 // (rejected by the header parse: the state stays zero)
+    if (threadIdx.x == 0) s_end = kNoEnd;
+    __syncthreads();
+    uint32_t carry_k = 0, carry_r = 0, e = kNoEnd;
+    for (uint32_t t0 = 0; t0 < im.ntile; t0 += kScanTilesThreads) {
+        const uint32_t t = t0 + threadIdx.x;
+        uint2 c = make_uint2(0u, kNoEnd);
+        if (t < im.ntile) c = tile_cnt[im.tile_base + t];
+        if (c.y != kNoEnd) atomicMin(&s_end, c.y);
+        __syncthreads();
+        e = s_end;
+        // tiles behind the one that holds the end do not count (and are never compacted)
+        const uint32_t last = e == kNoEnd ? 0xFFFFFFFFu : tile_of_pos((uint32_t)(im.raw_off & 15u), e, kUnstuffTile);
+        const bool in = t < im.ntile && t <= last;
+        uint32_t ek, er, tk, tr;
+        block_excl_scan2<kScanTilesThreads>(in ? (c.x & 0xFFFFu) : 0u, in ? (c.x >> 16) : 0u, ek, er, tk, tr, s_tmp);
+        if (in) tile_ex[im.tile_base + t] = make_uint2(carry_k + ek, carry_r + er);
+        carry_k += tk; carry_r += tr;
+        if (e != kNoEnd) break;
+    }
+    if (threadIdx.x == 0) {
+        HuffImgState s;
+        s.raw_len = e == kNoEnd ? im.raw_len : e;
+        s.end_code = e == kNoEnd ? 0x100u : (uint32_t)__ldg(files + im.raw_off + e + 1);
+        const bool invalid = s.end_code != 0xD9u;                          // "File ended prematurely" / "Invalid marker during compressed data scan"
+        s.clean_len = carry_k; s.nrst = carry_r;
+        s.nseg = invalid ? 0u : min(carry_r + 1u, im.nseg);
+        s.nsub = 0;
+        // segments whose marker is missing are never decoded: everything from their first unit on reads as zero
+        s.first_zero = invalid ? 0u : ((s.nseg < im.nseg) ? s.nseg * im.ri * im.bpm : 0xFFFFFFFFu);
+        s.status = invalid ? kStatusInvalid : ((im.ri != 0 && carry_r + 1u != im.nseg) ? 1u : 0u);
+        s.first_zero0 = s.first_zero; s.status0 = s.status;
+        s.pad_[0] = s.pad_[1] = 0;
+        st[img] = s;
+        seg_off[im.seg_base] = 0;
+        if (!invalid) seg_off[im.seg_base + s.nseg] = carry_k;
+    }
 }
 
 // exclusive scan over the CTA of a packed pair of counters (low 16 bits / high 16 bits; totals stay below 2^16)
@@ -145,43 +235,30 @@ __device__ __forceinline__ uint32_t block_excl_scan_packed(uint32_t v, uint32_t 
     return inc - v + s_tmp[warp];
 }
 
-// One pass: classify, count, compact the surviving bytes in shared memory and store them as coalesced 32-bit words,
-// byte-swapped so that stream byte o lands at address o ^ 3 (huff_core.h "bit reader").  Where the tile's bytes go
-// (surviving bytes and restart markers of the image before this tile) comes from the host: its walk over the scan
-// visits every FF anyway and counts per tile what will be dropped (parse.h: ScanTiles) - so there is no counting
-// pass and no chaining between CTAs.  A tile's output starts at an arbitrary byte, so the (at most two) words it
-// shares with its neighbours are written bytewise.  The image's last tile also writes the image's state.
+// Compaction: classify again, scan inside the tile, compact the surviving bytes in shared memory and store them as
+// coalesced 32-bit words, byte-swapped so that stream byte o lands at address o ^ 3 (huff_core.h "bit reader").  Where
+// the tile's bytes go comes from k_scan_tiles, so there is no chaining between CTAs.  A tile's output starts at an
+// arbitrary byte, so the (at most two) words it shares with its neighbours are written bytewise.
 __global__ void __launch_bounds__(kUnstuffThreads)
 k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img,
-          const uint2 *__restrict__ tile_ex, HuffImgState *__restrict__ st, uint32_t *__restrict__ clean, uint32_t *__restrict__ seg_off) {
+          const uint2 *__restrict__ tile_ex, const HuffImgState *__restrict__ st, uint32_t *__restrict__ clean, uint32_t *__restrict__ seg_off) {
     __shared__ uint32_t s_tmp[kUnstuffThreads / 32 + 1];
     __shared__ __align__(16) uint8_t s_out[kUnstuffTile + 16];
     const uint32_t img = tile_img[blockIdx.x];
     const HuffImg &im = imgs[img];
+    const uint32_t tile = blockIdx.x - im.tile_base;
+    const uint32_t raw_len = st[img].raw_len;
+    if (st[img].status == kStatusInvalid) return;
+    if ((int64_t)tile * kUnstuffTile - (int64_t)(im.raw_off & 15u) >= (int64_t)raw_len) return;   // the scan ended in front of this tile
     const uint2 base = __ldg(tile_ex + blockIdx.x);
-    uint32_t keep, rst;
-    uint4 bytes;
-    classify16(files, im, blockIdx.x - im.tile_base, keep, rst, bytes);
+    const Chunk16 c = classify16<false>(files, im, tile, raw_len);
+    const uint32_t keep = c.keep, rst = c.rst;
     uint32_t tot;
     const uint32_t ex = block_excl_scan_packed<kUnstuffThreads>(__popc(keep) | (__popc(rst) << 16), tot, s_tmp);
-    const uint32_t ea = ex & 0xFFFFu, eb = ex >> 16, ta = tot & 0xFFFFu, tb = tot >> 16;
-    if (threadIdx.x == 0 && blockIdx.x - im.tile_base + 1 == im.ntile) {   // the image's totals
-        const uint32_t ca = base.x + ta, cb = base.y + tb;
-        HuffImgState s;
-        s.clean_len = ca; s.nrst = cb;
-        s.nseg = min(cb + 1u, im.nseg);
-        s.nsub = 0;
-        // segments whose marker is missing are never decoded: everything from their first unit on reads as zero
-        s.first_zero = (s.nseg < im.nseg) ? s.nseg * im.ri * im.bpm : 0xFFFFFFFFu;
-        s.status = (im.ri != 0 && cb + 1u != im.nseg) ? 1u : 0u;
-        s.pad_[0] = s.pad_[1] = 0;
-        st[img] = s;
-        seg_off[im.seg_base] = 0;
-        seg_off[im.seg_base + s.nseg] = ca;
-    }
+    const uint32_t ea = ex & 0xFFFFu, eb = ex >> 16, ta = tot & 0xFFFFu;
     const uint32_t mis = base.x & 3u;                 // s_out[mis + k] = k-th surviving byte of the tile
     {
-        const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
+        const uint32_t w[4] = {c.bytes.x, c.bytes.y, c.bytes.z, c.bytes.w};
         uint32_t pos = mis + ea;
 #pragma unroll
         for (int i = 0; i < 16; i++) {
@@ -213,6 +290,39 @@ k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, c
                 if (4 * k + b >= mis && 4 * k + b < end) db[b ^ 3u] = (uint8_t)(v >> (8 * b));
         }
     }
+}
+
+// CTA -> image maps of the kernels above and below and the tile list of the K2/K3 kernel, expanded on the device from
+// the per-image records (the host's layout pass is O(images), not O(CTAs)).  One CTA per image; runs once per layout
+// (with the upload), not once per decode.
+__global__ void __launch_bounds__(256)
+k_expand_maps(const HuffImg *__restrict__ imgs, const ImgDev *__restrict__ idev, uint32_t *__restrict__ tile_img, uint32_t *__restrict__ blk_img,
+              uint32_t *__restrict__ wblk_img, uint32_t *__restrict__ dcc_img, TileDev *__restrict__ tiles) {
+    const uint32_t img = blockIdx.x;
+    const HuffImg &im = imgs[img];
+    if (!im.valid) return;
+    for (uint32_t k = threadIdx.x; k < im.ntile; k += blockDim.x) tile_img[im.tile_base + k] = img;
+    for (uint32_t k = threadIdx.x; k < im.nblk; k += blockDim.x) blk_img[im.blk_base + k] = img;
+    for (uint32_t k = threadIdx.x; k < (im.nblk << im.slices_log2); k += blockDim.x) wblk_img[im.wblk_base + k] = img;
+    for (uint32_t k = threadIdx.x; k < im.ndcc; k += blockDim.x) dcc_img[im.dcc_base + k] = img;
+    const ImgDev &id = idev[img];
+    const uint32_t tile_mcus = kTileThreads / id.bpm, per_row = (id.nmx + tile_mcus - 1) / tile_mcus;
+    for (uint32_t q = threadIdx.x; q < id.nmy * per_row; q += blockDim.x) {
+        const uint32_t my = q / per_row, mx = (q - my * per_row) * tile_mcus;
+        TileDev t;
+        t.img = img; t.my = (uint16_t)my; t.mx0 = (uint16_t)mx;
+        t.nm = (uint16_t)min(tile_mcus, id.nmx - mx);
+        t.ndu = (uint16_t)(t.nm * id.bpm);
+        t.du0 = id.du_base + (my * id.nmx + mx) * id.bpm;
+        tiles[id.tile0 + q] = t;
+    }
+}
+
+// A re-launch of the write pass (the fix-up had not converged when it first ran: batch.h, batch_sync) starts from the
+// state K0 left, not from what the write pass made of it on unsettled entry states.
+__global__ void k_reset_state(HuffImgState *__restrict__ st, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { st[i].first_zero = st[i].first_zero0; st[i].status = st[i].status0; }
 }
 
 // ------------------------------------------------------------------------------------------------ K0d: sub-sequences

@@ -50,7 +50,7 @@ __device__ __forceinline__ void color8(const uint4 &yv, const unsigned *fw, cons
 // ------------------------------------------------------------------------------------------------ fast layout
 __global__ void __launch_bounds__(kTileThreads, 4)
 k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_plane, const ImgDev *__restrict__ imgs,
-             const TileDev *__restrict__ tiles, uint8_t *__restrict__ out) {
+             const QTab *__restrict__ qtabs, const TileDev *__restrict__ tiles, uint8_t *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint4 *s_du = reinterpret_cast<uint4 *>(smem);
     uint32_t *s_q = reinterpret_cast<uint32_t *>(smem + kSmemDu);
@@ -90,7 +90,10 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
     const ImgDev *__restrict__ im = imgs + t.img;
     const int hs = im->hs, vs = im->vs, ncomp = im->ncomp, bpm = im->bpm;
     const int nm = t.nm;
-    for (int i = tid; i < 3 * kQPitch; i += kTileThreads) s_q[i] = (&im->q16[0][0])[i];
+    {
+        const uint32_t *__restrict__ q = &qtabs[im->qslot].q16[0][0];
+        for (int i = tid; i < 3 * kQPitch; i += kTileThreads) s_q[i] = __ldg(q + i);
+    }
     __syncthreads();
 
     // ---- stage 1: one thread = one unit: de-zigzag (with the reference's 48/52 quirk), dequantise, IDCT

@@ -136,24 +136,11 @@ inline void skip_segment(Cursor &c) {
     if (length >= 2) { const size_t adv = length - 2; if (c.i + adv > c.n) { c.i = c.n; c.eof = true; } else c.i += adv; }
 }
 
-// Per-tile byte counts of a scan, for the un-stuff kernel (K0): that kernel cuts the file buffer into aligned
-// tiles of kScanTile bytes and has to know where each tile's surviving bytes go.  The walk below visits every FF
-// of the scan anyway, so it counts, per tile, the bytes the scan-byte rules drop (the 00 after a stuffed FF, both
-// bytes of an RSTn marker, fill FFs) and the RSTn markers: the kernel then needs no pass of its own to find out.
-constexpr uint32_t kScanTile = 4096;
-struct ScanTiles {
-    uint32_t *dropped = nullptr;  // per tile: bytes of the scan that do not survive
-    uint32_t *rst = nullptr;      // per tile: RSTn markers (counted where their code byte sits)
-    uint32_t ntile = 0;           // capacity
-    uint32_t mis = 0;             // position of the first scan byte inside tile 0
-    void drop(size_t scan_index) { const size_t t = (scan_index + mis) / kScanTile; if (t < ntile) dropped[t]++; }
-    void marker(size_t scan_index) { const size_t t = (scan_index + mis) / kScanTile; if (t < ntile) rst[t]++; }
-};
-
 // Locate the end of the entropy-coded segment (src/jpeg_scanner.cpp:405-433): the first FF that is followed by
 // something other than 00 / RSTn / FF.  EOI ends the scan; anything else makes the file invalid.
-// memchr keeps this at memory speed; FF bytes are ~0.5% of a scan.
-inline int find_scan_end(const uint8_t *p, size_t n, size_t start, size_t *end, ScanTiles *tiles = nullptr) {
+// Only bj_parse_header (the public, stand-alone restatement of read_JPEG) walks the scan like this; the decode path
+// leaves it to the GPU (kernels_huff.cuh: k_scan_count / k_scan_tiles apply the same rule).
+inline int find_scan_end(const uint8_t *p, size_t n, size_t start, size_t *end) {
     size_t i = start;
     for (;;) {
         if (i >= n) return BJ_ERR_INVALID_JPEG;                           // "File ended prematurely"
@@ -163,16 +150,16 @@ inline int find_scan_end(const uint8_t *p, size_t n, size_t start, size_t *end, 
         if (i + 1 >= n) return BJ_ERR_INVALID_JPEG;
         const unsigned m = p[i + 1];
         if (m == 0xD9) { *end = i; return BJ_OK; }
-        if (m == 0x00) { if (tiles) tiles->drop(i + 1 - start); i += 2; continue; }
-        if (m >= 0xD0 && m <= 0xD7) { if (tiles) { tiles->drop(i - start); tiles->drop(i + 1 - start); tiles->marker(i + 1 - start); } i += 2; continue; }
-        if (m == 0xFF) { if (tiles) tiles->drop(i - start); i += 1; continue; }
+        if (m == 0x00) { i += 2; continue; }
+        if (m >= 0xD0 && m <= 0xD7) { i += 2; continue; }
+        if (m == 0xFF) { i += 1; continue; }
         return BJ_ERR_INVALID_JPEG;                                       // "Invalid marker during compressed data scan"
     }
 }
 
-// tiles (optional): filled for the scan; tiles->mis must hold the misalignment of the FILE's first byte in the device
-// buffer (mod 16) on entry and holds that of the scan's first byte inside its first tile on return.
-inline int parse_header(const uint8_t *file, size_t len, bj_image_desc *out, ScanTiles *tiles = nullptr) {
+// walk_scan = false (the decode path): only the headers are read (a few hundred bytes); scan_len is then an UPPER
+// BOUND - everything up to the end of the file - and whether the scan ends properly is decided on the device.
+inline int parse_header(const uint8_t *file, size_t len, bj_image_desc *out, bool walk_scan = true) {
     bj_image_desc &d = *out;
     memset(&d, 0, sizeof(d));
     d.hs = d.vs = 1;
@@ -198,11 +185,15 @@ inline int parse_header(const uint8_t *file, size_t len, bj_image_desc *out, Sca
     }
     if (!st.valid || !sos || c.eof) return BJ_ERR_INVALID_JPEG;
     d.scan_off = c.i;
-    size_t end = 0;
-    if (tiles) tiles->mis = (uint32_t)((tiles->mis + c.i) & 15u);
-    const int rc = find_scan_end(file, len, c.i, &end, tiles);
-    if (rc != BJ_OK) return rc;
-    d.scan_len = end - c.i;
+    if (walk_scan) {
+        size_t end = 0;
+        const int rc = find_scan_end(file, len, c.i, &end);
+        if (rc != BJ_OK) return rc;
+        d.scan_len = end - c.i;
+    } else {
+        if (c.i >= len) return BJ_ERR_INVALID_JPEG;                        // "File ended prematurely"
+        d.scan_len = len - c.i;
+    }
     if (d.frame_type != 0xC0) return BJ_ERR_UNSUPPORTED;                  // SOF2: parsed, never decodable
     if (d.scan_ncomp != d.ncomp) return BJ_ERR_UNSUPPORTED;               // non-interleaved scans: reference output is garbage
     return BJ_OK;

@@ -27,6 +27,125 @@ struct HostSink {
 struct SliceRec { uint32_t p, cz, cnt; };
 }  // namespace
 
+
+// ------------------------------------------------------------------------------------------------ K0, as the kernels run it
+// The device buffer holds the file at `file_pos` (any alignment; what lies around it is arbitrary).  Tiles of
+// kTile raw bytes, 256 "threads" of one aligned 16-byte chunk each: k_scan_count (per tile: bytes that survive and
+// RSTn markers in front of the scan's end, where the scan ends), k_scan_tiles (per image: scan over the tiles, the
+// image's state), k_unstuff (compaction, byte o stored at o ^ 3; segment starts).  Same shared code as the kernels:
+// classify_words[_end], clip_chunk, chunk_mask_before, tile_of_pos.
+namespace {
+constexpr uint32_t kTile = 4096;
+struct K0Out {
+    uint32_t status = 0;         // 0 ok, 2 invalid (no EOI where the scan ends)
+    uint32_t raw_len = 0, end_code = 0x100, clean_len = 0, nrst = 0;
+    std::vector<uint8_t> clean;  // swizzled (o ^ 3), zero padded
+    std::vector<uint32_t> seg_off;   // starts of the segments found (without the closing entry)
+};
+struct Chunk { uint32_t keep, rst, end; uint32_t w[4]; int64_t r0; };
+
+Chunk classify_chunk(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t tile, uint32_t thread, uint32_t raw_len, bool with_end) {
+    Chunk c;
+    const uint64_t a0 = (raw_off & ~(uint64_t)15) + (uint64_t)tile * kTile + (uint64_t)thread * 16;
+    c.r0 = (int64_t)a0 - (int64_t)raw_off;
+    const bool live = c.r0 < (int64_t)raw_len && c.r0 + 16 > 0;
+    auto at = [&](uint64_t a) -> uint32_t { return a < buf.size() ? buf[a] : 0xEEu; };
+    uint32_t w[6] = {0, 0, 0, 0, 0, 0};
+    if (live) for (int b = 0; b < 16; b++) w[1 + b / 4] |= at(a0 + b) << (8 * (b & 3));
+    // the neighbours' edge bytes: from the adjacent lanes (a lane that is not live holds zeros), from memory at the
+    // warp's edges - exactly what classify16 does
+    const bool prev_live = c.r0 - 16 < (int64_t)raw_len && c.r0 > 0, next_live = c.r0 + 16 < (int64_t)raw_len && c.r0 + 32 > 0;
+    if (thread % 32 == 0) w[0] = (live && a0 > 0) ? at(a0 - 1) << 24 : 0u;
+    else w[0] = prev_live ? at(a0 - 1) << 24 : 0u;
+    if (thread % 32 == 31) w[5] = live ? at(a0 + 16) : 0u;
+    else w[5] = next_live ? at(a0 + 16) : 0u;
+    for (int k = 0; k < 4; k++) c.w[k] = w[k + 1];
+    if (with_end) classify_words_end(w, c.keep, c.rst, c.end);
+    else { classify_words(w, c.keep, c.rst); c.end = 0; }
+    clip_chunk(c.r0, raw_len, c.keep, c.rst, c.end);
+    return c;
+}
+
+void k0_emulate(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t raw_len_max, uint32_t nseg_expected, K0Out *o) {
+    const uint32_t mis = (uint32_t)(raw_off & 15u);
+    const uint32_t ntile = std::max<uint32_t>(1u, (uint32_t)((mis + (uint64_t)raw_len_max + kTile - 1) / kTile));
+    // k_scan_count
+    std::vector<uint32_t> cnt_k(ntile), cnt_r(ntile), cnt_e(ntile);
+    for (uint32_t t = 0; t < ntile; t++) {
+        uint32_t e = kNoScanEnd;
+        std::vector<Chunk> cs;
+        for (uint32_t th = 0; th < 256; th++) {
+            cs.push_back(classify_chunk(buf, raw_off, t, th, raw_len_max, true));
+            if (cs.back().end) e = std::min(e, (uint32_t)(cs.back().r0 + __builtin_ctz(cs.back().end)));
+        }
+        uint32_t k = 0, r = 0;
+        for (auto &c : cs) { const uint32_t m = chunk_mask_before(c.r0, e); k += __builtin_popcount(c.keep & m); r += __builtin_popcount(c.rst & m); }
+        cnt_k[t] = k; cnt_r[t] = r; cnt_e[t] = e;
+    }
+    // k_scan_tiles
+    std::vector<uint32_t> ex_k(ntile, 0xDEADu), ex_r(ntile, 0xDEADu);
+    uint32_t e = kNoScanEnd, ck = 0, cr = 0;
+    for (uint32_t t = 0; t < ntile; t++) if (cnt_e[t] != kNoScanEnd) { e = cnt_e[t]; break; }
+    const uint32_t last = e == kNoScanEnd ? 0xFFFFFFFFu : tile_of_pos(mis, e, kTile);
+    for (uint32_t t = 0; t < ntile && t <= last; t++) { ex_k[t] = ck; ex_r[t] = cr; ck += cnt_k[t]; cr += cnt_r[t]; }
+    o->raw_len = e == kNoScanEnd ? raw_len_max : e;
+    o->end_code = e == kNoScanEnd ? 0x100u : buf[raw_off + e + 1];
+    o->status = o->end_code != 0xD9u ? 2u : 0u;
+    o->clean_len = ck; o->nrst = cr;
+    o->clean.assign(((size_t)raw_len_max / 4 + 4 + 96) * 4, 0);
+    o->seg_off.assign(1, 0);
+    if (o->status) return;
+    const uint32_t nseg = std::min(cr + 1u, nseg_expected);
+    o->seg_off.assign(nseg, 0xFFFFFFFFu);
+    o->seg_off[0] = 0;
+    // k_unstuff
+    for (uint32_t t = 0; t < ntile; t++) {
+        if ((int64_t)t * kTile - (int64_t)mis >= (int64_t)o->raw_len) continue;
+        uint32_t pos = ex_k[t], sidx = ex_r[t] + 1;
+        for (uint32_t th = 0; th < 256; th++) {
+            const Chunk c = classify_chunk(buf, raw_off, t, th, o->raw_len, false);
+            for (int i = 0; i < 16; i++) {
+                if (c.keep & (1u << i)) { o->clean[pos ^ 3u] = (uint8_t)(c.w[i >> 2] >> ((i & 3) * 8)); pos++; }
+                else if (c.rst & (1u << i)) { if (sidx < nseg_expected && sidx < nseg) o->seg_off[sidx] = pos; sidx++; }
+            }
+        }
+    }
+}
+}  // namespace
+
+// K0 alone against the per-byte rules and the host's scan walk (find_scan_end): the file sits `file_pos` bytes into a
+// device buffer filled with `fill` (what a neighbouring file or stale memory may hold).  Returns 0 when status, true
+// scan length, surviving bytes, marker count and segment starts all agree; a positive code says what differs.
+extern "C" int emu_k0_check(const uint8_t *file, size_t len, int file_pos, int fill, int nseg_expected) {
+    bj_image_desc d;
+    const int rc_hdr = parse_header(file, len, &d, /*walk_scan=*/false);
+    if (rc_hdr == BJ_ERR_INVALID_JPEG) { bj_image_desc d2; return parse_header(file, len, &d2, true) != BJ_OK ? 0 : 7; }   // rejected on the header alone
+    if (rc_hdr != BJ_OK && rc_hdr != BJ_ERR_UNSUPPORTED) return rc_hdr;
+    std::vector<uint8_t> buf((size_t)file_pos + len + 8192, (uint8_t)fill);
+    memcpy(buf.data() + file_pos, file, len);
+    K0Out o;
+    k0_emulate(buf, (uint64_t)file_pos + d.scan_off, (uint32_t)d.scan_len, (uint32_t)nseg_expected, &o);
+    size_t end = 0;
+    const int rc_walk = find_scan_end(file, len, d.scan_off, &end);
+    if ((rc_walk != BJ_OK) != (o.status != 0)) return 1;
+    if (rc_walk != BJ_OK) return 0;                               // both reject the file
+    if (o.raw_len != end - d.scan_off) return 2;
+    const uint8_t *raw = file + d.scan_off;
+    std::vector<uint8_t> want;
+    std::vector<uint32_t> seg(1, 0);
+    uint32_t nrst = 0;
+    for (size_t i = 0; i < o.raw_len; i++) {
+        const unsigned prev = i ? raw[i - 1] : 0u, bb = raw[i], next = raw[i + 1];
+        if (scan_keep(prev, bb, next)) want.push_back((uint8_t)bb);
+        else if (scan_is_rst(prev, bb)) { nrst++; if (seg.size() < (size_t)nseg_expected) seg.push_back((uint32_t)want.size()); }
+    }
+    if (o.clean_len != want.size() || o.nrst != nrst) return 3;
+    for (size_t i = 0; i < want.size(); i++) if (o.clean[i ^ 3] != want[i]) return 4;
+    if (o.seg_off.size() != std::min<size_t>(nrst + 1, (size_t)nseg_expected)) return 5;
+    for (size_t i = 0; i < o.seg_off.size(); i++) if (o.seg_off[i] != seg[i]) return 6;
+    return 0;
+}
+
 // optional: per Jacobi round, how many sub-sequences were decoded (set by emu_set_round_hist; 64 entries)
 static uint32_t *g_round_hist = nullptr;
 extern "C" void emu_set_round_hist(uint32_t *hist) { g_round_hist = hist; }
@@ -36,12 +155,7 @@ extern "C" void emu_set_round_hist(uint32_t *hist) { g_round_hist = hist; }
 // info[3] = number of units written more or less than once (must be 0 for a clean stream)
 extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int slices, int16_t *coef_zz, uint32_t *info) {
     bj_image_desc d;
-    // the parser's per-tile counts of dropped bytes / restart markers (what K0 is told instead of counting itself)
-    const uint32_t tile_cap = (uint32_t)((len + 15 + kScanTile - 1) / kScanTile + 1);
-    std::vector<uint32_t> host_dropped(tile_cap, 0), host_rst(tile_cap, 0);
-    ScanTiles tiles;
-    tiles.dropped = host_dropped.data(); tiles.rst = host_rst.data(); tiles.ntile = tile_cap; tiles.mis = 0;
-    int rc = parse_header(file, len, &d, &tiles);
+    int rc = parse_header(file, len, &d, /*walk_scan=*/false);    // the decode path's parse: headers only
     if (rc != BJ_OK) return rc;
     const uint32_t sub_bytes = (uint32_t)slice_bytes * (uint32_t)slices, slice_bits = (uint32_t)slice_bytes * 8u;
     const uint32_t nmx = (d.mcu_w + d.hs - 1) / d.hs, nmy = (d.mcu_h + d.vs - 1) / d.vs, nmcu = nmx * nmy;
@@ -51,40 +165,19 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int
     const uint32_t ri = d.restart_interval;
     const uint32_t nseg_expected = ri ? (nmcu + ri - 1) / ri : 1;
 
-    // K0: classify, compact (byte o stored at o ^ 3), segment starts
-    const uint8_t *raw = file + d.scan_off;
-    const size_t rl = d.scan_len;
-    std::vector<uint8_t> clean(((rl + 3) / 4 + 4) * 4, 0);
-    std::vector<uint32_t> seg_off(1, 0);
-    size_t o = 0;
-    // the kernels' chunking: 16 bytes per thread, classified four bytes per word (classify_words); the byte before the
-    // scan is the SOS header's last byte and the byte after it the FF of the closing marker, as in the file
-    for (size_t i0 = 0; i0 < rl; i0 += 16) {
-        uint32_t w[6] = {0, 0, 0, 0, 0, 0};
-        auto at = [&](long long i) -> uint32_t { const long long a = (long long)d.scan_off + i; return (a >= 0 && (size_t)a < len) ? file[a] : 0u; };
-        w[0] = at((long long)i0 - 1) << 24;
-        for (int b = 0; b < 16; b++) w[1 + b / 4] |= at((long long)i0 + b) << (8 * (b & 3));
-        w[5] = at((long long)i0 + 16);
-        uint32_t keep, rst;
-        classify_words(w, keep, rst);
-        for (int b = 0; b < 16 && i0 + b < rl; b++) {
-            const unsigned prev = i0 + b ? raw[i0 + b - 1] : 0u, bb = raw[i0 + b], next = i0 + b + 1 < rl ? raw[i0 + b + 1] : 0xFFu;
-            if (((keep >> b) & 1u) != (scan_keep(prev, bb, next) ? 1u : 0u) || ((rst >> b) & 1u) != (scan_is_rst(prev, bb) ? 1u : 0u)) return -200;
-            if ((keep >> b) & 1u) { clean[o ^ 3] = (uint8_t)bb; o++; }
-            else if (((rst >> b) & 1u) && seg_off.size() < nseg_expected) seg_off.push_back((uint32_t)o);
-        }
+    // K0 (count, scan, compact) on a device-buffer image of the file at an odd alignment
+    K0Out k0;
+    {
+        const size_t file_pos = 16 + (len % 13);
+        std::vector<uint8_t> buf(file_pos + len + 8192, 0xFF);
+        memcpy(buf.data() + file_pos, file, len);
+        k0_emulate(buf, file_pos + d.scan_off, (uint32_t)d.scan_len, nseg_expected, &k0);
     }
-    {   // ... and the same counts from the kernels' own classification, tile by tile
-        std::vector<uint32_t> dev_dropped(tile_cap, 0), dev_rst(tile_cap, 0);
-        if (tiles.mis != (d.scan_off & 15u)) return -201;
-        for (size_t i = 0; i < rl; i++) {
-            const unsigned prev = i ? raw[i - 1] : 0u, bb = raw[i], next = i + 1 < rl ? raw[i + 1] : 0xFFu;
-            const size_t t = (i + tiles.mis) / kScanTile;
-            if (!scan_keep(prev, bb, next)) dev_dropped[t]++;
-            if (scan_is_rst(prev, bb)) dev_rst[t]++;
-        }
-        if (dev_dropped != host_dropped || dev_rst != host_rst) return -202;
-    }
+    if (k0.status) return BJ_ERR_INVALID_JPEG;
+    std::vector<uint8_t> &clean = k0.clean;
+    std::vector<uint32_t> seg_off = k0.seg_off;
+    for (uint32_t sg : seg_off) if (sg == 0xFFFFFFFFu) return -203;
+    const size_t o = k0.clean_len;
     const uint32_t clean_len = (uint32_t)o;
     const uint32_t nseg = (uint32_t)seg_off.size();
     seg_off.push_back(clean_len);
@@ -257,36 +350,18 @@ extern "C" int emu_classify_check(const uint8_t *bytes, size_t n) {
         w[0] = at((long long)i0 - 1) << 24;
         for (int b = 0; b < 16; b++) w[1 + b / 4] |= at((long long)i0 + b) << (8 * (b & 3));
         w[5] = at((long long)i0 + 16);
-        uint32_t keep, rst;
+        uint32_t keep, rst, keep2, rst2, end2;
         classify_words(w, keep, rst);
+        classify_words_end(w, keep2, rst2, end2);
+        bad += keep != keep2 || rst != rst2;
         for (int b = 0; b < 16; b++) {
             const unsigned prev = at((long long)i0 + b - 1), bb = at((long long)i0 + b), next = at((long long)i0 + b + 1);
             bad += ((keep >> b) & 1u) != (scan_keep(prev, bb, next) ? 1u : 0u);
             bad += ((rst >> b) & 1u) != (scan_is_rst(prev, bb) ? 1u : 0u);
+            bad += ((end2 >> b) & 1u) != (scan_is_end(bb, next) ? 1u : 0u);
         }
     }
     return bad;
-}
-
-// The parser's per-tile counts (dropped bytes, restart markers) against the per-byte rules, for a file whose first
-// byte sits at `base_mis` (mod 16) in the device buffer.  Returns 0, a parse status < 0, or 1 on a mismatch.
-extern "C" int emu_scan_tiles_check(const uint8_t *file, size_t len, int base_mis) {
-    bj_image_desc d;
-    const uint32_t tile_cap = (uint32_t)((len + 15 + kScanTile - 1) / kScanTile + 1);
-    std::vector<uint32_t> host_dropped(tile_cap, 0), host_rst(tile_cap, 0), dev_dropped(tile_cap, 0), dev_rst(tile_cap, 0);
-    ScanTiles tiles;
-    tiles.dropped = host_dropped.data(); tiles.rst = host_rst.data(); tiles.ntile = tile_cap; tiles.mis = (uint32_t)base_mis;
-    const int rc = parse_header(file, len, &d, &tiles);
-    if (rc != BJ_OK) return rc;
-    if (tiles.mis != ((uint32_t)base_mis + d.scan_off) % 16u) return 1;
-    const uint8_t *raw = file + d.scan_off;
-    for (size_t i = 0; i < d.scan_len; i++) {
-        const unsigned prev = i ? raw[i - 1] : 0u, bb = raw[i], next = i + 1 < d.scan_len ? raw[i + 1] : 0xFFu;
-        const size_t t = (i + tiles.mis) / kScanTile;
-        if (!scan_keep(prev, bb, next)) dev_dropped[t]++;
-        if (scan_is_rst(prev, bb)) dev_rst[t]++;
-    }
-    return (dev_dropped == host_dropped && dev_rst == host_rst) ? 0 : 1;
 }
 
 // The device form of UnitWalk keeps (completed units << 8 | unit index << 4) in one register and advances it by the

@@ -169,35 +169,59 @@ def test_word_at_a_time_byte_classification():
         assert lib.emu_classify_check(ol._ptr(b), b.size) == 0
 
 
-def test_parser_counts_dropped_bytes_per_tile():
-    """The un-stuff kernel is told by the host where every 4 KB tile's surviving bytes go: the header parse counts, per
-    tile, the bytes the scan-byte rules drop and the RSTn markers while it looks for the end of the scan.  Checked
-    against the per-byte rules on scans dense in stuffed FFs, restart markers and fill bytes, at every alignment."""
+def _scan_soup(rng, nbytes):
+    """Scan bytes dense in everything the scan-byte rules care about (never an end-of-scan marker)."""
+    parts, n = [], 0
+    while n < nbytes:
+        k = int(rng.integers(0, 6))
+        if k == 0:
+            piece = bytes([0xFF, 0x00])
+        elif k == 1:
+            piece = bytes([0xFF, 0xD0 + int(rng.integers(0, 8))])
+        elif k == 2:
+            piece = bytes([0xFF] * int(rng.integers(1, 4)) + [0xFF, 0xD0 + int(rng.integers(0, 8))])   # fill bytes before a marker
+        else:
+            piece = bytes(int(x) for x in rng.integers(0, 255, int(rng.integers(1, 40))))            # no FF
+        parts.append(piece)
+        n += len(piece)
+    return b"".join(parts)
+
+
+def test_device_side_scan_end_counts_and_compaction():
+    """K0 never gets a scan length from the host: k_scan_count / k_scan_tiles find the FF that ends the scan, count what
+    survives in front of it per 4 KB tile, and k_unstuff compacts.  Their shared code, run tile by tile and chunk by
+    chunk like the kernels, against the per-byte rules and the host's scan walk: scans dense in stuffed FFs, restart
+    markers and fill bytes, every alignment of the file in the device buffer, arbitrary bytes around the file, ends on
+    tile and chunk boundaries, trailing garbage behind EOI, and files the reference rejects (no EOI, another marker
+    inside the scan, FF as the last byte)."""
     lib = emu()
-    lib.emu_scan_tiles_check.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    lib.emu_k0_check.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
     base = js.synth_jpeg(64, 48, seed=1, subsampling=2)
     h = ol.Restated(base, 0).h
     head = base[:h.scan_off]
     rng = np.random.default_rng(11)
-    for trial in range(6):
-        parts = []
-        n = 0
-        while n < 3 * 4096 + 500 * trial:
-            k = int(rng.integers(0, 6))
-            if k == 0:
-                piece = bytes([0xFF, 0x00])
-            elif k == 1:
-                piece = bytes([0xFF, 0xD0 + int(rng.integers(0, 8))])
-            elif k == 2:
-                piece = bytes([0xFF] * int(rng.integers(1, 4)) + [0xFF, 0xD0 + int(rng.integers(0, 8))])   # fill bytes before a marker
-            else:
-                piece = bytes(int(x) for x in rng.integers(0, 255, int(rng.integers(1, 40))))            # no FF
-            parts.append(piece)
-            n += len(piece)
-        data = head + b"".join(parts) + b"\xFF\xD9"
+
+    def check(data, expect_valid, nseg=1 << 20):
         buf = np.frombuffer(data, dtype=np.uint8)
-        for mis in (0, 1, 7, 15):
-            assert lib.emu_scan_tiles_check(ol._ptr(buf), len(data), mis) == 0, (trial, mis)
+        for pos, fill in ((0, 0x00), (1, 0xFF), (7, 0xD9), (15, 0xFF), (16, 0x00), (4099, 0xFF)):
+            assert lib.emu_k0_check(ol._ptr(buf), len(data), pos, fill, nseg) == 0, (len(data), pos, fill)
+        assert (ol.Restated(data, 0).rc == 0) == expect_valid
+
+    for trial in range(6):
+        soup = _scan_soup(rng, 3 * 4096 + 500 * trial)
+        check(head + soup + b"\xFF\xD9", True)
+        check(head + soup + b"\xFF\xD9" + _scan_soup(rng, 700) + b"\xFF\xD9\xFF\xC0junk", True)      # garbage behind EOI
+        check(head + soup, False)                                                                    # file ends inside the scan
+        check(head + soup + b"\xFF", False)                                                          # ... on an FF
+        check(head + soup + b"\xFF\xC4" + soup[:100] + b"\xFF\xD9", False)                           # another marker first
+        check(head + soup + b"\xFF\xFF\xFF\xD9", True)                                               # fill bytes before EOI
+        check(head + soup + b"\xFF\xD9", True, nseg=3)                                               # more markers than segments expected
+    # the end at every position around a tile / chunk boundary
+    soup = _scan_soup(rng, 2 * 4096)
+    for cut in list(range(4096 - len(head) - 20, 4096 - len(head) + 20)) + [16, 17, 31, 32, 33]:
+        check(head + soup[:cut].rstrip(b"\xFF") + b"\x01\xFF\xD9", True)
+    check(head + b"\xFF\xD9", True)                                                                  # empty scan
+    check(head, False)
 
 
 def test_lut_matches_bit_serial_search():
