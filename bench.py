@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the B200 JPEG decode back end (contract: see the task statement / DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config3|config4|config5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config3|config4|config5|compat] [--batch B]
+    python bench.py --workload config5 --stream 65536      # BASELINE configs[4]: one stream dealt over the ranks (strong scaling)
     python bench.py --impl reference ...        # the reference's own CPU implementation on the host cores
 
 A "step" = one pass of the hot path (un-stuff, Huffman decode, dequantise, IDCT, upsample, colour, BMP bytes)
@@ -33,6 +34,24 @@ UNIT = "Mpixel/s"
 
 MIX = [((500, 375), 0.40), ((375, 500), 0.15), ((640, 480), 0.15), ((224, 224), 0.10), ((1024, 768), 0.10),
        ((1920, 1080), 0.07), ((3840, 2160), 0.03)]
+
+
+def kernel_sources_sha():
+    """Identifies the kernel sources a profile was taken from (profiles/ncu_traffic.json carries the same key)."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "pim_jpeg_decoder_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "pim_jpeg_decoder_b200", "csrc", "*.h"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def stream_pool_specs(unique):
+    """The pool of BASELINE configs[4] (SURVEY 8d): `unique` files, sizes drawn with default_rng(5) from the fixed mix;
+    the same on every rank - the stream is ONE list that the ranks share out."""
+    rng = np.random.default_rng(5)
+    sizes = rng.choice(len(MIX), size=unique, p=[m[1] for m in MIX])
+    return [(MIX[s][0][0], MIX[s][0][1], 5_000_000 + i, 2, False, 0) for i, s in enumerate(sizes)]
 
 
 def workload_specs(name, batch, unique, rank):
@@ -236,6 +255,121 @@ def bind_to_gpu_numa_node(index):
         pass
 
 
+def twin_spec(spec):
+    """Restart-parity rule: a subsampled image with restart markers must equal the reference's
+    decode of its restart-free twin (same pixels, quality, tables)."""
+    w, h, seed, sub, gray, ri = spec
+    return (w, h, seed, sub, gray, 0) if (ri and sub != 0 and not gray) else spec
+
+
+def sha_file(path):
+    import hashlib
+    with open(path, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
+def pack_pinned(bj, blobs):
+    total = sum(len(b) for b in blobs)
+    pin = bj.PinnedBuffer(total + 16)
+    off, o = np.zeros(len(blobs), dtype=np.uint64), 0
+    for i, b in enumerate(blobs):
+        pin.array[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
+        off[i] = o
+        o += len(b)
+    return pin, off, np.array([len(b) for b in blobs], dtype=np.uint64)
+
+
+def out_sizes(bj, blobs, specs):
+    cache, sizes = {}, []
+    for b, sp in zip(blobs, specs):
+        key = sp[:2] + sp[3:5]                 # BMP size depends on the dimensions only
+        if key not in cache:
+            st, d = bj.parse_header(b)
+            cache[key] = bj.lib().bj_output_size(d, bj.BJ_OUT_BMP)
+        sizes.append(cache[key])
+    return sizes
+
+
+def d2h_probe(torch, dist, world, hview, nb):
+    """Pinned copy-out rate with EVERY rank copying at the same time (barrier in front of each repetition): what the
+    host can take back from all its GPUs at once.  -> (this rank alone-ish best GB/s, aggregate GB/s over all ranks)."""
+    dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    best_single, best_agg = 0.0, 0.0
+    for rep in range(4):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hview.copy_(dbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best_single = max(best_single, nb / dt / 1e9)
+        best_agg = max(best_agg, world * nb / float(t.item()) / 1e9)
+    a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); dbuf.copy_(hview, non_blocking=True); b2.record(); torch.cuda.synchronize()
+    h2d = nb / (a.elapsed_time(b2) * 1e-3) / 1e9
+    del dbuf
+    return best_single, best_agg, h2d
+
+
+def run_compat(args, rank, local_rank, world):
+    """--workload compat: Level 0 of INTEGRATION.md - bj_exec_mcus, the literal stand-in for pim.exec() on the
+    reference's own metadata/mcus buffers (src/decoder_host.cpp:276-308) - against the reference's DPU program
+    (src/decoder_dpu.c through oracle/_ref/libref.so) on the host cores."""
+    import oracle_lib as ol
+    import torch
+    import pim_jpeg_decoder_b200 as bj
+    torch.cuda.set_device(local_rank)
+    nimg = args.batch or 64
+    specs, _ = workload_specs("config2", nimg, min(nimg, 32), rank)
+    blobs = generate(specs, max(1, args.gen_workers))
+    uniq = {}
+    for sp, b in zip(specs, blobs):
+        if sp not in uniq:
+            uniq[sp] = ol.Restated(b, 0)
+    md = np.concatenate([uniq[sp].metadata for sp in specs])
+    pre = np.concatenate([uniq[sp].mcus_pre for sp in specs])
+    post = np.concatenate([uniq[sp].mcus_post for sp in specs])
+    nchunk = md.shape[0]
+    px = pixels_of(specs)
+    dec = bj.Decoder(local_rank)
+    got = dec.exec_mcus(md, pre)
+    if not np.array_equal(got, post):
+        raise SystemExit("bench compat: bj_exec_mcus differs from the oracle")
+    for _ in range(max(args.warmup, 3)):
+        dec.exec_mcus(md, pre)
+    t0 = time.perf_counter()
+    kern_ms = 0.0
+    for _ in range(args.steps):
+        dec.exec_mcus(md, pre)
+        kern_ms += dec.stat("exec_ms")
+    wall = time.perf_counter() - t0
+    dec.close()
+    cpu = None
+    if ol.ref_available():
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 and time.perf_counter() - t0 < 10:
+            ol.ref_exec_mcus(md, pre)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": px / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
+               "sample": f"the reference's DPU program (decoder_dpu.c, 11 tasklets run in turn) on {nchunk} chunks, one host thread, {reps} passes"}
+    chunk_bytes = 64 * 100 * 3 * 2
+    line = {"metric": METRIC, "value": px * args.steps / (kern_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": kern_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int16 fixed point",
+            "data": "synthetic", "config": {"workload": f"compat: bj_exec_mcus on {nchunk} DPU chunks ({nimg} x 500x375 4:2:0), the reference's mcus/metadata layout, in place"},
+            "roofline": {"bound": "hbm", "kernel": "k_exec_mcus", "achieved": 2.0 * nchunk * chunk_bytes / (kern_ms / args.steps * 1e-3) / 1e9,
+                         "peak": 6540.2, "unit": "GB/s", "frac": 2.0 * nchunk * chunk_bytes / (kern_ms / args.steps * 1e-3) / 1e9 / 6540.2, "traffic": None},
+            "e2e": {"value": px * args.steps / wall / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(md.nbytes + pre.nbytes), "d2h_bytes_per_step": int(pre.nbytes),
+                    "timer": "host wall clock around bj_exec_mcus (pageable numpy buffers in and out, like the reference's std::vector)"},
+            "cpu_baseline": cpu, "gpu_launches": args.steps, "parity": {"checked": nchunk, "mismatches": 0, "against": "oracle restatement of the DPU program, whole buffers"}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -243,7 +377,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2")
-    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 4096 for config2/5, 16 for config3/4)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 4096 for config2/5, 16 for config3/4; BASELINE states configs 3 and 4 as single images: --batch 1 / 2)")
+    ap.add_argument("--stream", type=int, default=0, help="config5 only: ONE stream of this many images (pool of --unique files cycled), dealt over the ranks by compressed size (LPT): strong scaling")
     ap.add_argument("--unique", type=int, default=1024, help="distinct synthetic images generated per rank (cycled to fill the batch)")
     ap.add_argument("--subseq-bits", type=int, default=0, help="sub-sequence length of the Huffman synchronisation pass (0 = library default: per image, about 4096 bits)")
     ap.add_argument("--slices", type=int, default=0, help="slices of a sub-sequence the Huffman write pass works on (0 = library default: 1)")
@@ -253,11 +388,12 @@ def main():
     ap.add_argument("--sub-batch-mb", type=int, default=0, help="compressed MB per sub-batch of the one-call path (0 = library default)")
     ap.add_argument("--host-threads", type=int, default=0, help="host worker threads of the one-call path (0 = library default)")
     ap.add_argument("--no-ramp", action="store_true", help="one-call path: all sub-batches the same size")
-    ap.add_argument("--direct-inputs", action="store_true", help="one-call path: upload the files straight from the (pinned) input buffer instead of through the library's staging copy")
+    ap.add_argument("--staged-inputs", action="store_true", help="one-call path: force the pinned staging copy of the input files (default: they are uploaded straight from the pinned input buffer)")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--gen-workers", type=int, default=min(32, os.cpu_count() or 1))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the CLI-to-CLI leg (decoder_b200 vs the reference CLI on the same tmpfs files)")
     ap.add_argument("--clock-sample-ms", type=int, default=100, help="nvidia-smi polling interval while the timed regions run (0 = no sampling: for A/B only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -269,12 +405,33 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.workload == "compat":
+        run_compat(args, rank, local_rank, world)
+        return
 
     bind_to_gpu_numa_node(local_rank)
-    batch_n = args.batch or (4096 if args.workload in ("config2", "config5") else 16)
-    specs, desc = workload_specs(args.workload, batch_n, args.unique, rank)
     workers = max(1, args.gen_workers // max(1, world))
-    blobs = generate(specs, workers)                          # CPU, before CUDA comes up
+    stream = args.stream if args.workload == "config5" else 0
+    if stream:
+        # ONE stream for the whole job (BASELINE configs[4]): pool cycled, dealt over the ranks by compressed size
+        pool_specs = stream_pool_specs(args.unique)
+        pool = generate(pool_specs, workers)
+        import pim_jpeg_decoder_b200 as bj0
+        costs = [len(pool[i % len(pool)]) for i in range(stream)]
+        mine = bj0.lpt_shards(costs, world)[rank]
+        specs = [pool_specs[i % len(pool)] for i in mine]
+        blobs = [pool[i % len(pool)] for i in mine]
+        desc = (f"ONE stream of {stream} mixed-size 4:2:0 q=90 JPEGs (pool of {len(pool)} unique files cycled {stream // len(pool)}x; SURVEY 8d mix), "
+                f"dealt over {world} rank(s) by compressed size (LPT)")
+        batch_n = len(blobs)
+        total_px = sum(pool_specs[i % len(pool)][0] * pool_specs[i % len(pool)][1] for i in range(stream))
+        total_images = stream
+    else:
+        batch_n = args.batch or (4096 if args.workload in ("config2", "config5") else 16)
+        specs, desc = workload_specs(args.workload, batch_n, args.unique, rank)
+        blobs = generate(specs, workers)                          # CPU, before CUDA comes up
+        total_px = pixels_of(specs) * world
+        total_images = batch_n * world
     px = pixels_of(specs)
 
     import torch
@@ -290,6 +447,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     dec = bj.Decoder(local_rank)                              # raises without a GPU: no CPU fallback exists
     if args.subseq_bits:
         dec.set_option("subseq_bits", args.subseq_bits)
@@ -303,78 +466,79 @@ def main():
     sampler.start()
     windows = []
 
-    # ---- (1) device-resident: compressed batch already in HBM when the clock starts
-    stream = torch.cuda.Stream()
-    sp = stream.cuda_stream
-    batch = bj.Batch(dec, blobs, bj.BJ_OUT_BMP)
-    batch.upload(sp)
+    # ---- (1) device-resident: compressed batch already in HBM when the clock starts.  A stream is cut into resident
+    # chunks of <= 4096 images, decoded one after the other (each uploaded before its clock starts).
+    cuda_stream = torch.cuda.Stream()
+    sp = cuda_stream.cuda_stream
+    chunk = 4096 if stream else max(1, len(blobs))
+    chunks = [(i, min(i + chunk, len(blobs))) for i in range(0, len(blobs), chunk)] or [(0, 0)]
     stage_ms = {"unstuff": 0.0, "sync": 0.0, "write": 0.0, "idct": 0.0}
-
-    def step(accumulate=False):
-        batch.decode(sp)
-        batch.sync()
-        if accumulate:
+    agg = {"scan_bytes": 0, "clean_bytes": 0, "data_units": 0, "subsequences": 0, "out_bytes": 0}
+    launches = 0
+    ms_total = 0.0
+    first_hash = None
+    steps = args.steps if not stream else 1                  # a stream is decoded once (it is 16x to 64x the default batch)
+    barrier()
+    t_wall0 = time.perf_counter()
+    for ci, (c0, c1) in enumerate(chunks):
+        batch = bj.Batch(dec, blobs[c0:c1], bj.BJ_OUT_BMP)
+        batch.upload(sp)
+        for _ in range(max(args.warmup, 1) if ci == 0 else 1):
+            batch.decode(sp)
+            batch.sync()
+        bad = [s for s in batch.status() if s != 0]
+        if bad:
+            raise SystemExit(f"bench: {len(bad)} images did not decode cleanly: {bad[:4]}")
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if not stream:
+            barrier()
+            t_wall0 = time.perf_counter()
+        ev0.record(cuda_stream)
+        for _ in range(steps):
+            batch.decode(sp)
+            batch.sync()
             i = batch.info()
             stage_ms["unstuff"] += i.ms_unstuff; stage_ms["sync"] += i.ms_sync; stage_ms["write"] += i.ms_write; stage_ms["idct"] += i.ms_idct
-
-    for _ in range(max(args.warmup, 1)):
-        step()
-    bad = [s for s in batch.status() if s != 0]
-    if bad:
-        raise SystemExit(f"bench: {len(bad)} images did not decode cleanly: {bad[:4]}")
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev1.record(cuda_stream)
+        torch.cuda.synchronize()
+        ms_total += ev0.elapsed_time(ev1)
+        info = batch.info()
+        launches += info.launches * steps
+        for k in agg:
+            agg[k] += getattr(info, k)
+        if rank == 0 and ci == 0:
+            import hashlib
+            first = batch.download(only=[0])[0]
+            first_hash = hashlib.sha256(first.tobytes()).hexdigest()
+        batch.destroy()
     barrier()
-    t0 = time.perf_counter()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step(True)
-    ev1.record(stream)
-    barrier()
-    windows.append((t0, time.perf_counter()))
-    ms = ev0.elapsed_time(ev1)
-    info = batch.info()
-    launches = info.launches * args.steps
-    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
-    first_hash = None
-    if rank == 0:
-        import hashlib
-        first = batch.download(only=[0])[0]
-        first_hash = hashlib.sha256(first.tobytes()).hexdigest()
-    batch.destroy()
+    windows.append((t_wall0, time.perf_counter()))
+    ms_max = allmax(ms_total)
 
     # ---- (2) end to end through the one-call C ABI: host buffers in, host buffers out
     e2e = None
+    parity = None
+    pin_out = None
     if not args.no_e2e:
-        in_total = sum(len(b) for b in blobs)
-        pin_in = bj.PinnedBuffer(in_total)
-        in_off, o = [], 0
-        for b in blobs:
-            pin_in.array[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
-            in_off.append(o)
-            o += len(b)
-        in_off = np.array(in_off, dtype=np.uint64)
-        in_len = np.array([len(b) for b in blobs], dtype=np.uint64)
-        sizes = []
-        for b in blobs[:1] if len(set(specs)) == 1 else blobs:
-            st, d = bj.parse_header(b)
-            sizes.append(bj.lib().bj_output_size(d, bj.BJ_OUT_BMP))
-        if len(sizes) == 1:
-            sizes = sizes * len(blobs)
-        offs, o = [], 0
-        for s in sizes:
-            offs.append(o)
-            o += (s + 15) // 16 * 16
-        pin_out = bj.PinnedBuffer(o)
-        out_off = np.array(offs, dtype=np.uint64)
+        pin_in, in_off, in_len = pack_pinned(bj, blobs)
+        sizes = out_sizes(bj, blobs, specs)
+        padded = np.array([(s + 15) // 16 * 16 for s in sizes], dtype=np.uint64)
+        # a stream's outputs go to a ring of <= 8 GB (they are consumed as they come); a batch's outputs all stay
+        ring = min(int(padded.sum()), 8 << 30) if stream else int(padded.sum())
+        pin_out = bj.PinnedBuffer(ring + 16)
+        calls = []                                            # [(i0, i1, out offsets)] : one bj_decode_batch per call
+        i0 = 0
+        while i0 < len(blobs):
+            i1, acc = i0, 0
+            while i1 < len(blobs) and acc + int(padded[i1]) <= ring:
+                acc += int(padded[i1]); i1 += 1
+            offs = np.concatenate([[0], np.cumsum(padded[i0:i1])]).astype(np.uint64)[:-1]
+            calls.append((i0, i1, offs))
+            i0 = i1
         dec.set_option("packed_outputs", 1)
-        # pin_in is one pinned allocation, so the files could go up straight from it (option "packed_inputs": half the
-        # host work); measured on these boxes the copy-out then runs a little slower (the staged copy leaves the bytes
-        # in the CPU's cache for the upload to pick up), so the default stays the staging copy
-        # (also with 4 ranks on one host, where it halves a host time of 70 ms per step: 112 ms per call against 97)
-        dec.set_option("packed_inputs", 1 if args.direct_inputs else 0)
+        # the input files sit in ONE pinned buffer from bj_host_alloc: the library uploads them straight from there
+        # (no staging copy, no host pass over the compressed bytes); --staged-inputs forces the copy for A/B
+        dec.set_option("packed_inputs", -1 if args.staged_inputs else 0)
         if args.sub_batch_mb:
             dec.set_option("sub_batch_bytes", args.sub_batch_mb << 20)
         # host worker threads of this rank: its share of the box's cores (the library's own default, min(4, cores/2),
@@ -385,55 +549,73 @@ def main():
             dec.set_option("host_threads", host_threads)
         if args.no_ramp:
             dec.set_option("sub_batch_ramp", 0)
-        # what the link gives this process: one large pinned copy each way (the e2e number is bounded by the D2H one)
-        pcie = {}
-        nb = min(o, 1 << 30)
-        dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        # what the link gives: one large pinned copy each way, all ranks at the same time
+        nb = min(ring, 1 << 30)
         hview = torch.from_numpy(pin_out.array[:nb])
-        for name, dst, src in (("d2h_gbs", hview, dbuf), ("h2d_gbs", dbuf, hview)):
-            best = 0.0
-            for _ in range(3):
-                a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); dst.copy_(src, non_blocking=True); b2.record(); torch.cuda.synchronize()
-                best = max(best, nb / (a.elapsed_time(b2) * 1e-3) / 1e9)
-            pcie[name] = best
-        del dbuf
-        k2 = args.e2e_steps or max(2, min(args.steps, 5))
-        for _ in range(max(1, min(args.warmup, 2))):
-            dec.decode_packed(pin_in.array, in_off, in_len, pin_out.array, out_off, bj.BJ_OUT_BMP)
+        d2h_single, d2h_agg, h2d_single = d2h_probe(torch, dist, world, hview, nb)
+
+        def one_pass():
+            st_all = []
+            for (a, b, offs) in calls:
+                st_all.append(dec.decode_packed(pin_in.array, in_off[a:b], in_len[a:b], pin_out.array, offs, bj.BJ_OUT_BMP))
+            return st_all
+
+        k2 = args.e2e_steps or (1 if stream else max(2, min(args.steps, 5)))
+        e2e_single = None
+        if world > 1:                                         # rank 0 alone first: the denominator of the e2e scaling efficiency
+            if rank == 0:
+                one_pass()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    one_pass()
+                e2e_single = px * 2 / (time.perf_counter() - t0) / 1e6
+            barrier()
+        for _ in range(max(1, min(args.warmup, 2)) if not stream else 0):
+            one_pass()
         barrier()
-        host_ms = wait_ms = 0.0
+        stat_names = ["decode_batch_host_ms", "decode_batch_wait_ms", "decode_batch_h2d_bytes", "decode_batch_d2h_bytes", "decode_batch_sub_batches",
+                      "decode_batch_d2h_copies", "decode_batch_direct_uploads", "decode_batch_launches"]
+        acc = dict.fromkeys(stat_names, 0.0)
         t0 = time.perf_counter()
         for _ in range(k2):
-            st = dec.decode_packed(pin_in.array, in_off, in_len, pin_out.array, out_off, bj.BJ_OUT_BMP)
-            host_ms += dec.stat("decode_batch_host_ms"); wait_ms += dec.stat("decode_batch_wait_ms")
+            for (a, b, offs) in calls:
+                st = dec.decode_packed(pin_in.array, in_off[a:b], in_len[a:b], pin_out.array, offs, bj.BJ_OUT_BMP)
+                if st.any():
+                    raise SystemExit("bench e2e: images failed to decode")
+                for nme in stat_names:
+                    acc[nme] += dec.stat(nme)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         windows.append((t0, t1))
-        te = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-        if rank == 0:
+        e2e_s = allmax(t1 - t0)
+        if rank == 0 and len(calls) == 1:
             import hashlib
-            assert not st.any(), "e2e: images failed to decode"
             assert hashlib.sha256(pin_out.array[:sizes[0]].tobytes()).hexdigest() == first_hash, "e2e and device-resident paths disagree"
-        e2e = {"value": px * world * k2 / e2e_s / 1e6, "unit": UNIT, "images_per_s": batch_n * world * k2 / e2e_s,
+        d2h_per_step = acc["decode_batch_d2h_bytes"] / k2
+        floor_ms = 1e3 * d2h_per_step / (d2h_agg / world * 1e9) if d2h_agg else None
+        e2e_value = total_px * k2 / e2e_s / 1e6
+        e2e = {"value": e2e_value, "unit": UNIT, "images_per_s": total_images * k2 / e2e_s,
                "ms_per_step": 1e3 * e2e_s / k2, "steps": k2,
-               "h2d_bytes_per_step": int(dec.stat("decode_batch_h2d_bytes")), "d2h_bytes_per_step": int(dec.stat("decode_batch_d2h_bytes")),
-               "sub_batches_per_step": int(dec.stat("decode_batch_sub_batches")), "d2h_copies_per_step": int(dec.stat("decode_batch_d2h_copies")), "host_threads": int(dec.stat("host_threads")),
-               "host_prepare_ms_per_step": host_ms / k2, "host_wait_gpu_ms_per_step": wait_ms / k2,
-               "pcie_pinned_copy": pcie,
-               "d2h_floor_ms_per_step": 1e3 * dec.stat("decode_batch_d2h_bytes") / (pcie["d2h_gbs"] * 1e9) if pcie.get("d2h_gbs") else None,
-               "timer": "host wall clock around the blocking bj_decode_batch call (pinned host buffers in and out), max over ranks"}
+               "h2d_bytes_per_step": int(acc["decode_batch_h2d_bytes"] / k2), "d2h_bytes_per_step": int(d2h_per_step),
+               "sub_batches_per_step": int(acc["decode_batch_sub_batches"] / k2), "d2h_copies_per_step": int(acc["decode_batch_d2h_copies"] / k2),
+               "direct_uploads_per_step": int(acc["decode_batch_direct_uploads"] / k2), "calls_per_step": len(calls),
+               "host_threads": int(dec.stat("host_threads")),
+               "host_prepare_ms_per_step": acc["decode_batch_host_ms"] / k2, "host_wait_gpu_ms_per_step": acc["decode_batch_wait_ms"] / k2,
+               "pcie_pinned_copy": {"d2h_gbs": d2h_single, "h2d_gbs": h2d_single},
+               # the copy-out bounds this path (3 B per pixel go back over PCIe): its floor with every rank copying at once
+               "aggregate_d2h_gbs": d2h_agg, "d2h_floor_ms_per_step": floor_ms, "frac_of_floor": (floor_ms / (1e3 * e2e_s / k2)) if floor_ms else None,
+               "single_rank_value": e2e_single, "e2e_efficiency": (e2e_value / (world * e2e_single)) if e2e_single and not stream else None,
+               "timer": "host wall clock around the blocking bj_decode_batch call(s) (pinned host buffers in and out), max over ranks; "
+                        "aggregate_d2h_gbs: all ranks copying out at once behind a barrier"}
         pin_in.free()
-        pin_out.free()
-    sampler.stop()
-    dec.close()
 
     # ---- (3) the reference on this box's host cores, bounded sample (rank 0, N=1 only): passes over the first
-    # 128 x cores images of the batch until about 10 s of wall time (= 10 s x cores of CPU work) have been spent
+    # 128 x cores images of the batch until about 10 s of wall time (= 10 s x cores of CPU work) have been spent.
+    # The BMP files it writes are the parity check of this run: the GPU's BMP bytes of the same images must be identical
+    # (for a subsampled image with restart markers: the reference's decode of its restart-free twin).
     cpu = None
+    cli = None
+    rule = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = args.ref_sample or (128 if args.workload in ("config2", "config5") else 2) * (os.cpu_count() or 1)
         n = min(n, len(blobs))
@@ -443,10 +625,54 @@ def main():
             while passes < 12 and t < 10.0:
                 t += ref.step()
                 passes += 1
+            cpu = {"value": ref.pixels * passes / t / 1e6, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "images_per_s": n * passes / t,
+                   "sample": f"first {n} images of the batch, {passes} passes, {min(ref.cores, n)} processes x 2 threads of the reference CLI on tmpfs (BMP written), {t:.2f} s"}
+            # ---- parity against what the reference just wrote
+            if pin_out is not None:
+                want = {}
+                twins = [twin_spec(sp) for sp in specs[:n]]
+                if any(tw != sp for tw, sp in zip(twins, specs[:n])):
+                    rule = ("restart-parity rule: subsampled images with restart markers are compared with the reference's decode of the restart-free twin "
+                            "(the reference's own restart handling is wrong for subsampled files, SURVEY 0.7)")
+                    tw_uniq = sorted(set(twins))
+                    tw_blobs = dict(zip(tw_uniq, generate(tw_uniq, 1)))
+                    tref = CpuReference([tw_blobs[tw] for tw in twins], 0)
+                    tref.step()
+                    want = {i: sha_file(f[:-4] + ".bmp") for i, f in enumerate(tref.files)}
+                    tref.close()
+                else:
+                    want = {i: sha_file(f[:-4] + ".bmp") for i, f in enumerate(ref.files)}
+                import hashlib
+                a0, b0, offs0 = calls[0]
+                nchk = min(n, b0 - a0)
+                mism = [i for i in range(nchk) if hashlib.sha256(pin_out.array[int(offs0[i]):int(offs0[i]) + sizes[i]].tobytes()).hexdigest() != want[i]]
+                parity = {"checked": nchk, "mismatches": len(mism), "against": "the BMP files the reference CLI (oracle/_ref/decoder) wrote in this run", "rule": rule}
+            # ---- CLI to CLI on the same tmpfs files: decoder_b200 (file -> BMP file, one process, every visible GPU)
+            cli_bin = os.path.join(ROOT, "pim_jpeg_decoder_b200", "host", "_build", "decoder_b200")
+            if not args.no_cli and os.path.exists(cli_bin) and ref.kind == "reference":
+                dec.close()
+                dec = None
+                refs = {f: sha_file(f[:-4] + ".bmp") for f in ref.files} if rule is None else None
+                for f in ref.files:
+                    os.remove(f[:-4] + ".bmp")
+                tc = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    subprocess.run([cli_bin] + ref.files, stdout=subprocess.DEVNULL, check=True, env=dict(os.environ, B200JPEG_DEVICES="1"))
+                    tc.append(time.perf_counter() - t0)
+                bad = sum(1 for f in ref.files if refs is not None and sha_file(f[:-4] + ".bmp") != refs[f])
+                cli = {"b200": {"value": ref.pixels / min(tc) / 1e6, "unit": UNIT, "seconds": min(tc), "runs": tc,
+                                "what": "decoder_b200 <files>: process start, CUDA context, file read, decode on one GPU, BMP files written (tmpfs)"},
+                       "reference": {"value": cpu["value"], "unit": UNIT, "what": "the reference CLI, one process per host core on a slice of the same files"},
+                       "ratio": (ref.pixels / min(tc) / 1e6) / cpu["value"], "images": n,
+                       "bmp_files_identical": (bad == 0) if refs is not None else None}
         finally:
             ref.close()
-        cpu = {"value": ref.pixels * passes / t / 1e6, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "images_per_s": n * passes / t,
-               "sample": f"first {n} images of the batch, {passes} passes, {min(ref.cores, n)} processes x 2 threads of the reference CLI on tmpfs (BMP written), {t:.2f} s"}
+    if pin_out is not None:
+        pin_out.free()
+    sampler.stop()
+    if dec is not None:
+        dec.close()
 
     if rank != 0:
         if world > 1:
@@ -461,58 +687,72 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
-    # algorithmic bytes per launch (DESIGN.md "Roofline"): per kernel group of ONE step on ONE GPU
-    clean = float(info.clean_bytes)
-    units = float(info.data_units)
-    nsub = float(info.subsequences)
+    # algorithmic bytes per launch (DESIGN.md "Roofline"): per kernel group of ONE step on ONE GPU (rank 0)
+    clean = float(agg["clean_bytes"])
+    units = float(agg["data_units"])
+    nsub = float(agg["subsequences"])
+    scan = float(agg["scan_bytes"])
+    outb = float(agg["out_bytes"])
     alg = {
-        "unstuff": 1.0 * info.scan_bytes + clean,                     # raw bytes read once + clean bytes written
+        "unstuff": 2.0 * scan + clean,                                # raw bytes read twice (count, compact) + clean bytes written
         "sync": clean + (28.0 + 16.0 * (args.slices or 1) + 64.0) * nsub,    # stream read once + per-sub-sequence states/totals + slice entry states + 4 quarter records written
         "write": clean + 128.0 * units,                               # stream read once + every coefficient unit written once
-        "idct": 128.0 * units + float(info.out_bytes),                # coefficients read once + pixels written once
+        "idct": 128.0 * units + outb,                                 # coefficients read once + pixels written once
     }
     stages = {}
     for k in stage_ms:
-        t = stage_ms[k] / args.steps
+        t = stage_ms[k] / steps
         stages[k] = {"ms": t, "alg_bytes": alg[k], "achieved_gbs": alg[k] / (t * 1e-3) / 1e9 if t > 0 else None,
                      "frac": (alg[k] / (t * 1e-3) / 1e9 / peak) if t > 0 else None}
-    stages["sync"]["compressed_gbs"] = info.scan_bytes / (stages["sync"]["ms"] * 1e-3) / 1e9 if stages["sync"]["ms"] else None
+    stages["sync"]["compressed_gbs"] = scan / (stages["sync"]["ms"] * 1e-3) / 1e9 if stages["sync"]["ms"] else None
     ent_ms = stages["unstuff"]["ms"] + stages["sync"]["ms"] + stages["write"]["ms"]
     dom = max(stage_ms, key=lambda k: stage_ms[k])
-    traffic = None
+    # DRAM traffic per launch group: from the committed ncu --set full capture, valid only for the kernel sources and
+    # the workload it was taken with (else null: a stale constant must not ride along)
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(dom)
+            tj = json.load(f)
+        if tj.get("kernel_sources_sha") == kernel_sources_sha() and tj.get("workload") == args.workload and not stream and batch_n == tj.get("images"):
+            traffic = tj.get(dom)
+            traffic_src = f"profiles/ncu_traffic.json: ncu --set full capture of {tj.get('capture')}, same kernel sources ({tj.get('kernel_sources_sha')})"
+        else:
+            traffic_src = "profiles/ncu_traffic.json was taken with other kernel sources or another workload: not reported"
     except (OSError, ValueError):
         pass
-    kname = {"unstuff": "k_unstuff+k_subseq_table", "sync": "k_huff_sync (all rounds)",
-             "write": "k_huff_write (+k_zero_tail)", "idct": "k_idct_color"}
+    kname = {"unstuff": "k_scan_count+k_scan_tiles+k_unstuff+k_subseq_table", "sync": "k_huff_sync (all rounds)",
+             "write": "k_huff_write (+k_zero_tail, k_dc_predict)", "idct": "k_idct_color"}
     roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "frac": stages[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "note": "Huffman kernels are latency/issue bound, not HBM bound: the fraction is reported against HBM as SURVEY 8d prescribes"}
     total_s = ms_max * 1e-3
+    images_rank0 = len(blobs)
     line = {
-        "metric": METRIC, "value": px * world * args.steps / total_s / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": total_px * steps / total_s / 1e6, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": ms_max / steps, "ms_per_image": ms_max / steps / max(1, images_rank0), "higher_is_better": True, "scaling": "strong" if stream else "weak", "vs_baseline": None,
         "dtype": "int32/int16 fixed point (u8 pixels)", "data": "synthetic",
-        "images_per_s": batch_n * world * args.steps / total_s,
-        "config": {"workload": desc, "images_per_gpu_per_step": batch_n, "output": "BMP bytes (bit-exact to the reference's write_BMP)",
-                   "l2": "per-step working set (coefficients + pixels) is far larger than the 126 MB L2; no explicit flush",
-                   "subseq_bits": args.subseq_bits or "per image, 2400-4096 (sub-sequences fill whole CTAs)", "slices": args.slices or 1,
-                   "sharding": "by image, no collective on the data path"},
+        "images_per_s": total_images * steps / total_s,
+        "config": {"workload": desc, "images_per_gpu_per_step": images_rank0, "output": "BMP bytes (bit-exact to the reference's write_BMP)",
+                   "l2": "per-step working set (coefficients + pixels) is far larger than the 126 MB L2; no explicit flush" if px > 40e6 else
+                         "working set of one step is smaller than the 126 MB L2 and stays there between steps (single-image latency case); inputs are re-read from HBM-resident buffers",
+                   "subseq_bits": args.subseq_bits or "per image (library default)", "slices": args.slices or "per image (library default)",
+                   "sharding": "ONE list dealt over the ranks by compressed size (LPT), no collective on the data path" if stream else "by image, no collective on the data path",
+                   "restart_parity_rule": rule or ("files with restart markers that are subsampled follow the restart-parity rule (DESIGN.md section 4)" if args.workload == "config3" else None)},
         "roofline": roofline, "stages": stages,
-        "entropy": {"ms": ent_ms, "compressed_gbs": info.scan_bytes / (ent_ms * 1e-3) / 1e9 if ent_ms else None},
+        "entropy": {"ms": ent_ms, "compressed_gbs": scan / (ent_ms * 1e-3) / 1e9 if ent_ms else None},
         # the whole decode as one box: compressed bytes in + 3 B/px out; the coefficient round trip is overhead, not credit
-        "whole_decode": {"alg_bytes": float(info.scan_bytes) + float(info.out_bytes),
-                         "achieved_gbs": (float(info.scan_bytes) + float(info.out_bytes)) / (ms_max / args.steps * 1e-3) / 1e9,
-                         "frac": (float(info.scan_bytes) + float(info.out_bytes)) / (ms_max / args.steps * 1e-3) / 1e9 / peak},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "whole_decode": {"alg_bytes": scan + outb,
+                         "achieved_gbs": (scan + outb) / (ms_total / steps * 1e-3) / 1e9,
+                         "frac": (scan + outb) / (ms_total / steps * 1e-3) / 1e9 / peak},
+        "cpu_baseline": cpu, "e2e": e2e, "cli_e2e": cli, "parity": parity, "gpu_launches": int(launches),
         "clocks": sampler.summary(windows),
         "first_bmp_sha256": first_hash,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity and parity["mismatches"]:
+        raise SystemExit(f"bench: {parity['mismatches']} of {parity['checked']} images differ from the reference's BMP files")
 
 
 if __name__ == "__main__":

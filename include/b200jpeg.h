@@ -98,6 +98,11 @@ typedef struct {
  * BJ_ERR_INVALID_JPEG exactly where the reference sets valid=false; BJ_ERR_UNSUPPORTED for SOF2 or a scan that
  * does not interleave all frame components (the reference cannot decode those either). */
 int bj_parse_header(const uint8_t *file, size_t len, bj_image_desc *desc);
+/* The same without the walk over the entropy-coded bytes: only the headers are read (what the decode entries do
+ * internally - they find the end of the scan on the GPU).  scan_len is then an UPPER BOUND (everything up to the end of
+ * the file), and a file whose scan does not end in EOI is only found out by the decode (per-image BJ_ERR_INVALID_JPEG).
+ * Enough to size output buffers with bj_output_size. */
+int bj_peek_header(const uint8_t *file, size_t len, bj_image_desc *desc);
 
 /* Output layouts of the full path. */
 typedef enum {
@@ -203,7 +208,11 @@ int bj_set_option(bj_ctx *ctx, const char *name, long value);
  * "decode_batch_d2h_bytes", "decode_batch_d2h_copies", "decode_batch_host_ms" (header parse + layout [+ staging copy]),
  * "decode_batch_wait_ms" (caller blocked on the GPU), "host_threads", "devices", and the kernel time per stage summed
  * over the sub-batches - the reference's per-stage "Profiles" lines (src/decoder_host.cpp:379-394) -
- * "decode_batch_ms_unstuff", "decode_batch_ms_sync", "decode_batch_ms_write", "decode_batch_ms_idct".
+ * "decode_batch_ms_unstuff", "decode_batch_ms_sync", "decode_batch_ms_write", "decode_batch_ms_idct";
+ * "decode_batch_direct_uploads" (sub-batches whose files went up straight from the caller's page-locked memory).
+ * "total_<counter>" (total_sub_batches, total_launches, total_h2d_bytes, total_d2h_bytes, total_host_ms, total_wait_ms,
+ * total_d2h_copies, total_ms_unstuff, total_ms_sync, total_ms_write, total_ms_idct, total_direct_uploads): the same
+ * summed over every bj_decode_batch / bj_submit job since the context was created.
  * For a multi-GPU context: byte and launch counts are sums, times the maximum over the devices.
  * Environment: B200JPEG_TRACE=1 prints one line per sub-batch of bj_decode_batch (host prepare, kernels, copy-out). */
 int bj_get_stat(const bj_ctx *ctx, const char *name, double *value);

@@ -129,6 +129,9 @@ static void parse_sos(rd_t *r, rs_header *h, const uint8_t used_in_frame[3], int
     unsigned ss = rd_get(r), se = rd_get(r), a = rd_get(r);
     if (h->frame_type == 0xC0) {
         if (ss != 0 || se != 63 || a != 0) { h->valid = 0; return; }
+    } else if (h->frame_type == 0xC2) {                  /* :79-106 (a progressive file is never decoded, but its scan header is checked) */
+        unsigned ah = a >> 4, al = a & 15;
+        if (ss > se || se > 63 || (ss == 0 && se != 0) || (ss != 0 && ns != 1) || (ah != 0 && al != ah - 1)) { h->valid = 0; return; }
     }
     for (unsigned i = 0; i < h->ncomp; i++) {
         if (!in_scan[i]) continue;

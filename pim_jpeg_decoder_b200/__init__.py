@@ -7,4 +7,4 @@ program, ``Decoder.decode`` = decode_Huffman_data + DPU program + BMP pixel gath
 """
 from ._lib import (BJ_ERR_CORRUPT_SCAN, BJ_ERR_CUDA, BJ_ERR_INVALID_JPEG, BJ_ERR_UNSUPPORTED, BJ_OK, BJ_OUT_BMP,  # noqa: F401
                    BJ_OUT_RGB8, BatchInfo, BjError, ImageDesc, lib)
-from .decoder import Batch, Decoder, PinnedBuffer, decode_files, parse_header, shard_by_size  # noqa: F401
+from .decoder import Batch, Decoder, Job, PinnedBuffer, decode_files, lpt_shards, parse_header, shard_by_size  # noqa: F401

@@ -56,17 +56,24 @@ class BatchInfo(C.Structure):
 SYMBOLS = {
     # name: (restype, argtypes)
     "bj_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "bj_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]),
+    "bj_device_count": (C.c_int, [C.c_void_p]),
     "bj_destroy": (None, [C.c_void_p]),
     "bj_status_string": (C.c_char_p, [C.c_int]),
     "bj_last_error": (C.c_char_p, [C.c_void_p]),
     "bj_device_sm_count": (C.c_int, [C.c_void_p]),
     "bj_host_alloc": (C.c_void_p, [C.c_size_t]),
     "bj_host_free": (None, [C.c_void_p]),
+    "bj_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "bj_host_unregister": (C.c_int, [C.c_void_p]),
     "bj_exec_mcus": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bj_exec_mcus_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "bj_parse_header": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(ImageDesc)]),
+    "bj_peek_header": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(ImageDesc)]),
     "bj_output_size": (C.c_size_t, [C.POINTER(ImageDesc), C.c_int]),
     "bj_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bj_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bj_wait": (C.c_int, [C.c_void_p]),
     "bj_batch_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "bj_batch_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bj_batch_decode": (C.c_int, [C.c_void_p, C.c_void_p]),

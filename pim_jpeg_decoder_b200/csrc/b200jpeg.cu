@@ -192,6 +192,13 @@ extern "C" int bj_get_stat(const bj_ctx *c, const char *name, double *value) {
     if (!strcmp(name, "decode_batch_ms_sync")) { *value = c->stats[8]; return BJ_OK; }
     if (!strcmp(name, "decode_batch_ms_write")) { *value = c->stats[9]; return BJ_OK; }
     if (!strcmp(name, "decode_batch_ms_idct")) { *value = c->stats[10]; return BJ_OK; }
+    if (!strncmp(name, "total_", 6)) {                           // the same counters summed over every call since bj_create
+        static const char *const names[] = {"sub_batches", "launches", "h2d_bytes", "d2h_bytes", "host_ms", "wait_ms", "d2h_copies",
+                                            "ms_unstuff", "ms_sync", "ms_write", "ms_idct", "direct_uploads"};
+        for (int i = 0; i < 12; i++) if (!strcmp(name + 6, names[i])) { *value = c->totals[i]; return BJ_OK; }
+        return BJ_ERR_ARG;
+    }
+    if (!strcmp(name, "decode_batch_direct_uploads")) { *value = c->stats[11]; return BJ_OK; }   // sub-batches uploaded straight from the caller's memory
     if (!strcmp(name, "devices")) { *value = c->children.empty() ? 1 : (double)c->children.size(); return BJ_OK; }
     if (!strcmp(name, "host_threads")) { *value = (c->children.empty() ? c : c->children[0])->host_pool.threads(); return BJ_OK; }
     return BJ_ERR_ARG;
@@ -258,6 +265,11 @@ extern "C" int bj_exec_mcus(bj_ctx *c, const uint32_t *metadata, int16_t *mcus, 
 extern "C" int bj_parse_header(const uint8_t *file, size_t len, bj_image_desc *desc) {
     if (!file || !desc) return BJ_ERR_ARG;
     return parse_header(file, len, desc);
+}
+
+extern "C" int bj_peek_header(const uint8_t *file, size_t len, bj_image_desc *desc) {
+    if (!file || !desc) return BJ_ERR_ARG;
+    return parse_header(file, len, desc, /*walk_scan=*/false);
 }
 
 extern "C" size_t bj_output_size(const bj_image_desc *d, int format) {
@@ -435,7 +447,7 @@ struct RangeSource {
         return true;
     }
 };
-enum { ST_SUB = 0, ST_LAUNCH, ST_H2D, ST_D2H, ST_HOST_MS, ST_WAIT_MS, ST_D2H_COPIES, ST_MS_UNSTUFF, ST_MS_SYNC, ST_MS_WRITE, ST_MS_IDCT, ST_COUNT };
+enum { ST_SUB = 0, ST_LAUNCH, ST_H2D, ST_D2H, ST_HOST_MS, ST_WAIT_MS, ST_D2H_COPIES, ST_MS_UNSTUFF, ST_MS_SYNC, ST_MS_WRITE, ST_MS_IDCT, ST_DIRECT, ST_COUNT };
 }  // namespace
 
 // One device's share of a call: pull ranges from `src` until it runs dry.
@@ -511,14 +523,14 @@ static int decode_worker(bj_ctx *c, RangeSource *src, const uint8_t *const *file
                 break;
             }
             first[slot] = i0; count[slot] = m; busy[slot] = true;
-            st[ST_SUB] += 1;
+            st[ST_SUB] += 1; st[ST_DIRECT] += b->direct_src ? 1 : 0;
             i0 += m; k++;
         }
     }
     // drain in submission order
     for (int j = 0; j < kSlots; j++) { const int slot = (k + j) % kSlots; if (busy[slot]) { const int r = finish(slot); if (rc == BJ_OK) rc = r; } }
     if (ev_base) cudaEventDestroy(ev_base);
-    for (int i = 0; i < ST_COUNT; i++) c->stats[i] = st[i];
+    for (int i = 0; i < ST_COUNT; i++) { c->stats[i] = st[i]; c->totals[i] += st[i]; }
     return rc;
 }
 
@@ -538,11 +550,12 @@ static int decode_batch_now(bj_ctx *c, const uint8_t *const *files, const size_t
     for (auto &t : th) t.join();
     int rc = BJ_OK;
     for (int i = 0; i < ST_COUNT; i++) c->stats[i] = 0;
+    struct Fold { bj_ctx *c; ~Fold() { for (int i = 0; i < ST_COUNT; i++) c->totals[i] += c->stats[i]; } } fold{c};
     for (size_t d = 0; d < c->children.size(); d++) {
         if (rc == BJ_OK) rc = rcs[d];
         if (rcs[d] != BJ_OK) c->last_error = c->children[d]->last_error;
         for (int i = 0; i < ST_COUNT; i++) {
-            const bool is_time = i == ST_HOST_MS || i == ST_WAIT_MS || i >= ST_MS_UNSTUFF;
+            const bool is_time = i == ST_HOST_MS || i == ST_WAIT_MS || (i >= ST_MS_UNSTUFF && i <= ST_MS_IDCT);
             c->stats[i] = is_time ? std::max(c->stats[i], c->children[d]->stats[i]) : c->stats[i] + c->children[d]->stats[i];   // devices work side by side
         }
     }

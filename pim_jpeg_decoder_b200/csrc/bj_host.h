@@ -161,7 +161,8 @@ struct bj_ctx {
     struct bj_batch *slots[bj::kSlots] = {};          // sub-batches of bj_decode_batch in flight (one stream each)
     bj::HostPool host_pool;
     int host_threads = 0;                // 0 = default: min(4, hardware threads / 2)
-    double stats[16] = {};
+    double stats[16] = {};               // counters of the last bj_decode_batch / job (b200jpeg.cu: ST_*)
+    double totals[16] = {};              // ... summed over every call since bj_create
     cudaStream_t streams[bj::kSlots] = {};
     cudaEvent_t ev_exec[2] = {nullptr, nullptr};      // bj_exec_mcus: around the kernel ("DPU execution" profile line)
     std::vector<bj_ctx *> children;      // bj_create_multi: one single-device context per GPU; this one only deals the work

@@ -123,16 +123,41 @@ class Batch:
             pass
 
 
-class Decoder:
-    """One context = one GPU (one process per GPU)."""
+class Job:
+    """A batch handed to bj_submit: wait() blocks until its outputs are in host memory and returns the status array."""
 
-    def __init__(self, device=0):
+    def __init__(self, dec, handle, keep, status, n):
+        self.dec, self.h, self._keep, self._status, self.n = dec, handle, keep, status, n
+
+    def wait(self):
+        if self.h is not None:
+            h, self.h = self.h, None
+            L.check(L.lib().bj_wait(h), "bj_wait", self.dec.ctx)
+        return self._status[: self.n]
+
+
+class Decoder:
+    """One context.  Decoder(device) drives one GPU (one process per GPU, the torchrun way); Decoder(devices=[...])
+    - or devices="all" - drives several GPUs of the box from this one process (bj_create_multi), the way the
+    reference's single process takes every DPU (src/decoder_host.cpp:32-33)."""
+
+    def __init__(self, device=0, devices=None):
         self.ctx = C.c_void_p()
-        st = L.lib().bj_create(C.byref(self.ctx), device)
+        if devices is None:
+            st = L.lib().bj_create(C.byref(self.ctx), device)
+            what = "bj_create"
+        elif isinstance(devices, str):
+            st = L.lib().bj_create_multi(C.byref(self.ctx), None, 0)
+            what = "bj_create_multi"
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            st = L.lib().bj_create_multi(C.byref(self.ctx), arr, len(devices))
+            what = "bj_create_multi"
         if st != L.BJ_OK:
             self.ctx = None
-            raise L.BjError(st, "bj_create (this back end has no CPU fallback)")
+            raise L.BjError(st, what + " (this back end has no CPU fallback)")
         self.device = device
+        self.device_count = L.lib().bj_device_count(self.ctx)
 
     def close(self):
         if self.ctx:
@@ -213,6 +238,34 @@ class Decoder:
         L.check(L.lib().bj_decode_batch(self.ctx, ip.ctypes.data_as(C.c_void_p), il.ctypes.data_as(C.c_void_p), n, fmt,
                                         op.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p)), "bj_decode_batch", self.ctx)
         return status[:n]
+
+
+    def submit_packed(self, src, src_off, src_len, dst, dst_off, fmt=L.BJ_OUT_RGB8):
+        """decode_packed without waiting (bj_submit): returns a Job; job.wait() gives the status array."""
+        n = len(src_off)
+        ip = (np.asarray(src_off, dtype=np.uint64) + np.uint64(src.__array_interface__["data"][0]))
+        il = np.ascontiguousarray(src_len, dtype=np.uint64)
+        op = (np.asarray(dst_off, dtype=np.uint64) + np.uint64(dst.__array_interface__["data"][0]))
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        h = C.c_void_p()
+        L.check(L.lib().bj_submit(self.ctx, ip.ctypes.data_as(C.c_void_p), il.ctypes.data_as(C.c_void_p), n, fmt,
+                                  op.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p), C.byref(h)), "bj_submit", self.ctx)
+        return Job(self, h, (ip, il, op, src, dst), status, n)
+
+
+def lpt_shards(costs, world_size):
+    """Deal a stream of images over `world_size` ranks: longest processing time first - sort by cost (compressed size,
+    the reference's sort key, src/decoder_host.cpp:46-61) descending and give each image to the rank with the least
+    work so far.  Returns world_size index lists (each in ascending index order)."""
+    import heapq
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    heap = [(0, r) for r in range(world_size)]
+    out = [[] for _ in range(world_size)]
+    for i in order:
+        load, r = heapq.heappop(heap)
+        out[r].append(i)
+        heapq.heappush(heap, (load + costs[i], r))
+    return [sorted(o) for o in out]
 
 
 def shard_by_size(sizes, world_size):

@@ -1,21 +1,32 @@
 // decoder_b200 - the reference CLI (`./bin/decoder <jpeg_1> ...`, src/decoder_host.cpp:352-394) on the B200 back end,
-// full path: file bytes -> bj_decode_batch (Huffman + dequant + IDCT + colour + BMP bytes on the GPU) -> one
-// write() per image.  Same user-visible behaviour as the reference:
+// full path: file bytes -> bj_submit (Huffman + dequant + IDCT + colour + BMP bytes on the GPU) -> one write() per image.
+// Same user-visible behaviour as the reference:
 //   * inputs are sorted ascending by file size                      (src/decoder_host.cpp:46-61, :360)
 //   * `<name>.bmp` is written next to each input                    (:326-331)
 //   * an unreadable / invalid file prints "<file>: Error - Invalid JPEG" and is skipped   (:120-123)
-//   * a "Profiles:" block is printed at the end                     (:379-394)
-// One process drives one GPU.  For a multi-GPU job start one process per GPU (torchrun-style environment:
-// RANK / WORLD_SIZE / LOCAL_RANK, or B200JPEG_DEVICE); the sorted list is dealt round-robin to the ranks - images
-// are independent, there is no collective.  There is no CPU fallback: without a CUDA device bj_create fails.
+//   * a "Profiles:" block is printed at the end, with the per-stage lines   (:379-394)
+// and the same shape of pipeline: the reference overlaps its producer (parse + Huffman) with its consumer (offload +
+// BMP write) on two threads and a queue (:25-38, :364-365); here three stages run side by side on groups of images -
+// a reader thread (file bytes straight into page-locked memory, header peek), the GPU decode (bj_submit / bj_wait,
+// zero-copy upload) and a writer thread (one fwrite per BMP).
+// Devices: like the reference's single process takes every DPU (DPU_ALLOCATE_ALL, :32), one process takes every visible
+// GPU (bj_create_multi) unless told otherwise: B200JPEG_DEVICES=<n> limits the count, B200JPEG_DEVICE=<i> picks one;
+// under a one-process-per-GPU launcher (RANK / WORLD_SIZE / LOCAL_RANK) each process takes its LOCAL_RANK GPU and its
+// round-robin share of the sorted list - images are independent, there is no collective.
+// There is no CPU fallback: without a CUDA device bj_create fails.
 #include <sys/stat.h>
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b200jpeg.h"
@@ -34,15 +45,42 @@ static int env_int(const char *name, int dflt) {
 struct Input {
     std::string path;
     size_t size = 0;
-    std::vector<uint8_t> bytes;
-    bj_image_desc desc;
-    int parse = BJ_ERR_INVALID_JPEG;
-    size_t out_bytes = 0;
 };
 
 static std::string bmp_name(const std::string &p) {
     const size_t pos = p.find_last_of('.');
     return (pos == std::string::npos ? p : p.substr(0, pos)) + ".bmp";
+}
+
+// One group of images on its way through the three stages.  Its buffers are page-locked and reused.
+struct Group {
+    size_t i0 = 0, n = 0;                       // images [i0, i0 + n) of the sorted list
+    uint8_t *in = nullptr, *out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    std::vector<const uint8_t *> files;
+    std::vector<size_t> lens, out_bytes;
+    std::vector<uint8_t *> outs;
+    std::vector<int> status;
+    bj_job *job = nullptr;
+    bool last = false;
+};
+
+template <class T> class Channel {              // the queue between two stages (src/decoder_host.cpp:35-38: batched_queue, mtx, cv)
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<T> q_;
+public:
+    void push(T v) { { std::lock_guard<std::mutex> l(m_); q_.push_back(v); } cv_.notify_one(); }
+    T pop() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return !q_.empty(); }); T v = q_.front(); q_.pop_front(); return v; }
+};
+
+static bool grow(uint8_t **p, size_t *cap, size_t need) {
+    if (need <= *cap) return true;
+    if (*p) bj_host_free(*p);
+    *cap = need + need / 4 + 4096;
+    *p = static_cast<uint8_t *>(bj_host_alloc(*cap));
+    if (!*p) { fprintf(stderr, "decoder_b200: pinned allocation of %zu bytes failed\n", *cap); *cap = 0; return false; }
+    return true;
 }
 
 int main(int argc, char **argv) {
@@ -51,8 +89,9 @@ int main(int argc, char **argv) {
         return 1;
     }
     const int rank = env_int("RANK", 0), world = std::max(1, env_int("WORLD_SIZE", 1));
-    const int device = env_int("B200JPEG_DEVICE", env_int("LOCAL_RANK", 0));
-    const size_t out_budget = (size_t)env_int("B200JPEG_OUT_MB", 4096) << 20;     // pinned output bytes per call
+    const size_t out_budget = (size_t)env_int("B200JPEG_OUT_MB", 1024) << 20;      // decoded bytes per group
+    const size_t in_budget = (size_t)env_int("B200JPEG_IN_MB", 256) << 20;         // compressed bytes per group
+    const size_t max_images = (size_t)std::max(1, env_int("B200JPEG_GROUP_IMAGES", 1 << 20));   // images per group
 
     const double t_start = now_s();
     std::vector<Input> all(argc - 1);
@@ -66,95 +105,140 @@ int main(int argc, char **argv) {
     for (size_t i = rank; i < all.size(); i += world) in.push_back(std::move(all[i]));
 
     bj_ctx *ctx = nullptr;
-    int rc = bj_create(&ctx, device);
+    int rc;
+    if (world > 1 || getenv("B200JPEG_DEVICE")) {
+        const int device = env_int("B200JPEG_DEVICE", env_int("LOCAL_RANK", 0));
+        rc = bj_create(&ctx, device);
+    } else {
+        rc = bj_create_multi(&ctx, nullptr, env_int("B200JPEG_DEVICES", 0));       // 0 = every visible GPU
+    }
     if (rc != BJ_OK) {
-        fprintf(stderr, "decoder_b200: bj_create(device %d): %s\n", device, bj_status_string(rc));
+        fprintf(stderr, "decoder_b200: bj_create: %s\n", bj_status_string(rc));
         return 2;
     }
     bj_set_option(ctx, "packed_outputs", 1);
-    printf("B200 device %d: %d SMs\n", device, bj_device_sm_count(ctx));
+    printf("B200 devices: %d (%d SMs each)\n", bj_device_count(ctx), bj_device_sm_count(ctx));
 
+    constexpr int kGroups = 4;                   // one being read, one decoding, one queued behind it, one being written
+    Group groups[kGroups];
+    Channel<Group *> to_decode, to_write, to_read;
+    for (auto &g : groups) to_read.push(&g);
     double t_read = 0, t_decode = 0, t_write = 0;
     int calls = 0, failures = 0;
-    uint8_t *pin = nullptr;
-    size_t pin_cap = 0;
-    size_t i0 = 0;
-    while (i0 < in.size()) {
-        // ---- read + parse a group whose outputs fit the pinned buffer
-        double t0 = now_s();
-        size_t i1 = i0, out_total = 0;
-        while (i1 < in.size()) {
-            Input &f = in[i1];
-            FILE *fp = fopen(f.path.c_str(), "rb");
-            if (fp) {
-                f.bytes.resize(f.size);
-                const size_t got = f.size ? fread(f.bytes.data(), 1, f.size, fp) : 0;
-                fclose(fp);
-                f.bytes.resize(got);
-                f.parse = got ? bj_parse_header(f.bytes.data(), got, &f.desc) : BJ_ERR_INVALID_JPEG;
-            }
-            f.out_bytes = f.parse == BJ_OK ? bj_output_size(&f.desc, BJ_OUT_BMP) : 0;
-            const size_t padded = (f.out_bytes + 15) / 16 * 16;
-            if (i1 > i0 && out_total + padded > out_budget) { f.bytes.clear(); f.bytes.shrink_to_fit(); break; }
-            out_total += padded;
-            i1++;
-        }
-        t_read += now_s() - t0;
+    std::atomic<bool> fatal{false};
 
-        // ---- decode (one call; the library double-buffers sub-batches over its own streams)
-        t0 = now_s();
-        if (out_total + 64 > pin_cap) {
-            if (pin) bj_host_free(pin);
-            pin_cap = out_total + out_total / 8 + 64;
-            pin = static_cast<uint8_t *>(bj_host_alloc(pin_cap));
-            if (!pin) { fprintf(stderr, "decoder_b200: pinned allocation of %zu bytes failed\n", pin_cap); return 2; }
+    // ---- stage 1: read the files of a group into page-locked memory, peek at the headers to size the outputs
+    std::thread reader([&] {
+        size_t i0 = 0;
+        while (true) {
+            Group *g = to_read.pop();
+            const double t0 = now_s();
+            g->i0 = i0; g->n = 0; g->last = false;
+            size_t in_bytes = 0, out_total = 0, i1 = i0;
+            while (i1 < in.size() && i1 - i0 < max_images && (i1 == i0 || in_bytes + in[i1].size + 16 <= in_budget)) { in_bytes += in[i1].size + 16; i1++; }
+            if (!grow(&g->in, &g->in_cap, in_bytes + 64)) { fatal = true; g->last = true; to_decode.push(g); return; }
+            g->files.clear(); g->lens.clear(); g->out_bytes.clear();
+            size_t o = 0, k = i0;
+            for (; k < i1; k++) {
+                size_t got = 0;
+                FILE *fp = fopen(in[k].path.c_str(), "rb");
+                if (fp) { got = in[k].size ? fread(g->in + o, 1, in[k].size, fp) : 0; fclose(fp); }
+                bj_image_desc d;
+                const size_t ob = (got && bj_peek_header(g->in + o, got, &d) == BJ_OK) ? bj_output_size(&d, BJ_OUT_BMP) : 0;
+                const size_t padded = (ob + 15) / 16 * 16;
+                if (k > i0 && out_total + padded > out_budget) break;          // (this file is read again with the next group)
+                g->files.push_back(g->in + o); g->lens.push_back(got); g->out_bytes.push_back(ob);
+                out_total += padded;
+                o += got;
+            }
+            g->n = k - i0;
+            i0 = k;
+            g->last = i0 >= in.size();
+            if (!grow(&g->out, &g->out_cap, out_total + 64)) { fatal = true; g->last = true; g->n = 0; to_decode.push(g); return; }
+            g->outs.assign(g->n, nullptr); g->status.assign(g->n, 0);
+            size_t oo = 0;
+            for (size_t j = 0; j < g->n; j++) { g->outs[j] = g->out_bytes[j] ? g->out + oo : nullptr; oo += (g->out_bytes[j] + 15) / 16 * 16; }
+            t_read += now_s() - t0;
+            const bool last = g->last;
+            to_decode.push(g);
+            if (last) return;
         }
-        const int n = (int)(i1 - i0);
-        std::vector<const uint8_t *> files(n);
-        std::vector<size_t> lens(n);
-        std::vector<uint8_t *> outs(n);
-        std::vector<int> status(n, 0);
-        size_t o = 0;
-        for (int k = 0; k < n; k++) {
-            Input &f = in[i0 + k];
-            files[k] = f.bytes.data(); lens[k] = f.bytes.size();
-            outs[k] = f.parse == BJ_OK ? pin + o : nullptr;
-            o += (f.out_bytes + 15) / 16 * 16;
+    });
+
+    // ---- stage 3: write the BMPs of a finished group.  Like the reference, a scan that fails to decode still produces
+    // its (partial) image (the result of decode_Huffman_data is ignored, src/decoder_host.cpp:181).
+    std::thread writer([&] {
+        while (true) {
+            Group *g = to_write.pop();
+            const double t0 = now_s();
+            for (size_t k = 0; k < g->n; k++) {
+                const Input &f = in[g->i0 + k];
+                if (g->status[k] != BJ_OK && g->status[k] != BJ_ERR_CORRUPT_SCAN) {
+                    printf("%s: Error - Invalid JPEG\n", f.path.c_str());
+                    failures++;
+                } else {
+                    FILE *fp = fopen(bmp_name(f.path).c_str(), "wb");
+                    if (!fp || fwrite(g->outs[k], 1, g->out_bytes[k], fp) != g->out_bytes[k]) { printf("%s: Error - cannot write BMP\n", f.path.c_str()); failures++; }
+                    if (fp) fclose(fp);
+                }
+            }
+            t_write += now_s() - t0;
+            const bool last = g->last;
+            to_read.push(g);
+            if (last) return;
         }
-        rc = bj_decode_batch(ctx, files.data(), lens.data(), n, BJ_OUT_BMP, outs.data(), status.data());
-        if (rc != BJ_OK) {
-            fprintf(stderr, "decoder_b200: bj_decode_batch: %s (%s)\n", bj_status_string(rc), bj_last_error(ctx));
-            return 2;
+    });
+
+    // ---- stage 2 (this thread): hand each group to the GPU as soon as it is read; keep one job decoding while the next
+    // is submitted, pass finished groups on to the writer
+    Group *running = nullptr;
+    double t_run0 = 0;
+    auto finish_running = [&]() {
+        if (!running) return;
+        const int r = bj_wait(running->job);
+        running->job = nullptr;
+        if (r != BJ_OK) {
+            fprintf(stderr, "decoder_b200: decode: %s (%s)\n", bj_status_string(r), bj_last_error(ctx));
+            for (auto &s : running->status) s = r;
+            fatal = true;
         }
+        t_decode += now_s() - t_run0;
         calls++;
-        t_decode += now_s() - t0;
-
-        // ---- write.  Like the reference, a scan that fails to decode still produces its (partial) image
-        // (the result of decode_Huffman_data is ignored, src/decoder_host.cpp:181).
-        t0 = now_s();
-        for (int k = 0; k < n; k++) {
-            Input &f = in[i0 + k];
-            if (status[k] != BJ_OK && status[k] != BJ_ERR_CORRUPT_SCAN) {
-                printf("%s: Error - Invalid JPEG\n", f.path.c_str());
-                failures++;
-            } else {
-                FILE *fp = fopen(bmp_name(f.path).c_str(), "wb");
-                if (!fp || fwrite(outs[k], 1, f.out_bytes, fp) != f.out_bytes) { printf("%s: Error - cannot write BMP\n", f.path.c_str()); failures++; }
-                if (fp) fclose(fp);
-            }
-            f.bytes.clear(); f.bytes.shrink_to_fit();
-        }
-        t_write += now_s() - t0;
-        i0 = i1;
+        to_write.push(running);
+        running = nullptr;
+    };
+    while (true) {
+        Group *g = to_decode.pop();
+        bj_job *job = nullptr;
+        int r = g->n ? bj_submit(ctx, g->files.data(), g->lens.data(), (int)g->n, BJ_OUT_BMP, g->outs.data(), g->status.data(), &job) : BJ_OK;
+        if (r != BJ_OK) { fprintf(stderr, "decoder_b200: bj_submit: %s\n", bj_status_string(r)); fatal = true; for (auto &s : g->status) s = r; }
+        finish_running();                          // (the new job is already queued behind it)
+        if (job) { g->job = job; running = g; t_run0 = now_s(); }
+        else to_write.push(g);
+        if (g->last) break;
     }
-    if (pin) bj_host_free(pin);
+    finish_running();
+    reader.join();
+    writer.join();
+
+    double ms[4] = {0, 0, 0, 0}, direct = 0, subs = 0;
+    bj_get_stat(ctx, "total_ms_unstuff", &ms[0]); bj_get_stat(ctx, "total_ms_sync", &ms[1]);
+    bj_get_stat(ctx, "total_ms_write", &ms[2]); bj_get_stat(ctx, "total_ms_idct", &ms[3]);
+    bj_get_stat(ctx, "total_direct_uploads", &direct); bj_get_stat(ctx, "total_sub_batches", &subs);
+    for (auto &g : groups) { if (g.in) bj_host_free(g.in); if (g.out) bj_host_free(g.out); }
     bj_destroy(ctx);
 
+    // (the reference prints: total, queue waiting, CPU-DPU transfer, DPU execution, DPU-CPU transfer, BMP write, and the
+    // DPU program's own split into initialization / dequantization / IDCT / colour conversion)
     printf("\nProfiles:\n");
     printf("End-to-end execution time: %gs\n", now_s() - t_start);
-    printf(" - File read + header parse time: %gs\n", t_read);
-    printf(" - B200 decode time (H2D + kernels + D2H): %gs\n", t_decode);
-    printf(" - BMP write time: %gs\n", t_write);
-    printf(" - Total %d calls, %zu images, %d failed\n", calls, in.size(), failures);
-    return 0;
+    printf(" - File read + header peek time (reader thread): %gs\n", t_read);
+    printf(" - B200 decode time (H2D + kernels + D2H, overlapped with reading and writing): %gs\n", t_decode);
+    printf("    - scan filter / segmenter kernels: %gs\n", ms[0] * 1e-3);
+    printf("    - Huffman synchronisation kernels: %gs\n", ms[1] * 1e-3);
+    printf("    - Huffman write + DC prediction kernels: %gs\n", ms[2] * 1e-3);
+    printf("    - dequantisation + IDCT + colour conversion kernel: %gs\n", ms[3] * 1e-3);
+    printf(" - BMP write time (writer thread): %gs\n", t_write);
+    printf(" - Total %d groups, %d sub-batches (%d uploaded without a staging copy), %zu images, %d failed\n", calls, (int)subs, (int)direct, in.size(), failures);
+    return fatal ? 2 : 0;
 }

@@ -70,6 +70,25 @@ def test_decoder_b200_cli(golden, golden_dir, tmp_path):
     assert "missing.jpg: Error - Invalid JPEG" in out.stdout
 
 
+def test_decoder_b200_pipeline_of_many_groups(golden, golden_dir, tmp_path):
+    """Groups of 5 images: the reader thread, the GPU jobs (bj_submit / bj_wait) and the writer thread overlap over ~8
+    groups that rotate through 4 sets of pinned buffers; every device of the box is used (bj_create_multi)."""
+    exe = os.path.join(HOST, "_build", "decoder_b200")
+    names = _valid_names(golden) + ["bad_not_jpeg", "bad_truncated"]
+    paths = _copy(names, golden, golden_dir, tmp_path)
+    env = dict(os.environ, B200JPEG_GROUP_IMAGES="5")
+    out = subprocess.run([exe] + paths, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Huffman synchronisation kernels" in out.stdout and "IDCT + colour conversion kernel" in out.stdout
+    groups = int(out.stdout.split(" - Total ")[1].split(" groups")[0])
+    assert groups >= len(names) // 5
+    for n, p in zip(names, paths):
+        if golden[n].get("invalid"):
+            assert not os.path.exists(p[:-4] + ".bmp")
+        else:
+            assert _sha(p[:-4] + ".bmp") == golden[golden[n]["expect"]]["bmp_sha256"], n
+
+
 def test_decoder_b200_sharded_by_rank(golden, golden_dir, tmp_path):
     """Two 'ranks' (processes) on the same GPU each take their share of the sorted list; together they cover it."""
     exe = os.path.join(HOST, "_build", "decoder_b200")

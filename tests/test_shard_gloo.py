@@ -80,3 +80,22 @@ def test_shard_by_size_properties():
             assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
             for s in shards:                                 # ascending by size inside a shard, like the reference's sort
                 assert [sizes[i] for i in s] == sorted(sizes[i] for i in s)
+
+
+def test_lpt_stream_dealing_properties():
+    """bench.py --workload config5 --stream N: ONE stream (a pool cycled) dealt over the ranks by compressed size,
+    longest first (LPT): shards are disjoint, cover the stream, and their byte loads differ by less than one image."""
+    sys.path.insert(0, ROOT)
+    from pim_jpeg_decoder_b200.decoder import lpt_shards
+    rng = np.random.default_rng(5)
+    pool = [int(x) for x in rng.choice([75_000, 120_000, 20_000, 300_000, 800_000, 3_200_000], size=64, p=[.55, .15, .1, .1, .07, .03])]
+    for world in (1, 2, 4, 8):
+        for n in (0, 1, 63, 4096):
+            costs = [pool[i % len(pool)] for i in range(n)]
+            shards = lpt_shards(costs, world)
+            assert len(shards) == world and sorted(i for s in shards for i in s) == list(range(n))
+            loads = [sum(costs[i] for i in s) for s in shards]
+            if n >= world:
+                assert max(loads) - min(loads) <= max(costs)
+            for s in shards:
+                assert s == sorted(s)
