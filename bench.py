@@ -655,16 +655,17 @@ def main():
                 refs = {f: sha_file(f[:-4] + ".bmp") for f in ref.files} if rule is None else None
                 for f in ref.files:
                     os.remove(f[:-4] + ".bmp")
-                tc = []
+                tc, cli_out = [], ""
                 for _ in range(3):
                     t0 = time.perf_counter()
-                    subprocess.run([cli_bin] + ref.files, stdout=subprocess.DEVNULL, check=True, env=dict(os.environ, B200JPEG_DEVICES="1"))
+                    cli_out = subprocess.run([cli_bin] + ref.files, capture_output=True, text=True, check=True, env=dict(os.environ, B200JPEG_DEVICES="1")).stdout
                     tc.append(time.perf_counter() - t0)
                 bad = sum(1 for f in ref.files if refs is not None and sha_file(f[:-4] + ".bmp") != refs[f])
                 cli = {"b200": {"value": ref.pixels / min(tc) / 1e6, "unit": UNIT, "seconds": min(tc), "runs": tc,
                                 "what": "decoder_b200 <files>: process start, CUDA context, file read, decode on one GPU, BMP files written (tmpfs)"},
                        "reference": {"value": cpu["value"], "unit": UNIT, "what": "the reference CLI, one process per host core on a slice of the same files"},
                        "ratio": (ref.pixels / min(tc) / 1e6) / cpu["value"], "images": n,
+                       "b200_profiles": [ln.strip() for ln in cli_out.split("Profiles:")[-1].splitlines() if ln.strip()],
                        "bmp_files_identical": (bad == 0) if refs is not None else None}
         finally:
             ref.close()
@@ -694,7 +695,7 @@ def main():
     scan = float(agg["scan_bytes"])
     outb = float(agg["out_bytes"])
     alg = {
-        "unstuff": 2.0 * scan + clean,                                # raw bytes read twice (count, compact) + clean bytes written
+        "unstuff": 1.0 * scan + clean,                                # raw bytes read once + clean bytes written
         "sync": clean + (28.0 + 16.0 * (args.slices or 1) + 64.0) * nsub,    # stream read once + per-sub-sequence states/totals + slice entry states + 4 quarter records written
         "write": clean + 128.0 * units,                               # stream read once + every coefficient unit written once
         "idct": 128.0 * units + outb,                                 # coefficients read once + pixels written once
@@ -720,7 +721,7 @@ def main():
             traffic_src = "profiles/ncu_traffic.json was taken with other kernel sources or another workload: not reported"
     except (OSError, ValueError):
         pass
-    kname = {"unstuff": "k_scan_count+k_scan_tiles+k_unstuff+k_subseq_table", "sync": "k_huff_sync (all rounds)",
+    kname = {"unstuff": "k_unstuff+k_subseq_table", "sync": "k_huff_sync (all rounds)",
              "write": "k_huff_write (+k_zero_tail, k_dc_predict)", "idct": "k_idct_color"}
     roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": stages[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

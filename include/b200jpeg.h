@@ -107,10 +107,18 @@ int bj_peek_header(const uint8_t *file, size_t len, bj_image_desc *desc);
 /* Output layouts of the full path. */
 typedef enum {
     BJ_OUT_RGB8 = 0,   /* top-down packed R,G,B bytes, width*height*3 */
-    BJ_OUT_BMP = 1     /* the exact file bytes write_BMP produces (src/bmp_writer.cpp:19-67): 26-byte header,
+    BJ_OUT_BMP = 1,    /* the exact file bytes write_BMP produces (src/bmp_writer.cpp:19-67): 26-byte header,
                           bottom-up B,G,R rows, width%4 zero bytes after every row */
+    BJ_OUT_REF_MCUS = 2 /* the reference's own `mcus` buffers after pim.exec() + pim.copy(batch.mcus, "mcus")
+                          (src/decoder_host.cpp:292,308): R,G,B as int16 in the [block][component][position][64] tile
+                          layout (src/decoder_dpu.c:134-156), nchunks x 64*MAX_MCU_PER_DPU*3 shorts per image, every
+                          short of every chunk as the DPUs leave it (unused tiles 128) - what the UNCHANGED write_BMP
+                          (src/bmp_writer.cpp:19-67) takes.  MAX_MCU_PER_DPU: option "ref_max_mcu_per_dpu" (default 100) */
 } bj_out_format;
-size_t bj_output_size(const bj_image_desc *desc, int format);
+size_t bj_output_size(const bj_image_desc *desc, int format);          /* BJ_OUT_REF_MCUS: for MAX_MCU_PER_DPU = 100 */
+/* BJ_OUT_REF_MCUS for any MAX_MCU_PER_DPU (a multiple of 4): bytes of the image's chunks; *nchunks = how many
+ * (need_dpus of src/decoder_host.cpp:125-128). */
+size_t bj_ref_mcus_size(const bj_image_desc *desc, int max_mcu_per_dpu, int *nchunks);
 
 /* ---------------------------------------------------------------------------------------------------------
  * FULL PATH, one call.  Replaces, per image, decode_Huffman_data (src/jpeg_scanner.cpp:707-756) + the DPU
@@ -122,6 +130,19 @@ size_t bj_output_size(const bj_image_desc *desc, int format);
  * Internally: sub-batches double-buffered over pinned staging on CUDA streams; blocks until outs are written. */
 int bj_decode_batch(bj_ctx *ctx, const uint8_t *const *files, const size_t *lens, int n, int format,
                     uint8_t *const *outs, int *status);
+
+/* FULL PATH behind the UNCHANGED scanner.  Replaces decode_Huffman_data(header, MCU_buffer, dpu_offset) + pim.copy /
+ * pim.exec / pim.copy (src/decoder_host.cpp:181, :268-312) for a host that keeps read_JPEG in front: it fills one
+ * bj_image_desc per `Header` (field for field) and hands over the scan bytes -
+ *   BJ_SCAN_UNSTUFFED  Header::huffman_data as read_JPEG leaves it (FF00 un-stuffed, RSTn removed, src/jpeg_scanner.cpp:
+ *                      405-433).  Only for restart_interval == 0: read_JPEG throws the RSTn positions away, and with them
+ *                      the segment boundaries (per-image BJ_ERR_UNSUPPORTED otherwise)
+ *   BJ_SCAN_RAW        the scan as it is in the file (stuffed, with RSTn), with or without the EOI behind it
+ * scan_kinds == NULL: all BJ_SCAN_RAW.  desc->scan_off / scan_len are ignored.  With format BJ_OUT_REF_MCUS the outputs
+ * are the `mcus` buffers the unchanged write_BMP reads. */
+typedef enum { BJ_SCAN_RAW = 0, BJ_SCAN_UNSTUFFED = 1 } bj_scan_kind;
+int bj_decode_batch_desc(bj_ctx *ctx, const bj_image_desc *descs, const uint8_t *const *scans, const size_t *scan_lens,
+                         const int *scan_kinds, int n, int format, uint8_t *const *outs, int *status);
 
 /* FULL PATH, asynchronous.  bj_submit hands the batch to the context's worker thread and returns at once; bj_wait blocks
  * until that batch's outputs are in host memory, returns what bj_decode_batch would have returned and releases the job.
@@ -194,6 +215,8 @@ int bj_stage_entropy(bj_ctx *ctx, const uint8_t *file, size_t len, int16_t *coef
  *                      through a pinned staging copy otherwise;  1: the caller states that the files lie in ONE
  *                      page-locked allocation the library does not know (e.g. cudaHostAlloc) - only set it when that
  *                      is true, pageable memory would make the upload synchronous;  -1: always stage
+ *   "ref_max_mcu_per_dpu"  BJ_OUT_REF_MCUS: the MAX_MCU_PER_DPU the reading host was compiled with (Makefile:2; default
+ *                      100, a multiple of 4)
  *   "max_image_pixels" images with more pixels get BJ_ERR_UNSUPPORTED (default 2^28), like the reference's "Too high
  *                      resolution" (src/decoder_host.cpp:146-149): a tiny file cannot claim tens of GB of buffers
  *   "sub_batch_out_bytes"  decoded bytes per sub-batch of bj_decode_batch (default 1 GiB)

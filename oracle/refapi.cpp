@@ -99,6 +99,17 @@ void ref_exec_mcus(const uint32_t *metadata /*[nchunk][276]*/, short *mcus /*[nc
     for (int i = 0; i < nchunk; i++) oracle_dpu_run(metadata + (size_t)i * 276, mcus + (size_t)i * len);
 }
 
+// The reference's own write_BMP (bmp_writer.cpp:19-67) on caller-supplied post-exec chunks: what a host that keeps its
+// BMP writer does with the buffers a back end hands back (decoder_host.cpp:330).
+int ref_write_bmp(const uint32_t *metadata276, const short *mcus /*[nchunk][64*M*3]*/, int nchunk, const char *path) {
+    const int len = oracle_dpu_mcus_len();
+    std::vector<uint32_t> md(metadata276, metadata276 + 276);
+    std::vector<std::vector<short>> buf(nchunk, std::vector<short>(len));
+    for (int i = 0; i < nchunk; i++) std::memcpy(buf[i].data(), mcus + (size_t)i * len, len * sizeof(short));
+    write_BMP(md, buf, 0, path);
+    return 0;
+}
+
 int ref_max_mcu_per_dpu(void) { return MAX_MCU_PER_DPU; }
 
 }  // extern "C"

@@ -6,5 +6,5 @@ program, ``Decoder.decode`` = decode_Huffman_data + DPU program + BMP pixel gath
 ``./bin/decoder <jpeg...>`` CLI) used by the tests and the benchmark.  There is no CPU decode path.
 """
 from ._lib import (BJ_ERR_CORRUPT_SCAN, BJ_ERR_CUDA, BJ_ERR_INVALID_JPEG, BJ_ERR_UNSUPPORTED, BJ_OK, BJ_OUT_BMP,  # noqa: F401
-                   BJ_OUT_RGB8, BatchInfo, BjError, ImageDesc, lib)
+                   BJ_OUT_REF_MCUS, BJ_OUT_RGB8, BJ_SCAN_RAW, BJ_SCAN_UNSTUFFED, BatchInfo, BjError, ImageDesc, lib)
 from .decoder import Batch, Decoder, Job, PinnedBuffer, decode_files, lpt_shards, parse_header, shard_by_size  # noqa: F401

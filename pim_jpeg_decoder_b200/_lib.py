@@ -20,6 +20,9 @@ BJ_ERR_CORRUPT_SCAN = -6
 
 BJ_OUT_RGB8 = 0
 BJ_OUT_BMP = 1
+BJ_OUT_REF_MCUS = 2
+BJ_SCAN_RAW = 0
+BJ_SCAN_UNSTUFFED = 1
 
 
 class ImageDesc(C.Structure):
@@ -71,6 +74,8 @@ SYMBOLS = {
     "bj_parse_header": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(ImageDesc)]),
     "bj_peek_header": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(ImageDesc)]),
     "bj_output_size": (C.c_size_t, [C.POINTER(ImageDesc), C.c_int]),
+    "bj_ref_mcus_size": (C.c_size_t, [C.POINTER(ImageDesc), C.c_int, C.POINTER(C.c_int)]),
+    "bj_decode_batch_desc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bj_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bj_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "bj_wait": (C.c_int, [C.c_void_p]),

@@ -58,7 +58,11 @@ extern "C" int bj_create(bj_ctx **out, int device) {
     cudaDeviceProp prop;
     if (rc == BJ_OK) rc = c->check(cudaGetDeviceProperties(&prop, device));
     if (rc == BJ_OK) c->sm_count = prop.multiProcessorCount;
-    if (rc == BJ_OK) rc = c->check(cudaFuncSetAttribute(k_idct_color, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemIdctColor));
+    c->ri_split_threads = c->sm_count * 256;
+    if (const char *e = getenv("B200JPEG_RI_SPLIT")) c->ri_split_threads = atoi(e);          // (experiments)
+    if (const char *e = getenv("B200JPEG_MIN_SUB")) c->min_sub_bytes = std::max(16, atoi(e));
+    if (rc == BJ_OK) rc = c->check(cudaFuncSetAttribute(k_idct_color<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemIdctColor));
+    if (rc == BJ_OK) rc = c->check(cudaFuncSetAttribute(k_idct_color<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemIdctColor));
     if (rc == BJ_OK) rc = batch_kernels_init(c);
     for (int i = 0; i < kSlots && rc == BJ_OK; i++) rc = c->check(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
     for (int i = 0; i < 2 && rc == BJ_OK; i++) rc = c->check(cudaEventCreate(&c->ev_exec[i]));
@@ -168,6 +172,7 @@ extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
     if (!strcmp(name, "sub_batch_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_bytes = (size_t)value; return BJ_OK; }
     if (!strcmp(name, "packed_outputs")) { c->packed_outputs = value != 0; return BJ_OK; }
     if (!strcmp(name, "packed_inputs")) { if (value < -1 || value > 1) return BJ_ERR_ARG; c->packed_inputs = (int)value; return BJ_OK; }
+    if (!strcmp(name, "ref_max_mcu_per_dpu")) { if (value < 4 || value % 4 || value > (1 << 20)) return BJ_ERR_ARG; c->ref_m = (int)value; return BJ_OK; }
     if (!strcmp(name, "debug_poison")) { c->debug_poison = value != 0; return BJ_OK; }
     if (!strcmp(name, "max_image_pixels")) { if (value < 1) return BJ_ERR_ARG; c->max_image_pixels = (size_t)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_out_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_out_bytes = (size_t)value; return BJ_OK; }
@@ -272,12 +277,12 @@ extern "C" int bj_peek_header(const uint8_t *file, size_t len, bj_image_desc *de
     return parse_header(file, len, desc, /*walk_scan=*/false);
 }
 
-extern "C" size_t bj_output_size(const bj_image_desc *d, int format) {
-    if (!d) return 0;
-    const size_t w = d->width, h = d->height;
-    if (format == BJ_OUT_RGB8) return w * h * 3;
-    if (format == BJ_OUT_BMP) return 26 + h * (w * 3 + w % 4);
-    return 0;
+extern "C" size_t bj_output_size(const bj_image_desc *d, int format) { return d ? output_bytes(*d, format, 100) : 0; }
+
+extern "C" size_t bj_ref_mcus_size(const bj_image_desc *d, int max_mcu_per_dpu, int *nchunks) {
+    if (!d || max_mcu_per_dpu < 4 || max_mcu_per_dpu % 4) return 0;
+    if (nchunks) *nchunks = (int)ref_mcus_chunks(*d, max_mcu_per_dpu);
+    return output_bytes(*d, BJ_OUT_REF_MCUS, max_mcu_per_dpu);
 }
 
 // ------------------------------------------------------------------------------------------------ stage entry
@@ -303,7 +308,7 @@ extern "C" int bj_stage_idct_color(bj_ctx *c, const bj_image_desc *desc, const i
     if (rc == BJ_OK) rc = c->check(cudaMemcpyAsync(dti.p, tiles.data(), tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
     if (rc == BJ_OK) {
         const uint8_t *base = (const uint8_t *)dim.p;
-        k_idct_color<<<(unsigned)tiles.size(), kTileThreads, kSmemIdctColor, s>>>((const int16_t *)dco.p, nullptr, (const ImgDev *)base, (const QTab *)(base + offsetof(StageRec, q)),
+        k_idct_color<false><<<(unsigned)tiles.size(), kTileThreads, kSmemIdctColor, s>>>((const int16_t *)dco.p, nullptr, (const ImgDev *)base, (const QTab *)(base + offsetof(StageRec, q)),
                                                                                  (const TileDev *)dti.p, (uint8_t *)dout.p);
         rc = c->check(cudaGetLastError());
     }
@@ -451,8 +456,14 @@ enum { ST_SUB = 0, ST_LAUNCH, ST_H2D, ST_D2H, ST_HOST_MS, ST_WAIT_MS, ST_D2H_COP
 }  // namespace
 
 // One device's share of a call: pull ranges from `src` until it runs dry.
-static int decode_worker(bj_ctx *c, RangeSource *src, const uint8_t *const *files, const size_t *lens, int format,
-                         uint8_t *const *outs, int *status) {
+struct CallInput {                       // what a call decodes: files, or (bj_decode_batch_desc) descriptors + scans
+    const uint8_t *const *files; const size_t *lens;
+    const bj_image_desc *descs; const int *kinds;
+};
+
+static int decode_worker(bj_ctx *c, RangeSource *src, const CallInput &in, int format, uint8_t *const *outs, int *status) {
+    const uint8_t *const *files = in.files;
+    const size_t *lens = in.lens;
     if (c->check(cudaSetDevice(c->device)) != BJ_OK) return BJ_ERR_CUDA;
     for (auto &b : c->slots) if (!b) { b = new (std::nothrow) bj_batch(); if (!b) return BJ_ERR_NOMEM; }
     int first[kSlots] = {}, count[kSlots] = {};
@@ -502,7 +513,7 @@ static int decode_worker(bj_ctx *c, RangeSource *src, const uint8_t *const *file
             bj_batch *b = c->slots[slot];
             cudaStream_t s = c->streams[slot];
             const double t0 = wall_ms();
-            rc = batch_assign(b, c, files + i0, lens + i0, r1 - i0, format, c->sub_batch_out_bytes);
+            rc = batch_assign(b, c, files + i0, lens + i0, r1 - i0, format, c->sub_batch_out_bytes, in.descs ? in.descs + i0 : nullptr, in.kinds ? in.kinds + i0 : nullptr);
             const int m = rc == BJ_OK ? b->n : 0;
             st[ST_HOST_MS] += wall_ms() - t0;
             host_t[slot][0] = t0 - wall0; host_t[slot][1] = wall_ms() - wall0;
@@ -534,19 +545,20 @@ static int decode_worker(bj_ctx *c, RangeSource *src, const uint8_t *const *file
     return rc;
 }
 
-static int decode_batch_now(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, uint8_t *const *outs, int *status) {
+static int decode_batch_now(bj_ctx *c, const CallInput &in, int n, int format, uint8_t *const *outs, int *status) {
+    const size_t *lens = in.lens;
     RangeSource src;
     src.lens = lens; src.n = n;
     src.budget = c->sub_batch_bytes ? c->sub_batch_bytes : ((size_t)24 << 20);    // compressed bytes per sub-batch
     src.ramp = c->sub_batch_ramp != 0;
-    if (c->children.empty()) return decode_worker(c, &src, files, lens, format, outs, status);
+    if (c->children.empty()) return decode_worker(c, &src, in, format, outs, status);
     // multi-GPU context: one host thread per device, all pulling sub-batches from the same source
     if (status) for (int i = 0; i < n; i++) status[i] = BJ_ERR_CUDA;                // (overwritten by whoever decodes the image)
     std::vector<int> rcs(c->children.size(), BJ_OK);
     std::vector<std::thread> th;
     for (size_t d = 1; d < c->children.size(); d++)
-        th.emplace_back([&, d] { rcs[d] = decode_worker(c->children[d], &src, files, lens, format, outs, status); });
-    rcs[0] = decode_worker(c->children[0], &src, files, lens, format, outs, status);
+        th.emplace_back([&, d] { rcs[d] = decode_worker(c->children[d], &src, in, format, outs, status); });
+    rcs[0] = decode_worker(c->children[0], &src, in, format, outs, status);
     for (auto &t : th) t.join();
     int rc = BJ_OK;
     for (int i = 0; i < ST_COUNT; i++) c->stats[i] = 0;
@@ -565,9 +577,20 @@ static int decode_batch_now(bj_ctx *c, const uint8_t *const *files, const size_t
 extern "C" int bj_decode_batch(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format,
                                uint8_t *const *outs, int *status) {
     if (!c || n < 0 || (n > 0 && (!files || !lens || !outs))) return BJ_ERR_ARG;
-    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP && format != BJ_OUT_REF_MCUS) return BJ_ERR_ARG;
     if (c->async && c->async->pending()) return BJ_ERR_ARG;                          // jobs of bj_submit are still running on this context
-    return decode_batch_now(c, files, lens, n, format, outs, status);
+    return decode_batch_now(c, CallInput{files, lens, nullptr, nullptr}, n, format, outs, status);
+}
+
+// The same for a caller that already holds the parsed header (the reference's `Header`, src/headers/jpeg.h:146-179) and
+// the scan bytes: replaces decode_Huffman_data + the DPU round trip (src/decoder_host.cpp:181, :268-312) while
+// read_JPEG stays in front and - with BJ_OUT_REF_MCUS - write_BMP behind.
+extern "C" int bj_decode_batch_desc(bj_ctx *c, const bj_image_desc *descs, const uint8_t *const *scans, const size_t *scan_lens,
+                                    const int *scan_kinds, int n, int format, uint8_t *const *outs, int *status) {
+    if (!c || n < 0 || (n > 0 && (!descs || !scans || !scan_lens || !outs))) return BJ_ERR_ARG;
+    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP && format != BJ_OUT_REF_MCUS) return BJ_ERR_ARG;
+    if (c->async && c->async->pending()) return BJ_ERR_ARG;
+    return decode_batch_now(c, CallInput{scans, scan_lens, descs, scan_kinds}, n, format, outs, status);
 }
 
 // ------------------------------------------------------------------------------------------------ full path, asynchronous
@@ -591,7 +614,7 @@ void bj::AsyncWorker::run() {
             if (q.empty()) return;
             j = q.front();
         }
-        const int rc = decode_batch_now(j->ctx, j->files, j->lens, j->n, j->format, j->outs, j->status);
+        const int rc = decode_batch_now(j->ctx, CallInput{j->files, j->lens, nullptr, nullptr}, j->n, j->format, j->outs, j->status);
         {
             std::lock_guard<std::mutex> l(m);
             q.pop_front();
@@ -603,7 +626,7 @@ void bj::AsyncWorker::run() {
 
 extern "C" int bj_submit(bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, uint8_t *const *outs, int *status, bj_job **job) {
     if (!c || !job || n < 0 || (n > 0 && (!files || !lens || !outs))) return BJ_ERR_ARG;
-    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP && format != BJ_OUT_REF_MCUS) return BJ_ERR_ARG;
     *job = nullptr;
     bj_job *j = new (std::nothrow) bj_job{files, lens, n, format, outs, status};
     if (!j) return BJ_ERR_NOMEM;

@@ -5,7 +5,7 @@
 // touches the entropy-coded bytes: it reads the file HEADERS (parse.h, a few hundred bytes per file), builds one small
 // record per image and the lookup tables, and hands the file bytes to the GPU - straight from the caller's memory when
 // that is page-locked, through a pinned staging copy otherwise.  Where a scan ends, what survives un-stuffing, and
-// every per-CTA table are worked out on the device (kernels_huff.cuh: k_scan_count / k_scan_tiles / k_expand_maps).
+// every per-CTA table are worked out on the device (kernels_huff.cuh: k_unstuff / k_expand_maps).
 #pragma once
 #include <map>
 #include <string>
@@ -85,9 +85,11 @@ struct bj_batch {
     uint32_t n_idct_tiles = 0, n_blk = 0, n_utile = 0, n_dcc = 0, n_seg_entries = 0, n_sub_slots = 0, lut_smem = 0;
     size_t clean_words = 0, coef_units = 0, out_bytes = 0;
     uint64_t pixels = 0, scan_bytes_max = 0;
+    uint32_t nseg_max = 0;              // most restart segments of one image
+    uint32_t ref_blocks_max = 0;        // BJ_OUT_REF_MCUS: blocks of the largest image (grid of the padding kernel)
 
     // device
-    bj::DevBuf d_files, d_meta, d_maps, d_tilecnt, d_tileex, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_quarter, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
+    bj::DevBuf d_files, d_meta, d_maps, d_look, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_quarter, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels, copied out
     cudaEvent_t ev_done = nullptr;       // one-call path: recorded behind the copy-out, created for a sleeping wait
     cudaStream_t last_stream = nullptr;
@@ -107,7 +109,7 @@ struct bj_batch {
     template <class T> T *dmap(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(d_maps.p) + off); }
 
     void release() {
-        for (bj::DevBuf *b : {&d_files, &d_meta, &d_maps, &d_tilecnt, &d_tileex, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_quarter, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
+        for (bj::DevBuf *b : {&d_files, &d_meta, &d_maps, &d_look, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_quarter, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
         h_files.release(); h_meta.release(); h_res.release();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (ev_done) { cudaEventDestroy(ev_done); ev_done = nullptr; }
@@ -123,8 +125,13 @@ constexpr int kMaxRounds = 64;
 //             b->n tells how many.  A few hostile headers (a 1 KB file that declares 65535 x 65535) cannot make a
 //             sub-batch of the one-call path arbitrarily large, and an image above ctx->max_image_pixels is refused
 //             on its own (BJ_ERR_UNSUPPORTED) like the reference's "Too high resolution" (src/decoder_host.cpp:146-149).
-inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, size_t out_cap = ~(size_t)0) {
-    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP) return BJ_ERR_ARG;
+//   descs     (bj_decode_batch_desc) the images come as descriptor + scan bytes instead of files: files[i] / lens[i] are
+//             then the scan itself - raw (stuffed, with RSTn; kinds[i] = BJ_SCAN_RAW) or the reference's
+//             Header::huffman_data (un-stuffed, markers removed; BJ_SCAN_UNSTUFFED, only without a restart interval:
+//             read_JPEG throws the RSTn positions away) - and nothing is parsed.
+inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, const size_t *lens, int n, int format, size_t out_cap = ~(size_t)0,
+                        const bj_image_desc *descs = nullptr, const int *kinds = nullptr) {
+    if (format != BJ_OUT_RGB8 && format != BJ_OUT_BMP && format != BJ_OUT_REF_MCUS) return BJ_ERR_ARG;
     b->ctx = c; b->n = n; b->format = format;
     b->uploaded = b->decoded = b->synced = false;
     b->desc.resize(n); b->parse_status.assign(n, BJ_OK);
@@ -136,7 +143,17 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     c->host_pool.parallel_for(n, 64, [&](int i0, int i1) {
         for (int i = i0; i < i1; i++) {
             bj_image_desc &d = b->desc[i];
-            int rc = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &d, /*walk_scan=*/false) : BJ_ERR_INVALID_JPEG;
+            int rc;
+            if (descs) {                                                  // a caller-made descriptor: checked before it sizes anything
+                d = descs[i];
+                d.scan_off = 0; d.scan_len = lens[i];
+                rc = !files[i] ? BJ_ERR_ARG : (!desc_is_sane(d) ? BJ_ERR_INVALID_JPEG : BJ_OK);
+                for (int j = 0; rc == BJ_OK && j < d.ncomp; j++)
+                    if (!d.qt_set[d.qt_id[j]] || !d.dc_set[d.dc_id[j]] || !d.ac_set[d.ac_id[j]]) rc = BJ_ERR_INVALID_JPEG;
+                if (rc == BJ_OK && (d.frame_type != 0xC0 || d.scan_ncomp != d.ncomp)) rc = BJ_ERR_UNSUPPORTED;
+                if (rc == BJ_OK && kinds && kinds[i] == BJ_SCAN_UNSTUFFED && d.restart_interval != 0) rc = BJ_ERR_UNSUPPORTED;
+            } else
+                rc = (files[i] && lens[i]) ? parse_header(files[i], lens[i], &d, /*walk_scan=*/false) : BJ_ERR_INVALID_JPEG;
             if (rc == BJ_OK && d.scan_len >= ((size_t)1 << 31)) rc = BJ_ERR_UNSUPPORTED;   // byte counts travel in 31 bits
             if (rc == BJ_OK && (size_t)d.width * d.height > c->max_image_pixels) rc = BJ_ERR_UNSUPPORTED;
             if (rc == BJ_OK) geo[i] = geometry_of(d);
@@ -148,7 +165,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         size_t acc = 0;
         int m = 0;
         while (m < n) {
-            const size_t sz = b->parse_status[m] == BJ_OK ? align_up(bj_output_size(&b->desc[m], format), 16) : 0;
+            const size_t sz = b->parse_status[m] == BJ_OK ? align_up(output_bytes(b->desc[m], format, c->ref_m), 16) : 0;
             if (m > 0 && acc + sz > out_cap) break;
             acc += sz; m++;
         }
@@ -165,7 +182,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     // copied on the host.  Otherwise the files are packed into this batch's pinned staging buffer (worker pool).
     b->direct_src = nullptr;
     uint64_t span_lo = ~0ull, span_hi = 0, span_sum = 0;
-    if (c->packed_inputs >= 0) {
+    if (c->packed_inputs >= 0 && !descs) {            // (scans handed over one by one are always staged: what precedes them in memory is not ours)
         for (int i = 0; i < n; i++) {
             if (b->parse_status[i] != BJ_OK) continue;
             const uint64_t a = (uint64_t)(uintptr_t)files[i];
@@ -190,16 +207,22 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     uint32_t fixed_rl = c->slices == 2 ? 1u : c->slices == 4 ? 2u : c->slices == 8 ? 3u : 0u;
     if (fixed_sub) while (fixed_rl && fixed_sub % (1u << fixed_rl)) fixed_rl--;
     uint32_t nominal_sub = 512;
-    uint64_t total_scan = 0;
-    for (int i = 0; i < n; i++) if (b->parse_status[i] == BJ_OK) total_scan += b->desc[i].scan_len;
-    if (!fixed_sub) nominal_sub = (uint32_t)std::min<uint64_t>(512u, std::max<uint64_t>(128u, total_scan / ((uint64_t)c->sm_count * 3072u)));
+    uint64_t total_scan = 0, total_ri_segs = 0;
+    for (int i = 0; i < n; i++) if (b->parse_status[i] == BJ_OK) {
+        total_scan += b->desc[i].scan_len;
+        if (b->desc[i].restart_interval) total_ri_segs += (geo[i].nmcu + b->desc[i].restart_interval - 1) / b->desc[i].restart_interval;
+    }
+    if (!fixed_sub) nominal_sub = (uint32_t)std::min<uint64_t>(512u, std::max<uint64_t>((uint64_t)c->min_sub_bytes, total_scan / ((uint64_t)c->sm_count * 3072u)));
+    // whole restart segments as sub-sequences need no speculation, but a batch with few of them (a single 4K image with
+    // a restart interval of 8 MCUs: 4 050) would leave most of the GPU idle: then segments are cut like any other stream
+    const bool ri_whole = total_ri_segs >= (uint64_t)c->ri_split_threads;
     auto round_sub = [&](uint32_t len, uint32_t rl) { const uint32_t q = 4u << rl; return (std::max(len, 64u) + q - 1u) / q * q; };
     auto sub_layout_of = [&](uint32_t raw_len, uint32_t nseg, uint32_t *rl) -> uint32_t {
         *rl = c->slices ? fixed_rl : 0u;
         if (fixed_sub) return fixed_sub;
         if (nseg > 1) {
             const uint32_t avg = raw_len / nseg;
-            if (avg <= 1024) {
+            if (avg <= 1024 && (ri_whole || nominal_sub >= avg)) {
                 if (!c->slices) *rl = total_scan < ((uint64_t)16 << 20) ? 3u : 2u;
                 return round_sub(std::max(2 * avg, nominal_sub), *rl);
             }
@@ -222,7 +245,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
     uint32_t seg_entries = 0, nblk = 0, n_utile = 0, n_wblk = 0, n_dcc = 0, n_tiles = 0;
     int prev = -1;                                  // last valid image: its table slots are reused when the tables match
-    b->pixels = 0; b->scan_bytes_max = 0; b->lut_smem = 0; b->multi_blk = false; b->phased = c->sync_phased != 0;
+    b->pixels = 0; b->scan_bytes_max = 0; b->ref_blocks_max = 0; b->nseg_max = 0; b->lut_smem = 0; b->multi_blk = false; b->phased = c->sync_phased != 0;
     uint32_t rgb_max = 0;
     auto same_tables = [](const bj_image_desc &a, const bj_image_desc &q) {
         if (a.ncomp != q.ncomp || memcmp(a.dc_id, q.dc_id, 3) || memcmp(a.ac_id, q.ac_id, 3)) return false;
@@ -302,12 +325,14 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         if (rc != BJ_OK) { seg_entries += 2; hi.ndc = hi.nac = 0; continue; }
         fbytes += align_up(lens[i] + 16, 16);
         hi.valid = 1;
+        hi.flags = descs ? (uint8_t)((kinds && kinds[i] == BJ_SCAN_UNSTUFFED) ? (kImgClean | kImgExact) : kImgExact) : (uint8_t)0;
         hi.raw_off = b->file_off[i] + d.scan_off;
         hi.raw_len = (uint32_t)d.scan_len;                                   // upper bound: up to the end of the file
         hi.ntile = std::max<uint32_t>(1u, (uint32_t)(((hi.raw_off & 15u) + hi.raw_len + kUnstuffTile - 1) / kUnstuffTile));
         n_utile += hi.ntile;
         hi.nmcu = g.nmcu; hi.ri = d.restart_interval;
         hi.nseg = hi.ri ? (g.nmcu + hi.ri - 1) / hi.ri : 1u;
+        b->nseg_max = std::max(b->nseg_max, hi.nseg);
         hi.bpm = (uint8_t)g.bpm; hi.ny = (uint8_t)(d.hs * d.vs); hi.ncomp = d.ncomp;
         hi.ndu = g.ndu;
         {
@@ -329,9 +354,10 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         clean_words += hi.raw_len / 4 + 4;
         b->du_base[i] = (uint32_t)coef_units; b->ndu[i] = g.ndu;
         coef_units += g.ndu;
-        b->out_size[i] = bj_output_size(&d, format);
+        b->out_size[i] = output_bytes(d, format, c->ref_m);
         b->out_off[i] = out_bytes;
         fill_imgdev(d, g, format, hi.du_base, out_bytes, &idev[i]);
+        if (format == BJ_OUT_REF_MCUS) { idev[i].ref_blocks = ref_mcus_chunks(d, c->ref_m) * (uint32_t)(c->ref_m / 4); b->ref_blocks_max = std::max(b->ref_blocks_max, idev[i].ref_blocks); }
         idev[i].dc_sep = 1;
         idev[i].tile0 = n_tiles;
         n_tiles += idct_tile_count(g);
@@ -387,7 +413,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     }
     // ---- device buffers
     if (b->d_files.reserve(b->files_bytes + 4096) || b->d_meta.reserve(b->meta_bytes) || b->d_maps.reserve(b->maps_bytes + 16) ||
-        b->d_tilecnt.reserve((size_t)n_utile * 8 + 16) || b->d_tileex.reserve((size_t)n_utile * 8 + 16) || b->d_clean.reserve(b->clean_words * 4) ||
+        b->d_look.reserve((size_t)n_utile * 8 + 16) || b->d_clean.reserve(b->clean_words * 4) ||
         b->d_seg.reserve((size_t)(seg_entries + 2) * 4 * 2) || b->d_subseg.reserve((size_t)b->n_sub_slots * 4 + 16) ||
         b->d_stin.reserve((size_t)b->n_sub_slots * 8 + 16) || b->d_stout.reserve((size_t)b->n_sub_slots * 8 + 16) ||
         b->d_tot.reserve((size_t)b->n_sub_slots * 4 + 16) || b->d_pre.reserve((size_t)b->n_sub_slots * 8 + 16) ||
@@ -452,13 +478,13 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
         cudaMemsetAsync(st, 0, (size_t)n * sizeof(HuffImgState), s);                  // (rejected files keep an all-zero state)
         b->launches = 0;
         if (b->n_utile) {
-            uint2 *tile_cnt = (uint2 *)b->d_tilecnt.p, *tile_ex = (uint2 *)b->d_tileex.p;
-            k_scan_count<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_cnt);
-            k_scan_tiles<<<n, kScanTilesThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, tile_cnt, tile_ex, st, seg_off);
-            k_unstuff<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, tile_ex, st, clean, seg_off);
-            b->launches += 3;
+            uint64_t *look = (uint64_t *)b->d_look.p;                                 // look-back words of the tiles + the ticket counter behind them
+            cudaMemsetAsync(look, 0, (size_t)b->n_utile * 8 + 8, s);
+            k_unstuff<<<b->n_utile, kUnstuffThreads, 0, s>>>((const uint8_t *)b->d_files.p, himg, utile_img, look, (uint32_t *)(look + b->n_utile), st, clean, seg_off);
+            b->launches++;
         }
-        k_subseq_table<<<n, 256, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg);
+        if (b->nseg_max > 256) k_subseq_table<1024><<<n, 1024, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg);
+        else k_subseq_table<256><<<n, 256, 0, s>>>(himg, st, seg_off, seg_sub0, sub_seg);
         b->launches++;
         b->sync_rounds = 0;
         cudaEventRecord(b->ev[1], s);
@@ -491,8 +517,13 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     }
     if (!b->n_blk) cudaEventRecord(b->ev[2], s);
     cudaEventRecord(b->ev[3], s);
-    if (b->n_idct_tiles) {
-        k_idct_color<<<b->n_idct_tiles, kTileThreads, b->idct_smem, s>>>((const int16_t *)b->d_coef.p, dcp, idev, qtabs, tiles, (uint8_t *)b->d_out.p);
+    if (b->n_idct_tiles && b->format == BJ_OUT_REF_MCUS) {
+        const unsigned gx = std::min<unsigned>(64u, (b->ref_blocks_max * 12u + 255u) / 256u);
+        k_ref_mcus_pad<<<dim3(std::max(gx, 1u), n), 256, 0, s>>>(idev, (uint8_t *)b->d_out.p);
+        k_idct_color<true><<<b->n_idct_tiles, kTileThreads, b->idct_smem, s>>>((const int16_t *)b->d_coef.p, dcp, idev, qtabs, tiles, (uint8_t *)b->d_out.p);
+        b->launches += 2;
+    } else if (b->n_idct_tiles) {
+        k_idct_color<false><<<b->n_idct_tiles, kTileThreads, b->idct_smem, s>>>((const int16_t *)b->d_coef.p, dcp, idev, qtabs, tiles, (uint8_t *)b->d_out.p);
         b->launches++;
     }
     cudaEventRecord(b->ev[4], s);

@@ -26,6 +26,7 @@ struct ImgDev {
     uint8_t  pad_[1];
     uint32_t qslot;               // this image's quantiser set in the batch's pool of QTab (deduplicated across the batch)
     uint32_t tile0;               // index of this image's first K2/K3 tile in the batch's tile list
+    uint32_t ref_blocks;          // BJ_OUT_REF_MCUS: 2x2-position blocks in this image's output (whole chunks of MAX_MCU_PER_DPU / 4)
 };
 
 // One set of quantisation tables as the K2 kernel stages it: per component (quantiser << 16) in ZIG-ZAG (file) order.

@@ -154,6 +154,9 @@ struct bj_ctx {
     int packed_outputs = 0;              // see batch_download_async
     int packed_inputs = 0;               // see batch_assign: 0 = upload straight from the caller's memory when it is known to be page-locked
                                          // (bj_host_alloc / bj_host_register), 1 = the caller says it is, -1 = always stage
+    int min_sub_bytes = 128;             // shortest sub-sequence the automatic layout picks (small batches)
+    int ri_split_threads = 0;            // restart segments below which a batch cuts them into shorter sub-sequences (set in bj_create: one wave of CTAs)
+    int ref_m = 100;                     // BJ_OUT_REF_MCUS: MAX_MCU_PER_DPU of the host that reads the buffer (Makefile:2 of the reference)
     int debug_poison = 0;                // fill coefficient / DC / output buffers with 0xA5 before every decode (tests: every byte must be written)
     size_t max_image_pixels = (size_t)1 << 28;   // larger images are refused (BJ_ERR_UNSUPPORTED), like the reference's "Too high resolution"
     size_t sub_batch_out_bytes = (size_t)1 << 30; // decoded bytes per sub-batch of bj_decode_batch
@@ -206,7 +209,10 @@ inline void fill_imgdev(const bj_image_desc &d, const Geometry &g, int format, u
     im->hs = d.hs; im->vs = d.vs; im->ncomp = d.ncomp; im->bpm = (uint8_t)g.bpm;
     im->row_bytes = d.width * 3;
     im->valid = 1;
-    if (format == BJ_OUT_BMP) {
+    if (format == BJ_OUT_REF_MCUS) {
+        im->row_pad = 0; im->out_pitch = 0; im->row_dir = 1; im->bgr = 0;
+        im->out_row0 = out_base;                       // byte offset of the image's first chunk
+    } else if (format == BJ_OUT_BMP) {
         im->row_pad = d.width % 4;
         im->out_pitch = d.width * 3 + im->row_pad;
         im->out_row0 = out_base + 26 + (uint64_t)(d.height - 1) * im->out_pitch;
@@ -250,6 +256,19 @@ inline bool desc_is_sane(const bj_image_desc &d) {
     for (int j = 0; j < d.ncomp; j++) if (d.qt_id[j] > 3 || d.dc_id[j] > 3 || d.ac_id[j] > 3) return false;
     if (d.mcu_w != (d.width + 7) / 8 || d.mcu_h != (d.height + 7) / 8) return false;
     return true;
+}
+
+// BJ_OUT_REF_MCUS: DPU chunks of an image (src/decoder_host.cpp:125-128) and the bytes of its `mcus` buffers.
+inline uint32_t ref_mcus_chunks(const bj_image_desc &d, int M) {
+    const uint32_t pw = (d.mcu_w_real + 1) / 2 * 2, ph = (d.mcu_h_real + 1) / 2 * 2;
+    return (pw * ph + (uint32_t)M - 1) / (uint32_t)M;
+}
+inline size_t output_bytes(const bj_image_desc &d, int format, int M) {
+    const size_t w = d.width, h = d.height;
+    if (format == BJ_OUT_RGB8) return w * h * 3;
+    if (format == BJ_OUT_BMP) return 26 + h * (w * 3 + w % 4);
+    if (format == BJ_OUT_REF_MCUS) return (size_t)ref_mcus_chunks(d, M) * 64 * (size_t)M * 3 * sizeof(int16_t);
+    return 0;
 }
 
 inline uint32_t idct_tile_count(const Geometry &g) { return g.nmy * ((g.nmx + g.tile_mcus - 1) / g.tile_mcus); }

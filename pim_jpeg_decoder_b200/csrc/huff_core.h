@@ -290,10 +290,6 @@ BJ_HD uint32_t chunk_mask_before(int64_t r0, uint32_t e) {
     const int64_t lim = e == kNoScanEnd ? 16 : (int64_t)e - r0;
     return lim >= 16 ? 0xFFFFu : (lim <= 0 ? 0u : ((1u << (uint32_t)lim) - 1u));
 }
-// The tile (of tile_bytes raw bytes, aligned in the file buffer) that holds scan-relative position e, for a scan whose
-// first byte sits `mis` bytes into its first tile.
-BJ_HD uint32_t tile_of_pos(uint32_t mis, uint32_t e, uint32_t tile_bytes) { return (uint32_t)(((uint64_t)mis + e) / tile_bytes); }
-
 // ------------------------------------------------------------------------------------------------ bit reader
 // The un-stuffed stream is stored as 32-bit words whose most significant byte is the earliest byte (the
 // un-stuff kernel writes byte o to address o ^ 3), so a window is two aligned words and one funnel shift.

@@ -1,10 +1,10 @@
 // K0/K1: entropy stage on sm_100a.  Replaces the host-side, single-threaded, bit-serial Huffman decode of the
 // reference (src/jpeg_scanner.cpp:405-520, 707-756) with data-parallel kernels:
 //
-//   k_scan_count, k_scan_tiles, k_unstuff                 (K0)  raw scan bytes -> un-stuffed big-endian words,
-//                                                          restart-segment byte offsets, and WHERE THE SCAN ENDS: count per
-//                                                          tile -> per-image scan over the tiles -> compact.  The host reads
-//                                                          only the file headers; it never walks the entropy-coded bytes
+//   k_unstuff                                             (K0)  raw scan bytes -> un-stuffed big-endian words,
+//                                                          restart-segment byte offsets, and WHERE THE SCAN ENDS, in one
+//                                                          pass (decoupled look-back between an image's tiles).  The host
+//                                                          reads only the file headers; it never walks the entropy-coded bytes
 //   k_expand_maps                                               CTA -> image maps and the K2/K3 tile list, from per-image records
 //   k_subseq_table                                        (K0d) per image: split every segment into sub-sequences
 //   k_huff_sync                                           (K1b) speculative decode of every sub-sequence + fix-up
@@ -47,7 +47,7 @@ struct HuffImg {
     uint16_t dc_lut[3], ac_lut[3];   // pool index of each staged DC / AC slot
     uint8_t dc_slot[3], ac_slot[3];  // per component: staged slot
     uint8_t slices_log2;     // the write pass works on 2^slices_log2 slices of every sub-sequence
-    uint8_t pad_[1];
+    uint8_t flags;           // kImgClean / kImgExact (input handed over as a scan, not as a file: bj_decode_batch_desc)
     uint16_t dc_n4[3], ac_n4[3];     // used size of each staged table in 16-byte chunks (tables are staged packed)
     uint32_t sub_bytes;      // length of this image's sub-sequences (synchronisation pass), a multiple of the slice count
     uint32_t wblk_base;      // first CTA of k_huff_write (nblk << slices_log2 of them)
@@ -68,6 +68,8 @@ struct HuffImgState {
                                      // re-launch of the write pass (batch.h: batch_sync) starts from these again
     uint32_t pad_[2];
 };
+constexpr uint8_t kImgClean = 1;           // the bytes are the reference's Header::huffman_data: already un-stuffed, markers removed - every byte is data
+constexpr uint8_t kImgExact = 2;           // raw_len is the scan's exact length: it need not end in a marker
 constexpr uint32_t kStatusInvalid = 2u;    // read_JPEG's scan-byte loop would set valid = false (src/jpeg_scanner.cpp:405-433)
 constexpr uint32_t kNoEnd = kNoScanEnd;
 
@@ -110,24 +112,27 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------ K0: un-stuff
-// Three small kernels, all over aligned tiles of kUnstuffTile raw bytes (one thread = one aligned 16-byte chunk of the
-// file buffer = one 128-bit load, classified branch-free four bytes per 32-bit word):
-//   k_scan_count   per tile: where the scan ends if it ends inside the tile (the first FF followed by something other
-//                  than 00 / FF / RSTn, src/jpeg_scanner.cpp:405-433), and how many bytes survive / how many RSTn
-//                  markers lie before that point
-//   k_scan_tiles   per image: scan over its tiles -> every tile's output position, the image's totals, the scan's true
-//                  length and whether it ends in EOI (a file the reference rejects is flagged here: kStatusInvalid)
-//   k_unstuff      per tile: compact the surviving bytes in shared memory, store them as big-endian words
-// The host passes only an upper bound of the scan (first scan byte .. end of file): it never touches the
-// entropy-coded bytes.  The byte before the scan is the SOS header's Ah/Al byte (0 in a baseline file), so the rule
-// "the first byte has no FF before it" holds without a special case.
+// ONE pass over aligned tiles of kUnstuffTile raw bytes (one thread = one aligned 16-byte chunk of the file buffer = one
+// 128-bit load, classified branch-free four bytes per 32-bit word).  A tile
+//   * finds where the scan ends if it ends inside the tile: the first FF followed by something other than 00 / FF /
+//     RSTn (src/jpeg_scanner.cpp:405-433) - the host passes only an upper bound of the scan (first scan byte .. end of
+//     the file) and never touches the entropy-coded bytes;
+//   * counts the bytes that survive and the RSTn markers in front of that point and scans them inside the CTA;
+//   * learns what the image's earlier tiles contribute by a DECOUPLED LOOK-BACK: every tile publishes its own counts
+//     (one 64-bit word: status, "the scan has ended", surviving bytes, markers), then its first warp reads the words of
+//     up to 32 predecessors at a time and adds them up until it meets one that already carries an inclusive prefix.
+//     Tiles take their index from a ticket counter, so a tile only ever waits for tiles that have started;
+//   * compacts its surviving bytes in shared memory and stores them as big-endian words at their final place;
+//   * the tile in which the scan ends (or, if it never does, the image's last tile) writes the image's state: true scan
+//     length, totals, and kStatusInvalid when the scan does not end in EOI - the files read_JPEG rejects.
+// The byte before the scan is the SOS header's Ah/Al byte (0 in a baseline file), so the rule "the first byte has no
+// FF before it" holds without a special case.
 struct Chunk16 {
     uint4 bytes;
     uint32_t keep, rst, end;   // bit i = byte i survives / is the code byte of an RSTn marker / is the FF that ends the scan
     int64_t r0;                // scan-relative index of byte 0 (may be < 0)
 };
 
-template <bool WITH_END>
 __device__ __forceinline__ Chunk16 classify16(const uint8_t *__restrict__ files, const HuffImg &im, uint32_t tile, uint32_t raw_len) {
     Chunk16 c;
     const uint64_t a0 = (im.raw_off & ~(uint64_t)15) + (uint64_t)tile * kUnstuffTile + (uint64_t)threadIdx.x * 16;
@@ -140,81 +145,10 @@ __device__ __forceinline__ Chunk16 classify16(const uint8_t *__restrict__ files,
     if (lane == 0) prevw = (live && a0 > 0) ? ((uint32_t)__ldg(files + a0 - 1) << 24) : 0u;
     if (lane == 31) nextw = live ? (uint32_t)__ldg(files + a0 + 16) : 0u;
     const uint32_t w[6] = {prevw, c.bytes.x, c.bytes.y, c.bytes.z, c.bytes.w, nextw};
-    if (WITH_END) classify_words_end(w, c.keep, c.rst, c.end);
-    else { classify_words(w, c.keep, c.rst); c.end = 0u; }
+    if (im.flags & kImgClean) { c.keep = 0xFFFFu; c.rst = 0u; c.end = 0u; }
+    else classify_words_end(w, c.keep, c.rst, c.end);
     clip_chunk(c.r0, raw_len, c.keep, c.rst, c.end);                       // bytes outside [0, raw_len) do not count
     return c;
-}
-
-// Per tile: x = surviving bytes | RSTn markers << 16 (both counted only in front of the scan's end), y = scan-relative
-// position of the FF that ends the scan if it lies in this tile, else kNoEnd.
-__global__ void __launch_bounds__(kUnstuffThreads)
-k_scan_count(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img, uint2 *__restrict__ tile_cnt) {
-    __shared__ uint32_t s_end, s_cnt;
-    const uint32_t img = tile_img[blockIdx.x];
-    const HuffImg &im = imgs[img];
-    if (threadIdx.x == 0) { s_end = kNoEnd; s_cnt = 0u; }
-    const Chunk16 c = classify16<true>(files, im, blockIdx.x - im.tile_base, im.raw_len);
-    __syncthreads();
-    if (c.end) atomicMin(&s_end, (uint32_t)(c.r0 + (__ffs(c.end) - 1)));
-    __syncthreads();
-    const uint32_t e = s_end;
-    const uint32_t m = chunk_mask_before(c.r0, e);                         // bytes of this chunk in front of the end
-    uint32_t v = __popc(c.keep & m) | (__popc(c.rst & m) << 16);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt, v);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = make_uint2(s_cnt, e);
-}
-
-// One CTA per image: exclusive scan of the per-tile counts up to the tile in which the scan ends -> tile_ex (surviving
-// bytes / RSTn markers of the image in front of each tile); then the image's state.
-constexpr int kScanTilesThreads = 1024;
-__global__ void __launch_bounds__(kScanTilesThreads)
-k_scan_tiles(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint2 *__restrict__ tile_cnt, uint2 *__restrict__ tile_ex,
-             HuffImgState *__restrict__ st, uint32_t *__restrict__ seg_off) {
-    __shared__ uint32_t s_tmp[2 * (kScanTilesThreads / 32) + 2];
-    __shared__ uint32_t s_end;
-    const uint32_t img = blockIdx.x;
-    const HuffImg &im = imgs[img];
-    if (!im.valid) return;                                                 // (rejected by the header parse: the state stays zero)
-    if (threadIdx.x == 0) s_end = kNoEnd;
-    __syncthreads();
-    uint32_t carry_k = 0, carry_r = 0, e = kNoEnd;
-    for (uint32_t t0 = 0; t0 < im.ntile; t0 += kScanTilesThreads) {
-        const uint32_t t = t0 + threadIdx.x;
-        uint2 c = make_uint2(0u, kNoEnd);
-        if (t < im.ntile) c = tile_cnt[im.tile_base + t];
-        if (c.y != kNoEnd) atomicMin(&s_end, c.y);
-        __syncthreads();
-        e = s_end;
-        // tiles behind the one that holds the end do not count (and are never compacted)
-        const uint32_t last = e == kNoEnd ? 0xFFFFFFFFu : tile_of_pos((uint32_t)(im.raw_off & 15u), e, kUnstuffTile);
-        const bool in = t < im.ntile && t <= last;
-        uint32_t ek, er, tk, tr;
-        block_excl_scan2<kScanTilesThreads>(in ? (c.x & 0xFFFFu) : 0u, in ? (c.x >> 16) : 0u, ek, er, tk, tr, s_tmp);
-        if (in) tile_ex[im.tile_base + t] = make_uint2(carry_k + ek, carry_r + er);
-        carry_k += tk; carry_r += tr;
-        if (e != kNoEnd) break;
-    }
-    if (threadIdx.x == 0) {
-        HuffImgState s;
-        s.raw_len = e == kNoEnd ? im.raw_len : e;
-        s.end_code = e == kNoEnd ? 0x100u : (uint32_t)__ldg(files + im.raw_off + e + 1);
-        const bool invalid = s.end_code != 0xD9u;                          // "File ended prematurely" / "Invalid marker during compressed data scan"
-        s.clean_len = carry_k; s.nrst = carry_r;
-        s.nseg = invalid ? 0u : min(carry_r + 1u, im.nseg);
-        s.nsub = 0;
-        // segments whose marker is missing are never decoded: everything from their first unit on reads as zero
-        s.first_zero = invalid ? 0u : ((s.nseg < im.nseg) ? s.nseg * im.ri * im.bpm : 0xFFFFFFFFu);
-        s.status = invalid ? kStatusInvalid : ((im.ri != 0 && carry_r + 1u != im.nseg) ? 1u : 0u);
-        s.first_zero0 = s.first_zero; s.status0 = s.status;
-        s.pad_[0] = s.pad_[1] = 0;
-        st[img] = s;
-        seg_off[im.seg_base] = 0;
-        if (!invalid) seg_off[im.seg_base + s.nseg] = carry_k;
-    }
 }
 
 // exclusive scan over the CTA of a packed pair of counters (low 16 bits / high 16 bits; totals stay below 2^16)
@@ -235,27 +169,96 @@ __device__ __forceinline__ uint32_t block_excl_scan_packed(uint32_t v, uint32_t 
     return inc - v + s_tmp[warp];
 }
 
-// Compaction: classify again, scan inside the tile, compact the surviving bytes in shared memory and store them as
-// coalesced 32-bit words, byte-swapped so that stream byte o lands at address o ^ 3 (huff_core.h "bit reader").  Where
-// the tile's bytes go comes from k_scan_tiles, so there is no chaining between CTAs.  A tile's output starts at an
-// arbitrary byte, so the (at most two) words it shares with its neighbours are written bytewise.
+// The look-back word of a tile: bits 1..0 status (0 nothing yet, 1 the tile's own counts, 2 inclusive prefix of the
+// image up to and including the tile), bit 2 "the scan has ended" (in this tile / at or before it), bits 33..3 surviving
+// bytes, bits 63..34 RSTn markers.  One 64-bit store publishes it, so data and status arrive together.
+constexpr uint64_t kLookOwn = 1, kLookIncl = 2;
+__device__ __forceinline__ uint64_t look_pack(uint64_t status, bool ended, uint32_t kept, uint32_t rst) {
+    return status | (ended ? 4ull : 0ull) | ((uint64_t)kept << 3) | ((uint64_t)rst << 34);
+}
+__device__ __forceinline__ uint64_t look_load(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void look_store(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// look[] and *ticket are zero when the kernel starts (one memset per decode).
 __global__ void __launch_bounds__(kUnstuffThreads)
 k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img,
-          const uint2 *__restrict__ tile_ex, const HuffImgState *__restrict__ st, uint32_t *__restrict__ clean, uint32_t *__restrict__ seg_off) {
+          uint64_t *__restrict__ look, uint32_t *__restrict__ ticket, HuffImgState *__restrict__ st, uint32_t *__restrict__ clean,
+          uint32_t *__restrict__ seg_off) {
     __shared__ uint32_t s_tmp[kUnstuffThreads / 32 + 1];
     __shared__ __align__(16) uint8_t s_out[kUnstuffTile + 16];
-    const uint32_t img = tile_img[blockIdx.x];
+    __shared__ uint32_t s_tile, s_end, s_base[3];
+    if (threadIdx.x == 0) { s_tile = atomicAdd(ticket, 1u); s_end = kNoEnd; }
+    __syncthreads();
+    const uint32_t gtile = s_tile;
+    const uint32_t img = tile_img[gtile];
     const HuffImg &im = imgs[img];
-    const uint32_t tile = blockIdx.x - im.tile_base;
-    const uint32_t raw_len = st[img].raw_len;
-    if (st[img].status == kStatusInvalid) return;
-    if ((int64_t)tile * kUnstuffTile - (int64_t)(im.raw_off & 15u) >= (int64_t)raw_len) return;   // the scan ended in front of this tile
-    const uint2 base = __ldg(tile_ex + blockIdx.x);
-    const Chunk16 c = classify16<false>(files, im, tile, raw_len);
-    const uint32_t keep = c.keep, rst = c.rst;
+    const uint32_t tile = gtile - im.tile_base;
+    const Chunk16 c = classify16(files, im, tile, im.raw_len);
+    if (c.end) atomicMin(&s_end, (uint32_t)(c.r0 + (__ffs(c.end) - 1)));
+    __syncthreads();
+    const uint32_t e = s_end;                                              // where the scan ends, if in this tile
+    const uint32_t m = chunk_mask_before(c.r0, e);
+    const uint32_t keep = c.keep & m, rst = c.rst & m;
     uint32_t tot;
     const uint32_t ex = block_excl_scan_packed<kUnstuffThreads>(__popc(keep) | (__popc(rst) << 16), tot, s_tmp);
-    const uint32_t ea = ex & 0xFFFFu, eb = ex >> 16, ta = tot & 0xFFFFu;
+    const uint32_t ea = ex & 0xFFFFu, eb = ex >> 16, ta = tot & 0xFFFFu, tb = tot >> 16;
+
+    if (threadIdx.x < 32) {                                                // ---- look-back (first warp)
+        const int lane = threadIdx.x;
+        uint32_t pk = 0, pr = 0;                                           // what the image's earlier tiles contribute
+        bool ended = false;                                                // ... and whether the scan has ended in one of them
+        if (tile > 0) {
+            if (lane == 0) look_store(look + gtile, look_pack(kLookOwn, e != kNoEnd, ta, tb));
+            int near = (int)tile - 1;                                      // image-local index of the nearest tile not yet added
+            for (;;) {
+                const int idx = near - lane;
+                uint64_t v = look_pack(kLookIncl, false, 0u, 0u);          // in front of the image's first tile: nothing
+                if (idx >= 0) { do { v = look_load(look + im.tile_base + idx); } while ((v & 3ull) == 0ull); }
+                const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v & 3ull) == kLookIncl);
+                const int stop = incl ? __ffs(incl) - 1 : 31;              // add lanes 0..stop
+                uint32_t k = lane <= stop ? (uint32_t)(v >> 3) & 0x7FFFFFFFu : 0u, r = lane <= stop ? (uint32_t)(v >> 34) : 0u;
+                const bool en = lane <= stop && (v & 4ull);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) { k += __shfl_xor_sync(0xFFFFFFFFu, k, d); r += __shfl_xor_sync(0xFFFFFFFFu, r, d); }
+                pk += k; pr += r;
+                ended = ended || __any_sync(0xFFFFFFFFu, en);
+                if (incl) break;
+                near -= 32;
+            }
+        }
+        if (lane == 0) {
+            look_store(look + gtile, look_pack(kLookIncl, ended || e != kNoEnd, pk + ta, pr + tb));
+            s_base[0] = pk; s_base[1] = pr; s_base[2] = ended ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    const uint2 base = make_uint2(s_base[0], s_base[1]);
+    if (s_base[2]) return;                                                 // the scan ended in front of this tile
+    if (threadIdx.x == 0 && (e != kNoEnd || tile + 1 == im.ntile)) {       // the image's state
+        HuffImgState s;
+        s.raw_len = e == kNoEnd ? im.raw_len : e;
+        s.end_code = e == kNoEnd ? 0x100u : (uint32_t)__ldg(files + im.raw_off + e + 1);
+        // "File ended prematurely" / "Invalid marker during compressed data scan" - unless the caller handed over the scan itself
+        const bool invalid = s.end_code != 0xD9u && !(e == kNoEnd && (im.flags & (kImgClean | kImgExact)));
+        const uint32_t ca = base.x + ta, cb = base.y + tb;
+        s.clean_len = ca; s.nrst = cb;
+        s.nseg = invalid ? 0u : min(cb + 1u, im.nseg);
+        s.nsub = 0;
+        // segments whose marker is missing are never decoded: everything from their first unit on reads as zero
+        s.first_zero = invalid ? 0u : ((s.nseg < im.nseg) ? s.nseg * im.ri * im.bpm : 0xFFFFFFFFu);
+        s.status = invalid ? kStatusInvalid : ((im.ri != 0 && cb + 1u != im.nseg) ? 1u : 0u);
+        s.first_zero0 = s.first_zero; s.status0 = s.status;
+        s.pad_[0] = s.pad_[1] = 0;
+        st[img] = s;
+        seg_off[im.seg_base] = 0;
+        if (!invalid) seg_off[im.seg_base + s.nseg] = ca;
+    }
     const uint32_t mis = base.x & 3u;                 // s_out[mis + k] = k-th surviving byte of the tile
     {
         const uint32_t w[4] = {c.bytes.x, c.bytes.y, c.bytes.z, c.bytes.w};
@@ -269,8 +272,8 @@ k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, c
     if (rst) {                                        // restart markers: where the next segment starts (rare)
         // (marker k of an image is its segment k's start; markers beyond the expected count are ignored)
         uint32_t sidx = base.y + eb + 1;
-        for (uint32_t m = rst; m; m &= m - 1) {
-            const int i = __ffs(m) - 1;
+        for (uint32_t mm = rst; mm; mm &= mm - 1) {
+            const int i = __ffs(mm) - 1;
             if (sidx < im.nseg) seg_off[im.seg_base + sidx] = base.x + ea + __popc(keep & ((1u << i) - 1u));
             sidx++;
         }
@@ -326,18 +329,19 @@ __global__ void k_reset_state(HuffImgState *__restrict__ st, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ K0d: sub-sequences
-// One CTA per image.  Segment s of the image covers un-stuffed bytes [seg_off[s], seg_off[s+1]) and is cut into
+// One CTA per image (of NT threads: 256, or 1024 when an image of the batch has more segments than that).  Segment s of the image covers un-stuffed bytes [seg_off[s], seg_off[s+1]) and is cut into
 // max(1, ceil(len / sub_bytes)) sub-sequences; seg_sub0[s] = index of its first one, sub_seg[j] = owner segment.
-__global__ void __launch_bounds__(256)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_subseq_table(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ st, const uint32_t *__restrict__ seg_off,
                uint32_t *__restrict__ seg_sub0, uint32_t *__restrict__ sub_seg) {
-    __shared__ uint32_t s_tmp[2 * 8 + 2];
-    __shared__ uint32_t s_first[257];
+    __shared__ uint32_t s_tmp[2 * (NT / 32) + 2];
+    __shared__ uint32_t s_first[NT + 1];
     const HuffImg &im = imgs[blockIdx.x];
     const uint32_t sub_bytes = im.sub_bytes;
     const uint32_t nseg = st[blockIdx.x].nseg;
     uint32_t carry = 0;
-    for (uint32_t s0 = 0; s0 < nseg; s0 += 256) {
+    for (uint32_t s0 = 0; s0 < nseg; s0 += NT) {
         const uint32_t s = s0 + threadIdx.x;
         uint32_t cnt = 0;
         if (s < nseg) {
@@ -345,15 +349,15 @@ k_subseq_table(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ st, 
             cnt = max(1u, (len + sub_bytes - 1) / sub_bytes);
         }
         uint32_t ex, e2, tot, t2;
-        block_excl_scan2<256>(cnt, 0u, ex, e2, tot, t2, s_tmp);
+        block_excl_scan2<NT>(cnt, 0u, ex, e2, tot, t2, s_tmp);
         s_first[threadIdx.x] = carry + ex;
-        if (threadIdx.x == 0) s_first[256] = carry + tot;
+        if (threadIdx.x == 0) s_first[NT] = carry + tot;
         if (s < nseg) seg_sub0[im.seg_base + s] = carry + ex;
         __syncthreads();
         if (nseg > 1) {
             // fill sub_seg for this chunk's sub-sequences: binary search among the chunk's segment starts
-            const uint32_t nchunk = min(256u, nseg - s0);
-            for (uint32_t j = s_first[0] + threadIdx.x; j < s_first[256]; j += 256) {
+            const uint32_t nchunk = min((uint32_t)NT, nseg - s0);
+            for (uint32_t j = s_first[0] + threadIdx.x; j < s_first[NT]; j += NT) {
                 uint32_t lo = 0, hi = nchunk;                             // last k with s_first[k] <= j
                 while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= j) lo = mid; else hi = mid; }
                 sub_seg[im.sub_base + j] = s0 + lo;

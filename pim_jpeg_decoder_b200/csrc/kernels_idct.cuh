@@ -48,6 +48,14 @@ __device__ __forceinline__ void color8(const uint4 &yv, const unsigned *fw, cons
 }
 
 // ------------------------------------------------------------------------------------------------ fast layout
+// REF_MCUS = false: packed 8-bit pixels (RGB8 or the BMP byte stream).  REF_MCUS = true: the reference's own post-exec
+// `mcus` layout - R, G, B as shorts inside the block-tiled buffer that the unchanged write_BMP reads
+// (src/bmp_writer.cpp:43-61; layout src/decoder_dpu.c:134-156, destination index src/jpeg_scanner.cpp:733-741): for the
+// 8x8 position (pr, pc) of a grid that is W = mcu_width_real positions wide,
+//     block = (pr / 2) * ((W + 1) / 2) + pc / 2,  pos = (pr % 2) * 2 + pc % 2,
+//     short index = block * 768 + component * 256 + pos * 64 + row * 8 + x
+// (the split into MAX_MCU_PER_DPU chunks is the same linear buffer: a chunk is MAX_MCU_PER_DPU / 4 whole blocks).
+template <bool REF_MCUS>
 __global__ void __launch_bounds__(kTileThreads, 4)
 k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_plane, const ImgDev *__restrict__ imgs,
              const QTab *__restrict__ qtabs, const TileDev *__restrict__ tiles, uint8_t *__restrict__ out) {
@@ -171,12 +179,27 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
                 const unsigned fw[4] = {fv.x, fv.y, fv.z, fv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
                 color8<false>(yv, fw, lw, kF, kL, gF, gL, c0, c1, c2);
             }
+            if (REF_MCUS) {
+                // straight to HBM: three 16-byte rows (R, G, B as shorts) of position (pr, pc)
+                const unsigned pr = (unsigned)t.my * vs + by, pc = ((unsigned)t.mx0 + m) * hs + bx, W = im->nmx * hs;
+                const size_t blk = (size_t)(pr >> 1) * ((W + 1u) >> 1) + (pc >> 1);
+                int16_t *ob = reinterpret_cast<int16_t *>(out + im->out_row0) + blk * 768 + ((pr & 1u) * 2u + (pc & 1u)) * 64u + r * 8;
+                auto pack8 = [](const int (&c)[8]) {
+                    return make_uint4(clamp255(c[0]) | (clamp255(c[1]) << 16), clamp255(c[2]) | (clamp255(c[3]) << 16),
+                                      clamp255(c[4]) | (clamp255(c[5]) << 16), clamp255(c[6]) | (clamp255(c[7]) << 16));
+                };
+                __stcs(reinterpret_cast<uint4 *>(ob), pack8(c0));
+                __stcs(reinterpret_cast<uint4 *>(ob + 256), pack8(c1));
+                __stcs(reinterpret_cast<uint4 *>(ob + 512), pack8(c2));
+                continue;
+            }
             uint2 *dst = reinterpret_cast<uint2 *>(s_rgb + py * pitch + s * 24);
             dst[0] = make_uint2(pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]));
             dst[1] = make_uint2(pack_sat4(c2[2], c0[3], c1[3], c2[3]), pack_sat4(c0[4], c1[4], c2[4], c0[5]));
             dst[2] = make_uint2(pack_sat4(c1[5], c2[5], c0[6], c1[6]), pack_sat4(c2[6], c0[7], c1[7], c2[7]));
         }
     }
+    if (REF_MCUS) return;
     __syncthreads();
 
     // ---- stage 3: copy-out.  Each pixel row of the tile is a contiguous byte run in HBM with arbitrary
@@ -246,6 +269,29 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
             const long long hdr = (long long)im->out_row0 - (long long)(H - 1) * (long long)im->out_pitch - 26;
             out[hdr + tid] = (uint8_t)v;
         }
+    }
+}
+
+// REF_MCUS: what the DPUs leave in the parts of the buffer no pixel lives in - positions of the 2x2-padded grid outside
+// the image's own, and the unused blocks at the end of the last chunk: zero coefficients, so R = G = B = 128
+// (every DPU runs all its blocks whether used or not, src/decoder_dpu.c:130).  One thread = one (position, component).
+__global__ void __launch_bounds__(256)
+k_ref_mcus_pad(const ImgDev *__restrict__ imgs, uint8_t *__restrict__ out) {
+    const ImgDev &im = imgs[blockIdx.y];
+    if (!im.valid) return;
+    const unsigned W = im.nmx * im.hs, H = im.nmy * im.vs, bpr = (W + 1u) >> 1;
+    const unsigned real_blocks = bpr * ((H + 1u) >> 1);
+    int16_t *base = reinterpret_cast<int16_t *>(out + im.out_row0);
+    const uint4 v128 = make_uint4(0x00800080u, 0x00800080u, 0x00800080u, 0x00800080u);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < im.ref_blocks * 12u; i += gridDim.x * blockDim.x) {
+        const unsigned blk = i / 12u, pc12 = i - blk * 12u, pos = pc12 & 3u, comp = pc12 >> 2;
+        if (blk < real_blocks) {
+            const unsigned pr = (blk / bpr) * 2u + (pos >> 1), pcx = (blk % bpr) * 2u + (pos & 1u);
+            if (pr < H && pcx < W) continue;                            // a real position: the IDCT kernel writes it
+        }
+        uint4 *d = reinterpret_cast<uint4 *>(base + (size_t)blk * 768 + comp * 256 + pos * 64);
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[k] = v128;
     }
 }
 

@@ -139,7 +139,7 @@ inline void skip_segment(Cursor &c) {
 // Locate the end of the entropy-coded segment (src/jpeg_scanner.cpp:405-433): the first FF that is followed by
 // something other than 00 / RSTn / FF.  EOI ends the scan; anything else makes the file invalid.
 // Only bj_parse_header (the public, stand-alone restatement of read_JPEG) walks the scan like this; the decode path
-// leaves it to the GPU (kernels_huff.cuh: k_scan_count / k_scan_tiles apply the same rule).
+// leaves it to the GPU (kernels_huff.cuh: k_unstuff applies the same rule).
 inline int find_scan_end(const uint8_t *p, size_t n, size_t start, size_t *end) {
     size_t i = start;
     for (;;) {

@@ -225,6 +225,23 @@ class Decoder:
         return [o if s in (L.BJ_OK, L.BJ_ERR_CORRUPT_SCAN) else None for o, s in zip(outs, st)], st
 
 
+    def decode_desc(self, descs, scans, kinds=None, fmt=L.BJ_OUT_REF_MCUS):
+        """bj_decode_batch_desc: the caller holds parsed headers (ImageDesc, e.g. filled from the reference's `Header`) and
+        the scan bytes.  Returns (list of arrays - int16 for BJ_OUT_REF_MCUS, uint8 otherwise -, list of status)."""
+        n = len(descs)
+        arr = (L.ImageDesc * max(n, 1))(*descs)
+        keep, ptrs, lens = _file_arrays(scans)
+        m = C.c_int(0)
+        sizes = [L.lib().bj_ref_mcus_size(C.byref(d), 100, C.byref(m)) if fmt == L.BJ_OUT_REF_MCUS else L.lib().bj_output_size(C.byref(d), fmt) for d in descs]
+        outs = [np.zeros(s, dtype=np.uint8) for s in sizes]
+        optrs = (C.c_void_p * max(n, 1))(*[o.__array_interface__["data"][0] for o in outs])
+        kp = (C.c_int * max(n, 1))(*kinds) if kinds is not None else None
+        status = (C.c_int * max(n, 1))()
+        L.check(L.lib().bj_decode_batch_desc(self.ctx, arr, ptrs, lens, kp, n, fmt, optrs, status), "bj_decode_batch_desc", self.ctx)
+        if fmt == L.BJ_OUT_REF_MCUS:
+            outs = [o.view(np.int16) for o in outs]
+        return outs, list(status)[:n]
+
     def decode_packed(self, src, src_off, src_len, dst, dst_off, fmt=L.BJ_OUT_RGB8):
         """bj_decode_batch for a batch-pipeline caller: the n files sit in ONE host buffer `src` (uint8 array, ideally
         a PinnedBuffer) at byte offsets `src_off` with lengths `src_len`; image i is written to `dst[dst_off[i]:]`

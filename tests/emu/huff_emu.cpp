@@ -30,10 +30,11 @@ struct SliceRec { uint32_t p, cz, cnt; };
 
 // ------------------------------------------------------------------------------------------------ K0, as the kernels run it
 // The device buffer holds the file at `file_pos` (any alignment; what lies around it is arbitrary).  Tiles of
-// kTile raw bytes, 256 "threads" of one aligned 16-byte chunk each: k_scan_count (per tile: bytes that survive and
-// RSTn markers in front of the scan's end, where the scan ends), k_scan_tiles (per image: scan over the tiles, the
-// image's state), k_unstuff (compaction, byte o stored at o ^ 3; segment starts).  Same shared code as the kernels:
-// classify_words[_end], clip_chunk, chunk_mask_before, tile_of_pos.
+// kTile raw bytes, 256 "threads" of one aligned 16-byte chunk each, as k_unstuff works: per tile, where the scan ends
+// (if in this tile), the bytes that survive and the RSTn markers in front of that point; what the earlier tiles of the
+// image contribute (the kernel's look-back; here a running prefix, tiles in order); compaction (byte o stored at
+// o ^ 3), segment starts, the image's state.  Same shared code as the kernel: classify_words_end, clip_chunk,
+// chunk_mask_before.
 namespace {
 constexpr uint32_t kTile = 4096;
 struct K0Out {
@@ -44,7 +45,7 @@ struct K0Out {
 };
 struct Chunk { uint32_t keep, rst, end; uint32_t w[4]; int64_t r0; };
 
-Chunk classify_chunk(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t tile, uint32_t thread, uint32_t raw_len, bool with_end) {
+Chunk classify_chunk(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t tile, uint32_t thread, uint32_t raw_len) {
     Chunk c;
     const uint64_t a0 = (raw_off & ~(uint64_t)15) + (uint64_t)tile * kTile + (uint64_t)thread * 16;
     c.r0 = (int64_t)a0 - (int64_t)raw_off;
@@ -60,8 +61,7 @@ Chunk classify_chunk(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t
     if (thread % 32 == 31) w[5] = live ? at(a0 + 16) : 0u;
     else w[5] = next_live ? at(a0 + 16) : 0u;
     for (int k = 0; k < 4; k++) c.w[k] = w[k + 1];
-    if (with_end) classify_words_end(w, c.keep, c.rst, c.end);
-    else { classify_words(w, c.keep, c.rst); c.end = 0; }
+    classify_words_end(w, c.keep, c.rst, c.end);
     clip_chunk(c.r0, raw_len, c.keep, c.rst, c.end);
     return c;
 }
@@ -69,47 +69,42 @@ Chunk classify_chunk(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t
 void k0_emulate(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t raw_len_max, uint32_t nseg_expected, K0Out *o) {
     const uint32_t mis = (uint32_t)(raw_off & 15u);
     const uint32_t ntile = std::max<uint32_t>(1u, (uint32_t)((mis + (uint64_t)raw_len_max + kTile - 1) / kTile));
-    // k_scan_count
-    std::vector<uint32_t> cnt_k(ntile), cnt_r(ntile), cnt_e(ntile);
+    o->clean.assign(((size_t)raw_len_max / 4 + 4 + 96) * 4, 0);
+    o->seg_off.assign(nseg_expected, 0xFFFFFFFFu);
+    // what the look-back hands a tile: surviving bytes / markers of the image's earlier tiles, and whether the scan has ended
+    uint32_t pk = 0, pr = 0;
+    bool ended = false, state_written = false;
     for (uint32_t t = 0; t < ntile; t++) {
         uint32_t e = kNoScanEnd;
         std::vector<Chunk> cs;
         for (uint32_t th = 0; th < 256; th++) {
-            cs.push_back(classify_chunk(buf, raw_off, t, th, raw_len_max, true));
+            cs.push_back(classify_chunk(buf, raw_off, t, th, raw_len_max));
             if (cs.back().end) e = std::min(e, (uint32_t)(cs.back().r0 + __builtin_ctz(cs.back().end)));
         }
-        uint32_t k = 0, r = 0;
-        for (auto &c : cs) { const uint32_t m = chunk_mask_before(c.r0, e); k += __builtin_popcount(c.keep & m); r += __builtin_popcount(c.rst & m); }
-        cnt_k[t] = k; cnt_r[t] = r; cnt_e[t] = e;
-    }
-    // k_scan_tiles
-    std::vector<uint32_t> ex_k(ntile, 0xDEADu), ex_r(ntile, 0xDEADu);
-    uint32_t e = kNoScanEnd, ck = 0, cr = 0;
-    for (uint32_t t = 0; t < ntile; t++) if (cnt_e[t] != kNoScanEnd) { e = cnt_e[t]; break; }
-    const uint32_t last = e == kNoScanEnd ? 0xFFFFFFFFu : tile_of_pos(mis, e, kTile);
-    for (uint32_t t = 0; t < ntile && t <= last; t++) { ex_k[t] = ck; ex_r[t] = cr; ck += cnt_k[t]; cr += cnt_r[t]; }
-    o->raw_len = e == kNoScanEnd ? raw_len_max : e;
-    o->end_code = e == kNoScanEnd ? 0x100u : buf[raw_off + e + 1];
-    o->status = o->end_code != 0xD9u ? 2u : 0u;
-    o->clean_len = ck; o->nrst = cr;
-    o->clean.assign(((size_t)raw_len_max / 4 + 4 + 96) * 4, 0);
-    o->seg_off.assign(1, 0);
-    if (o->status) return;
-    const uint32_t nseg = std::min(cr + 1u, nseg_expected);
-    o->seg_off.assign(nseg, 0xFFFFFFFFu);
-    o->seg_off[0] = 0;
-    // k_unstuff
-    for (uint32_t t = 0; t < ntile; t++) {
-        if ((int64_t)t * kTile - (int64_t)mis >= (int64_t)o->raw_len) continue;
-        uint32_t pos = ex_k[t], sidx = ex_r[t] + 1;
-        for (uint32_t th = 0; th < 256; th++) {
-            const Chunk c = classify_chunk(buf, raw_off, t, th, o->raw_len, false);
+        uint32_t ta = 0, tb = 0;
+        for (auto &c : cs) { const uint32_t m = chunk_mask_before(c.r0, e); c.keep &= m; c.rst &= m; ta += __builtin_popcount(c.keep); tb += __builtin_popcount(c.rst); }
+        const uint32_t base_k = pk, base_r = pr;
+        const bool dead = ended;
+        pk += ta; pr += tb; ended = ended || e != kNoScanEnd;              // (the tile's inclusive word)
+        if (dead) continue;
+        if (e != kNoScanEnd || t + 1 == ntile) {                           // the image's state
+            if (state_written) { o->status = 99; return; }
+            state_written = true;
+            o->raw_len = e == kNoScanEnd ? raw_len_max : e;
+            o->end_code = e == kNoScanEnd ? 0x100u : buf[raw_off + e + 1];
+            o->status = o->end_code != 0xD9u ? 2u : 0u;
+            o->clean_len = base_k + ta; o->nrst = base_r + tb;
+            o->seg_off[0] = 0;
+        }
+        uint32_t pos = base_k, sidx = base_r + 1;
+        for (auto &c : cs)
             for (int i = 0; i < 16; i++) {
                 if (c.keep & (1u << i)) { o->clean[pos ^ 3u] = (uint8_t)(c.w[i >> 2] >> ((i & 3) * 8)); pos++; }
-                else if (c.rst & (1u << i)) { if (sidx < nseg_expected && sidx < nseg) o->seg_off[sidx] = pos; sidx++; }
+                else if (c.rst & (1u << i)) { if (sidx < nseg_expected) o->seg_off[sidx] = pos; sidx++; }
             }
-        }
     }
+    if (!state_written) { o->status = 98; return; }
+    o->seg_off.resize(o->status ? 1 : std::min(o->nrst + 1u, nseg_expected));
 }
 }  // namespace
 

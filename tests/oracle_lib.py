@@ -86,6 +86,8 @@ def ref():
         lib.ref_probe.argtypes = [C.c_char_p, C.POINTER(RefInfo)]
         lib.ref_decode_file.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.POINTER(RefInfo)]
         lib.ref_exec_mcus.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        if hasattr(lib, "ref_write_bmp"):
+            lib.ref_write_bmp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p]
         _ref = lib
     return _ref
 
@@ -166,3 +168,22 @@ def ref_exec_mcus(metadata, mcus):
     md = np.ascontiguousarray(metadata, dtype=np.uint32)
     ref().ref_exec_mcus(_ptr(md), _ptr(out), md.shape[0])
     return out
+
+
+def ref_write_bmp(metadata276, mcus, path):
+    """The reference's real write_BMP on post-exec chunks [nchunk][64*M*3]."""
+    md = np.ascontiguousarray(metadata276, dtype=np.uint32).reshape(-1)[:276]
+    m = np.ascontiguousarray(mcus, dtype=np.int16)
+    ref().ref_write_bmp(_ptr(md), _ptr(m), int(m.size // CHUNK), path.encode())
+
+
+def unstuffed_scan(data):
+    """Header::huffman_data as read_JPEG leaves it (un-stuffed, RSTn removed), from the restatement's scan filter."""
+    h = RsHeader()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    assert restate().rs_parse(_ptr(buf), len(data), C.byref(h)) == 0
+    scan = np.ascontiguousarray(buf[h.scan_off:h.scan_off + h.scan_len])
+    out = np.zeros(h.scan_len + 1, dtype=np.uint8)
+    n = restate().rs_unstuff(_ptr(scan), h.scan_len, _ptr(out), None, 0, None)
+    assert n >= 0
+    return bytes(out[:n]), bytes(scan)

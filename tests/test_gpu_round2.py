@@ -152,7 +152,7 @@ def test_poisoned_buffers_golden_set_and_mixed_batch(dec, golden, golden_dir):
 # ------------------------------------------------------------------ the scan's end is found on the device
 
 def test_scan_end_found_on_device(dec):
-    """The host reads headers only; k_scan_count / k_scan_tiles find where each scan ends.  Garbage behind EOI is
+    """The host reads headers only; k_unstuff finds where each scan ends.  Garbage behind EOI is
     ignored; a scan that ends in another marker, or not at all, makes the file invalid exactly like read_JPEG
     (src/jpeg_scanner.cpp:405-433) - per image, inside a batch whose other images decode normally."""
     import pim_jpeg_decoder_b200 as bj
@@ -323,3 +323,80 @@ def test_multi_device_context_and_async_jobs(golden, golden_dir):
         src.free()
     finally:
         md.close()
+
+
+# ------------------------------------------------------------------ behind the unchanged scanner, in front of the unchanged BMP writer
+
+def _desc_from_oracle_header(bj, data):
+    """What a host that keeps read_JPEG does: one bj_image_desc per `Header`, field for field.  Here the
+    parsed header comes from bj_peek_header; scan_off / scan_len are not used by bj_decode_batch_desc."""
+    import ctypes as C
+    d = bj.ImageDesc()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    assert bj.lib().bj_peek_header(buf.ctypes.data_as(C.c_void_p), len(data), C.byref(d)) == 0
+    d.scan_off = 0
+    d.scan_len = 0
+    return d
+
+
+def test_ref_mcus_output_and_descriptor_input(dec, golden, golden_dir, tmp_path):
+    """BJ_OUT_REF_MCUS = the reference's `mcus` buffers after pim.exec(): the WHOLE buffer (every chunk, the 128 fill of
+    unused tiles included) equals the reference's post-exec buffer - hash from golden.json, made by the real reference -
+    and the reference's own, unchanged write_BMP (through oracle/_ref/libref.so) turns it into the golden BMP.  Input
+    three ways: the file (bj_decode_batch), descriptor + Header::huffman_data (BJ_SCAN_UNSTUFFED, what read_JPEG leaves),
+    descriptor + raw scan bytes (BJ_SCAN_RAW, needed for files with restart markers)."""
+    import pim_jpeg_decoder_b200 as bj
+    names = _names()
+    files = [_load(golden, golden_dir, n) for n in names]
+    rs = [ol.Restated(f, 0) for f in files]
+    # (1) files in, mcus out - one batch
+    sizes = [r.mcus_post.nbytes for r in rs]
+    outs = [np.zeros(s, dtype=np.uint8) for s in sizes]
+    res, status = dec.decode(files, bj.BJ_OUT_REF_MCUS, outs=outs)
+    assert all(s == 0 for s in status)
+    for n, o, r in zip(names, outs, rs):
+        got = o.view(np.int16).reshape(r.mcus_post.shape)
+        assert np.array_equal(got, r.mcus_post), n
+        if golden[n]["expect"] == n:                                   # (not a restart-parity twin case)
+            assert sha(got) == golden[n]["mcus_post_sha256"], n
+    # (2) descriptor + scan, both kinds
+    descs = [_desc_from_oracle_header(bj, f) for f in files]
+    pairs = [ol.unstuffed_scan(f) for f in files]
+    ri0 = [i for i, d in enumerate(descs) if d.restart_interval == 0]
+    o_clean, st_clean = dec.decode_desc([descs[i] for i in ri0], [pairs[i][0] for i in ri0], [bj.BJ_SCAN_UNSTUFFED] * len(ri0))
+    assert st_clean == [0] * len(ri0)
+    for i, o in zip(ri0, o_clean):
+        assert np.array_equal(o.reshape(rs[i].mcus_post.shape), rs[i].mcus_post), names[i]
+    o_raw, st_raw = dec.decode_desc(descs, [p[1] for p in pairs], None)
+    assert st_raw == [0] * len(files)
+    for n, o, r in zip(names, o_raw, rs):
+        assert np.array_equal(o.reshape(r.mcus_post.shape), r.mcus_post), n
+    # un-stuffed data of a file WITH restart markers cannot be split into segments any more: refused, per image
+    with_ri = [i for i, d in enumerate(descs) if d.restart_interval != 0][:2]
+    _, st_bad = dec.decode_desc([descs[i] for i in with_ri], [pairs[i][0] for i in with_ri], [bj.BJ_SCAN_UNSTUFFED] * len(with_ri))
+    assert st_bad == [bj.BJ_ERR_UNSUPPORTED] * len(with_ri)
+    # BMP bytes straight from a descriptor, too
+    o_bmp, st_bmp = dec.decode_desc(descs, [p[1] for p in pairs], None, fmt=bj.BJ_OUT_BMP)
+    for n, o in zip(names, o_bmp):
+        assert sha(o) == golden[golden[n]["expect"]]["bmp_sha256"], n
+    # (3) the reference's own write_BMP on our buffers
+    if ol.ref_available() and hasattr(ol.ref(), "ref_write_bmp"):
+        for n, o, r in list(zip(names, o_raw, rs))[::3]:
+            path = str(tmp_path / (n + ".bmp"))
+            ol.ref_write_bmp(r.metadata[0], o, path)
+            assert sha(np.fromfile(path, dtype=np.uint8)) == golden[golden[n]["expect"]]["bmp_sha256"], n
+    # another MAX_MCU_PER_DPU: the same linear buffer, cut into other chunks
+    dec.set_option("ref_max_mcu_per_dpu", 400)
+    try:
+        import ctypes as C
+        i = names.index("ilsvrc_444")
+        m = C.c_int(0)
+        nbytes = bj.lib().bj_ref_mcus_size(C.byref(descs[i]), 400, C.byref(m))
+        out = np.zeros(nbytes, dtype=np.uint8)
+        _, st = dec.decode([files[i]], bj.BJ_OUT_REF_MCUS, outs=[out])
+        assert st == [0] and m.value == (rs[i].nchunk * 100 + 399) // 400
+        flat = rs[i].mcus_post.reshape(-1)
+        got = out.view(np.int16)
+        assert np.array_equal(got[:flat.size], flat) and (got[flat.size:] == 128).all()
+    finally:
+        dec.set_option("ref_max_mcu_per_dpu", 100)

@@ -188,8 +188,8 @@ def _scan_soup(rng, nbytes):
 
 
 def test_device_side_scan_end_counts_and_compaction():
-    """K0 never gets a scan length from the host: k_scan_count / k_scan_tiles find the FF that ends the scan, count what
-    survives in front of it per 4 KB tile, and k_unstuff compacts.  Their shared code, run tile by tile and chunk by
+    """K0 never gets a scan length from the host: k_unstuff finds the FF that ends the scan, counts what
+    survives in front of it per 4 KB tile (look-back between the tiles), and compacts.  Their shared code, run tile by tile and chunk by
     chunk like the kernels, against the per-byte rules and the host's scan walk: scans dense in stuffed FFs, restart
     markers and fill bytes, every alignment of the file in the device buffer, arbitrary bytes around the file, ends on
     tile and chunk boundaries, trailing garbage behind EOI, and files the reference rejects (no EOI, another marker
