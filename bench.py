@@ -384,6 +384,7 @@ def main():
     ap.add_argument("--slices", type=int, default=0, help="slices of a sub-sequence the Huffman write pass works on (0 = library default: 1)")
     ap.add_argument("--sync-rounds", type=int, default=0)
     ap.add_argument("--sync-phased", type=int, default=-1, help="1/0: Huffman synchronisation pass with / without early stop of re-decodes (-1 = library default)")
+    ap.add_argument("--sync-preroll", type=int, default=-1, help="bits of pre-roll of the Huffman synchronisation pass' first guess (-1 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--sub-batch-mb", type=int, default=0, help="compressed MB per sub-batch of the one-call path (0 = library default)")
     ap.add_argument("--host-threads", type=int, default=0, help="host worker threads of the one-call path (0 = library default)")
@@ -462,6 +463,8 @@ def main():
         dec.set_option("sync_rounds", args.sync_rounds)
     if args.sync_phased >= 0:
         dec.set_option("sync_phased", args.sync_phased)
+    if args.sync_preroll >= 0:
+        dec.set_option("sync_preroll_bits", args.sync_preroll)
     sampler = ClockSampler(local_rank, args.clock_sample_ms)
     sampler.start()
     windows = []

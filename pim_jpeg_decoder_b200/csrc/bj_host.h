@@ -1,5 +1,6 @@
 // Host-side plumbing of the library: context, grow-only device buffers, per-image geometry.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -154,8 +155,13 @@ struct bj_ctx {
     int packed_outputs = 0;              // see batch_download_async
     int packed_inputs = 0;               // see batch_assign: 0 = upload straight from the caller's memory when it is known to be page-locked
                                          // (bj_host_alloc / bj_host_register), 1 = the caller says it is, -1 = always stage
+    int idct_tma = 1;                    // K2/K3: persistent kernel with TMA-fed coefficient tiles (0: one CTA per tile, register-staged loads)
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeTiledFn encode_tiled = nullptr; // cuTensorMapEncodeTiled, through cudaGetDriverEntryPoint (no link against libcuda)
+    int sync_preroll_bits = 0;           // synchronisation pass: bits a sub-sequence's first guess is decoded ahead of its start (kernels_huff.cuh: PREROLL)
     int min_sub_bytes = 128;             // shortest sub-sequence the automatic layout picks (small batches)
-    int ri_split_threads = 0;            // restart segments below which a batch cuts them into shorter sub-sequences (set in bj_create: one wave of CTAs)
+    int ri_split_threads = 0;            // a batch with fewer restart segments than this cuts them into shorter sub-sequences (0: never; B200JPEG_RI_SPLIT for experiments)
     int ref_m = 100;                     // BJ_OUT_REF_MCUS: MAX_MCU_PER_DPU of the host that reads the buffer (Makefile:2 of the reference)
     int debug_poison = 0;                // fill coefficient / DC / output buffers with 0xA5 before every decode (tests: every byte must be written)
     size_t max_image_pixels = (size_t)1 << 28;   // larger images are refused (BJ_ERR_UNSUPPORTED), like the reference's "Too high resolution"

@@ -577,13 +577,37 @@ struct WriteCursor {
         const int32_t v = extend_entry(win, e);
         // index of the coefficient this symbol carries (0: the DC difference).  size 0 (ZRL, EOB, refused) stores nothing.
         if (v != 0) sink.put(((Sn & 0xFFu) - 1u) & 63u, (int16_t)v);
+        const bool fin = (Sn & 0x40u) != 0u;              // index >= 64: the unit ends one way or another
+        if (__builtin_expect(fin && ((bad & kLutBad) || Sn > dataS || ((Sn & 0xFFu) != 64u && !(e & kLutEob))), 0)) {
+            tab = ac; S = Sn;
+            redo_unit(luts, g, sink);
+            return true;
+        }
+#if defined(__CUDA_ARCH__) && defined(BJ_WRITE_SELECTS)
+        // The hand-over to the next unit without a branch (everything a select on `fin`).  About two of three warp steps
+        // have a lane that completes a unit, and the branch below runs its body for that one lane while the others wait
+        // (29 % of the kernel's instructions) - yet the branch-free form measured SLOWER on config 2 (2.14 ms against
+        // 2.00, profiles/r2_ab_write_sync.md): it adds a shared load and ten selects to EVERY step.  Kept for reference.
+        uint32_t dcn, acn, c1;
+        [[maybe_unused]] uint32_t stepw;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dcn), "=r"(acn), "=r"(stepw), "=r"(c1) : "r"(g.unit_tab + c * 16u));
+        st_du = fin ? du : 0xFFFFFFFFu;
+        du += fin ? 1u : 0u;
+        S = fin ? (Sn & ~0xFFu) : Sn;
+        tab = fin ? dcn : ac;
+        ac = fin ? acn : ac;
+        c = fin ? c1 : c;
+        S0 = fin ? S : S0;
+        bad = fin ? 0u : bad;
+        if (fin && (S >= endS || du >= du_end)) finish();
+        return fin;
+#else
         tab = ac;
         S = Sn;
-        if (!(Sn & 0x40u)) return false;
-        // index >= 64: the unit ends one way or another
-        if (__builtin_expect((bad & kLutBad) || Sn > dataS || ((Sn & 0xFFu) != 64u && !(e & kLutEob)), 0)) redo_unit(luts, g, sink);
-        else unit_done(g);
+        if (!fin) return false;
+        unit_done(g);
         return true;
+#endif
     }
     BJ_HD void unit_done(const HuffGeom &g) {
         st_du = du++;

@@ -26,7 +26,8 @@ namespace bj {
 
 constexpr int kHuffThreads = 256;          // sub-sequences per CTA
 constexpr int kUnstuffThreads = 256;
-constexpr int kUnstuffTile = kUnstuffThreads * 16;   // raw bytes per CTA of K0
+constexpr int kUnstuffChunks = 4;          // 16-byte chunks per thread of K0
+constexpr int kUnstuffTile = kUnstuffThreads * 16 * kUnstuffChunks;   // raw bytes per CTA of K0
 
 // Per image, written by the host.
 struct HuffImg {
@@ -112,8 +113,8 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------ K0: un-stuff
-// ONE pass over aligned tiles of kUnstuffTile raw bytes (one thread = one aligned 16-byte chunk of the file buffer = one
-// 128-bit load, classified branch-free four bytes per 32-bit word).  A tile
+// ONE pass over aligned tiles of kUnstuffTile raw bytes (one thread = four consecutive aligned 16-byte chunks of the
+// file buffer = four 128-bit loads, classified branch-free four bytes per 32-bit word).  A tile
 //   * finds where the scan ends if it ends inside the tile: the first FF followed by something other than 00 / FF /
 //     RSTn (src/jpeg_scanner.cpp:405-433) - the host passes only an upper bound of the scan (first scan byte .. end of
 //     the file) and never touches the entropy-coded bytes;
@@ -121,36 +122,13 @@ __device__ __forceinline__ void block_excl_scan2(uint32_t a, uint32_t b, uint32_
 //   * learns what the image's earlier tiles contribute by a DECOUPLED LOOK-BACK: every tile publishes its own counts
 //     (one 64-bit word: status, "the scan has ended", surviving bytes, markers), then its first warp reads the words of
 //     up to 32 predecessors at a time and adds them up until it meets one that already carries an inclusive prefix.
-//     Tiles take their index from a ticket counter, so a tile only ever waits for tiles that have started;
+//     A CTA takes its tile index inside its image from the image's ticket counter, so a tile only ever waits for tiles
+//     that have started (one counter per image: a single counter for the whole grid serialises 77 600 atomics);
 //   * compacts its surviving bytes in shared memory and stores them as big-endian words at their final place;
 //   * the tile in which the scan ends (or, if it never does, the image's last tile) writes the image's state: true scan
 //     length, totals, and kStatusInvalid when the scan does not end in EOI - the files read_JPEG rejects.
 // The byte before the scan is the SOS header's Ah/Al byte (0 in a baseline file), so the rule "the first byte has no
 // FF before it" holds without a special case.
-struct Chunk16 {
-    uint4 bytes;
-    uint32_t keep, rst, end;   // bit i = byte i survives / is the code byte of an RSTn marker / is the FF that ends the scan
-    int64_t r0;                // scan-relative index of byte 0 (may be < 0)
-};
-
-__device__ __forceinline__ Chunk16 classify16(const uint8_t *__restrict__ files, const HuffImg &im, uint32_t tile, uint32_t raw_len) {
-    Chunk16 c;
-    const uint64_t a0 = (im.raw_off & ~(uint64_t)15) + (uint64_t)tile * kUnstuffTile + (uint64_t)threadIdx.x * 16;
-    c.r0 = (int64_t)a0 - (int64_t)im.raw_off;
-    const bool live = c.r0 < (int64_t)raw_len && c.r0 + 16 > 0;
-    c.bytes = live ? __ldg(reinterpret_cast<const uint4 *>(files + a0)) : make_uint4(0, 0, 0, 0);
-    // neighbours' edge bytes: from the adjacent lanes, from memory at the warp's edges
-    const int lane = threadIdx.x & 31;
-    uint32_t prevw = __shfl_up_sync(0xFFFFFFFFu, c.bytes.w, 1), nextw = __shfl_down_sync(0xFFFFFFFFu, c.bytes.x, 1);
-    if (lane == 0) prevw = (live && a0 > 0) ? ((uint32_t)__ldg(files + a0 - 1) << 24) : 0u;
-    if (lane == 31) nextw = live ? (uint32_t)__ldg(files + a0 + 16) : 0u;
-    const uint32_t w[6] = {prevw, c.bytes.x, c.bytes.y, c.bytes.z, c.bytes.w, nextw};
-    if (im.flags & kImgClean) { c.keep = 0xFFFFu; c.rst = 0u; c.end = 0u; }
-    else classify_words_end(w, c.keep, c.rst, c.end);
-    clip_chunk(c.r0, raw_len, c.keep, c.rst, c.end);                       // bytes outside [0, raw_len) do not count
-    return c;
-}
-
 // exclusive scan over the CTA of a packed pair of counters (low 16 bits / high 16 bits; totals stay below 2^16)
 template <int NT>
 __device__ __forceinline__ uint32_t block_excl_scan_packed(uint32_t v, uint32_t &total, uint32_t *s_tmp /* NT/32 + 1 */) {
@@ -185,36 +163,85 @@ __device__ __forceinline__ void look_store(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// look[] and *ticket are zero when the kernel starts (one memset per decode).
+// look[] (one word per tile) and ticket[] (one counter per image) are zero when the kernel starts (one memset per decode).
+// One thread = kUnstuffChunks consecutive 16-byte chunks (64 bytes), a tile = 16 KB: the fixed costs of a tile - ticket,
+// barriers, the look-back's round trips through L2 - are paid once per 16 KB (with 4 KB tiles they were half of the
+// kernel's time: 77 600 CTAs that each live only a few microseconds).
 __global__ void __launch_bounds__(kUnstuffThreads)
 k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img,
           uint64_t *__restrict__ look, uint32_t *__restrict__ ticket, HuffImgState *__restrict__ st, uint32_t *__restrict__ clean,
           uint32_t *__restrict__ seg_off) {
+    constexpr int NC = kUnstuffChunks;
     __shared__ uint32_t s_tmp[kUnstuffThreads / 32 + 1];
-    __shared__ __align__(16) uint8_t s_out[kUnstuffTile + 16];
+    __shared__ __align__(16) uint8_t s_out[kUnstuffTile + 16];             // surviving byte k of the tile at s_out[4 + k]
     __shared__ uint32_t s_tile, s_end, s_base[3];
-    if (threadIdx.x == 0) { s_tile = atomicAdd(ticket, 1u); s_end = kNoEnd; }
-    __syncthreads();
-    const uint32_t gtile = s_tile;
-    const uint32_t img = tile_img[gtile];
+    const uint32_t img = tile_img[blockIdx.x];
     const HuffImg &im = imgs[img];
-    const uint32_t tile = gtile - im.tile_base;
-    const Chunk16 c = classify16(files, im, tile, im.raw_len);
-    if (c.end) atomicMin(&s_end, (uint32_t)(c.r0 + (__ffs(c.end) - 1)));
+    if (threadIdx.x == 0) { s_tile = atomicAdd(ticket + img, 1u); s_end = kNoEnd; }
+    __syncthreads();
+    const uint32_t tile = s_tile;                                          // which of the image's tiles this CTA works on
+    const uint32_t gtile = im.tile_base + tile;
+    const int lane = threadIdx.x & 31;
+
+    // ---- classify this thread's 64 bytes
+    const uint64_t a0 = (im.raw_off & ~(uint64_t)15) + (uint64_t)tile * kUnstuffTile + (uint64_t)threadIdx.x * (16 * NC);
+    const int64_t r0 = (int64_t)a0 - (int64_t)im.raw_off;                  // scan-relative index of the first byte (may be < 0)
+    uint32_t w[4 * NC + 2];                                                // w[0]: the word in front (its top byte counts), w[4 NC + 1]: the word behind
+    bool live[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        live[c] = r0 + 16 * c < (int64_t)im.raw_len && r0 + 16 * c + 16 > 0;
+        const uint4 v = live[c] ? __ldg(reinterpret_cast<const uint4 *>(files + a0) + c) : make_uint4(0, 0, 0, 0);
+        w[4 * c + 1] = v.x; w[4 * c + 2] = v.y; w[4 * c + 3] = v.z; w[4 * c + 4] = v.w;
+    }
+    // the neighbours' edge bytes: from the adjacent lanes, from memory at the warp's edges
+    w[0] = __shfl_up_sync(0xFFFFFFFFu, w[4 * NC], 1);
+    w[4 * NC + 1] = __shfl_down_sync(0xFFFFFFFFu, w[1], 1);
+    if (lane == 0) w[0] = (live[0] && a0 > 0) ? ((uint32_t)__ldg(files + a0 - 1) << 24) : 0u;
+    if (lane == 31) w[4 * NC + 1] = live[NC - 1] ? (uint32_t)__ldg(files + a0 + 16 * NC) : 0u;
+    uint32_t keep[NC], rst[NC], end[NC];
+    uint32_t my_end = kNoEnd;
+#pragma unroll
+    for (int c = NC - 1; c >= 0; c--) {
+        if (im.flags & kImgClean) { keep[c] = 0xFFFFu; rst[c] = 0u; end[c] = 0u; }
+        else classify_words_end(w + 4 * c, keep[c], rst[c], end[c]);
+        clip_chunk(r0 + 16 * c, im.raw_len, keep[c], rst[c], end[c]);      // bytes outside [0, raw_len) do not count
+        if (end[c]) my_end = (uint32_t)(r0 + 16 * c + (__ffs(end[c]) - 1));
+    }
+    if (my_end != kNoEnd) atomicMin(&s_end, my_end);
     __syncthreads();
     const uint32_t e = s_end;                                              // where the scan ends, if in this tile
-    const uint32_t m = chunk_mask_before(c.r0, e);
-    const uint32_t keep = c.keep & m, rst = c.rst & m;
+    uint32_t nk = 0, nr = 0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const uint32_t m = chunk_mask_before(r0 + 16 * c, e);
+        keep[c] &= m; rst[c] &= m;
+        nk += __popc(keep[c]); nr += __popc(rst[c]);
+    }
     uint32_t tot;
-    const uint32_t ex = block_excl_scan_packed<kUnstuffThreads>(__popc(keep) | (__popc(rst) << 16), tot, s_tmp);
+    const uint32_t ex = block_excl_scan_packed<kUnstuffThreads>(nk | (nr << 16), tot, s_tmp);
     const uint32_t ea = ex & 0xFFFFu, eb = ex >> 16, ta = tot & 0xFFFFu, tb = tot >> 16;
+    // publish this tile's counts at once: the successors' look-backs find them while this tile compacts
+    if (threadIdx.x == 0 && tile > 0) look_store(look + gtile, look_pack(kLookOwn, e != kNoEnd, ta, tb));
 
-    if (threadIdx.x < 32) {                                                // ---- look-back (first warp)
-        const int lane = threadIdx.x;
-        uint32_t pk = 0, pr = 0;                                           // what the image's earlier tiles contribute
-        bool ended = false;                                                // ... and whether the scan has ended in one of them
+    // ---- compact into shared memory (the tile's k-th surviving byte at s_out[4 + k])
+    {
+        uint32_t pos = 4u + ea;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (keep[c] & (1u << i)) s_out[pos] = (uint8_t)(w[4 * c + 1 + (i >> 2)] >> ((i & 3) * 8));
+                pos += (keep[c] >> i) & 1u;
+            }
+        }
+    }
+
+    // ---- look-back (first warp): what the image's earlier tiles contribute, and whether the scan has ended in one of them
+    if (threadIdx.x < 32) {
+        uint32_t pk = 0, pr = 0;
+        bool ended = false;
         if (tile > 0) {
-            if (lane == 0) look_store(look + gtile, look_pack(kLookOwn, e != kNoEnd, ta, tb));
             int near = (int)tile - 1;                                      // image-local index of the nearest tile not yet added
             for (;;) {
                 const int idx = near - lane;
@@ -259,38 +286,37 @@ k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, c
         seg_off[im.seg_base] = 0;
         if (!invalid) seg_off[im.seg_base + s.nseg] = ca;
     }
-    const uint32_t mis = base.x & 3u;                 // s_out[mis + k] = k-th surviving byte of the tile
-    {
-        const uint32_t w[4] = {c.bytes.x, c.bytes.y, c.bytes.z, c.bytes.w};
-        uint32_t pos = mis + ea;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            if (keep & (1u << i)) s_out[pos] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
-            pos += (keep >> i) & 1u;
-        }
-    }
-    if (rst) {                                        // restart markers: where the next segment starts (rare)
+    if (nr) {                                         // restart markers: where the next segment starts (rare)
         // (marker k of an image is its segment k's start; markers beyond the expected count are ignored)
-        uint32_t sidx = base.y + eb + 1;
-        for (uint32_t mm = rst; mm; mm &= mm - 1) {
-            const int i = __ffs(mm) - 1;
-            if (sidx < im.nseg) seg_off[im.seg_base + sidx] = base.x + ea + __popc(keep & ((1u << i) - 1u));
-            sidx++;
+        uint32_t sidx = base.y + eb + 1, kept = base.x + ea;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            for (uint32_t mm = rst[c]; mm; mm &= mm - 1) {
+                const int i = __ffs(mm) - 1;
+                if (sidx < im.nseg) seg_off[im.seg_base + sidx] = kept + __popc(keep[c] & ((1u << i) - 1u));
+                sidx++;
+            }
+            kept += __popc(keep[c]);
         }
     }
-    __syncthreads();
     if (ta == 0) return;
+    // ---- store: stream byte base.x + k = staged byte k.  Output word j (from the word that holds stream byte base.x)
+    // takes the staged bytes 4j - mis .. 4j - mis + 3: two aligned shared words and a funnel shift; the (at most two)
+    // words the tile shares with its neighbours are written bytewise.  Stream byte o lands at address o ^ 3.
+    const uint32_t mis = base.x & 3u;
     uint32_t *dstw = clean + im.clean_word0 + (base.x >> 2);
-    const uint32_t end = mis + ta;                    // staged bytes [mis, end)
-    const uint32_t nwords = (end + 3) >> 2;
+    const uint32_t end_b = mis + ta;                  // the tile covers bytes [mis, end_b) of its output words
+    const uint32_t nwords = (end_b + 3) >> 2;
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s_out);
     for (uint32_t k = threadIdx.x; k < nwords; k += kUnstuffThreads) {
-        const uint32_t v = *reinterpret_cast<const uint32_t *>(s_out + 4 * k);
-        if (4 * k >= mis && 4 * k + 4 <= end) dstw[k] = __byte_perm(v, 0, 0x0123);
+        const uint32_t idx = 4u + 4u * k - mis;       // staged position (in s_out) of the word's first byte
+        const uint32_t v = __funnelshift_r(s32[idx >> 2], s32[(idx >> 2) + 1], (idx & 3u) * 8u);
+        if (4 * k >= mis && 4 * k + 4 <= end_b) dstw[k] = __byte_perm(v, 0, 0x0123);
         else {
             uint8_t *db = reinterpret_cast<uint8_t *>(dstw + k);
 #pragma unroll
             for (uint32_t b = 0; b < 4; b++)
-                if (4 * k + b >= mis && 4 * k + b < end) db[b ^ 3u] = (uint8_t)(v >> (8 * b));
+                if (4 * k + b >= mis && 4 * k + b < end_b) db[b ^ 3u] = (uint8_t)(v >> (8 * b));
         }
     }
 }
@@ -449,6 +475,19 @@ __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (l
 //          host launches rounds until a round reports 0.
 // Every decode also (re)writes the entry states of the sub-sequence's slices (slot 0 = the sub-sequence's own entry
 // state, written at the end); the last decode of a sub-sequence is the one from its final entry state.
+// The state a decode that starts `back` bits in front of a sub-sequence - blind: unit 0, DC expected - has when it
+// reaches the sub-sequence's first bit (first step boundary at or after it).  Out of line: inlined into k_huff_sync it
+// costs the symbol loops of that kernel registers (measured: 8 bytes of spills, 1.5 -> 2.2 ms).
+__device__ __noinline__ uint2 preroll_state(const uint32_t *__restrict__ words, HuffGeom g, uint32_t start_bit, uint32_t back) {
+    HuffState in;
+    in.p = start_bit - back; in.cz = 0u;
+    uint32_t n;
+    LutMem luts;
+    struct { __device__ __forceinline__ void operator()(uint32_t, uint32_t, uint32_t, uint32_t) const {} } rec;
+    const HuffState o = decode_span(words, luts, g, in, in.p, start_bit, back, rec, &n);
+    return make_uint2(o.p, o.cz);
+}
+
 struct SliceStore {
     uint4 *base;
     __device__ __forceinline__ void operator()(uint32_t k, uint32_t p, uint32_t cz, uint32_t cnt) const { base[k] = make_uint4(p, cz, cnt, 0u); }
@@ -477,7 +516,8 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
             const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
             const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
             uint2 *__restrict__ st_in, uint2 *__restrict__ st_out, uint32_t *__restrict__ sub_tot, uint2 *__restrict__ sub_pre,
-            uint4 *__restrict__ slices, uint4 *__restrict__ quarters, BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round) {
+            uint4 *__restrict__ slices, uint4 *__restrict__ quarters, BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round,
+            uint32_t preroll_bits) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
@@ -512,6 +552,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     bool need = false;
     if (round == 0) {
         if (active) { s_in[tid] = make_uint2(u.start_bit, 0u); need = true; }
+        // (the guess is improved below, once the tables are staged: preroll)
     } else {
         if (active) { s_in[tid] = st_in[gj]; s_out[tid] = st_out[gj]; s_tot[tid] = sub_tot[gj]; }
         if (tid == 0 && !u.head && j > 0) {
@@ -531,6 +572,20 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
     const uint32_t slices_log2 = im.slices_log2;
     const uint32_t slice_bits = (im.sub_bytes >> slices_log2) * 8u;
     uint4 *img_slices = slices + im.slice_base;
+
+    // PREROLL (round 0, option "sync_preroll_bits"): a sub-sequence that is not a segment head does not start from the
+    // blind guess "a unit begins at my first bit" but from where a decode that begins `preroll_bits` earlier (blind
+    // there: unit 0, DC) stands when it reaches the sub-sequence: a JPEG stream synchronises within some hundred bits,
+    // so this state is the true one for most sub-sequences, their first decode is already the final one and the
+    // hand-over below finds nothing to redo.  Whatever the guess, the fixed point of the iteration is the same: the
+    // preroll only buys speed.
+    if (round == 0 && preroll_bits != 0u) {
+        __syncthreads();                                                    // (the tables are staged)
+        if (active && !u.head) {
+            const uint32_t seg_bit0 = u.start_bit - u.k * im.sub_bytes * 8u;    // the segment's first bit: nothing to guess there
+            s_in[tid] = preroll_state(words, g, u.start_bit, min(preroll_bits, u.start_bit - seg_bit0));
+        }
+    }
 
     const uint32_t ql2 = slices_log2 > 2u ? slices_log2 : 2u;               // PHASED: quarters (or eighths) per sub-sequence
     const uint32_t qbits = (im.sub_bytes >> ql2) * 8u;

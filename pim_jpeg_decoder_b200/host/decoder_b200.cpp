@@ -89,8 +89,8 @@ int main(int argc, char **argv) {
         return 1;
     }
     const int rank = env_int("RANK", 0), world = std::max(1, env_int("WORLD_SIZE", 1));
-    const size_t out_budget = (size_t)env_int("B200JPEG_OUT_MB", 384) << 20;      // decoded bytes per group
-    const size_t in_budget = (size_t)env_int("B200JPEG_IN_MB", 64) << 20;         // compressed bytes per group
+    const size_t out_budget = (size_t)env_int("B200JPEG_OUT_MB", 192) << 20;      // decoded bytes per group
+    const size_t in_budget = (size_t)env_int("B200JPEG_IN_MB", 32) << 20;         // compressed bytes per group
     const size_t max_images = (size_t)std::max(1, env_int("B200JPEG_GROUP_IMAGES", 1 << 20));   // images per group
 
     const double t_start = now_s();

@@ -30,13 +30,13 @@ struct SliceRec { uint32_t p, cz, cnt; };
 
 // ------------------------------------------------------------------------------------------------ K0, as the kernels run it
 // The device buffer holds the file at `file_pos` (any alignment; what lies around it is arbitrary).  Tiles of
-// kTile raw bytes, 256 "threads" of one aligned 16-byte chunk each, as k_unstuff works: per tile, where the scan ends
+// kTile raw bytes, 256 "threads" of four consecutive aligned 16-byte chunks each, as k_unstuff works: per tile, where the scan ends
 // (if in this tile), the bytes that survive and the RSTn markers in front of that point; what the earlier tiles of the
 // image contribute (the kernel's look-back; here a running prefix, tiles in order); compaction (byte o stored at
 // o ^ 3), segment starts, the image's state.  Same shared code as the kernel: classify_words_end, clip_chunk,
 // chunk_mask_before.
 namespace {
-constexpr uint32_t kTile = 4096;
+constexpr uint32_t kTile = 16384;
 struct K0Out {
     uint32_t status = 0;         // 0 ok, 2 invalid (no EOI where the scan ends)
     uint32_t raw_len = 0, end_code = 0x100, clean_len = 0, nrst = 0;
@@ -45,21 +45,23 @@ struct K0Out {
 };
 struct Chunk { uint32_t keep, rst, end; uint32_t w[4]; int64_t r0; };
 
-Chunk classify_chunk(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t tile, uint32_t thread, uint32_t raw_len) {
+// chunk q of the tile: thread q / 4 (a thread holds four consecutive chunks), its chunk q % 4
+Chunk classify_chunk(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t tile, uint32_t q, uint32_t raw_len) {
     Chunk c;
-    const uint64_t a0 = (raw_off & ~(uint64_t)15) + (uint64_t)tile * kTile + (uint64_t)thread * 16;
+    const uint64_t a0 = (raw_off & ~(uint64_t)15) + (uint64_t)tile * kTile + (uint64_t)q * 16;
     c.r0 = (int64_t)a0 - (int64_t)raw_off;
-    const bool live = c.r0 < (int64_t)raw_len && c.r0 + 16 > 0;
+    auto live_at = [&](int64_t r) { return r < (int64_t)raw_len && r + 16 > 0; };
+    const bool live = live_at(c.r0);
     auto at = [&](uint64_t a) -> uint32_t { return a < buf.size() ? buf[a] : 0xEEu; };
     uint32_t w[6] = {0, 0, 0, 0, 0, 0};
     if (live) for (int b = 0; b < 16; b++) w[1 + b / 4] |= at(a0 + b) << (8 * (b & 3));
-    // the neighbours' edge bytes: from the adjacent lanes (a lane that is not live holds zeros), from memory at the
-    // warp's edges - exactly what classify16 does
-    const bool prev_live = c.r0 - 16 < (int64_t)raw_len && c.r0 > 0, next_live = c.r0 + 16 < (int64_t)raw_len && c.r0 + 32 > 0;
-    if (thread % 32 == 0) w[0] = (live && a0 > 0) ? at(a0 - 1) << 24 : 0u;
-    else w[0] = prev_live ? at(a0 - 1) << 24 : 0u;
-    if (thread % 32 == 31) w[5] = live ? at(a0 + 16) : 0u;
-    else w[5] = next_live ? at(a0 + 16) : 0u;
+    // the neighbours' edge bytes, exactly as k_unstuff gets them: inside a thread and between the lanes of a warp from
+    // registers (a chunk that is not live holds zeros), at the warp's edges from memory
+    const uint32_t thread = q / 4, sub = q % 4, lane = thread % 32;
+    if (sub == 0 && lane == 0) w[0] = (live && a0 > 0) ? at(a0 - 1) << 24 : 0u;
+    else w[0] = live_at(c.r0 - 16) ? at(a0 - 1) << 24 : 0u;
+    if (sub == 3 && lane == 31) w[5] = live ? at(a0 + 16) : 0u;
+    else w[5] = live_at(c.r0 + 16) ? at(a0 + 16) : 0u;
     for (int k = 0; k < 4; k++) c.w[k] = w[k + 1];
     classify_words_end(w, c.keep, c.rst, c.end);
     clip_chunk(c.r0, raw_len, c.keep, c.rst, c.end);
@@ -77,7 +79,7 @@ void k0_emulate(const std::vector<uint8_t> &buf, uint64_t raw_off, uint32_t raw_
     for (uint32_t t = 0; t < ntile; t++) {
         uint32_t e = kNoScanEnd;
         std::vector<Chunk> cs;
-        for (uint32_t th = 0; th < 256; th++) {
+        for (uint32_t th = 0; th < kTile / 16; th++) {
             cs.push_back(classify_chunk(buf, raw_off, t, th, raw_len_max));
             if (cs.back().end) e = std::min(e, (uint32_t)(cs.back().r0 + __builtin_ctz(cs.back().end)));
         }

@@ -54,6 +54,26 @@ def test_unmodified_reference_host_on_gpu(nr_dpus, golden, golden_dir, tmp_path)
         assert _sha(p[:-4] + ".bmp") == golden[n]["bmp_sha256"], n
 
 
+def test_reference_scanner_and_bmp_writer_around_the_gpu(golden, golden_dir, tmp_path):
+    """decoder_hybrid: the reference's unmodified read_JPEG in front, its unmodified write_BMP behind, and between them
+    ONE call - bj_decode_batch_desc(..., BJ_OUT_REF_MCUS) - instead of decode_Huffman_data + pim.copy / exec / copy.
+    Header::huffman_data goes in as it is for files without restart markers; files with them hand over their raw scan.
+    BMP files == the golden ones (restart-parity rule for subsampled files with restart markers)."""
+    exe = os.path.join(HOST, "_build", "decoder_hybrid")
+    if not os.path.exists(exe):
+        pytest.skip("decoder_hybrid is built where the reference sources are (dev container) and shipped prebuilt")
+    names = _valid_names(golden) + ["bad_not_jpeg", "bad_truncated"]
+    paths = _copy(names, golden, golden_dir, tmp_path)
+    out = subprocess.run([exe] + paths, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "read_JPEG (the reference's scanner)" in out.stdout
+    for n, p in zip(names, paths):
+        if golden[n].get("invalid"):
+            assert not os.path.exists(p[:-4] + ".bmp")
+        else:
+            assert _sha(p[:-4] + ".bmp") == golden[golden[n]["expect"]]["bmp_sha256"], n
+
+
 def test_decoder_b200_cli(golden, golden_dir, tmp_path):
     subprocess.run(["make", "-s", "-C", HOST, os.path.join(HOST, "_build", "decoder_b200")], check=True)
     exe = os.path.join(HOST, "_build", "decoder_b200")

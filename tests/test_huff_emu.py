@@ -189,7 +189,7 @@ def _scan_soup(rng, nbytes):
 
 def test_device_side_scan_end_counts_and_compaction():
     """K0 never gets a scan length from the host: k_unstuff finds the FF that ends the scan, counts what
-    survives in front of it per 4 KB tile (look-back between the tiles), and compacts.  Their shared code, run tile by tile and chunk by
+    survives in front of it per 16 KB tile (look-back between the tiles), and compacts.  Their shared code, run tile by tile and chunk by
     chunk like the kernels, against the per-byte rules and the host's scan walk: scans dense in stuffed FFs, restart
     markers and fill bytes, every alignment of the file in the device buffer, arbitrary bytes around the file, ends on
     tile and chunk boundaries, trailing garbage behind EOI, and files the reference rejects (no EOI, another marker
@@ -203,12 +203,12 @@ def test_device_side_scan_end_counts_and_compaction():
 
     def check(data, expect_valid, nseg=1 << 20):
         buf = np.frombuffer(data, dtype=np.uint8)
-        for pos, fill in ((0, 0x00), (1, 0xFF), (7, 0xD9), (15, 0xFF), (16, 0x00), (4099, 0xFF)):
+        for pos, fill in ((0, 0x00), (1, 0xFF), (7, 0xD9), (15, 0xFF), (16, 0x00), (16387, 0xFF)):
             assert lib.emu_k0_check(ol._ptr(buf), len(data), pos, fill, nseg) == 0, (len(data), pos, fill)
         assert (ol.Restated(data, 0).rc == 0) == expect_valid
 
     for trial in range(6):
-        soup = _scan_soup(rng, 3 * 4096 + 500 * trial)
+        soup = _scan_soup(rng, 2 * 16384 + 3000 * trial)
         check(head + soup + b"\xFF\xD9", True)
         check(head + soup + b"\xFF\xD9" + _scan_soup(rng, 700) + b"\xFF\xD9\xFF\xC0junk", True)      # garbage behind EOI
         check(head + soup, False)                                                                    # file ends inside the scan
@@ -217,8 +217,8 @@ def test_device_side_scan_end_counts_and_compaction():
         check(head + soup + b"\xFF\xFF\xFF\xD9", True)                                               # fill bytes before EOI
         check(head + soup + b"\xFF\xD9", True, nseg=3)                                               # more markers than segments expected
     # the end at every position around a tile / chunk boundary
-    soup = _scan_soup(rng, 2 * 4096)
-    for cut in list(range(4096 - len(head) - 20, 4096 - len(head) + 20)) + [16, 17, 31, 32, 33]:
+    soup = _scan_soup(rng, 2 * 16384)
+    for cut in list(range(16384 - len(head) - 20, 16384 - len(head) + 20)) + [16, 17, 31, 32, 33, 63, 64, 65, 2047 - len(head), 2048 - len(head), 2049 - len(head)]:
         check(head + soup[:cut].rstrip(b"\xFF") + b"\x01\xFF\xD9", True)
     check(head + b"\xFF\xD9", True)                                                                  # empty scan
     check(head, False)
