@@ -155,7 +155,8 @@ struct bj_ctx {
     int packed_outputs = 0;              // see batch_download_async
     int packed_inputs = 0;               // see batch_assign: 0 = upload straight from the caller's memory when it is known to be page-locked
                                          // (bj_host_alloc / bj_host_register), 1 = the caller says it is, -1 = always stage
-    int idct_tma = 1;                    // K2/K3: persistent kernel with TMA-fed coefficient tiles (0: one CTA per tile, register-staged loads)
+    int idct_tma = 0;                    // K2/K3: 1 = persistent kernel with TMA-fed, double-buffered coefficient tiles; 0 (default, faster: DESIGN.md section 9) =
+                                         // one CTA per tile, register-staged loads
     typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                       CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     EncodeTiledFn encode_tiled = nullptr; // cuTensorMapEncodeTiled, through cudaGetDriverEntryPoint (no link against libcuda)

@@ -117,6 +117,7 @@ int main(int argc, char **argv) {
         return 2;
     }
     bj_set_option(ctx, "packed_outputs", 1);
+    const double t_ready = now_s();
     printf("B200 devices: %d (%d SMs each)\n", bj_device_count(ctx), bj_device_sm_count(ctx));
 
     constexpr int kGroups = 4;                   // one being read, one decoding, one queued behind it, one being written
@@ -232,6 +233,7 @@ int main(int argc, char **argv) {
     // DPU program's own split into initialization / dequantization / IDCT / colour conversion)
     printf("\nProfiles:\n");
     printf("End-to-end execution time: %gs\n", now_s() - t_start);
+    printf(" - Start-up (CUDA context, kernel image): %gs\n", t_ready - t_start);
     printf(" - File read + header peek time (reader thread): %gs\n", t_read);
     printf(" - B200 decode time (H2D + kernels + D2H, overlapped with reading and writing): %gs\n", t_decode);
     printf("    - scan filter / segmenter kernels: %gs\n", ms[0] * 1e-3);
