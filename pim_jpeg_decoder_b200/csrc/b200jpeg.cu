@@ -102,12 +102,17 @@ extern "C" int bj_create_multi(bj_ctx **out, const int *devices, int ndev) {
     if (ndev > count && !devices) return BJ_ERR_ARG;
     bj_ctx *c = new (std::nothrow) bj_ctx();
     if (!c) return BJ_ERR_NOMEM;
-    for (int i = 0; i < ndev; i++) {
-        bj_ctx *ch = nullptr;
-        const int rc = bj_create(&ch, devices ? devices[i] : i);
-        if (rc != BJ_OK) { bj_destroy(c); return rc; }
-        c->children.push_back(ch);
+    // one CUDA context per device, created side by side (a context takes some hundred milliseconds)
+    std::vector<bj_ctx *> made(ndev, nullptr);
+    std::vector<int> rcs(ndev, BJ_OK);
+    {
+        std::vector<std::thread> th;
+        for (int i = 1; i < ndev; i++) th.emplace_back([&, i] { rcs[i] = bj_create(&made[i], devices ? devices[i] : i); });
+        rcs[0] = bj_create(&made[0], devices ? devices[0] : 0);
+        for (auto &t : th) t.join();
     }
+    for (int i = 0; i < ndev; i++) if (made[i]) c->children.push_back(made[i]);
+    for (int i = 0; i < ndev; i++) if (rcs[i] != BJ_OK) { const int rc = rcs[i]; bj_destroy(c); return rc; }
     c->device = c->children[0]->device;
     c->sm_count = c->children[0]->sm_count;
     // the host threads of all devices together stay within the process' cores

@@ -74,6 +74,17 @@ public:
     T pop() { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return !q_.empty(); }); T v = q_.front(); q_.pop_front(); return v; }
 };
 
+// fn(k) for k in [0, n) on `threads` threads (file reads and BMP writes of a group are independent per image)
+template <class F> static void parallel_each(size_t n, int threads, F fn) {
+    if (n == 0) return;
+    std::atomic<size_t> next{0};
+    auto work = [&] { for (size_t k; (k = next.fetch_add(1)) < n;) fn(k); };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads && (size_t)t < n; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
+
 static bool grow(uint8_t **p, size_t *cap, size_t need) {
     if (need <= *cap) return true;
     if (*p) bj_host_free(*p);
@@ -91,6 +102,7 @@ int main(int argc, char **argv) {
     const int rank = env_int("RANK", 0), world = std::max(1, env_int("WORLD_SIZE", 1));
     const size_t out_budget = (size_t)env_int("B200JPEG_OUT_MB", 192) << 20;      // decoded bytes per group
     const size_t in_budget = (size_t)env_int("B200JPEG_IN_MB", 32) << 20;         // compressed bytes per group
+    const int io_threads = std::max(1, env_int("B200JPEG_IO_THREADS", 4));                  // file reads / BMP writes side by side
     const size_t max_images = (size_t)std::max(1, env_int("B200JPEG_GROUP_IMAGES", 1 << 20));   // images per group
 
     const double t_start = now_s();
@@ -139,18 +151,22 @@ int main(int argc, char **argv) {
             while (i1 < in.size() && i1 - i0 < max_images && (i1 == i0 || in_bytes + in[i1].size + 16 <= in_budget)) { in_bytes += in[i1].size + 16; i1++; }
             if (!grow(&g->in, &g->in_cap, in_bytes + 64)) { fatal = true; g->last = true; to_decode.push(g); return; }
             g->files.clear(); g->lens.clear(); g->out_bytes.clear();
-            size_t o = 0, k = i0;
-            for (; k < i1; k++) {
-                size_t got = 0;
-                FILE *fp = fopen(in[k].path.c_str(), "rb");
-                if (fp) { got = in[k].size ? fread(g->in + o, 1, in[k].size, fp) : 0; fclose(fp); }
+            // read the candidates side by side (each file at its place in the pinned buffer), then keep as many as the
+            // output budget allows
+            std::vector<size_t> in_off(i1 - i0 + 1, 0), got(i1 - i0, 0), obytes(i1 - i0, 0);
+            for (size_t k = i0; k < i1; k++) in_off[k - i0 + 1] = in_off[k - i0] + in[k].size;
+            parallel_each(i1 - i0, io_threads, [&](size_t j) {
+                FILE *fp = fopen(in[i0 + j].path.c_str(), "rb");
+                if (fp) { got[j] = in[i0 + j].size ? fread(g->in + in_off[j], 1, in[i0 + j].size, fp) : 0; fclose(fp); }
                 bj_image_desc d;
-                const size_t ob = (got && bj_peek_header(g->in + o, got, &d) == BJ_OK) ? bj_output_size(&d, BJ_OUT_BMP) : 0;
-                const size_t padded = (ob + 15) / 16 * 16;
-                if (k > i0 && out_total + padded > out_budget) break;          // (this file is read again with the next group)
-                g->files.push_back(g->in + o); g->lens.push_back(got); g->out_bytes.push_back(ob);
+                obytes[j] = (got[j] && bj_peek_header(g->in + in_off[j], got[j], &d) == BJ_OK) ? bj_output_size(&d, BJ_OUT_BMP) : 0;
+            });
+            size_t k = i0;
+            for (; k < i1; k++) {
+                const size_t padded = (obytes[k - i0] + 15) / 16 * 16;
+                if (k > i0 && out_total + padded > out_budget) break;          // (the rest is read again with the next group)
+                g->files.push_back(g->in + in_off[k - i0]); g->lens.push_back(got[k - i0]); g->out_bytes.push_back(obytes[k - i0]);
                 out_total += padded;
-                o += got;
             }
             g->n = k - i0;
             i0 = k;
@@ -172,17 +188,21 @@ int main(int argc, char **argv) {
         while (true) {
             Group *g = to_write.pop();
             const double t0 = now_s();
-            for (size_t k = 0; k < g->n; k++) {
+            std::atomic<int> bad{0};
+            std::mutex print_m;
+            parallel_each(g->n, io_threads, [&](size_t k) {
                 const Input &f = in[g->i0 + k];
                 if (g->status[k] != BJ_OK && g->status[k] != BJ_ERR_CORRUPT_SCAN) {
+                    std::lock_guard<std::mutex> l(print_m);
                     printf("%s: Error - Invalid JPEG\n", f.path.c_str());
-                    failures++;
+                    bad++;
                 } else {
                     FILE *fp = fopen(bmp_name(f.path).c_str(), "wb");
-                    if (!fp || fwrite(g->outs[k], 1, g->out_bytes[k], fp) != g->out_bytes[k]) { printf("%s: Error - cannot write BMP\n", f.path.c_str()); failures++; }
+                    if (!fp || fwrite(g->outs[k], 1, g->out_bytes[k], fp) != g->out_bytes[k]) { std::lock_guard<std::mutex> l(print_m); printf("%s: Error - cannot write BMP\n", f.path.c_str()); bad++; }
                     if (fp) fclose(fp);
                 }
-            }
+            });
+            failures += bad;
             t_write += now_s() - t0;
             const bool last = g->last;
             to_read.push(g);
