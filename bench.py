@@ -620,6 +620,9 @@ def main():
                     one_pass()
                 e2e_single = px * 2 / (time.perf_counter() - t0) / 1e6
             barrier()
+        if stream:                                            # a stream is decoded once; its first call twice (buffers reach their size)
+            a, b, offs = calls[0]
+            dec.decode_packed(pin_in.array, in_off[a:b], in_len[a:b], pin_out.array, offs, bj.BJ_OUT_BMP)
         for _ in range(max(1, min(args.warmup, 2)) if not stream else 0):
             one_pass()
         barrier()
@@ -667,8 +670,8 @@ def main():
     cli = None
     rule = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = args.ref_sample or (128 if args.workload in ("config2", "config5") else 2) * (os.cpu_count() or 1)
-        n = min(n, len(blobs))
+        n = args.ref_sample or (256 if args.workload in ("config2", "config5") else 2) * (os.cpu_count() or 1)
+        n = min(n, len(blobs), 4096)
         ref = CpuReference(blobs[:n], pixels_of(specs[:n]))
         try:
             t, passes = 0.0, 0

@@ -167,13 +167,20 @@ __device__ __forceinline__ void look_store(uint64_t *p, uint64_t v) {
 // One thread = kUnstuffChunks consecutive 16-byte chunks (64 bytes), a tile = 16 KB: the fixed costs of a tile - ticket,
 // barriers, the look-back's round trips through L2 - are paid once per 16 KB (with 4 KB tiles they were half of the
 // kernel's time: 77 600 CTAs that each live only a few microseconds).
-__global__ void __launch_bounds__(kUnstuffThreads)
+#ifndef BJ_UNSTUFF_CTAS
+#define BJ_UNSTUFF_CTAS 6                // 40 registers (8 bytes of spills outside the loops) for 6 CTAs per SM; 56 registers allow 4
+#endif
+// Shared-memory staging of the surviving bytes: a thread writes its (up to) 64 bytes one by one, and the 32 threads of a
+// warp write 64 bytes apart - 16 of them into the same bank.  XOR-ing the word-in-block bits with the 128-byte block
+// index spreads a warp's byte stores over all 32 banks (and keeps the word reads of the store loop conflict free).
+__device__ __forceinline__ uint32_t unstuff_swz(uint32_t a) { return a ^ (((a >> 7) & 15u) << 2); }
+__global__ void __launch_bounds__(kUnstuffThreads, BJ_UNSTUFF_CTAS)
 k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, const uint32_t *__restrict__ tile_img,
           uint64_t *__restrict__ look, uint32_t *__restrict__ ticket, HuffImgState *__restrict__ st, uint32_t *__restrict__ clean,
           uint32_t *__restrict__ seg_off) {
     constexpr int NC = kUnstuffChunks;
     __shared__ uint32_t s_tmp[kUnstuffThreads / 32 + 1];
-    __shared__ __align__(16) uint8_t s_out[kUnstuffTile + 16];             // surviving byte k of the tile at s_out[4 + k]
+    __shared__ __align__(128) uint8_t s_out[kUnstuffTile + 128];           // surviving byte k of the tile at s_out[unstuff_swz(4 + k)]
     __shared__ uint32_t s_tile, s_end, s_base[3];
     const uint32_t img = tile_img[blockIdx.x];
     const HuffImg &im = imgs[img];
@@ -231,7 +238,7 @@ k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, c
         for (int c = 0; c < NC; c++) {
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                if (keep[c] & (1u << i)) s_out[pos] = (uint8_t)(w[4 * c + 1 + (i >> 2)] >> ((i & 3) * 8));
+                if (keep[c] & (1u << i)) s_out[unstuff_swz(pos)] = (uint8_t)(w[4 * c + 1 + (i >> 2)] >> ((i & 3) * 8));
                 pos += (keep[c] >> i) & 1u;
             }
         }
@@ -310,7 +317,7 @@ k_unstuff(const uint8_t *__restrict__ files, const HuffImg *__restrict__ imgs, c
     const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s_out);
     for (uint32_t k = threadIdx.x; k < nwords; k += kUnstuffThreads) {
         const uint32_t idx = 4u + 4u * k - mis;       // staged position (in s_out) of the word's first byte
-        const uint32_t v = __funnelshift_r(s32[idx >> 2], s32[(idx >> 2) + 1], (idx & 3u) * 8u);
+        const uint32_t v = __funnelshift_r(s32[unstuff_swz(idx & ~3u) >> 2], s32[unstuff_swz((idx & ~3u) + 4u) >> 2], (idx & 3u) * 8u);
         if (4 * k >= mis && 4 * k + 4 <= end_b) dstw[k] = __byte_perm(v, 0, 0x0123);
         else {
             uint8_t *db = reinterpret_cast<uint8_t *>(dstw + k);
