@@ -168,7 +168,7 @@ __device__ __forceinline__ void look_store(uint64_t *p, uint64_t v) {
 // barriers, the look-back's round trips through L2 - are paid once per 16 KB (with 4 KB tiles they were half of the
 // kernel's time: 77 600 CTAs that each live only a few microseconds).
 #ifndef BJ_UNSTUFF_CTAS
-#define BJ_UNSTUFF_CTAS 6                // 40 registers (8 bytes of spills outside the loops) for 6 CTAs per SM; 56 registers allow 4
+#define BJ_UNSTUFF_CTAS 4                // measured on config 2: 4 CTAs per SM (56 registers) 0.425 ms, 5 (48) 0.449 ms, 6 (40, 8 bytes of spills) 0.434 ms
 #endif
 // Shared-memory staging of the surviving bytes: a thread writes its (up to) 64 bytes one by one, and the 32 threads of a
 // warp write 64 bytes apart - 16 of them into the same bank.  XOR-ing the word-in-block bits with the 128-byte block
