@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--sync-rounds", type=int, default=0)
     ap.add_argument("--sync-phased", type=int, default=-1, help="1/0: Huffman synchronisation pass with / without early stop of re-decodes (-1 = library default)")
     ap.add_argument("--sync-preroll", type=int, default=-1, help="bits of pre-roll of the Huffman synchronisation pass' first guess (-1 = library default)")
-    ap.add_argument("--streams", type=int, default=1, help="device-resident value: decode the batch as this many independent parts on as many CUDA streams")
+    ap.add_argument("--streams", type=int, default=2, help="device-resident value: decode the batch as this many independent parts on as many CUDA streams (1: one stream; the per-stage times always come from a one-stream pass)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--sub-batch-mb", type=int, default=0, help="compressed MB per sub-batch of the one-call path (0 = library default)")
     ap.add_argument("--host-threads", type=int, default=0, help="host worker threads of the one-call path (0 = library default)")
