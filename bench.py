@@ -629,14 +629,17 @@ def main():
         stat_names = ["decode_batch_host_ms", "decode_batch_wait_ms", "decode_batch_h2d_bytes", "decode_batch_d2h_bytes", "decode_batch_sub_batches",
                       "decode_batch_d2h_copies", "decode_batch_direct_uploads", "decode_batch_launches"]
         acc = dict.fromkeys(stat_names, 0.0)
+        step_ms = []
         t0 = time.perf_counter()
         for _ in range(k2):
+            ts = time.perf_counter()
             for (a, b, offs) in calls:
                 st = dec.decode_packed(pin_in.array, in_off[a:b], in_len[a:b], pin_out.array, offs, bj.BJ_OUT_BMP)
                 if st.any():
                     raise SystemExit("bench e2e: images failed to decode")
                 for nme in stat_names:
                     acc[nme] += dec.stat(nme)
+            step_ms.append(1e3 * (time.perf_counter() - ts))
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         windows.append((t0, t1))
@@ -648,7 +651,7 @@ def main():
         floor_ms = 1e3 * d2h_per_step / (d2h_agg / world * 1e9) if d2h_agg else None
         e2e_value = total_px * k2 / e2e_s / 1e6
         e2e = {"value": e2e_value, "unit": UNIT, "images_per_s": total_images * k2 / e2e_s,
-               "ms_per_step": 1e3 * e2e_s / k2, "steps": k2,
+               "ms_per_step": 1e3 * e2e_s / k2, "steps": k2, "rank0_step_ms": [round(x, 2) for x in step_ms],
                "h2d_bytes_per_step": int(acc["decode_batch_h2d_bytes"] / k2), "d2h_bytes_per_step": int(d2h_per_step),
                "sub_batches_per_step": int(acc["decode_batch_sub_batches"] / k2), "d2h_copies_per_step": int(acc["decode_batch_d2h_copies"] / k2),
                "direct_uploads_per_step": int(acc["decode_batch_direct_uploads"] / k2), "calls_per_step": len(calls),
