@@ -37,12 +37,14 @@ MIX = [((500, 375), 0.40), ((375, 500), 0.15), ((640, 480), 0.15), ((224, 224), 
 
 
 def kernel_sources_sha():
-    """Identifies the kernel sources a profile was taken from (profiles/ncu_traffic.json carries the same key)."""
-    import glob
+    """Identifies the DEVICE code a profile was taken from (profiles/ncu_traffic.json carries the same key): the kernel
+    files and the headers they share with nothing but the emulator; host-only files (batch.h, bj_host.h, parse.h) do not
+    change what a kernel moves through DRAM."""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "pim_jpeg_decoder_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "pim_jpeg_decoder_b200", "csrc", "*.h"))):
-        h.update(open(f, "rb").read())
+    d = os.path.join(ROOT, "pim_jpeg_decoder_b200", "csrc")
+    for f in ("kernels_huff.cuh", "kernels_idct.cuh", "idct_color.cuh", "huff_core.h", "bj_dev.h"):
+        h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
 

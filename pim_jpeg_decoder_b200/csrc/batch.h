@@ -191,8 +191,9 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
             const uint64_t a = (uint64_t)(uintptr_t)files[i];
             span_lo = std::min(span_lo, a); span_hi = std::max(span_hi, a + lens[i]); span_sum += lens[i];
         }
+        // (the upload starts at the 16-byte boundary at or below the first file: that, too, must be page-locked memory)
         if (span_hi > span_lo && span_hi - span_lo <= 2 * span_sum + (1u << 16) &&
-            (c->packed_inputs == 1 || pinned_ranges().contains((uintptr_t)span_lo, (uintptr_t)span_hi))) {
+            (c->packed_inputs == 1 || pinned_ranges().contains((uintptr_t)(span_lo & ~(uint64_t)15), (uintptr_t)span_hi))) {
             span_lo &= ~(uint64_t)15;
             b->direct_src = reinterpret_cast<const uint8_t *>((uintptr_t)span_lo);
         }
