@@ -191,6 +191,7 @@ extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
     if (!strcmp(name, "sub_batch_out_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_out_bytes = (size_t)value; return BJ_OK; }
     if (!strcmp(name, "host_threads")) { if (value < 1 || value > 256) return BJ_ERR_ARG; c->host_pool.resize((int)value); return BJ_OK; }
     if (!strcmp(name, "idct_tma")) { c->idct_tma = value != 0; return BJ_OK; }
+    if (!strcmp(name, "debug_sync_iters")) { if (value < 0) return BJ_ERR_ARG; c->debug_sync_iters = (int)value; return BJ_OK; }
     if (!strcmp(name, "sync_preroll_bits")) { if (value < 0 || value > (1 << 16) || value % 32) return BJ_ERR_ARG; c->sync_preroll_bits = (int)value; return BJ_OK; }
     if (!strcmp(name, "sync_rounds")) { if (value < 0 || value > kMaxRounds) return BJ_ERR_ARG; c->sync_rounds = (int)value; return BJ_OK; }
     return BJ_ERR_ARG;
@@ -555,6 +556,8 @@ static int decode_worker(bj_ctx *c, RangeSource *src, const CallInput &in, int f
     }
     // drain in submission order
     for (int j = 0; j < kSlots; j++) { const int slot = (k + j) % kSlots; if (busy[slot]) { const int r = finish(slot); if (rc == BJ_OK) rc = r; } }
+    // after a failure nobody may be left wondering: the images this device will not get to carry the error, too
+    if (rc != BJ_OK && status) while (src->take(nranges, &r0, &r1)) for (int i = r0; i < r1; i++) status[i] = rc;
     if (ev_base) cudaEventDestroy(ev_base);
     for (int i = 0; i < ST_COUNT; i++) { c->stats[i] = st[i]; c->totals[i] += st[i]; }
     return rc;

@@ -510,9 +510,9 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     if (b->n_blk) {
         for (int r = r0; r < r1; r++) {
             if (b->phased)
-                k_huff_sync<true><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, (uint4 *)b->d_quarter.p, agg, flags, r, (uint32_t)c->sync_preroll_bits);
+                k_huff_sync<true><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, (uint4 *)b->d_quarter.p, agg, flags, r, (uint32_t)c->sync_preroll_bits, (uint32_t)c->debug_sync_iters);
             else
-                k_huff_sync<false><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, nullptr, agg, flags, r, (uint32_t)c->sync_preroll_bits);
+                k_huff_sync<false><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, nullptr, agg, flags, r, (uint32_t)c->sync_preroll_bits, (uint32_t)c->debug_sync_iters);
             b->launches++; b->sync_rounds++;
         }
         cudaEventRecord(b->ev[2], s);

@@ -160,6 +160,7 @@ struct bj_ctx {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                       CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     EncodeTiledFn encode_tiled = nullptr; // cuTensorMapEncodeTiled, through cudaGetDriverEntryPoint (no link against libcuda)
+    int debug_sync_iters = 0;            // measurement only: stop the in-CTA fix-up after this many iterations (0: run to the fixed point)
     int sync_preroll_bits = 0;           // synchronisation pass: bits a sub-sequence's first guess is decoded ahead of its start (kernels_huff.cuh: PREROLL)
     int min_sub_bytes = 128;             // shortest sub-sequence the automatic layout picks (small batches)
     int ri_split_threads = 0;            // a batch with fewer restart segments than this cuts them into shorter sub-sequences (0: never; B200JPEG_RI_SPLIT for experiments)

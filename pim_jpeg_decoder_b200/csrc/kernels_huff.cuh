@@ -524,7 +524,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
             const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
             uint2 *__restrict__ st_in, uint2 *__restrict__ st_out, uint32_t *__restrict__ sub_tot, uint2 *__restrict__ sub_pre,
             uint4 *__restrict__ slices, uint4 *__restrict__ quarters, BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round,
-            uint32_t preroll_bits) {
+            uint32_t preroll_bits, uint32_t debug_max_iters) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
@@ -603,6 +603,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
         __syncthreads();
         const uint32_t nw = s_nwork[cur];
         if (nw == 0) break;
+        if (debug_max_iters && iter >= debug_max_iters) break;                // (measurement only: the result is not the fixed point)
         if (!PHASED) {
             for (uint32_t w = tid; w < nw; w += kHuffThreads) {
                 const uint32_t item = s_work[cur][w];
