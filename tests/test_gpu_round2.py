@@ -400,3 +400,73 @@ def test_ref_mcus_output_and_descriptor_input(dec, golden, golden_dir, tmp_path)
         assert np.array_equal(got[:flat.size], flat) and (got[flat.size:] == 128).all()
     finally:
         dec.set_option("ref_max_mcu_per_dpu", 100)
+
+
+# ------------------------------------------------------------------ edges: empty, ragged, extreme shapes, caller-made descriptors
+
+def test_empty_ragged_and_extreme_inputs(dec):
+    """Empty batch; a batch of nothing but rejects; zero-length and tiny inputs between good files; the widest and
+    tallest shapes the 16-bit frame header allows in one dimension (one MCU row / one MCU column), every sampling."""
+    import pim_jpeg_decoder_b200 as bj
+    outs, status = dec.decode([], bj.BJ_OUT_BMP)
+    assert outs == [] and status == []
+    junk = [b"", b"\xFF", b"\xFF\xD8", b"\xFF\xD8\xFF\xD9", b"not a jpeg at all" * 10]
+    outs, status = dec.decode(junk, bj.BJ_OUT_RGB8)
+    assert status == [bj.BJ_ERR_INVALID_JPEG] * len(junk) and all(o is None for o in outs)
+    good = js.synth_jpeg(37, 21, seed=8, subsampling=1)
+    outs, status = dec.decode([junk[0], good, junk[3], good, junk[1]], bj.BJ_OUT_BMP)
+    assert status == [bj.BJ_ERR_INVALID_JPEG, 0, bj.BJ_ERR_INVALID_JPEG, 0, bj.BJ_ERR_INVALID_JPEG]
+    want = ol.Restated(good, 0).bmp
+    assert np.array_equal(outs[1], want) and np.array_equal(outs[3], want)
+    # (libjpeg-turbo writes at most 65500 pixels per side; the full 65535 comes from the coefficient-level encoder)
+    comps = [(2, 2, 0, 0, 0), (1, 1, 1, 1, 1), (1, 1, 1, 1, 1)]
+    widest = js.encode_from_coefs(65535, 16, comps, js.random_coefs(comps, 65535, 16, seed=3, density=0.05), restart_interval=100)
+    tallest = js.encode_from_coefs(8, 65535, [(1, 1, 0, 0, 0)], js.random_coefs([(1, 1, 0, 0, 0)], 8, 65535, seed=4, density=0.05))
+    cases = [(widest, "65535x16 4:2:0 ri100"), (tallest, "8x65535 gray")]
+    for w, h, sub, gray, ri in [(65500, 9, 2, False, 0), (9, 65500, 2, False, 0), (65500, 8, 0, False, 64), (16, 65500, 1, False, 0),
+                                (65500, 1, 2, True, 0), (1, 65500, 2, True, 7), (8, 8, 2, False, 0), (1, 1, 0, False, 0)]:
+        cases.append((js.synth_jpeg(w, h, seed=w + 3 * h, subsampling=sub, gray=gray, restart_blocks=ri), (w, h, sub, gray, ri)))
+    for data, what in cases:
+        w = h = what
+        r = ol.Restated(data, 0)
+        assert r.valid and r.huff_rc == 0, what
+        outs, status = dec.decode([data, good], bj.BJ_OUT_BMP)
+        assert status == [0, 0], (w, h)
+        assert np.array_equal(outs[0], r.bmp), what
+        rgb, st = dec.decode([data], bj.BJ_OUT_RGB8)
+        assert st == [0] and np.array_equal(rgb[0].reshape(r.rgb.shape), r.rgb), (w, h)
+
+
+def test_caller_made_descriptors_are_checked(dec, golden, golden_dir):
+    """bj_decode_batch_desc / bj_stage_idct_color take descriptors the library did not parse: nonsense in them (zero
+    components, sampling factors the tile sizes do not cover, table ids out of range, tables never set, a size that does
+    not match the MCU counts) must come back as a status, never reach a kernel."""
+    import ctypes as C
+    import pim_jpeg_decoder_b200 as bj
+    data = _load(golden, golden_dir, "p420_320x240")
+    clean, raw = ol.unstuffed_scan(data)
+
+    def fresh():
+        return _desc_from_oracle_header(bj, data)
+
+    def broken(**kw):
+        d = fresh()
+        for k, v in kw.items():
+            if isinstance(v, tuple):
+                getattr(d, k)[v[0]] = v[1]
+            else:
+                setattr(d, k, v)
+        return d
+
+    bad = [broken(ncomp=0), broken(ncomp=4), broken(hs=3), broken(vs=0), broken(comp_h=(1, 2)), broken(qt_id=(0, 7)), broken(dc_id=(2, 9)),
+           broken(width=0), broken(mcu_w=5), broken(qt_set=(0, 0)), broken(ac_set=(0, 0)), broken(frame_type=0xC2), broken(scan_ncomp=1)]
+    descs = [fresh()] + bad + [fresh()]
+    outs, status = dec.decode_desc(descs, [raw] * len(descs), None, fmt=bj.BJ_OUT_BMP)
+    assert status[0] == 0 and status[-1] == 0
+    assert all(s in (bj.BJ_ERR_INVALID_JPEG, bj.BJ_ERR_UNSUPPORTED) for s in status[1:-1]), status
+    want = ol.Restated(data, 0)
+    assert np.array_equal(outs[0], want.bmp) and np.array_equal(outs[-1], want.bmp)
+    for d in bad[:9]:
+        out = np.zeros(16, dtype=np.uint8)
+        rc = bj.lib().bj_stage_idct_color(dec.ctx, C.byref(d), want.coef_zz.ctypes.data_as(C.c_void_p), bj.BJ_OUT_RGB8, out.ctypes.data_as(C.c_void_p))
+        assert rc == -1                                           # BJ_ERR_ARG
