@@ -413,7 +413,26 @@ def main():
         run_compat(args, rank, local_rank, world)
         return
 
-    bind_to_gpu_numa_node(local_rank)
+    # which GPU this rank drives.  With more GPUs visible than ranks, neighbouring ordinals often hang off the same PCIe
+    # switch and share its uplink for the copy-out (measured on an 8-GPU box: GPUs 0+1 together 72 GB/s, one alone 57,
+    # profiles/r2_d2h_probe_8gpu.txt); spreading the ranks over the visible devices gives each its own path to the host.
+    # B200JPEG_BENCH_SPREAD=0 keeps device = LOCAL_RANK.
+    device, dev_stride = local_rank, 1
+    if world > 1 and os.environ.get("B200JPEG_BENCH_SPREAD", "1") != "0":
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = pynvml.nvmlDeviceGetCount()
+            pynvml.nvmlShutdown()
+            cvd = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if cvd:
+                visible = len([x for x in cvd.split(",") if x.strip()])
+            if visible >= 2 * world and int(os.environ.get("LOCAL_WORLD_SIZE", world)) == world:
+                dev_stride = visible // world
+                device = local_rank * dev_stride
+        except Exception:
+            pass
+    bind_to_gpu_numa_node(device)
     workers = max(1, args.gen_workers // max(1, world))
     stream = args.stream if args.workload == "config5" else 0
     if stream:
@@ -441,10 +460,10 @@ def main():
     import torch
     import torch.distributed as dist
     import pim_jpeg_decoder_b200 as bj
-    torch.cuda.set_device(local_rank)
+    torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
 
     def barrier():
         if world > 1:
@@ -457,7 +476,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    dec = bj.Decoder(local_rank)                              # raises without a GPU: no CPU fallback exists
+    dec = bj.Decoder(device)                                  # raises without a GPU: no CPU fallback exists
     if args.subseq_bits:
         dec.set_option("subseq_bits", args.subseq_bits)
     if args.slices:
@@ -468,7 +487,7 @@ def main():
         dec.set_option("sync_phased", args.sync_phased)
     if args.sync_preroll >= 0:
         dec.set_option("sync_preroll_bits", args.sync_preroll)
-    sampler = ClockSampler(local_rank, args.clock_sample_ms)
+    sampler = ClockSampler(device, args.clock_sample_ms)
     sampler.start()
     windows = []
 
@@ -801,6 +820,7 @@ def main():
                          "working set of one step is smaller than the 126 MB L2 and stays there between steps (single-image latency case); inputs are re-read from HBM-resident buffers",
                    "subseq_bits": args.subseq_bits or "per image (library default)", "slices": args.slices or "per image (library default)",
                    "streams": nstreams, "value_one_stream": total_px * steps / (ms_serial * 1e-3) / 1e6, "ms_per_step_one_stream": ms_serial / steps,
+                   "devices": f"rank r drives GPU {dev_stride} x r" if dev_stride > 1 else "rank r drives GPU r",
                    "sharding": "ONE list dealt over the ranks by compressed size (LPT), no collective on the data path" if stream else "by image, no collective on the data path",
                    "restart_parity_rule": rule or ("files with restart markers that are subsampled follow the restart-parity rule (DESIGN.md section 4)" if args.workload == "config3" else None)},
         "roofline": roofline, "stages": stages,
