@@ -36,7 +36,8 @@ typedef struct bj_ctx bj_ctx;
  * (src/decoder_host.cpp:32,268).  `device` is the CUDA ordinal (LOCAL_RANK in a one-process-per-GPU job). */
 int bj_create(bj_ctx **ctx, int device);
 /* All GPUs from ONE process, like `DpuSet::allocate(DPU_ALLOCATE_ALL)` takes every DPU of the machine
- * (src/decoder_host.cpp:32-33).  devices == NULL: devices 0..ndev-1; ndev <= 0: every visible device.  bj_decode_batch /
+ * (src/decoder_host.cpp:32-33).  ndev <= 0: every visible device; devices == NULL: ndev devices spread evenly over the
+ * visible ones (0, count/ndev, 2 count/ndev ...: neighbouring ordinals often share a PCIe uplink).  bj_decode_batch /
  * bj_submit on such a context deal the image list to the GPUs sub-batch by sub-batch from one shared cursor (images are
  * independent: no collective); bj_exec_mcus splits its DPUs into equal contiguous shares; the staged and stage-level
  * entries run on the first device. */

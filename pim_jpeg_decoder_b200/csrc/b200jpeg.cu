@@ -107,7 +107,10 @@ extern "C" int bj_create_multi(bj_ctx **out, const int *devices, int ndev) {
     std::vector<int> rcs(ndev, BJ_OK);
     {
         std::vector<std::thread> th;
-        for (int i = 1; i < ndev; i++) th.emplace_back([&, i] { rcs[i] = bj_create(&made[i], devices ? devices[i] : i); });
+        // no list given and fewer devices wanted than there are: every (count / ndev)-th one - neighbouring ordinals
+        // often share a PCIe uplink, and the copy-out is what bounds this path (profiles/r2_bench_*gpu_spread.json)
+        const int stride = (!devices && ndev > 0 && count >= 2 * ndev) ? count / ndev : 1;
+        for (int i = 1; i < ndev; i++) th.emplace_back([&, i] { rcs[i] = bj_create(&made[i], devices ? devices[i] : i * stride); });
         rcs[0] = bj_create(&made[0], devices ? devices[0] : 0);
         for (auto &t : th) t.join();
     }
