@@ -31,8 +31,10 @@ def main():
                 w, h = int(rng.integers(1, 3000)), int(rng.integers(1, 40))
             sub, gray = int(rng.integers(0, 3)), bool(rng.integers(0, 6) == 0)
             ri = int(rng.choice([0, 0, 0, 1, 2, 5, 8, 33]))
-            data = js.synth_jpeg(w, h, seed=int(rng.integers(0, 1 << 30)), subsampling=sub, gray=gray, restart_blocks=ri,
-                                 quality=int(rng.choice([35, 60, 75, 90, 95, 100])), optimize=bool(rng.integers(0, 2)))
+            q, opt = int(rng.choice([35, 60, 75, 90, 95, 100])), bool(rng.integers(0, 2))
+            if q == 100 and opt:
+                opt = False                 # (Pillow's in-memory encoder gives up on quality 100 + optimised tables: "Suspension not allowed here")
+            data = js.synth_jpeg(w, h, seed=int(rng.integers(0, 1 << 30)), subsampling=sub, gray=gray, restart_blocks=ri, quality=q, optimize=opt)
             if ri == 0 and rng.integers(0, 4) == 0:
                 data, _ = _corrupt_scan(data, rng, int(rng.integers(1, 6)))
                 damaged += 1
