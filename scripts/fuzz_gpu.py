@@ -36,8 +36,11 @@ def main():
                 opt = False                 # (Pillow's in-memory encoder gives up on quality 100 + optimised tables: "Suspension not allowed here")
             data = js.synth_jpeg(w, h, seed=int(rng.integers(0, 1 << 30)), subsampling=sub, gray=gray, restart_blocks=ri, quality=q, optimize=opt)
             if ri == 0 and rng.integers(0, 4) == 0:
-                data, _ = _corrupt_scan(data, rng, int(rng.integers(1, 6)))
-                damaged += 1
+                try:
+                    data, _ = _corrupt_scan(data, rng, int(rng.integers(1, 6)))
+                    damaged += 1
+                except ValueError:          # (a scan of a few bytes: nothing to flip)
+                    pass
             elif rng.integers(0, 25) == 0:
                 data = data[: int(rng.integers(len(data) // 2, len(data)))]        # truncated: no EOI
             files.append(data)
