@@ -30,22 +30,53 @@ __device__ __forceinline__ uint4 pack_row(const int (&X)[64], int r) {
     return v;
 }
 
-// Eight pixels of one row: luma words yv, the chroma words of the first / last output channel (fw / lw; with 2:1
-// horizontal subsampling every sample feeds two pixels) -> unclamped channel values (src/decoder_dpu.c:376-378).
-template <bool HS2>
-__device__ __forceinline__ void color8(const uint4 &yv, const unsigned *fw, const unsigned *lw, unsigned kF, unsigned kL, unsigned gF,
-                                       unsigned gL, int (&c0)[8], int (&c1)[8], int (&c2)[8]) {
+// The chroma contributions of the samples that feed eight pixels of a row (src/decoder_dpu.c:376-378), with the +128 of
+// every channel folded in:  tF = ((kF * F) >> 22) + 128,  tL = ((kL * L) >> 22) + 128,  tG = 128 - ((gF * F) >> 22) -
+// ((gL * L) >> 22)  (32-bit wrapping products, arithmetic shifts; the sums are associative mod 2^32).  fw / lw: the chroma
+// words of the first / last output channel; with 2:1 horizontal subsampling four samples feed the eight pixels (NS = 4).
+// With 2:1 VERTICAL subsampling the same terms serve two pixel rows: they are computed once per row pair.
+template <int NS>
+__device__ __forceinline__ void chroma_terms_row(const unsigned *fw, const unsigned *lw, unsigned kF, unsigned kL, unsigned gF, unsigned gL,
+                                                 int (&tF)[NS], int (&tG)[NS], int (&tL)[NS]) {
+#pragma unroll
+    for (int ci = 0; ci < NS; ci++) {
+        const int f = (ci & 1) ? sext_hi(fw[ci >> 1]) : sext_lo(fw[ci >> 1]);
+        const int l = (ci & 1) ? sext_hi(lw[ci >> 1]) : sext_lo(lw[ci >> 1]);
+        tF[ci] = ((int)(kF * (unsigned)f) >> 22) + 128;
+        tG[ci] = 128 - ((int)(gF * (unsigned)f) >> 22) - ((int)(gL * (unsigned)l) >> 22);
+        tL[ci] = ((int)(kL * (unsigned)l) >> 22) + 128;
+    }
+}
+// Eight pixels of one row: luma words yv + the chroma terms above -> unclamped channel values.
+template <int NS>
+__device__ __forceinline__ void color_row(const uint4 &yv, const int (&tF)[NS], const int (&tG)[NS], const int (&tL)[NS], int (&c0)[8],
+                                          int (&c1)[8], int (&c2)[8]) {
     const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const int ci = HS2 ? (i >> 1) : i;                                 // chroma sample of pixel i
-        const int f = (ci & 1) ? sext_hi(fw[ci >> 1]) : sext_lo(fw[ci >> 1]);
-        const int l = (ci & 1) ? sext_hi(lw[ci >> 1]) : sext_lo(lw[ci >> 1]);
-        const int yy = ((i & 1) ? sext_hi(yw[i >> 1]) : sext_lo(yw[i >> 1])) + 128;
-        c0[i] = yy + ((int)(kF * (unsigned)f) >> 22);
-        c1[i] = yy - ((int)(gF * (unsigned)f) >> 22) - ((int)(gL * (unsigned)l) >> 22);
-        c2[i] = yy + ((int)(kL * (unsigned)l) >> 22);
+        const int ci = NS == 4 ? (i >> 1) : i;                             // chroma sample of pixel i
+        const int yy = (i & 1) ? sext_hi(yw[i >> 1]) : sext_lo(yw[i >> 1]);
+        c0[i] = yy + tF[ci];
+        c1[i] = yy + tG[ci];
+        c2[i] = yy + tL[ci];
     }
+}
+// 24 bytes of packed, clamped pixels (first, G, last per pixel) into the staging tile
+__device__ __forceinline__ void store_rgb24(uint8_t *p, const int (&c0)[8], const int (&c1)[8], const int (&c2)[8]) {
+    uint2 *dst = reinterpret_cast<uint2 *>(p);
+    dst[0] = make_uint2(pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]));
+    dst[1] = make_uint2(pack_sat4(c2[2], c0[3], c1[3], c2[3]), pack_sat4(c0[4], c1[4], c2[4], c0[5]));
+    dst[2] = make_uint2(pack_sat4(c1[5], c2[5], c0[6], c1[6]), pack_sat4(c2[6], c0[7], c1[7], c2[7]));
+}
+// the same as three 16-byte rows of shorts (R, G, B planes of the reference's block-tiled layout)
+__device__ __forceinline__ void store_ref_rows(int16_t *ob, const int (&c0)[8], const int (&c1)[8], const int (&c2)[8]) {
+    auto pack8 = [](const int (&c)[8]) {
+        return make_uint4(clamp255(c[0]) | (clamp255(c[1]) << 16), clamp255(c[2]) | (clamp255(c[3]) << 16),
+                          clamp255(c[4]) | (clamp255(c[5]) << 16), clamp255(c[6]) | (clamp255(c[7]) << 16));
+    };
+    __stcs(reinterpret_cast<uint4 *>(ob), pack8(c0));
+    __stcs(reinterpret_cast<uint4 *>(ob + 256), pack8(c1));
+    __stcs(reinterpret_cast<uint4 *>(ob + 512), pack8(c2));
 }
 
 // ------------------------------------------------------------------------------------------------ fast layout
@@ -58,10 +89,13 @@ __device__ __forceinline__ void color8(const uint4 &yv, const unsigned *fw, cons
 // (the split into MAX_MCU_PER_DPU chunks is the same linear buffer: a chunk is MAX_MCU_PER_DPU / 4 whole blocks).
 // Stages 1-3 of one tile, common to the two kernels below: the tile's coefficient units are in `s_du` (unit du's 16-byte
 // chunk c at chunk position c ^ (du & 7)), the image's quantiser set in `s_q`, the predicted DC values in `s_dc`.
-template <bool REF_MCUS>
+// HS, VS: the luma sampling factors as compile-time constants for three-component images (the index arithmetic of the
+// colour stage folds: 4:2:0 and 4:4:4 have their own instances), or 0, 0: whatever the image record says.
+template <bool REF_MCUS, int HS, int VS>
 __device__ __forceinline__ void tile_idct_color(uint4 *s_du, const uint32_t *s_q, uint8_t *s_rgb, const uint16_t *s_dc, const TileDev &t,
-                                                const ImgDev *__restrict__ im, const int hs, const int vs, const int ncomp, const int bpm,
+                                                const ImgDev *__restrict__ im, const int hs_rt, const int vs_rt, const int ncomp_rt, const int bpm_rt,
                                                 const bool dc_sep, uint8_t *__restrict__ out) {
+    const int hs = HS ? HS : hs_rt, vs = HS ? VS : vs_rt, ncomp = HS ? 3 : ncomp_rt, bpm = HS ? HS * VS + 2 : bpm_rt;
     const int tid = threadIdx.x;
     const int ndu = t.ndu, nm = t.nm;
     // ---- stage 1: one thread = one unit: de-zigzag (with the reference's 48/52 quirk), dequantise, IDCT
@@ -101,14 +135,16 @@ __device__ __forceinline__ void tile_idct_color(uint4 *s_du, const uint32_t *s_q
     }
     __syncthreads();
 
-    // ---- stage 2: colour.  One item = 8 horizontally adjacent pixels (one row of one luma unit); consecutive
-    // lanes take consecutive segments of the same pixel row.  Result: 24 bytes into the staging tile.
+    // ---- stage 2: colour.  One item = 8 horizontally adjacent pixels of one row of one luma unit - of TWO rows (2r, 2r + 1)
+    // when the image is subsampled 2:1 vertically: both rows take the same chroma row, whose terms are computed once.
+    // Consecutive lanes take consecutive segments of the same pixel row(s).  Result: 24 bytes per row into the staging tile.
     const int nseg = nm * hs;             // 8-pixel segments per tile row
     const int rows = vs * 8;
     const int pitch = nseg * 24;
     {
         const unsigned inv = nseg > 1 ? (0xFFFFFFFFu / (unsigned)nseg + 1u) : 0u;
-        const int items = rows * nseg;
+        const int nrow = vs == 2 ? 2 : 1;                                  // pixel rows per item
+        const int items = (rows / nrow) * nseg;
         // Output byte order R,G,B or B,G,R: instead of swapping per pixel, swap the roles of the two chroma planes
         // and of their constants once (src/decoder_dpu.c:376-378):  first = y + 128 + ((kF * F) >> 22),
         // last = y + 128 + ((kL * L) >> 22),  G = y + 128 - ((gF * F) >> 22) - ((gL * L) >> 22).
@@ -118,44 +154,51 @@ __device__ __forceinline__ void tile_idct_color(uint4 *s_du, const uint32_t *s_q
         const int fdu = bgr ? 0 : 1, ldu = bgr ? 1 : 0;                    // unit offsets of F and L from the Cb unit
         const bool has_f = bgr ? ncomp >= 2 : ncomp >= 3, has_l = bgr ? ncomp >= 3 : ncomp >= 2;
         for (int it = tid; it < items; it += kTileThreads) {
-            const int py = nseg > 1 ? (int)__umulhi((unsigned)it, inv) : it;
-            const int s = it - py * nseg;
+            const int pq = nseg > 1 ? (int)__umulhi((unsigned)it, inv) : it;
+            const int s = it - pq * nseg;
+            const int py = pq * nrow;                                      // first pixel row of the item
             const int m = hs == 2 ? (s >> 1) : s, bx = hs == 2 ? (s & 1) : 0;
             const int by = py >> 3, r = py & 7;
             const int ydu = m * bpm + by * hs + bx;
-            const uint4 yv = s_du[ydu * 8 + (r ^ (ydu & 7))];
             const int cdu = m * bpm + hs * vs;
             const int rc = vs == 2 ? (by * 4 + (r >> 1)) : r;
             uint4 fv = make_uint4(0, 0, 0, 0), lv = make_uint4(0, 0, 0, 0);
             if (has_f) fv = s_du[(cdu + fdu) * 8 + (rc ^ ((cdu + fdu) & 7))];
             if (has_l) lv = s_du[(cdu + ldu) * 8 + (rc ^ ((cdu + ldu) & 7))];
+            // destination of the item's first row: the staging tile, or (REF_MCUS) straight to HBM: three 16-byte rows
+            // (R, G, B as shorts) of position (pr, pc)
+            uint8_t *dst = s_rgb + py * pitch + s * 24;
+            int16_t *ob = nullptr;
+            if (REF_MCUS) {
+                const unsigned pr = (unsigned)t.my * vs + by, pc = ((unsigned)t.mx0 + m) * hs + bx, W = im->nmx * hs;
+                const size_t blk = (size_t)(pr >> 1) * ((W + 1u) >> 1) + (pc >> 1);
+                ob = reinterpret_cast<int16_t *>(out + im->out_row0) + blk * 768 + ((pr & 1u) * 2u + (pc & 1u)) * 64u + r * 8;
+            }
             int c0[8], c1[8], c2[8];
             if (hs == 2) {
                 // one unit row feeds two segments (left half / right half), every chroma sample twice
                 const unsigned fw[2] = {bx ? fv.z : fv.x, bx ? fv.w : fv.y}, lw[2] = {bx ? lv.z : lv.x, bx ? lv.w : lv.y};
-                color8<true>(yv, fw, lw, kF, kL, gF, gL, c0, c1, c2);
+                int tF[4], tG[4], tL[4];
+                chroma_terms_row<4>(fw, lw, kF, kL, gF, gL, tF, tG, tL);
+#pragma unroll 1
+                for (int k = 0; k < nrow; k++) {
+                    const uint4 yv = s_du[ydu * 8 + ((r + k) ^ (ydu & 7))];
+                    color_row<4>(yv, tF, tG, tL, c0, c1, c2);
+                    if (REF_MCUS) store_ref_rows(ob + k * 8, c0, c1, c2);
+                    else store_rgb24(dst + k * pitch, c0, c1, c2);
+                }
             } else {
                 const unsigned fw[4] = {fv.x, fv.y, fv.z, fv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
-                color8<false>(yv, fw, lw, kF, kL, gF, gL, c0, c1, c2);
+                int tF[8], tG[8], tL[8];
+                chroma_terms_row<8>(fw, lw, kF, kL, gF, gL, tF, tG, tL);
+#pragma unroll 1
+                for (int k = 0; k < nrow; k++) {
+                    const uint4 yv = s_du[ydu * 8 + ((r + k) ^ (ydu & 7))];
+                    color_row<8>(yv, tF, tG, tL, c0, c1, c2);
+                    if (REF_MCUS) store_ref_rows(ob + k * 8, c0, c1, c2);
+                    else store_rgb24(dst + k * pitch, c0, c1, c2);
+                }
             }
-            if (REF_MCUS) {
-                // straight to HBM: three 16-byte rows (R, G, B as shorts) of position (pr, pc)
-                const unsigned pr = (unsigned)t.my * vs + by, pc = ((unsigned)t.mx0 + m) * hs + bx, W = im->nmx * hs;
-                const size_t blk = (size_t)(pr >> 1) * ((W + 1u) >> 1) + (pc >> 1);
-                int16_t *ob = reinterpret_cast<int16_t *>(out + im->out_row0) + blk * 768 + ((pr & 1u) * 2u + (pc & 1u)) * 64u + r * 8;
-                auto pack8 = [](const int (&c)[8]) {
-                    return make_uint4(clamp255(c[0]) | (clamp255(c[1]) << 16), clamp255(c[2]) | (clamp255(c[3]) << 16),
-                                      clamp255(c[4]) | (clamp255(c[5]) << 16), clamp255(c[6]) | (clamp255(c[7]) << 16));
-                };
-                __stcs(reinterpret_cast<uint4 *>(ob), pack8(c0));
-                __stcs(reinterpret_cast<uint4 *>(ob + 256), pack8(c1));
-                __stcs(reinterpret_cast<uint4 *>(ob + 512), pack8(c2));
-                continue;
-            }
-            uint2 *dst = reinterpret_cast<uint2 *>(s_rgb + py * pitch + s * 24);
-            dst[0] = make_uint2(pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]));
-            dst[1] = make_uint2(pack_sat4(c2[2], c0[3], c1[3], c2[3]), pack_sat4(c0[4], c1[4], c2[4], c0[5]));
-            dst[2] = make_uint2(pack_sat4(c1[5], c2[5], c0[6], c1[6]), pack_sat4(c2[6], c0[7], c1[7], c2[7]));
         }
     }
     if (REF_MCUS) return;
@@ -171,42 +214,51 @@ __device__ __forceinline__ void tile_idct_color(uint4 *s_du, const uint32_t *s_q
         const int payload = wpx * 3;
         const int len = payload + ((x0 + nseg * 8 >= (int)im->width) ? (int)im->row_pad : 0);
         const int warp = tid >> 5, lane = tid & 31;
+        const long long row_step = (long long)im->row_dir * (long long)im->out_pitch;
+        const long long off0 = (long long)im->out_row0 + row_step * (long long)y0 + (long long)x0 * 3;
         for (int r = warp; r < rows_valid; r += kTileThreads / 32) {
-            const long long off = (long long)im->out_row0 + (long long)im->row_dir * (long long)(y0 + r) * (long long)im->out_pitch + (long long)x0 * 3;
-            uint8_t *g = out + off;
+            uint8_t *g = out + (off0 + row_step * r);
             const uint8_t *sp = s_rgb + r * pitch;
-            // head: the bytes up to the first 16-byte boundary, one per lane
+            // the run [0, len) = head bytes up to the first 16-byte boundary, nfull whole aligned chunks, ntail bytes
             const int head = min((int)((16u - ((unsigned)(uintptr_t)g & 15u)) & 15u), len);
-            if (lane < head) g[lane] = lane < payload ? sp[lane] : (uint8_t)0;
-            // body: whole aligned 16-byte chunks
             const int nfull = (len - head) >> 4;
-            {
-                const uint8_t *p0 = sp + head;
-                const unsigned a = (unsigned)__cvta_generic_to_shared(p0);
-                const unsigned sh = (a & 3u) * 8u;
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(p0 - (a & 3u));
-                uint4 *gp = reinterpret_cast<uint4 *>(g + head);
-                for (int i = lane; i < nfull; i += 32) {
-                    const uint32_t w0 = wp[4 * i], w1 = wp[4 * i + 1], w2 = wp[4 * i + 2], w3 = wp[4 * i + 3], w4 = wp[4 * i + 4];
-                    uint4 v;
-                    v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
-                    v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
-                    if (head + 16 * i + 16 > payload) {                    // BMP pad bytes (zero) inside this chunk
-                        const int keep = payload - head - 16 * i;          // data bytes in the chunk, < 16
-                        uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int w = 0; w < 4; w++) {
-                            const int kb = keep - 4 * w;
-                            vv[w] = kb >= 4 ? vv[w] : (kb <= 0 ? 0u : (vv[w] & (0xFFFFFFFFu >> (32 - 8 * kb))));
-                        }
-                        v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-                    }
-                    __stcs(gp + i, v);
-                }
-            }
-            // tail: what is left after the last whole chunk, one byte per lane
             const int tail0 = head + 16 * nfull;
-            if (tail0 + lane < len) g[tail0 + lane] = tail0 + lane < payload ? sp[tail0 + lane] : (uint8_t)0;
+            // head and tail bytes in one store: lanes 0-15 a head byte each, lanes 16-31 a tail byte each
+            {
+                const int idx = lane < 16 ? lane : tail0 + lane - 16;
+                const bool ok = lane < 16 ? lane < head : idx < len;
+                if (ok) g[idx] = idx < payload ? sp[idx] : (uint8_t)0;
+            }
+            // body: whole aligned 16-byte chunks.  Those that hold only pixel bytes first (no masking); BMP pad bytes
+            // (at most 3 per row) can only lie in the last whole chunk
+            const uint8_t *p0 = sp + head;
+            const unsigned a = (unsigned)__cvta_generic_to_shared(p0);
+            const unsigned sh = (a & 3u) * 8u;
+            const unsigned wa = a & ~3u;                                   // shared-memory address of the first word
+            uint4 *gp = reinterpret_cast<uint4 *>(g + head);
+            const int nbody = min(nfull, max(payload - head, 0) >> 4);
+            for (int i = lane; i < nbody; i += 32) {
+                uint32_t w0, w1, w2, w3, w4;
+                asm volatile("ld.shared.u32 %0, [%5];\n\tld.shared.u32 %1, [%5+4];\n\tld.shared.u32 %2, [%5+8];\n\tld.shared.u32 %3, [%5+12];\n\tld.shared.u32 %4, [%5+16];"
+                             : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4) : "r"(wa + 16u * (unsigned)i));
+                uint4 v;
+                v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+                v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+                __stcs(gp + i, v);
+            }
+            if (nbody < nfull && lane == 0) {                              // the chunk with pad bytes (zero) in it
+                const int i = nbody;
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(p0 - (a & 3u));
+                const uint32_t w0 = wp[4 * i], w1 = wp[4 * i + 1], w2 = wp[4 * i + 2], w3 = wp[4 * i + 3], w4 = wp[4 * i + 4];
+                uint32_t vv[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+                const int keep = payload - head - 16 * i;                  // data bytes in the chunk, < 16
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const int kb = keep - 4 * w;
+                    vv[w] = kb >= 4 ? vv[w] : (kb <= 0 ? 0u : (vv[w] & (0xFFFFFFFFu >> (32 - 8 * kb))));
+                }
+                __stcs(gp + i, make_uint4(vv[0], vv[1], vv[2], vv[3]));
+            }
         }
         // BMP file header (src/bmp_writer.cpp:26-41), written by the tile that owns the image's first MCU:
         // 'B','M', size(4), 0(4), 0x1A(4), 12(4), width(2), height(2), 1(2), 24(2)
@@ -279,7 +331,10 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
     }
     __syncthreads();
 
-    tile_idct_color<REF_MCUS>(s_du, s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, dc_plane != nullptr, out);
+    const bool dc_sep = dc_plane != nullptr;
+    if (ncomp == 3 && hs == 2 && vs == 2) tile_idct_color<REF_MCUS, 2, 2>(s_du, s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, dc_sep, out);
+    else if (ncomp == 3 && hs == 1 && vs == 1) tile_idct_color<REF_MCUS, 1, 1>(s_du, s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, dc_sep, out);
+    else tile_idct_color<REF_MCUS, 0, 0>(s_du, s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, dc_sep, out);
 }
 
 // ------------------------------------------------------------------------------------------------ fast layout, TMA
@@ -359,7 +414,7 @@ k_idct_color_tma(const __grid_constant__ CUtensorMap tmap, const int16_t *__rest
         s_dc[tid] = tid < (int)t.ndu ? (uint16_t)__ldg(dc_plane + (size_t)t.du0 + tid) : (uint16_t)0;
         if (!mbar_wait(&s_bar[buf], (it >> 1) & 1u)) { if (tid == 0) atomicAdd(err, 1u); return; }   // (never: see mbar_wait)
         __syncthreads();
-        tile_idct_color<false>(reinterpret_cast<uint4 *>(smem + buf * kTmaBufBytes), s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, true, out);
+        tile_idct_color<false, 0, 0>(reinterpret_cast<uint4 *>(smem + buf * kTmaBufBytes), s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, true, out);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // this buffer was written through the generic proxy; the next copy into it is the async proxy's
         __syncthreads();                                                   // s_rgb, s_q, s_dc and this buffer are free again
     }
