@@ -194,16 +194,21 @@ uint32_t lut_second(uint32_t tab, uint32_t e, uint32_t win
     return m.ld(tab + (e & 0xFFFFu) + (((win << kRootBits) >> (32u - ((e >> 16) & 15u))) << 2));
 }
 
-// win = the next 32 bits of the stream, MSB first; tab = position of the table.
-BJ_HD uint32_t lut_lookup(const LutMem &m, uint32_t tab, uint32_t win) {
-    uint32_t e = m.ld(tab + ((win >> (32 - kRootBits)) << 2));
-    if (__builtin_expect((int32_t)e < 0, 0)) {
+BJ_HD uint32_t lut_second_of(const LutMem &m, uint32_t tab, uint32_t e, uint32_t win) {
 #ifdef __CUDA_ARCH__
-        e = lut_second(tab, e, win);
+    (void)m;
+    return lut_second(tab, e, win);
 #else
-        e = lut_second(tab, e, win, m);
+    return lut_second(tab, e, win, m);
 #endif
-    }
+}
+
+// win = the next 32 bits of the stream, MSB first; tab = position of the table.  LM: where the tables live - LutMem, or
+// (kernels_huff.cuh) LutGlobal for the sparse fix-up kernel, whose threads work on different images.
+template <class LM>
+BJ_HD uint32_t lut_lookup(const LM &m, uint32_t tab, uint32_t win) {
+    uint32_t e = m.ld(tab + ((win >> (32 - kRootBits)) << 2));
+    if (__builtin_expect((int32_t)e < 0, 0)) e = lut_second_of(m, tab, e, win);
     return e;
 }
 
@@ -423,6 +428,22 @@ struct UnitWalk {
 #endif
 };
 BJ_HD constexpr uint32_t unit_walk_step(uint32_t c, uint32_t c1) { return 0x100u + 16u * (c1 - c); }
+// The same walk without the staged per-unit table (selects on the geometry): for code whose threads work on different
+// images (the sparse fix-up kernel of the synchronisation pass).
+struct UnitWalkSel {
+    uint32_t c, n;
+    BJ_HD void start(uint32_t c0) { c = c0; n = 0; }
+    BJ_HD uint32_t unit() const { return c; }
+    BJ_HD uint32_t ended() const { return n; }
+    BJ_HD void advance(const HuffGeom &g, bool fin, uint32_t &tab, uint32_t &ac) {
+        const uint32_t c1 = (c + 1u == g.bpm) ? 0u : c + 1u;
+        const uint32_t dcn = dc_of(g, c1), acn = ac_of(g, c1);
+        c = fin ? c1 : c;
+        n += fin ? 1u : 0u;
+        ac = fin ? acn : ac;
+        tab = fin ? dcn : ac;
+    }
+};
 
 // Magnitude extension of the `size` bits that follow a `len`-bit code in the window
 // (src/jpeg_scanner.cpp:480-482 / :513-516: first bit 0 => negative).  size 0 gives 0.
@@ -453,11 +474,11 @@ BJ_HD int32_t extend_entry(uint32_t win, uint32_t e) {
 // Every slice of the sub-sequence is reported exactly once per call, in order.  The AC tables are the grouped ones
 // (build_lut_sync), so a "step" may be several symbols; they never span a unit boundary, so the units counted
 // between two reported states are exactly the units whose DC symbol starts between them.
-template <class Rec>
-BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t start_bit,
+template <class Rec, class LM = LutMem, class UW = UnitWalk>
+BJ_HD HuffState decode_span(const uint32_t *words, const LM &luts, const HuffGeom &g, HuffState st, uint32_t start_bit,
                             uint32_t end_bit, uint32_t slice_bits, Rec &rec, uint32_t *units_started) {
     const uint32_t origin = st.p & ~31u;
-    UnitWalk u;
+    UW u;
     u.start(st.cz >> 8);
     uint32_t S = ((st.p - origin) << 8) | (st.cz & 0xFFu);
     const uint32_t endS = end_bit > origin ? (end_bit - origin) << 8 : 0u;
@@ -570,6 +591,17 @@ struct WriteCursor {
     // the reference stops.  (Damaged data only; at most 63 further symbols are read before the unit ends.)
     template <class Sink>
     BJ_HD bool step(const LutMem &luts, const HuffGeom &g, Sink &sink) {
+        const uint32_t r = step_sym(luts, g, sink);
+        if (r == kSymUnit) unit_done(g);
+        return r != 0u;
+    }
+    // The same in two halves, for a caller that lets a lane wait between the symbol that completes a unit and the
+    // hand-over to the next unit (k_huff_write takes several symbols per round and hands over once per round):
+    // 0 = the unit goes on;  kSymUnit = the unit is complete: call unit_done() before the next symbol;  kSymRedone = it
+    // was complete but had not ended well and has been decoded again, hand-over included.
+    static constexpr uint32_t kSymUnit = 1u, kSymRedone = 2u;
+    template <class Sink>
+    BJ_HD uint32_t step_sym(const LutMem &luts, const HuffGeom &g, Sink &sink) {
         const uint32_t win = bs.window(S);
         const uint32_t e = lut_lookup(luts, tab, win);
         const uint32_t Sn = S + (e & 0xFFFFu);
@@ -578,36 +610,13 @@ struct WriteCursor {
         // index of the coefficient this symbol carries (0: the DC difference).  size 0 (ZRL, EOB, refused) stores nothing.
         if (v != 0) sink.put(((Sn & 0xFFu) - 1u) & 63u, (int16_t)v);
         const bool fin = (Sn & 0x40u) != 0u;              // index >= 64: the unit ends one way or another
-        if (__builtin_expect(fin && ((bad & kLutBad) || Sn > dataS || ((Sn & 0xFFu) != 64u && !(e & kLutEob))), 0)) {
-            tab = ac; S = Sn;
-            redo_unit(luts, g, sink);
-            return true;
-        }
-#if defined(__CUDA_ARCH__) && defined(BJ_WRITE_SELECTS)
-        // The hand-over to the next unit without a branch (everything a select on `fin`).  About two of three warp steps
-        // have a lane that completes a unit, and the branch below runs its body for that one lane while the others wait
-        // (29 % of the kernel's instructions) - yet the branch-free form measured SLOWER on config 2 (2.14 ms against
-        // 2.00, profiles/r2_ab_write_sync.md): it adds a shared load and ten selects to EVERY step.  Kept for reference.
-        uint32_t dcn, acn, c1;
-        [[maybe_unused]] uint32_t stepw;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dcn), "=r"(acn), "=r"(stepw), "=r"(c1) : "r"(g.unit_tab + c * 16u));
-        st_du = fin ? du : 0xFFFFFFFFu;
-        du += fin ? 1u : 0u;
-        S = fin ? (Sn & ~0xFFu) : Sn;
-        tab = fin ? dcn : ac;
-        ac = fin ? acn : ac;
-        c = fin ? c1 : c;
-        S0 = fin ? S : S0;
-        bad = fin ? 0u : bad;
-        if (fin && (S >= endS || du >= du_end)) finish();
-        return fin;
-#else
         tab = ac;
         S = Sn;
-        if (!fin) return false;
-        unit_done(g);
-        return true;
-#endif
+        if (__builtin_expect(fin && ((bad & kLutBad) || Sn > dataS || ((Sn & 0xFFu) != 64u && !(e & kLutEob))), 0)) {
+            redo_unit(luts, g, sink);
+            return kSymRedone;
+        }
+        return fin ? kSymUnit : 0u;
     }
     BJ_HD void unit_done(const HuffGeom &g) {
         st_du = du++;

@@ -89,15 +89,10 @@ __device__ __forceinline__ void store_ref_rows(int16_t *ob, const int (&c0)[8], 
 // (the split into MAX_MCU_PER_DPU chunks is the same linear buffer: a chunk is MAX_MCU_PER_DPU / 4 whole blocks).
 // Stages 1-3 of one tile, common to the two kernels below: the tile's coefficient units are in `s_du` (unit du's 16-byte
 // chunk c at chunk position c ^ (du & 7)), the image's quantiser set in `s_q`, the predicted DC values in `s_dc`.
-// HS, VS: the luma sampling factors as compile-time constants for three-component images (the index arithmetic of the
-// colour stage folds: 4:2:0 and 4:4:4 have their own instances), or 0, 0: whatever the image record says.
-template <bool REF_MCUS, int HS, int VS>
-__device__ __forceinline__ void tile_idct_color(uint4 *s_du, const uint32_t *s_q, uint8_t *s_rgb, const uint16_t *s_dc, const TileDev &t,
-                                                const ImgDev *__restrict__ im, const int hs_rt, const int vs_rt, const int ncomp_rt, const int bpm_rt,
-                                                const bool dc_sep, uint8_t *__restrict__ out) {
-    const int hs = HS ? HS : hs_rt, vs = HS ? VS : vs_rt, ncomp = HS ? 3 : ncomp_rt, bpm = HS ? HS * VS + 2 : bpm_rt;
+// Stage 1 of one tile: dequantise + IDCT, one thread = one unit, in place in `s_du`.
+__device__ __forceinline__ void tile_idct(uint4 *s_du, const uint32_t *s_q, const uint16_t *s_dc, const int ndu, const int hs, const int vs,
+                                          const int bpm, const bool dc_sep) {
     const int tid = threadIdx.x;
-    const int ndu = t.ndu, nm = t.nm;
     // ---- stage 1: one thread = one unit: de-zigzag (with the reference's 48/52 quirk), dequantise, IDCT
     if (tid < ndu) {
         const int du = tid, sw = du & 7;
@@ -133,8 +128,17 @@ __device__ __forceinline__ void tile_idct_color(uint4 *s_du, const uint32_t *s_q
 #pragma unroll
         for (int r = 0; r < 8; r++) s_du[du * 8 + (r ^ sw)] = pack_row(X, r);
     }
-    __syncthreads();
+}
 
+// Stages 2 and 3 of one tile: colour conversion into the staging tile `s_rgb`, copy-out (REF_MCUS: straight to HBM).
+// HS, VS: the luma sampling factors as compile-time constants for three-component images (the index arithmetic of the
+// colour stage folds: 4:2:0 and 4:4:4 have their own instances), or 0, 0: whatever the image record says.
+template <bool REF_MCUS, int HS, int VS>
+__device__ __forceinline__ void tile_color_store(const uint4 *s_du, uint8_t *s_rgb, const TileDev &t, const ImgDev *__restrict__ im, const int hs_rt,
+                                                 const int vs_rt, const int ncomp_rt, const int bpm_rt, uint8_t *__restrict__ out) {
+    const int hs = HS ? HS : hs_rt, vs = HS ? VS : vs_rt, ncomp = HS ? 3 : ncomp_rt, bpm = HS ? HS * VS + 2 : bpm_rt;
+    const int tid = threadIdx.x;
+    const int nm = t.nm;
     // ---- stage 2: colour.  One item = 8 horizontally adjacent pixels of one row of one luma unit - of TWO rows (2r, 2r + 1)
     // when the image is subsampled 2:1 vertically: both rows take the same chroma row, whose terms are computed once.
     // Consecutive lanes take consecutive segments of the same pixel row(s).  Result: 24 bytes per row into the staging tile.
@@ -331,10 +335,11 @@ k_idct_color(const int16_t *__restrict__ coef, const int16_t *__restrict__ dc_pl
     }
     __syncthreads();
 
-    const bool dc_sep = dc_plane != nullptr;
-    if (ncomp == 3 && hs == 2 && vs == 2) tile_idct_color<REF_MCUS, 2, 2>(s_du, s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, dc_sep, out);
-    else if (ncomp == 3 && hs == 1 && vs == 1) tile_idct_color<REF_MCUS, 1, 1>(s_du, s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, dc_sep, out);
-    else tile_idct_color<REF_MCUS, 0, 0>(s_du, s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, dc_sep, out);
+    tile_idct(s_du, s_q, s_dc, ndu, hs, vs, bpm, dc_plane != nullptr);
+    __syncthreads();
+    if (ncomp == 3 && hs == 2 && vs == 2) tile_color_store<REF_MCUS, 2, 2>(s_du, s_rgb, t, im, hs, vs, ncomp, bpm, out);
+    else if (ncomp == 3 && hs == 1 && vs == 1) tile_color_store<REF_MCUS, 1, 1>(s_du, s_rgb, t, im, hs, vs, ncomp, bpm, out);
+    else tile_color_store<REF_MCUS, 0, 0>(s_du, s_rgb, t, im, hs, vs, ncomp, bpm, out);
 }
 
 // ------------------------------------------------------------------------------------------------ fast layout, TMA
@@ -414,7 +419,9 @@ k_idct_color_tma(const __grid_constant__ CUtensorMap tmap, const int16_t *__rest
         s_dc[tid] = tid < (int)t.ndu ? (uint16_t)__ldg(dc_plane + (size_t)t.du0 + tid) : (uint16_t)0;
         if (!mbar_wait(&s_bar[buf], (it >> 1) & 1u)) { if (tid == 0) atomicAdd(err, 1u); return; }   // (never: see mbar_wait)
         __syncthreads();
-        tile_idct_color<false, 0, 0>(reinterpret_cast<uint4 *>(smem + buf * kTmaBufBytes), s_q, s_rgb, s_dc, t, im, hs, vs, ncomp, bpm, true, out);
+        tile_idct(reinterpret_cast<uint4 *>(smem + buf * kTmaBufBytes), s_q, s_dc, t.ndu, hs, vs, bpm, true);
+        __syncthreads();
+        tile_color_store<false, 0, 0>(reinterpret_cast<const uint4 *>(smem + buf * kTmaBufBytes), s_rgb, t, im, hs, vs, ncomp, bpm, out);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // this buffer was written through the generic proxy; the next copy into it is the async proxy's
         __syncthreads();                                                   // s_rgb, s_q, s_dc and this buffer are free again
     }
