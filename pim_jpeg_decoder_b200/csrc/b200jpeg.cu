@@ -61,7 +61,6 @@ extern "C" int bj_create(bj_ctx **out, int device) {
     c->ri_split_threads = 0;       // measured (profiles/r2_latency_experiments.md): cutting restart segments finer is slower even for one 4K image
     if (const char *e = getenv("B200JPEG_RI_SPLIT")) c->ri_split_threads = atoi(e);          // (experiments)
     if (const char *e = getenv("B200JPEG_IDCT_TMA")) c->idct_tma = atoi(e) != 0;
-    if (const char *e = getenv("B200JPEG_SYNC_TAIL")) c->sync_tail = std::min(2, std::max(0, atoi(e)));   // (tests: the whole suite in forced tail mode)
     if (const char *e = getenv("B200JPEG_MIN_SUB")) c->min_sub_bytes = std::max(16, atoi(e));
     if (rc == BJ_OK) rc = c->check(cudaFuncSetAttribute(k_idct_color<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemIdctColor));
     if (rc == BJ_OK) rc = c->check(cudaFuncSetAttribute(k_idct_color<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemIdctColor));
@@ -185,8 +184,6 @@ extern "C" int bj_set_option(bj_ctx *c, const char *name, long value) {
     if (!strcmp(name, "subseq_bits")) { if (value != 0 && (value < 128 || value % 32 || value > (1 << 18))) return BJ_ERR_ARG; c->subseq_bits = (int)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_ramp")) { c->sub_batch_ramp = value != 0; return BJ_OK; }
     if (!strcmp(name, "sync_phased")) { c->sync_phased = value != 0; return BJ_OK; }
-    if (!strcmp(name, "sync_tail")) { if (value < 0 || value > 2) return BJ_ERR_ARG; c->sync_tail = (int)value; return BJ_OK; }
-    if (!strcmp(name, "sync_tail_rounds")) { if (value < 1 || value > kMaxTail - 2) return BJ_ERR_ARG; c->sync_tail_rounds = (int)value; return BJ_OK; }
     if (!strcmp(name, "slices")) { if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return BJ_ERR_ARG; c->slices = (int)value; return BJ_OK; }
     if (!strcmp(name, "sub_batch_bytes")) { if (value < (1 << 16)) return BJ_ERR_ARG; c->sub_batch_bytes = (size_t)value; return BJ_OK; }
     if (!strcmp(name, "packed_outputs")) { c->packed_outputs = value != 0; return BJ_OK; }

@@ -41,16 +41,14 @@ constexpr int kSmemHuffSyncMax = kSmemLutMax;
 
 inline int batch_kernels_init(bj_ctx *c) {
     if (c->check(cudaFuncSetAttribute(k_huff_write, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffWriteMax)) != BJ_OK) return BJ_ERR_CUDA;
-    if (c->check(cudaFuncSetAttribute(k_huff_sync<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
-    if (c->check(cudaFuncSetAttribute(k_huff_sync<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
-    if (c->check(cudaFuncSetAttribute(k_huff_sync<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
+    if (c->check(cudaFuncSetAttribute(k_huff_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
+    if (c->check(cudaFuncSetAttribute(k_huff_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHuffSyncMax)) != BJ_OK) return BJ_ERR_CUDA;
 #ifndef BJ_SYNC_CARVEOUT
 #define BJ_SYNC_CARVEOUT 72            // % of 228 KB: 164 KB of shared memory for 5 CTAs, the rest is L1 (kernels_huff.cuh: BJ_SYNC_CTAS)
 #endif
 #if BJ_SYNC_CARVEOUT > 0
-    if (c->check(cudaFuncSetAttribute(k_huff_sync<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, BJ_SYNC_CARVEOUT)) != BJ_OK) return BJ_ERR_CUDA;
-    if (c->check(cudaFuncSetAttribute(k_huff_sync<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, BJ_SYNC_CARVEOUT)) != BJ_OK) return BJ_ERR_CUDA;
-    if (c->check(cudaFuncSetAttribute(k_huff_sync<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, BJ_SYNC_CARVEOUT)) != BJ_OK) return BJ_ERR_CUDA;
+    if (c->check(cudaFuncSetAttribute(k_huff_sync<true>, cudaFuncAttributePreferredSharedMemoryCarveout, BJ_SYNC_CARVEOUT)) != BJ_OK) return BJ_ERR_CUDA;
+    if (c->check(cudaFuncSetAttribute(k_huff_sync<false>, cudaFuncAttributePreferredSharedMemoryCarveout, BJ_SYNC_CARVEOUT)) != BJ_OK) return BJ_ERR_CUDA;
 #endif
 #ifdef BJ_WRITE_CARVEOUT
     if (c->check(cudaFuncSetAttribute(k_huff_write, cudaFuncAttributePreferredSharedMemoryCarveout, BJ_WRITE_CARVEOUT)) != BJ_OK) return BJ_ERR_CUDA;
@@ -94,14 +92,13 @@ struct bj_batch {
     uint32_t ref_blocks_max = 0;        // BJ_OUT_REF_MCUS: blocks of the largest image (grid of the padding kernel)
 
     // device
-    bj::DevBuf d_files, d_meta, d_maps, d_look, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_quarter, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out, d_tail;
+    bj::DevBuf d_files, d_meta, d_maps, d_look, d_clean, d_seg, d_subseg, d_stin, d_stout, d_tot, d_pre, d_slice, d_quarter, d_blkagg, d_state, d_flags, d_coef, d_dc, d_dcagg, d_out;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, un-stuffed, synchronised, written, pixels, copied out
     cudaEvent_t ev_done = nullptr;       // one-call path: recorded behind the copy-out, created for a sleeping wait
     cudaStream_t last_stream = nullptr;
     bool uploaded = false, decoded = false, synced = false;
     bool phased = true;                  // which variant of the synchronisation kernel this batch was laid out for
     bool multi_blk = false;              // some image's sub-sequences span more than one CTA of the synchronisation pass
-    bool tail = false;                   // the synchronisation pass runs in tail mode (k_huff_sync_tail / k_huff_sync_final)
     bool redone = false;                 // batch_sync had to run extra fix-up rounds: everything after them was computed again
     uint32_t launches = 0, sync_rounds = 0;
     float ms_entropy = 0.f, ms_idct = 0.f, ms_unstuff = 0.f, ms_sync = 0.f, ms_write = 0.f;
@@ -115,7 +112,7 @@ struct bj_batch {
     template <class T> T *dmap(size_t off) { return reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(d_maps.p) + off); }
 
     void release() {
-        for (bj::DevBuf *b : {&d_files, &d_meta, &d_maps, &d_look, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_quarter, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out, &d_tail}) b->release();
+        for (bj::DevBuf *b : {&d_files, &d_meta, &d_maps, &d_look, &d_clean, &d_seg, &d_subseg, &d_stin, &d_stout, &d_tot, &d_pre, &d_slice, &d_quarter, &d_blkagg, &d_state, &d_flags, &d_coef, &d_dc, &d_dcagg, &d_out}) b->release();
         h_files.release(); h_meta.release(); h_res.release();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (ev_done) { cudaEventDestroy(ev_done); ev_done = nullptr; }
@@ -125,12 +122,6 @@ struct bj_batch {
 namespace bj {
 
 constexpr int kMaxRounds = 64;
-// Flag words (device -> host with every decode): [0, kMaxRounds) CTAs that changed per cross-CTA round of k_huff_sync;
-// [kMaxRounds] TMA failures of k_idct_color_tma; [kTailCnt0 + r] length of the list that fix-up round r of
-// k_huff_sync_tail works on (r = 0: written by k_huff_sync), r <= kMaxTail.
-constexpr int kMaxTail = 48;
-constexpr int kTailCnt0 = kMaxRounds + 4;
-constexpr int kFlagWords = kTailCnt0 + kMaxTail + 4;
 
 // (Re)fill a batch object from a list of files: parse the headers, lay out, (stage).  Host work only (plus buffer growth).
 //   out_cap   the batch takes images from the front of the list until their decoded bytes pass this (at least one):
@@ -258,7 +249,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     size_t fbytes = 0, clean_words = 0, out_bytes = 0, coef_units = 0;
     uint32_t seg_entries = 0, nblk = 0, n_utile = 0, n_wblk = 0, n_dcc = 0, n_tiles = 0;
     int prev = -1;                                  // last valid image: its table slots are reused when the tables match
-    b->pixels = 0; b->scan_bytes_max = 0; b->ref_blocks_max = 0; b->nseg_max = 0; b->lut_smem = 0; b->multi_blk = false; b->phased = c->sync_phased != 0; b->tail = false;
+    b->pixels = 0; b->scan_bytes_max = 0; b->ref_blocks_max = 0; b->nseg_max = 0; b->lut_smem = 0; b->multi_blk = false; b->phased = c->sync_phased != 0;
     uint32_t rgb_max = 0;
     auto same_tables = [](const bj_image_desc &a, const bj_image_desc &q) {
         if (a.ncomp != q.ncomp || memcmp(a.dc_id, q.dc_id, 3) || memcmp(a.ac_id, q.ac_id, 3)) return false;
@@ -389,10 +380,6 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     b->n_wblk = n_wblk; b->n_slice_slots = slice_slots;
     b->n_idct_tiles = n_tiles; b->n_blk = nblk; b->n_utile = n_utile;
     b->n_dcc = n_dcc; b->n_seg_entries = seg_entries; b->n_sub_slots = nblk * kHuffThreads;
-    // Tail mode of the synchronisation pass (kernels_huff.cuh: k_huff_sync_tail): pays when the pass runs in several waves
-    // of CTAs (the sparse iterations of a CTA then hold up the waves behind it); a small batch converges faster inside
-    // its CTAs than through extra launches.  Option "sync_tail": 0 never, 1 (default) by batch size, 2 always.
-    b->tail = b->phased && !c->debug_sync_iters && (c->sync_tail == 2 || (c->sync_tail == 1 && nblk >= (uint32_t)c->sm_count * 10u));
 
     // ---- descriptor blob (host -> device): one record per image, the table pools
     size_t o = 0;
@@ -412,7 +399,7 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
     b->m_dcc = o;   o = align_up(o + (size_t)n_dcc * 4, 256);
     b->maps_bytes = o;
     if (b->h_meta.reserve(b->meta_bytes) || (!b->direct_src && b->h_files.reserve(b->files_bytes)) ||
-        b->h_res.reserve(align_up((size_t)n * sizeof(HuffImgState), 64) + kFlagWords * 4 + 64)) return BJ_ERR_NOMEM;
+        b->h_res.reserve(align_up((size_t)n * sizeof(HuffImgState), 64) + kMaxRounds * 4 + 16 + 64)) return BJ_ERR_NOMEM;
     if (n) { memcpy(b->hmeta<HuffImg>(b->o_himg), himg.data(), (size_t)n * sizeof(HuffImg)); memcpy(b->hmeta<ImgDev>(b->o_idev), idev.data(), (size_t)n * sizeof(ImgDev)); }
     if (!qtabs.empty()) memcpy(b->hmeta<QTab>(b->o_qtab), qtabs.data(), qtabs.size() * sizeof(QTab));
     if (!luts_dc.empty()) memcpy(b->hmeta<uint32_t>(b->o_lutdc), luts_dc.data(), luts_dc.size() * 4);
@@ -438,9 +425,8 @@ inline int batch_assign(bj_batch *b, bj_ctx *c, const uint8_t *const *files, con
         b->d_slice.reserve(b->n_slice_slots * 16 + 16) || (b->phased && b->d_quarter.reserve((size_t)b->n_sub_slots * 8 * 16 + 16)) ||
         b->d_dc.reserve(coef_units * 2 + 64) || b->d_dcagg.reserve((size_t)b->n_dcc * sizeof(DcAgg) + 16) ||
         b->d_blkagg.reserve((size_t)nblk * sizeof(BlkAgg) + 16) ||
-        b->d_state.reserve((size_t)n * sizeof(HuffImgState) + 16) || b->d_flags.reserve(kFlagWords * 4) ||
-        b->d_coef.reserve(coef_units * 128 + 16) || b->d_out.reserve(out_bytes + 64) ||
-        (b->tail && b->d_tail.reserve((size_t)b->n_sub_slots * 8 + 64))) return BJ_ERR_NOMEM;
+        b->d_state.reserve((size_t)n * sizeof(HuffImgState) + 16) || b->d_flags.reserve(kMaxRounds * 4 + 16) ||
+        b->d_coef.reserve(coef_units * 128 + 16) || b->d_out.reserve(out_bytes + 64)) return BJ_ERR_NOMEM;
     // the coefficient buffer as a tensor of 128-byte rows for the TMA variant of the K2/K3 kernel
     b->use_tma = false;
     if (c->idct_tma && c->encode_tiled && format != BJ_OUT_REF_MCUS && coef_units > 0) {
@@ -502,7 +488,7 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
             cudaMemsetAsync(b->d_out.p, 0xA5, b->out_bytes, s);
             cudaMemsetAsync(b->d_clean.p, 0xA5, b->clean_words * 4, s);
         }
-        cudaMemsetAsync(flags, 0, kFlagWords * 4, s);
+        cudaMemsetAsync(flags, 0, kMaxRounds * 4 + 16, s);
         cudaMemsetAsync(st, 0, (size_t)n * sizeof(HuffImgState), s);                  // (rejected files keep an all-zero state)
         b->launches = 0;
         if (b->n_utile) {
@@ -521,32 +507,14 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
         k_reset_state<<<(n + 255) / 256, 256, 0, s>>>(st, n);
         b->launches++;
     }
-    if (b->n_blk && b->tail) {
-        // round 0 of k_huff_sync stops after two iterations and lists what is unsettled; fix-up rounds [r0, r1) work the
-        // lists off (a round whose list is empty returns at once); then the prefix sums and the slice table
-        uint32_t *lists[2] = {(uint32_t *)b->d_tail.p, (uint32_t *)b->d_tail.p + b->n_sub_slots};
-        uint32_t *cnt = flags + kTailCnt0;
-        if (r0 == 0) {
-            k_huff_sync<true, true><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, (uint4 *)b->d_quarter.p, agg, flags, 0, (uint32_t)c->sync_preroll_bits, 0u, lists[0], cnt);
-            b->launches++; b->sync_rounds++;
-        }
-        const unsigned tgrid = (unsigned)std::min<uint64_t>((uint64_t)c->sm_count * 12u, ((uint64_t)b->n_sub_slots + kTailThreads - 1) / kTailThreads);
-        for (int r = r0; r < r1; r++) {
-            k_huff_sync_tail<<<tgrid, kTailThreads, 0, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, (uint4 *)b->d_quarter.p, lists[r & 1], cnt + r, lists[(r + 1) & 1], cnt + r + 1);
-            b->launches++; b->sync_rounds++;
-        }
-        k_huff_sync_final<<<b->n_blk, kHuffThreads, 0, s>>>(himg, st, blk_img, seg_off, seg_sub0, sub_seg, st_in, tot, pre, slices, (const uint4 *)b->d_quarter.p, agg);
-        b->launches++;
-    } else if (b->n_blk) {
+    if (b->n_blk) {
         for (int r = r0; r < r1; r++) {
             if (b->phased)
-                k_huff_sync<true, false><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, (uint4 *)b->d_quarter.p, agg, flags, r, (uint32_t)c->sync_preroll_bits, (uint32_t)c->debug_sync_iters, nullptr, nullptr);
+                k_huff_sync<true><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, (uint4 *)b->d_quarter.p, agg, flags, r, (uint32_t)c->sync_preroll_bits, (uint32_t)c->debug_sync_iters);
             else
-                k_huff_sync<false, false><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, nullptr, agg, flags, r, (uint32_t)c->sync_preroll_bits, (uint32_t)c->debug_sync_iters, nullptr, nullptr);
+                k_huff_sync<false><<<b->n_blk, kHuffThreads, lut_smem, s>>>(himg, st, blk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_acs, st_in, st_out, tot, pre, slices, nullptr, agg, flags, r, (uint32_t)c->sync_preroll_bits, (uint32_t)c->debug_sync_iters);
             b->launches++; b->sync_rounds++;
         }
-    }
-    if (b->n_blk) {
         cudaEventRecord(b->ev[2], s);
         k_huff_write<<<b->n_wblk, kHuffThreads, kSmemHuffStage + lut_smem, s>>>(himg, st, wblk_img, clean, seg_off, seg_sub0, sub_seg, luts_dc, luts_ac, slices, pre, agg, (int16_t *)b->d_coef.p, dcp);
         b->launches++;
@@ -579,7 +547,7 @@ inline int batch_launch(bj_batch *b, cudaStream_t s, int r0, int r1) {
     }
     cudaEventRecord(b->ev[4], s);
     cudaMemcpyAsync(b->h_state(), st, (size_t)n * sizeof(HuffImgState), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(b->h_flags(), flags, kFlagWords * 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(b->h_flags(), flags, kMaxRounds * 4 + 16, cudaMemcpyDeviceToHost, s);
     return c->check(cudaGetLastError());
 }
 
@@ -594,7 +562,6 @@ inline int batch_decode(bj_batch *b, cudaStream_t s) {
     // image has more than one CTA: then round 0 is all there is to do (every CTA starts at an image head)
     b->rounds = c->sync_rounds > 0 ? (c->sync_rounds < 2 ? 2 : c->sync_rounds) : 3;
     if (!b->multi_blk) b->rounds = 1;
-    if (b->tail) b->rounds = c->sync_tail_rounds;                  // fix-up rounds of k_huff_sync_tail
     return batch_launch(b, s, 0, b->rounds);
 }
 
@@ -608,10 +575,9 @@ inline int batch_sync(bj_batch *b) {
     int rc = c->check(cudaStreamSynchronize(s));
     int r = b->rounds;
     b->redone = false;
-    // (tail mode: the list the last fix-up round left for the next one must be empty)
-    while (rc == BJ_OK && b->n_blk && (b->tail ? b->h_flags()[kTailCnt0 + r] != 0 : (b->multi_blk && b->h_flags()[r - 1] != 0))) {
+    while (rc == BJ_OK && b->n_blk && b->multi_blk && b->h_flags()[r - 1] != 0) {
         b->redone = true;
-        if (r + 2 > (b->tail ? kMaxTail : kMaxRounds)) { c->last_error = "entropy stage did not converge"; return BJ_ERR_CUDA; }
+        if (r + 2 > kMaxRounds) { c->last_error = "entropy stage did not converge"; return BJ_ERR_CUDA; }
         rc = batch_launch(b, s, r, r + 2);
         if (rc == BJ_OK) rc = c->check(cudaStreamSynchronize(s));
         r += 2;

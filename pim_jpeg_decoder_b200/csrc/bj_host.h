@@ -148,8 +148,6 @@ struct bj_ctx {
     int device = 0;
     int sm_count = 0;
     int subseq_bits = 0;                 // sub-sequence length of the synchronisation pass; 0 = automatic (per image)
-    int sync_tail = 1;                   // synchronisation pass: batch-wide work list for what two in-CTA iterations leave unsettled (0 never, 1 by batch size, 2 always)
-    int sync_tail_rounds = 5;            // ... fix-up rounds launched up front (more follow if the last one still changed something)
     int sync_phased = 1;                 // synchronisation pass: re-decodes stop where they meet the previous decode (kernels_huff.cuh)
     int slices = 0;                      // slices (write pass) per sub-sequence: 1, 2, 4, 8; 0 = default (1)
     size_t sub_batch_bytes = 0;          // 0 = default

@@ -194,21 +194,16 @@ uint32_t lut_second(uint32_t tab, uint32_t e, uint32_t win
     return m.ld(tab + (e & 0xFFFFu) + (((win << kRootBits) >> (32u - ((e >> 16) & 15u))) << 2));
 }
 
-BJ_HD uint32_t lut_second_of(const LutMem &m, uint32_t tab, uint32_t e, uint32_t win) {
-#ifdef __CUDA_ARCH__
-    (void)m;
-    return lut_second(tab, e, win);
-#else
-    return lut_second(tab, e, win, m);
-#endif
-}
-
-// win = the next 32 bits of the stream, MSB first; tab = position of the table.  LM: where the tables live - LutMem, or
-// (kernels_huff.cuh) LutGlobal for the sparse fix-up kernel, whose threads work on different images.
-template <class LM>
-BJ_HD uint32_t lut_lookup(const LM &m, uint32_t tab, uint32_t win) {
+// win = the next 32 bits of the stream, MSB first; tab = position of the table.
+BJ_HD uint32_t lut_lookup(const LutMem &m, uint32_t tab, uint32_t win) {
     uint32_t e = m.ld(tab + ((win >> (32 - kRootBits)) << 2));
-    if (__builtin_expect((int32_t)e < 0, 0)) e = lut_second_of(m, tab, e, win);
+    if (__builtin_expect((int32_t)e < 0, 0)) {
+#ifdef __CUDA_ARCH__
+        e = lut_second(tab, e, win);
+#else
+        e = lut_second(tab, e, win, m);
+#endif
+    }
     return e;
 }
 
@@ -428,22 +423,6 @@ struct UnitWalk {
 #endif
 };
 BJ_HD constexpr uint32_t unit_walk_step(uint32_t c, uint32_t c1) { return 0x100u + 16u * (c1 - c); }
-// The same walk without the staged per-unit table (selects on the geometry): for code whose threads work on different
-// images (the sparse fix-up kernel of the synchronisation pass).
-struct UnitWalkSel {
-    uint32_t c, n;
-    BJ_HD void start(uint32_t c0) { c = c0; n = 0; }
-    BJ_HD uint32_t unit() const { return c; }
-    BJ_HD uint32_t ended() const { return n; }
-    BJ_HD void advance(const HuffGeom &g, bool fin, uint32_t &tab, uint32_t &ac) {
-        const uint32_t c1 = (c + 1u == g.bpm) ? 0u : c + 1u;
-        const uint32_t dcn = dc_of(g, c1), acn = ac_of(g, c1);
-        c = fin ? c1 : c;
-        n += fin ? 1u : 0u;
-        ac = fin ? acn : ac;
-        tab = fin ? dcn : ac;
-    }
-};
 
 // Magnitude extension of the `size` bits that follow a `len`-bit code in the window
 // (src/jpeg_scanner.cpp:480-482 / :513-516: first bit 0 => negative).  size 0 gives 0.
@@ -474,11 +453,11 @@ BJ_HD int32_t extend_entry(uint32_t win, uint32_t e) {
 // Every slice of the sub-sequence is reported exactly once per call, in order.  The AC tables are the grouped ones
 // (build_lut_sync), so a "step" may be several symbols; they never span a unit boundary, so the units counted
 // between two reported states are exactly the units whose DC symbol starts between them.
-template <class Rec, class LM = LutMem, class UW = UnitWalk>
-BJ_HD HuffState decode_span(const uint32_t *words, const LM &luts, const HuffGeom &g, HuffState st, uint32_t start_bit,
+template <class Rec>
+BJ_HD HuffState decode_span(const uint32_t *words, const LutMem &luts, const HuffGeom &g, HuffState st, uint32_t start_bit,
                             uint32_t end_bit, uint32_t slice_bits, Rec &rec, uint32_t *units_started) {
     const uint32_t origin = st.p & ~31u;
-    UW u;
+    UnitWalk u;
     u.start(st.cz >> 8);
     uint32_t S = ((st.p - origin) << 8) | (st.cz & 0xFFu);
     const uint32_t endS = end_bit > origin ? (end_bit - origin) << 8 : 0u;

@@ -503,63 +503,6 @@ struct SliceStore {
 struct NoRec {
     __device__ __forceinline__ void operator()(uint32_t, uint32_t, uint32_t, uint32_t) const {}
 };
-// End of the synchronisation pass for one CTA of 256 sub-sequences: segmented exclusive scan over the CTA of the units
-// started (restarting at segment heads) -> sub_pre, the CTA's aggregate -> blk_agg, and the entry states of the write
-// pass' slices (slot 0: the sub-sequence's own entry state; with quarter records, slice k starts where quarter
-// k * step - 1 ended).  Called by all threads of the CTA.
-__device__ __forceinline__ void sync_epilogue(const HuffImg &im, const SubInfo &u, const bool active, const uint32_t j, const uint32_t gj,
-                                              const uint2 in, const uint32_t tot, uint2 *__restrict__ sub_pre, uint4 *__restrict__ slices,
-                                              const uint4 *__restrict__ quarters, BlkAgg *__restrict__ blk_agg, uint32_t *s_w, uint32_t *s_wf,
-                                              const bool from_quarters) {
-    const int tid = threadIdx.x;
-    const uint32_t slices_log2 = im.slices_log2;
-    uint32_t v0 = 0, f = 0;
-    if (active) { v0 = tot; f = u.head ? 1u : 0u; }
-    const uint32_t own0 = v0;
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, v0, d);
-        const uint32_t tf = __shfl_up_sync(0xFFFFFFFFu, f, d);
-        if (lane >= d) { if (!f) v0 += t0; f |= tf; }
-    }
-    if (lane == 31) { s_w[warp] = v0; s_wf[warp] = f; }
-    __syncthreads();
-    if (tid == 0) {                                                        // 8 warp totals: serial segmented scan
-        uint32_t c0 = 0, cf = 0;
-        for (int w = 0; w < kHuffThreads / 32; w++) {
-            const uint32_t a0 = s_w[w], af = s_wf[w];
-            s_w[w] = c0; s_wf[w] = cf;                                     // carry INTO warp w
-            if (af) { c0 = a0; cf = 1; } else c0 += a0;
-        }
-        BlkAgg a;
-        a.n = c0; a.has_head = cf;
-        blk_agg[blockIdx.x] = a;
-    }
-    __syncthreads();
-    if (active) {
-        uint32_t hf = f;
-        if (!f) { v0 += s_w[warp]; hf = s_wf[warp]; }
-        // exclusive: a head starts from zero; otherwise inclusive minus own
-        uint4 *img_slices = slices + im.slice_base;
-        img_slices[(size_t)j << slices_log2] = make_uint4(in.x, in.y, 0u, 0u);
-        if (from_quarters && slices_log2) {                                // slice k starts where quarter k * step - 1 ended
-            const uint32_t ql2 = slices_log2 > 2u ? slices_log2 : 2u;
-            const uint32_t slice_bits = (im.sub_bytes >> slices_log2) * 8u;
-            const uint32_t step = 1u << (ql2 - slices_log2);
-            const uint4 *qr = quarters + ((size_t)gj << 3);
-            const uint32_t nsl = u.end_bit > u.start_bit ? (u.end_bit - u.start_bit + slice_bits - 1u) / slice_bits : 1u;
-            uint32_t cnt = 0;
-            for (uint32_t k = 1; k < nsl; k++) {
-                uint4 e = qr[0];
-                for (uint32_t q = (k - 1u) * step; q < k * step; q++) { e = qr[q]; cnt += e.z; }
-                img_slices[((size_t)j << slices_log2) + k] = make_uint4(e.x, e.y, cnt, 0u);
-            }
-        }
-        sub_pre[gj] = u.head ? make_uint2(0u, 1u) : make_uint2(v0 - own0, hf);   // .y: a head precedes inside this CTA
-    }
-}
-
 // PHASED: from the second decode of a sub-sequence on, a decode stops as soon as it meets the trajectory of the
 // previous one.  Every decode runs quarter by quarter (eighth by eighth for images with 8 slices) and keeps, per
 // quarter, the state at its end and the units started in it (`quarters`, 8 entries per sub-sequence); a re-decode whose
@@ -567,7 +510,7 @@ __device__ __forceinline__ void sync_epilogue(const HuffImg &im, const SubInfo &
 // later quarters' counts are those of the previous decode.  Between quarters the sub-sequences still running are
 // compacted onto the first threads, like between the iterations.  The write pass' slice table is filled from the
 // quarter records at the end (a slice always starts at a quarter boundary).
-template <bool PHASED, bool TAIL>
+template <bool PHASED>
 // CTAs per SM the synchronisation pass is compiled for.  Every thread walks its own 128-byte lines of the stream, so
 // the L1 has to hold about one line per resident thread or the lines are evicted before their 32 words are used:
 // 5 CTAs with the shared-memory carve-out limited to 164 KB (92 KB of L1, batch.h) beat 6 CTAs with 56 KB of L1 by
@@ -581,12 +524,7 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
             const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
             uint2 *__restrict__ st_in, uint2 *__restrict__ st_out, uint32_t *__restrict__ sub_tot, uint2 *__restrict__ sub_pre,
             uint4 *__restrict__ slices, uint4 *__restrict__ quarters, BlkAgg *__restrict__ blk_agg, uint32_t *__restrict__ flags, int round,
-            uint32_t preroll_bits, uint32_t debug_max_iters, uint32_t *__restrict__ tail_list, uint32_t *__restrict__ tail_cnt) {
-    // TAIL ("tail mode", round 0 only): the CTA stops after its second iteration and hands what is still
-    // unsettled - the sub-sequences whose entry state changed in that iteration's hand-over, and its own first
-    // sub-sequence, whose predecessor lives in another CTA - to the batch-wide list of k_huff_sync_tail; the prefix sums
-    // and the slice table are then made by k_huff_sync_final, once everything has settled.
-    constexpr bool tail_mode = TAIL;
+            uint32_t preroll_bits, uint32_t debug_max_iters) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint2 s_in[kHuffThreads], s_out[kHuffThreads];
@@ -666,7 +604,6 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
         const uint32_t nw = s_nwork[cur];
         if (nw == 0) break;
         if (debug_max_iters && iter >= debug_max_iters) break;                // (measurement only: the result is not the fixed point)
-        if (tail_mode && iter >= 2u) break;                                   // the rest goes to the batch-wide list (below)
         if (!PHASED) {
             for (uint32_t w = tid; w < nw; w += kHuffThreads) {
                 const uint32_t item = s_work[cur][w];
@@ -722,157 +659,60 @@ k_huff_sync(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ i
         if (active && tid > 0 && !u.head) {
             const uint2 prev = s_out[tid - 1], mine = s_in[tid];
             if (prev.x != mine.x || prev.y != mine.y) {
-                // (tail mode, last iteration here: the entry state stays the one this sub-sequence was decoded from - the
-                // tail kernel compares it with the predecessor's exit state and takes over)
-                if (!(tail_mode && iter >= 1u)) s_in[tid] = prev;
+                s_in[tid] = prev;
                 s_work[cur ^ 1][atomicAdd(&s_nwork[cur ^ 1], 1u)] = (uint16_t)tid;
             }
         }
         cur ^= 1;
     }
 
-    if (tail_mode) {
-        // what is left: s_work[cur][0 .. s_nwork[cur]) and, unless it is a segment head, the CTA's first sub-sequence
-        __shared__ uint32_t s_tail_base;
-        const uint32_t npend = debug_max_iters ? 0u : s_nwork[cur];
-        const uint32_t first = (active && tid == 0 && !u.head && j > 0) ? 1u : 0u;
-        if (tid == 0) s_tail_base = (npend + first) ? atomicAdd(tail_cnt, npend + first) : 0u;
-        __syncthreads();
-        const uint32_t tb = s_tail_base;
-        for (uint32_t w = tid; w < npend; w += kHuffThreads) tail_list[tb + w] = gj - tid + s_work[cur][w];
-        if (first) tail_list[tb + npend] = gj;
-        if (active) { st_in[gj] = s_in[tid]; st_out[gj] = s_out[tid]; sub_tot[gj] = s_tot[tid]; }
-        return;
-    }
-
-    if (active) { st_in[gj] = s_in[tid]; st_out[gj] = s_out[tid]; sub_tot[gj] = s_tot[tid]; }
-    sync_epilogue(im, u, active, j, gj, active ? s_in[tid] : make_uint2(0u, 0u), active ? s_tot[tid] : 0u, sub_pre, slices, quarters, blk_agg, s_w, s_wf, PHASED);
-    if (round > 0 && tid == 0) atomicAdd(&flags[round], 1u);
-}
-
-// ------------------------------------------------------------------------------------------------ K1b: sparse fix-up
-// The tail of the synchronisation pass as a batch-wide work list (tail mode of k_huff_sync).  After two iterations
-// inside the CTAs about one sub-sequence in seven of a 4:2:0 stream still has to be decoded again (its predecessor had
-// not synchronised by its own end), then one in fifty, ... - inside k_huff_sync these few keep whole CTAs resident,
-// one sparse warp each, for three to five more decode latencies (the iterations from the third on took 0.44 ms of the
-// pass' 1.5 ms on config 2, for 6 % of its decode work).  Here they are dense: one thread = one listed sub-sequence,
-// whatever image it belongs to, so a round of the whole batch is one wave of full warps.
-//   item gj: if the predecessor's exit state st_out[gj - 1] differs from the entry state st_in[gj] this sub-sequence
-//   was last decoded from, decode it again from there, quarter by quarter against the recorded trajectory (the same
-//   early stop as in k_huff_sync); if the decode reaches the end and the exit state changes, the successor goes on the
-//   next round's list.  Rounds are separate launches (lists ping-pong); a round with an empty list does nothing.
-// Two listed neighbours in one round may race (gj reads st_out[gj - 1] while it is rewritten): whichever value gj reads,
-// it records it as its entry state, and the writer lists gj again for the next round - the fixed point is the same.
-// Tables are read from global memory (the threads of a warp work on different images): LutGlobal.
-struct LutGlobal {
-    const uint8_t *base;                                                  // table positions are byte offsets from here
-    __device__ __forceinline__ uint32_t ld(uint32_t off) const { return __ldg(reinterpret_cast<const uint32_t *>(base + off)); }
-};
-__device__ __noinline__ uint32_t lut_second_global(const uint8_t *base, uint32_t tab, uint32_t e, uint32_t win) {
-    return __ldg(reinterpret_cast<const uint32_t *>(base + tab + (e & 0xFFFFu) + (((win << kRootBits) >> (32u - ((e >> 16) & 15u))) << 2)));
-}
-__device__ __forceinline__ uint32_t lut_second_of(const LutGlobal &m, uint32_t tab, uint32_t e, uint32_t win) { return lut_second_global(m.base, tab, e, win); }
-
-constexpr int kTailThreads = 128;
-__global__ void __launch_bounds__(kTailThreads)
-k_huff_sync_tail(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
-                 const uint32_t *__restrict__ clean, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0,
-                 const uint32_t *__restrict__ sub_seg, const uint32_t *__restrict__ lut_dc_pool, const uint32_t *__restrict__ lut_ac_pool,
-                 uint2 *st_in, uint2 *st_out, uint32_t *sub_tot, uint4 *quarters, const uint32_t *__restrict__ list_in,
-                 const uint32_t *__restrict__ cnt_in, uint32_t *__restrict__ list_out, uint32_t *__restrict__ cnt_out) {
-    const uint32_t n = *cnt_in;
-    if (n == 0) return;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t stride = gridDim.x * kTailThreads;
-    LutGlobal luts;
-    luts.base = reinterpret_cast<const uint8_t *>(lut_dc_pool);
-    const uint32_t ac_base = (uint32_t)(reinterpret_cast<const uint8_t *>(lut_ac_pool) - reinterpret_cast<const uint8_t *>(lut_dc_pool));
-    for (uint32_t i0 = (blockIdx.x * kTailThreads + threadIdx.x) & ~31u; i0 < n; i0 += stride) {   // (uniform over the warp)
-        const uint32_t i = i0 + lane;
-        bool want = false;                                                  // list the successor for the next round
-        uint32_t gj = 0;
-        if (i < n) {
-            gj = list_in[i];
-            const uint32_t img = blk_img[gj / kHuffThreads];
-            const HuffImg &im = imgs[img];
-            const uint32_t nsub = ist[img].nsub, nseg = ist[img].nseg;
-            const uint32_t j = gj - im.sub_base;
-            if (j > 0 && j < nsub) {
-                HuffImgState is;
-                is.nsub = nsub; is.nseg = nseg;
-                const SubInfo u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg);
-                const uint2 prev = st_out[gj - 1], mine = st_in[gj];
-                if (!u.head && (prev.x != mine.x || prev.y != mine.y)) {
-                    st_in[gj] = prev;
-                    HuffGeom g;
-                    g.bpm = im.bpm; g.ny = im.ny; g.unit_tab = 0;
+    // segmented exclusive scan over the CTA of the units started, restarting at segment heads
+    uint32_t v0 = 0, f = 0;
+    if (active) { v0 = s_tot[tid]; f = u.head ? 1u : 0u; }
+    const uint32_t own0 = v0;
+    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        g.dc[k] = (uint32_t)im.dc_lut[im.dc_slot[k]] * (uint32_t)(kLutCapDC * 4);
-                        g.ac[k] = ac_base + (uint32_t)im.ac_lut[im.ac_slot[k]] * (uint32_t)(kLutCapAC * 4);
-                    }
-                    const uint32_t *__restrict__ words = clean + im.clean_word0;
-                    const uint32_t ql2 = im.slices_log2 > 2u ? im.slices_log2 : 2u;
-                    const uint32_t qbits = (im.sub_bytes >> ql2) * 8u;
-                    uint4 *qr = quarters + ((size_t)gj << 3);
-                    uint32_t tot = sub_tot[gj];
-                    HuffState e;
-                    e.p = prev.x; e.cz = prev.y;
-                    for (uint32_t q = 0; q < (1u << ql2); q++) {
-                        const uint32_t qs = u.start_bit + q * qbits, qe = min(qs + qbits, u.end_bit);
-                        uint32_t cnt;
-                        NoRec rec;
-                        const HuffState o = decode_span<NoRec, LutGlobal, UnitWalkSel>(words, luts, g, e, qs, qe, qbits, rec, &cnt);
-                        const uint4 old = qr[q];
-                        qr[q] = make_uint4(o.p, o.cz, cnt, 0u);
-                        tot += cnt - old.z;
-                        if (qe >= u.end_bit) {                              // the last quarter: the exit state
-                            const uint2 was = st_out[gj];
-                            if (was.x != o.p || was.y != o.cz) { st_out[gj] = make_uint2(o.p, o.cz); want = j + 1u < nsub; }
-                            break;
-                        }
-                        if (old.x == o.p && old.y == o.cz) break;           // back on the recorded trajectory
-                        e = o;
-                    }
-                    sub_tot[gj] = tot;
-                }
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, v0, d);
+        const uint32_t tf = __shfl_up_sync(0xFFFFFFFFu, f, d);
+        if (lane >= d) { if (!f) v0 += t0; f |= tf; }
+    }
+    if (lane == 31) { s_w[warp] = v0; s_wf[warp] = f; }
+    __syncthreads();
+    if (tid == 0) {                                                        // 8 warp totals: serial segmented scan
+        uint32_t c0 = 0, cf = 0;
+        for (int w = 0; w < kHuffThreads / 32; w++) {
+            const uint32_t a0 = s_w[w], af = s_wf[w];
+            s_w[w] = c0; s_wf[w] = cf;                                     // carry INTO warp w
+            if (af) { c0 = a0; cf = 1; } else c0 += a0;
+        }
+        BlkAgg a;
+        a.n = c0; a.has_head = cf;
+        blk_agg[blockIdx.x] = a;
+    }
+    __syncthreads();
+    if (active) {
+        uint32_t hf = f;
+        if (!f) { v0 += s_w[warp]; hf = s_wf[warp]; }
+        // exclusive: a head starts from zero; otherwise inclusive minus own
+        st_in[gj] = s_in[tid];
+        img_slices[(size_t)j << slices_log2] = make_uint4(s_in[tid].x, s_in[tid].y, 0u, 0u);
+        if (PHASED && slices_log2) {                                       // slice k starts where quarter k * step - 1 ended
+            const uint32_t step = 1u << (ql2 - slices_log2);
+            const uint4 *qr = img_quarters + ((size_t)j << 3);
+            const uint32_t nsl = u.end_bit > u.start_bit ? (u.end_bit - u.start_bit + slice_bits - 1u) / slice_bits : 1u;
+            uint32_t cnt = 0;
+            for (uint32_t k = 1; k < nsl; k++) {
+                uint4 e = qr[0];
+                for (uint32_t q = (k - 1u) * step; q < k * step; q++) { e = qr[q]; cnt += e.z; }
+                img_slices[((size_t)j << slices_log2) + k] = make_uint4(e.x, e.y, cnt, 0u);
             }
         }
-        __syncwarp();
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(cnt_out, (uint32_t)__popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (want) list_out[base + __popc(m & ((1u << lane) - 1u))] = gj + 1u;
-        }
+        st_out[gj] = s_out[tid];
+        sub_tot[gj] = s_tot[tid];
+        sub_pre[gj] = u.head ? make_uint2(0u, 1u) : make_uint2(v0 - own0, hf);   // .y: a head precedes inside this CTA
     }
-}
-
-// After the last fix-up round: per CTA of the synchronisation pass the segmented prefix sums of the units started, the
-// CTA's aggregate and the write pass' slice table - what k_huff_sync does itself at its end when it is not in tail mode.
-__global__ void __launch_bounds__(kHuffThreads)
-k_huff_sync_final(const HuffImg *__restrict__ imgs, const HuffImgState *__restrict__ ist, const uint32_t *__restrict__ blk_img,
-                  const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_sub0, const uint32_t *__restrict__ sub_seg,
-                  const uint2 *__restrict__ st_in, const uint32_t *__restrict__ sub_tot, uint2 *__restrict__ sub_pre, uint4 *__restrict__ slices,
-                  const uint4 *__restrict__ quarters, BlkAgg *__restrict__ blk_agg) {
-    __shared__ uint32_t s_w[kHuffThreads / 32 + 1];
-    __shared__ uint32_t s_wf[kHuffThreads / 32 + 1];
-    const uint32_t img = blk_img[blockIdx.x];
-    const HuffImg &im = imgs[img];
-    const HuffImgState is = ist[img];
-    const int tid = threadIdx.x;
-    const uint32_t j = (blockIdx.x - im.blk_base) * kHuffThreads + tid;
-    const uint32_t gj = im.sub_base + j;
-    if ((blockIdx.x - im.blk_base) * kHuffThreads >= is.nsub) return;
-    const bool active = j < is.nsub;
-    SubInfo u;
-    u.head = false; u.end_bit = 0; u.start_bit = 0;
-    uint32_t tot = 0;
-    uint2 in = make_uint2(0u, 0u);
-    if (active) { u = sub_info(im, is, j, seg_off, seg_sub0, sub_seg); tot = sub_tot[gj]; in = st_in[gj]; }
-    sync_epilogue(im, u, active, j, gj, in, tot, sub_pre, slices, quarters, blk_agg, s_w, s_wf, true);
+    if (round > 0 && tid == 0) atomicAdd(&flags[round], 1u);
 }
 
 // ------------------------------------------------------------------------------------------------ K1a: write

@@ -138,60 +138,6 @@ def test_stage_entropy_unphased_synchronisation(dec, bits, slices, rounds, golde
         dec.set_option("sync_rounds", 0)
 
 
-@pytest.mark.parametrize("bits,slices,tail_rounds", [(0, 0, 5), (128, 0, 1), (256, 2, 2), (1024, 4, 1), (512, 8, 3), (160, 0, 1), (0, 8, 1), (64, 0, 1)])
-def test_stage_entropy_tail_mode(dec, bits, slices, tail_rounds, golden, golden_dir):
-    """Option "sync_tail" = 2: the synchronisation kernel stops after two iterations inside its CTAs and hands what is
-    unsettled to the batch-wide list of k_huff_sync_tail; k_huff_sync_final makes the prefix sums and the slice table.
-    With too few fix-up rounds launched up front the host's convergence check must add rounds.  Same coefficients."""
-    dec.set_option("sync_tail", 2)
-    dec.set_option("sync_tail_rounds", tail_rounds)
-    dec.set_option("subseq_bits", bits)
-    dec.set_option("slices", slices)
-    try:
-        for name in _names():
-            data = _load(golden, golden_dir, name)
-            coef, status = dec.stage_entropy(data)
-            assert status == 0
-            assert np.array_equal(coef, ol.Restated(data, 0).coef_zz), (name, bits, slices)
-    finally:
-        dec.set_option("sync_tail", 1)
-        dec.set_option("sync_tail_rounds", 5)
-        dec.set_option("subseq_bits", 0)
-        dec.set_option("slices", 0)
-
-
-@pytest.mark.parametrize("tail_rounds", [1, 5])
-def test_full_path_tail_mode(dec, tail_rounds, golden, golden_dir):
-    """A mixed batch (golden set, larger synthetic images with and without restart markers, damaged scans) decoded in
-    tail mode and without it: identical bytes and statuses, and the golden hashes."""
-    import pim_jpeg_decoder_b200 as bj
-    names = _names()
-    files = [_load(golden, golden_dir, n) for n in names]
-    files += [js.synth_jpeg(1280, 720, seed=5, subsampling=2), js.synth_jpeg(640, 480, seed=6, subsampling=0, restart_blocks=7),
-              js.synth_jpeg(1920, 1080, seed=7, subsampling=2), js.synth_jpeg(500, 375, seed=8, subsampling=2, restart_blocks=3)]
-    rng = np.random.default_rng(11)
-    for k in (len(names), len(names) + 2):                       # damaged twins: some bytes of the scan's second half changed
-        d = bytearray(files[k])
-        for pos in rng.integers(len(d) // 2, len(d) - 2, size=3):
-            d[pos] = (d[pos] ^ 0x5A) & 0xFE                      # (never 0xFF: no new marker)
-        files.append(bytes(d))
-    dec.set_option("sync_tail", 0)
-    try:
-        ref, st_ref = dec.decode(files, bj.BJ_OUT_BMP)
-        dec.set_option("sync_tail", 2)
-        dec.set_option("sync_tail_rounds", tail_rounds)
-        outs, status = dec.decode(files, bj.BJ_OUT_BMP)
-        outs2, status2 = dec.decode(files, bj.BJ_OUT_BMP)        # again on the same context: buffers and lists are reused
-    finally:
-        dec.set_option("sync_tail", 1)
-        dec.set_option("sync_tail_rounds", 5)
-    assert status == st_ref and status2 == st_ref
-    for a, b, c2 in zip(outs, ref, outs2):
-        assert np.array_equal(a, b) and np.array_equal(c2, b)
-    for n, o in zip(names, outs):
-        assert sha(o) == golden[golden[n]["expect"]]["bmp_sha256"], n
-
-
 def test_full_path_unphased_synchronisation(dec, golden, golden_dir):
     import pim_jpeg_decoder_b200 as bj
     names = _names()
