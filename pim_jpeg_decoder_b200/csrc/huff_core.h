@@ -570,32 +570,31 @@ struct WriteCursor {
     // the reference stops.  (Damaged data only; at most 63 further symbols are read before the unit ends.)
     template <class Sink>
     BJ_HD bool step(const LutMem &luts, const HuffGeom &g, Sink &sink) {
-        const uint32_t r = step_sym(luts, g, sink);
-        if (r == kSymUnit) unit_done(g);
-        return r != 0u;
+        if (!step_plain(luts, sink)) return false;
+        unit_end(luts, g, sink);
+        return true;
     }
     // The same in two halves, for a caller that lets a lane wait between the symbol that completes a unit and the
-    // hand-over to the next unit (k_huff_write takes several symbols per round and hands over once per round):
-    // 0 = the unit goes on;  kSymUnit = the unit is complete: call unit_done() before the next symbol;  kSymRedone = it
-    // was complete but had not ended well and has been decoded again, hand-over included.
-    static constexpr uint32_t kSymUnit = 1u, kSymRedone = 2u;
+    // hand-over to the next unit (k_huff_write takes several symbols per round and hands over once per round, all lanes
+    // that completed a unit together).  step_plain: one symbol, no checks; true = the unit is complete: call unit_end()
+    // before the next symbol.  unit_end: the look back over the unit (see above), then the hand-over - or the unit again.
     template <class Sink>
-    BJ_HD uint32_t step_sym(const LutMem &luts, const HuffGeom &g, Sink &sink) {
+    BJ_HD bool step_plain(const LutMem &luts, Sink &sink) {
         const uint32_t win = bs.window(S);
         const uint32_t e = lut_lookup(luts, tab, win);
-        const uint32_t Sn = S + (e & 0xFFFFu);
+        S += e & 0xFFFFu;
         bad |= e;
         const int32_t v = extend_entry(win, e);
         // index of the coefficient this symbol carries (0: the DC difference).  size 0 (ZRL, EOB, refused) stores nothing.
-        if (v != 0) sink.put(((Sn & 0xFFu) - 1u) & 63u, (int16_t)v);
-        const bool fin = (Sn & 0x40u) != 0u;              // index >= 64: the unit ends one way or another
+        if (v != 0) sink.put(((S & 0xFFu) - 1u) & 63u, (int16_t)v);
         tab = ac;
-        S = Sn;
-        if (__builtin_expect(fin && ((bad & kLutBad) || Sn > dataS || ((Sn & 0xFFu) != 64u && !(e & kLutEob))), 0)) {
-            redo_unit(luts, g, sink);
-            return kSymRedone;
-        }
-        return fin ? kSymUnit : 0u;
+        return (S & 0x40u) != 0u;                         // index >= 64: the unit ends one way or another
+    }
+    template <class Sink>
+    BJ_HD void unit_end(const LutMem &luts, const HuffGeom &g, Sink &sink) {
+        // (kLutEob in `bad` can only come from the unit's last symbol: an end-of-block always ends the unit)
+        if (__builtin_expect((bad & kLutBad) || S > dataS || ((S & 0xFFu) != 64u && !(bad & kLutEob)), 0)) redo_unit(luts, g, sink);
+        else unit_done(g);
     }
     BJ_HD void unit_done(const HuffGeom &g) {
         st_du = du++;

@@ -737,10 +737,7 @@ struct SmemUnitSink {
 constexpr int kSmemHuffStage = kHuffThreads * 128;
 
 #ifndef BJ_WRITE_STEPS
-#define BJ_WRITE_STEPS 4               // symbols a lane may take per round of the write pass (hand-over and unit stores once per round); measured on config 2: 1: 2.00 ms, 2: 2.05, 3: 1.97, 4: 1.94 (profiles/r2_write_steps_ab.txt)
-#endif
-#ifndef BJ_WRITE_FLUSH4
-#define BJ_WRITE_FLUSH4 1              // four units per flush pass (eight lanes each) instead of two: pays once several units complete per round
+#define BJ_WRITE_STEPS 4               // symbols a lane may take per round of the write pass (hand-over and unit stores once per round); measured on config 2: 1: 2.00 ms, 2: 2.05, 3: 1.97, 4: 1.94, 6: 1.92, 8: 1.94 (profiles/r2_write_steps_ab.txt)
 #endif
 #ifndef BJ_WRITE_CTAS
 #define BJ_WRITE_CTAS 4                // shared memory allows 4; telling the compiler buys 52 registers instead of 40 (-2 %)
@@ -758,6 +755,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     __shared__ int s_h;
     __shared__ __align__(256) uint4 s_units[16];
     __shared__ uint32_t s_zero;                                            // what a finished lane reads as its table (WriteCursor::idle)
+    __shared__ uint2 s_slot[kHuffThreads / 32][32];                        // per warp: the lanes that completed a unit in this round and which unit (below)
 
     const uint32_t img = wblk_img[blockIdx.x];
     const HuffImg &im = imgs[img];
@@ -832,12 +830,6 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     uint32_t warp_stage = stage_addr + (tid & ~31) * 128 + ((lane & 7) << 4);     // + this lane's chunk
     asm volatile("mov.u32 %0, %0;" : "+r"(warp_stage));
     uint4 *out_lane = out + (lane & 7);
-#if BJ_WRITE_FLUSH4
-    uint32_t flusher = 1u + (uint32_t)(lane >> 3);                         // which of the four units of a flush pass this lane moves
-#else
-    uint32_t flusher = lane < 8 ? 1u : (lane < 16 ? 2u : 0u);              // which of the two units of a flush pass this lane moves
-#endif
-    asm volatile("mov.u32 %0, %0;" : "+r"(flusher));
     asm volatile("mov.u64 %0, %0;" : "+l"(out_lane));                      // (kept in registers, like warp_stage)
     asm volatile("mov.u64 %0, %0;" : "+l"(dcp));
     // a lane with nothing to do idles like one that has finished; every lane of the warp takes every step
@@ -846,39 +838,34 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
         cur.finish();
     }
     if (!__all_sync(0xFFFFFFFFu, done)) {
+        uint2 *slot = s_slot[warp];
         for (;;) {
             // a round: up to BJ_WRITE_STEPS symbols per lane, stopping at the one that completes a unit; then the lanes
-            // that completed one hand over to their next unit together, and the warp stores those units
-            uint32_t r = cur.step_sym(luts, g, sink);
+            // that completed one look back over it and hand over to their next unit together, and the warp stores those units
+            // (bit 6 of S = "the unit is complete" stays set until unit_end has handed over)
+            cur.step_plain(luts, sink);
 #if BJ_WRITE_STEPS > 1
 #pragma unroll 1
-            for (int k = 1; k < BJ_WRITE_STEPS && r == 0u; k++) r = cur.step_sym(luts, g, sink);
+            for (int k = 1; k < BJ_WRITE_STEPS && !(cur.S & 0x40u); k++) cur.step_plain(luts, sink);
 #endif
-            if (r == WriteCursor::kSymUnit) cur.unit_done(g);
-            const bool unit = r != 0u;
-            uint32_t m = __ballot_sync(0xFFFFFFFFu, unit);
+            const bool fin = (cur.S & 0x40u) != 0u;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, fin);
             if (m == 0) continue;
-            // lanes in m completed unit st_du (or ended on a refused DC symbol: nothing to store)
-            const uint32_t du_mine = unit ? cur.st_du : 0xFFFFFFFFu;
+            // lanes in m completed unit st_du (or ended on a refused DC symbol: nothing to store, st_du = UINT32_MAX):
+            // the k-th of them says so in slot k
+            if (fin) {
+                cur.unit_end(luts, g, sink);
+                slot[__popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)lane, cur.st_du);
+            }
             __syncwarp();
-            do {
-#if BJ_WRITE_FLUSH4
-                // four units per pass: lanes 0-7, 8-15, 16-23, 24-31 (flusher = 1 + lane / 8)
-                const uint32_t m1 = m & (m - 1u), m2 = m1 & (m1 - 1u), m3 = m2 & (m2 - 1u);
-                const uint32_t mm = flusher == 1u ? m : flusher == 2u ? m1 : flusher == 3u ? m2 : m3;
-                const int l = __ffs(mm) - 1;                               // -1: no unit for this group of lanes in this pass
-                m = m3 & (m3 - 1u);
-#else
-                // two units per pass: lanes 0-7 and 8-15
-                const uint32_t m1 = m & (m - 1u);
-                const int l0 = __ffs(m) - 1, l1 = __ffs(m1) - 1;           // l1 = -1: no second unit in this pass
-                const int l = flusher == 2u ? l1 : l0;                     // (selects, no branch: the shuffle is warp-wide)
-                m = m1 & (m1 - 1u);
-#endif
-                const uint32_t du_l = __shfl_sync(0xFFFFFFFFu, du_mine, l & 31);
-                if (flusher != 0u && l >= 0) {
-                    const uint32_t x = (l & 7) << 4;
-                    const uint32_t a = (warp_stage + l * 128) ^ x;         // rows are 128-byte aligned
+            const uint32_t nun = (uint32_t)__popc(m);
+            for (uint32_t base = 0; base < nun; base += 4u) {              // four units per pass: lanes 0-7, 8-15, 16-23, 24-31
+                const uint32_t idx = base + ((uint32_t)lane >> 3);
+                if (idx < nun) {
+                    const uint2 sl = slot[idx];
+                    const uint32_t l = sl.x, du_l = sl.y;
+                    const uint32_t x = (l & 7u) << 4;
+                    const uint32_t a = (warp_stage + l * 128u) ^ x;        // rows are 128-byte aligned
                     uint4 v;
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
                     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
@@ -887,7 +874,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
                         __stcs(out_lane + (size_t)du_l * 8, v);
                     }
                 }
-            } while (m);
+            }
             __syncwarp();
             if (__all_sync(0xFFFFFFFFu, cur.done != 0u)) break;
         }
