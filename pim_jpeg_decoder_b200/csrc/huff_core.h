@@ -311,47 +311,51 @@ constexpr uint32_t kWordS = 32u << 8;
 #define BJ_STREAM_LD "ld.global.nc.u32"
 #endif
 struct BitStream {
-    const uint32_t *w;            // -> word holding the current position
+    const uint32_t *base;         // -> the word holding the span's origin
+    uint32_t wi;                  // index (from base) of the word holding the current position
     uint32_t cur, nxt, nx2;       // that word and the two after it (the load runs one word ahead of its use)
     uint32_t word_end;            // S value of the first bit after `cur`
     BJ_HD void open(const uint32_t *words, uint32_t p) {
-        w = words + (p >> 5);
+        base = words + (p >> 5);
+        wi = 0u;
 #ifdef __CUDA_ARCH__
-        cur = __ldg(w); nxt = __ldg(w + 1); nx2 = __ldg(w + 2);
+        cur = __ldg(base); nxt = __ldg(base + 1); nx2 = __ldg(base + 2);
+        asm volatile("mov.u64 %0, %0;" : "+l"(base));                       // a register pair, not an address rebuilt from the kernel's parameters in the symbol loops
 #else
-        cur = w[0]; nxt = w[1]; nx2 = w[2];
+        cur = base[0]; nxt = base[1]; nx2 = base[2];
 #endif
         word_end = kWordS;
     }
     // back to an earlier position of the same span (the write pass re-reads a unit that did not end well)
     BJ_HD void seek(uint32_t S) {
-        w -= ((word_end >> 13) - 1u) - (S >> 13);
+        wi = S >> 13;
 #ifdef __CUDA_ARCH__
-        cur = __ldg(w); nxt = __ldg(w + 1); nx2 = __ldg(w + 2);
+        cur = __ldg(base + wi); nxt = __ldg(base + wi + 1); nx2 = __ldg(base + wi + 2);
 #else
-        cur = w[0]; nxt = w[1]; nx2 = w[2];
+        cur = base[wi]; nxt = base[wi + 1]; nx2 = base[wi + 2];
 #endif
-        word_end = ((S >> 13) + 1u) << 13;
+        word_end = (wi + 1u) << 13;
     }
     // the next 32 bits at S, moving on to the next word first if S has left the current one
     BJ_HD uint32_t window(uint32_t S) {
 #ifdef __CUDA_ARCH__
         // predicated, no branch; the load writes nx2 directly (a select on the loaded value would stall on it).
-        // The pointer moves by a 0-or-1 select folded into a multiply-add: a predicated 64-bit add comes out of
-        // ptxas as an add, a carry add, two selects and two moves.
+        // The position is a 32-bit word index: its predicated increment is one instruction and the address of the word
+        // the load would fetch one multiply-add (a 64-bit pointer moved by a 0-or-1 select came out of ptxas as four
+        // instructions, a mad.wide inside the asm block likewise).
+        const uint32_t *ahead = base + wi + 3;                             // (wi + 1) + 2: what becomes nx2 when the position moves on
         asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .u32 a;\n\t"
-            "setp.ge.u32 p, %5, %4;\n\t"
-            "selp.u32 a, 1, 0, p;\n\t"
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ge.u32 p, %6, %4;\n\t"
             "@p mov.b32 %0, %1;\n\t"
             "@p mov.b32 %1, %2;\n\t"
-            "mad.wide.u32 %3, a, 4, %3;\n\t"
+            "@p add.u32 %3, %3, 1;\n\t"
             "@p add.u32 %4, %4, 8192;\n\t"
-            "@p " BJ_STREAM_LD " %2, [%3+8];\n\t}"
-            : "+r"(cur), "+r"(nxt), "+r"(nx2), "+l"(w), "+r"(word_end)
-            : "r"(S));
+            "@p " BJ_STREAM_LD " %2, [%5];\n\t}"
+            : "+r"(cur), "+r"(nxt), "+r"(nx2), "+r"(wi), "+r"(word_end)
+            : "l"(ahead), "r"(S));
 #else
-        if (S >= word_end) { cur = nxt; nxt = nx2; w++; nx2 = w[2]; word_end += kWordS; }
+        if (S >= word_end) { cur = nxt; nxt = nx2; wi++; nx2 = base[wi + 2]; word_end += kWordS; }
 #endif
         return funnel_l(cur, nxt, S >> 8);
     }
@@ -433,10 +437,18 @@ BJ_HD int32_t extend_value(uint32_t win, uint32_t len, uint32_t size) {
 }
 // The same from a table entry; all shifts are wrap-mode (mod 32), fed by plain shifts of the entry.
 BJ_HD int32_t extend_entry(uint32_t win, uint32_t e) {
+    // a = -1 if the first magnitude bit is 1 (the value is the `size` bits as they are), 0 if it is 0 (the value is minus
+    // the complemented bits):  x = top `size` bits of (a ? t : ~t),  value = a ? x : -x = (x ^ ~a) + a + 1
     const uint32_t t = funnel_l(win, 0u, e >> 16);                        // win << len
-    const uint32_t raw = funnel_l(0u, t, e >> 24);                        // top `size` bits of t
-    const uint32_t m = funnel_l(0xFFFFFFFFu, 0u, e >> 24) + 1u;           // 1 - 2^size
-    return (int32_t)(raw + (m & ~(uint32_t)((int32_t)t >> 31)));
+    const uint32_t a = (uint32_t)((int32_t)t >> 31);
+#ifdef __CUDA_ARCH__
+    uint32_t ta;
+    asm("lop3.b32 %0, %1, %2, 0, 0xC3;" : "=r"(ta) : "r"(t), "r"(a));     // t ^ ~a in one instruction
+#else
+    const uint32_t ta = t ^ ~a;
+#endif
+    const uint32_t x = funnel_l(0u, ta, e >> 24);
+    return (int32_t)((x ^ ~a) + a + 1u);
 }
 
 // ------------------------------------------------------------------------------------------------ pass 1: synchronise

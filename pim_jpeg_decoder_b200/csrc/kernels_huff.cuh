@@ -737,7 +737,7 @@ struct SmemUnitSink {
 constexpr int kSmemHuffStage = kHuffThreads * 128;
 
 #ifndef BJ_WRITE_STEPS
-#define BJ_WRITE_STEPS 4               // symbols a lane may take per round of the write pass (hand-over and unit stores once per round); measured on config 2: 1: 2.00 ms, 2: 2.05, 3: 1.97, 4: 1.94, 6: 1.92, 8: 1.94 (profiles/r2_write_steps_ab.txt)
+#define BJ_WRITE_STEPS 6               // symbols a lane may take per round of the write pass (look-back, hand-over and unit stores once per round); measured on config 2 (profiles/r2_write_round_ab.txt): 4: 1.589 ms, 6: 1.550, 8: 1.556 (one symbol per round, hand-over inside the step: 2.00)
 #endif
 #ifndef BJ_WRITE_CTAS
 #define BJ_WRITE_CTAS 4                // shared memory allows 4; telling the compiler buys 52 registers instead of 40 (-2 %)
@@ -834,7 +834,7 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
     asm volatile("mov.u64 %0, %0;" : "+l"(dcp));
     // a lane with nothing to do idles like one that has finished; every lane of the warp takes every step
     if (done) {
-        if (!active) { cur.bs.w = clean + im.clean_word0; cur.bs.nx2 = 0u; cur.bs.word_end = kWordS; cur.endS = 0u; cur.dataS = 0xFFFFFFFFu; cur.c = 0u; cur.S0 = 0u; cur.bad = 0u; }
+        if (!active) { cur.bs.base = clean + im.clean_word0; cur.bs.wi = 0u; cur.bs.nx2 = 0u; cur.bs.word_end = kWordS; cur.endS = 0u; cur.dataS = 0xFFFFFFFFu; cur.c = 0u; cur.S0 = 0u; cur.bad = 0u; }
         cur.finish();
     }
     if (!__all_sync(0xFFFFFFFFu, done)) {
