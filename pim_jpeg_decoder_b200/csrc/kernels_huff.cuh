@@ -845,7 +845,11 @@ k_huff_write(const HuffImg *__restrict__ imgs, HuffImgState *__restrict__ ist, c
             // (bit 6 of S = "the unit is complete" stays set until unit_end has handed over)
             cur.step_plain(luts, sink);
 #if BJ_WRITE_STEPS > 1
+#ifdef BJ_WRITE_ROLLED
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
             for (int k = 1; k < BJ_WRITE_STEPS && !(cur.S & 0x40u); k++) cur.step_plain(luts, sink);
 #endif
             const bool fin = (cur.S & 0x40u) != 0u;
