@@ -737,7 +737,7 @@ struct SmemUnitSink {
 constexpr int kSmemHuffStage = kHuffThreads * 128;
 
 #ifndef BJ_WRITE_STEPS
-#define BJ_WRITE_STEPS 6               // symbols a lane may take per round of the write pass (look-back, hand-over and unit stores once per round); measured on config 2 (profiles/r2_write_round_ab.txt): 4: 1.589 ms, 6: 1.550, 8: 1.556 (one symbol per round, hand-over inside the step: 2.00)
+#define BJ_WRITE_STEPS 8               // symbols a lane may take per round of the write pass (look-back, hand-over and unit stores once per round); config 2: one symbol per round with the hand-over inside the step 2.00 ms; rounds of 4 / 6 / 8 symbols 1.589 / 1.550 / 1.556 (profiles/r2_write_round_ab.txt); unrolled, with the leaner bit reader, 5 / 6 / 8: 1.513 / 1.503 / 1.493 (profiles/r2_write_unroll_ab.txt)
 #endif
 #ifndef BJ_WRITE_CTAS
 #define BJ_WRITE_CTAS 4                // shared memory allows 4; telling the compiler buys 52 registers instead of 40 (-2 %)
