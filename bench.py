@@ -36,15 +36,37 @@ MIX = [((500, 375), 0.40), ((375, 500), 0.15), ((640, 480), 0.15), ((224, 224), 
        ((1920, 1080), 0.07), ((3840, 2160), 0.03)]
 
 
-def kernel_sources_sha():
+def _strip_comments(text):
+    """C/C++ source without comments and with runs of white space collapsed (string literals are kept as they are)."""
+    out, i, n = [], 0, len(text)
+    while i < n:
+        c = text[i]
+        if c == '"' or c == "'":
+            j = i + 1
+            while j < n and text[j] != c:
+                j += 2 if text[j] == "\\" else 1
+            out.append(text[i:j + 1]); i = j + 1
+        elif text.startswith("//", i):
+            j = text.find("\n", i)
+            i = n if j < 0 else j
+        elif text.startswith("/*", i):
+            j = text.find("*/", i + 2)
+            i = n if j < 0 else j + 2
+            out.append(" ")
+        else:
+            out.append(c); i += 1
+    return " ".join("".join(out).split())
+
+
+def kernel_sources_sha(root=None):
     """Identifies the DEVICE code a profile was taken from (profiles/ncu_traffic.json carries the same key): the kernel
-    files and the headers they share with nothing but the emulator; host-only files (batch.h, bj_host.h, parse.h) do not
-    change what a kernel moves through DRAM."""
+    files and the headers they share with nothing but the emulator, comments and white space removed (a reworded comment
+    does not change what a kernel moves through DRAM); host-only files (batch.h, bj_host.h, parse.h) do not either."""
     import hashlib
     h = hashlib.sha256()
-    d = os.path.join(ROOT, "pim_jpeg_decoder_b200", "csrc")
+    d = os.path.join(root or ROOT, "pim_jpeg_decoder_b200", "csrc")
     for f in ("kernels_huff.cuh", "kernels_idct.cuh", "idct_color.cuh", "huff_core.h", "bj_dev.h"):
-        h.update(open(os.path.join(d, f), "rb").read())
+        h.update(_strip_comments(open(os.path.join(d, f), "r", encoding="utf-8").read()).encode())
     return h.hexdigest()[:16]
 
 

@@ -361,6 +361,28 @@ extern "C" int emu_classify_check(const uint8_t *bytes, size_t n) {
     return bad;
 }
 
+// The magnitude extension from a table entry (extend_entry: wrap-mode shifts fed by plain shifts of the entry, sign handled by
+// complementing the window) against the plain form extend_value (src/jpeg_scanner.cpp:480-482 / :513-516), for every code
+// length, every size (0 = no magnitude bits) and windows that exercise both signs and the extreme magnitudes.
+extern "C" int emu_extend_check(void) {
+    uint32_t x = 0x2545F491u;
+    for (uint32_t len = 1; len <= 16; len++) {
+        for (uint32_t size = 0; size <= 11; size++) {
+            const uint32_t e = (1u) | ((len + size) << 8) | (len << 16) | (size << 24) | kLutEob;   // (flag bits above the fields must not disturb the shifts)
+            for (int i = 0; i < 400; i++) {
+                x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+                uint32_t win = x;
+                if (i == 0) win = 0u;
+                if (i == 1) win = 0xFFFFFFFFu;
+                if (i == 2) win = 0x80000000u >> len;                     // first magnitude bit set, the rest clear
+                if (i == 3) win = ~(0x80000000u >> len);
+                if (extend_entry(win, e) != extend_value(win, len, size)) return (int)(len * 100 + size);
+            }
+        }
+    }
+    return 0;
+}
+
 // The device form of UnitWalk keeps (completed units << 8 | unit index << 4) in one register and advances it by the
 // table's step (unit_walk_step); the BitStream can be moved back inside its span (seek).  Both are device-side
 // shortcuts of what the host code above does with separate variables: check the arithmetic here.

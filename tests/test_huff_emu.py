@@ -242,6 +242,12 @@ def test_lut_matches_bit_serial_search():
     assert lib.emu_lut_check(ol._ptr(off), ol._ptr(sy), 1) == 0
 
 
+def test_magnitude_extension_from_table_entry():
+    """extend_entry (what the write pass computes per symbol: eight instructions on the device) against the plain
+    form of the reference's extension, for every code length x size and both signs."""
+    assert emu().emu_extend_check() == 0
+
+
 def test_unit_walk_and_stream_seek_arithmetic():
     """The packed unit counter of the synchronisation pass (completed << 8 | unit << 4, advanced by the table's step)
     and the bit reader's seek (the write pass re-reads a damaged unit) against the plain forms."""
