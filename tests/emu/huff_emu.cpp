@@ -146,6 +146,9 @@ extern "C" int emu_k0_check(const uint8_t *file, size_t len, int file_pos, int f
 // optional: per Jacobi round, how many sub-sequences were decoded (set by emu_set_round_hist; 64 entries)
 static uint32_t *g_round_hist = nullptr;
 extern "C" void emu_set_round_hist(uint32_t *hist) { g_round_hist = hist; }
+// 0: the write pass one symbol per step, slice after slice; n > 0: warps of 32 slices in rounds of n symbols, as k_huff_write
+static int g_write_rounds = 0;
+extern "C" void emu_set_write_rounds(int n) { g_write_rounds = n; }
 
 // slice_bytes = granularity of the write pass; a sub-sequence of the synchronisation pass is `slices` of them.
 // Returns 0 ok, <0 parse status.  info[0] = fix-up rounds, info[1] = first_zero (UINT32_MAX none), info[2] = nsub,
@@ -251,10 +254,17 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int
     }
     if (order_bad) return -300;
 
-    // prefix sum of the units started per segment, then the write pass (DC differences into their own plane):
-    // one cursor per slice, one symbol per step, the finished unit stored when the step says so
+    // prefix sum of the units started per segment, then the write pass (DC differences into their own plane).
+    // g_write_rounds == 0: one cursor per slice, one symbol per step, the finished unit stored when the step says so.
+    // g_write_rounds  > 0: as k_huff_write runs it - "warps" of 32 consecutive slices work in rounds: every lane takes up
+    // to g_write_rounds symbols without any check (step_plain) and stops at the one that completes its unit; then the
+    // lanes that completed a unit look back over it and hand over (unit_end), announce (lane, unit) in the warp's slot
+    // array in lane order, and the units are stored from the lanes' stages in slot order; a lane that has finished sits
+    // the rounds out.  Every stage is cleared when its unit has been stored; a unit is stored at most once.
     std::vector<uint8_t> written(ndu, 0);
     std::vector<int16_t> dcp(ndu, 0x5A5A);
+    struct Lane { WriteCursor cur; HostSink sink; bool done, active, last; };
+    std::vector<Lane> lanes;
     uint32_t n_ex = 0;
     for (size_t i = 0; i < ns; i++) {
         const Sub &u = subs[i];
@@ -267,29 +277,63 @@ extern "C" int emu_entropy(const uint8_t *file, size_t len, int slice_bytes, int
             uint32_t cnt = 0;
             if (k) { st.p = slice[i * slices + k].p; st.cz = slice[i * slices + k].cz; cnt = slice[i * slices + k].cnt; }
             const uint32_t end_bit = std::min(u.start_bit + (k + 1) * slice_bits, u.end_bit);
-            HostSink sink;
-            WriteCursor cur;
-            cur.idle = 0;
-            bool done = (cur.open(words, lm, g, st, end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex + cnt, du_end) & kEvDone) != 0;
-            while (!done) {
-                const bool unit = cur.step(lm, g, sink);
-                done = cur.done != 0;
-                if (unit) {
-                    const uint32_t du = cur.st_du;
-                    if (du < ndu) {
-                        dcp[du] = sink.unit[0];
-                        sink.unit[0] = 0;
-                        memcpy(coef_zz + (size_t)du * 64, sink.unit, sizeof(sink.unit));
-                        written[du]++;
-                    }
-                    memset(sink.unit, 0, sizeof(sink.unit));
-                }
-            }
-            // the last slice of a segment must have produced the segment's last unit
-            if (cur.fail == 0 && u.last && k + 1 == nsl && cur.du < du_end) cur.first_zero = cur.du;
-            first_zero = std::min(first_zero, cur.first_zero);
+            lanes.emplace_back();
+            Lane &L = lanes.back();
+            L.cur.idle = 0;
+            L.active = true;
+            L.last = u.last && k + 1 == nsl;
+            L.done = (L.cur.open(words, lm, g, st, end_bit, seg_off[u.seg + 1] * 8, du0 + n_ex + cnt, du_end) & kEvDone) != 0;
         }
         n_ex += tot[i];
+    }
+    auto store_unit = [&](Lane &L, uint32_t du) {
+        if (du < ndu) {
+            dcp[du] = L.sink.unit[0];
+            L.sink.unit[0] = 0;
+            memcpy(coef_zz + (size_t)du * 64, L.sink.unit, sizeof(L.sink.unit));
+            written[du]++;
+        }
+        memset(L.sink.unit, 0, sizeof(L.sink.unit));
+    };
+    if (g_write_rounds <= 0) {
+        for (Lane &L : lanes) {
+            while (!L.done) {
+                const bool unit = L.cur.step(lm, g, L.sink);
+                L.done = L.cur.done != 0;
+                if (unit) store_unit(L, L.cur.st_du);
+            }
+        }
+    } else {
+        for (size_t w0 = 0; w0 < lanes.size(); w0 += 32) {
+            const size_t w1 = std::min(lanes.size(), w0 + 32);
+            for (;;) {
+                bool all_done = true;
+                for (size_t l = w0; l < w1; l++) all_done = all_done && lanes[l].done;
+                if (all_done) break;
+                struct Slot { uint32_t lane, du; } slot[32];
+                uint32_t nun = 0;
+                bool fin[32] = {};
+                for (size_t l = w0; l < w1; l++) {                           // the symbols of the round
+                    Lane &L = lanes[l];
+                    if (L.done) continue;
+                    for (int k = 0; k < g_write_rounds && !(L.cur.S & 0x40u); k++) L.cur.step_plain(lm, L.sink);
+                    fin[l - w0] = (L.cur.S & 0x40u) != 0u;
+                }
+                for (size_t l = w0; l < w1; l++) {                           // look-back + hand-over, slots in lane order
+                    if (!fin[l - w0]) continue;
+                    Lane &L = lanes[l];
+                    L.cur.unit_end(lm, g, L.sink);
+                    L.done = L.cur.done != 0;
+                    slot[nun].lane = (uint32_t)(l - w0); slot[nun].du = L.cur.st_du; nun++;
+                }
+                for (uint32_t k = 0; k < nun; k++) store_unit(lanes[w0 + slot[k].lane], slot[k].du);   // the flush
+            }
+        }
+    }
+    for (Lane &L : lanes) {
+        // the last slice of a segment must have produced the segment's last unit
+        if (L.cur.fail == 0 && L.last && L.cur.du < L.cur.du_end) L.cur.first_zero = L.cur.du;
+        first_zero = std::min(first_zero, L.cur.first_zero);
     }
     // K1c: DC prediction over the plane, restarting at every restart interval; then merged into slot 0 for the comparison
     {

@@ -28,6 +28,7 @@ def emu():
     lib = C.CDLL(EMU)
     lib.emu_entropy.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.emu_lut_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.emu_set_write_rounds.argtypes = [C.c_int]
     return lib
 
 
@@ -90,6 +91,52 @@ def test_truncated_scan_zero_fills_like_the_reference():
     r, got, info = run_emu(bad, 128)
     assert r.huff_rc != 0
     assert info[1] != 0xFFFFFFFF
+    assert np.array_equal(got, r.coef_zz)
+
+
+@pytest.fixture
+def write_rounds():
+    """Sets how the emulator runs the write pass (0: one symbol per step, slice after slice; n: warps of 32 slices in
+    rounds of n symbols, look-back + hand-over once per round, units stored in slot order - the control flow of
+    k_huff_write) and puts the default back afterwards."""
+    lib = emu()
+    yield lib.emu_set_write_rounds
+    lib.emu_set_write_rounds(0)
+
+
+@pytest.mark.parametrize("rounds", [1, 3, 8])
+@pytest.mark.parametrize("sub_bytes,slices", [(4, 1), (16, 8), (128, 4)])
+def test_write_pass_in_rounds_matches_oracle(rounds, sub_bytes, slices, write_rounds, golden, golden_dir):
+    """The write pass as the kernel runs it: several symbols per lane and round with no check in between, the look-back
+    over a completed unit, the hand-over to the next unit and the stores once per round."""
+    write_rounds(rounds)
+    for name in _golden_names():
+        data = open(os.path.join(golden_dir, golden[name]["file"]), "rb").read()
+        r, got, info = run_emu(data, sub_bytes, slices)
+        assert r.huff_rc == 0, name
+        assert info[3] == 0, "a data unit was written twice or never"
+        assert np.array_equal(got, r.coef_zz), name
+
+
+@pytest.mark.parametrize("rounds", [1, 4, 8])
+@pytest.mark.parametrize("sub,sub_bytes,slices", [(2, 128, 4), (0, 16, 8), (1, 1024, 1)])
+def test_write_pass_in_rounds_stops_where_the_reference_stops(rounds, sub, sub_bytes, slices, write_rounds):
+    """Damaged Huffman data through the rounds: a unit that did not end well is found by the look-back at the end of the
+    round (no symbol is checked on the way) and decoded again, exactly; truncated data likewise."""
+    write_rounds(rounds)
+    rng = np.random.default_rng(77 * rounds + 1000 * sub + slices)
+    base = js.synth_jpeg(200, 152, seed=40 + sub, subsampling=sub)
+    failed = 0
+    for trial in range(16):
+        bad, _ = _corrupt_scan(base, rng, 1 + trial % 8)
+        r, got, info = run_emu(bad, sub_bytes, slices)
+        failed += r.huff_rc != 0
+        assert (info[1] != 0xFFFFFFFF) == (r.huff_rc != 0), trial
+        assert np.array_equal(got, r.coef_zz), trial
+    assert failed >= 2
+    cut = bytes(base[:len(base) - 2 - 700]) + b"\xFF\xD9"
+    r, got, info = run_emu(cut, sub_bytes, slices)
+    assert r.huff_rc != 0 and info[1] != 0xFFFFFFFF
     assert np.array_equal(got, r.coef_zz)
 
 
