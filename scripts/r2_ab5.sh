@@ -1,3 +1,4 @@
+# (record of an experiment: applies to commit c8d30e7 "Synchronisation pass, tail mode", which was measured with this script and reverted - the B200JPEG_SYNC_TAIL switch does not exist at HEAD)
 # usage (on the GPU box): bash scripts/r2_ab5.sh <tag> - tail mode of the synchronisation pass: GPU tests (default options, then the
 # whole suite with tail mode forced), device-resident bench per stage with and without it, launch list of the sync kernels
 tag=${1:-ab5}
